@@ -1,0 +1,93 @@
+"""ctypes binding of libggp_b200.so (the C ABI in include/ggp_b200.h).
+
+There is NO CPU fallback: if the CUDA library is missing or a call fails this module raises.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libggp_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+c_double_p = ctypes.c_void_p  # device pointers are passed as integers
+c_int_p = ctypes.c_void_p
+
+
+class GgpCfg(ctypes.Structure):
+    _fields_ = [("kernel", ctypes.c_int32), ("precision", ctypes.c_int32),
+                ("chunk_rows", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+KERNELS = {"rbf": 0, "matern32": 1, "matern52": 2}
+PRECISIONS = {"fp64": 0, "tf32x3": 1}
+LIKELIHOODS = {"gaussian": 0, "bernoulli": 1}
+
+# every symbol include/ggp_b200.h declares: name -> (restype, argtypes)
+_I, _I64, _D, _P, _SZP = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)
+_CFG = ctypes.POINTER(GgpCfg)
+SYMBOLS = {
+    "ggp_version": (_I, []),
+    "ggp_last_error": (ctypes.c_char_p, []),
+    "ggp_create": (_I, [ctypes.POINTER(ctypes.c_void_p), _I]),
+    "ggp_destroy": (_I, [_P]),
+    "ggp_workspace_bytes": (_I, [_CFG, _I64, _I, _I, _I, _SZP]),
+    "ggp_reserve": (_I, [_P, _CFG, _I64, _I, _I, _I]),
+    "ggp_sgpr_factor": (_I, [_P, _CFG, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "ggp_sgpr_pass1": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _P]),
+    "ggp_sgpr_finish": (_I, [_P, _CFG, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "ggp_sgpr_pass2": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _P]),
+    "ggp_sgpr_predict": (_I, [_P, _CFG, _P, _P, _I64, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "ggp_svgp_elbo": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I, _I, _I, _D, _I, _I, _P, _P, _P]),
+    "ggp_chol_batched": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "ggp_gemm_nt": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _D, _D]),
+    "ggp_kernel_matrix": (_I, [_P, _CFG, _P, _P, _I64, _P, _I64, _P, _I, _P]),
+    "ggp_probe_dmma_peak": (_I, [_P, _P, _I, ctypes.POINTER(ctypes.c_double)]),
+}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "--shared", "-Xcompiler", "-fPIC"]
+
+
+def build(verbose=False):
+    """Compile csrc/ggp_api.cu for sm_100a into libggp_b200.so (in-tree, travels with gpurun)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "ggp_api.cu")]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built (python -c 'import __graft_entry__ as g; "
+            "g.build()').  There is no CPU fallback for the sparse-GP hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class GgpError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().ggp_last_error()
+        raise GgpError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,351 @@
+// m x m section kernels: diagonal-block Cholesky + inverse, transposes, element-wise assembly, gemv, reductions.
+// All matrices are row-major [Mp x Mp] (Mp = 64 * 2^j >= M, identity on the padding) unless noted.
+#pragma once
+#include "common.cuh"
+#include "kernel_tiles.cuh"
+
+namespace ggp {
+
+constexpr int NB = 64;  // diagonal block size of the blocked Cholesky / recursive triangular inverse
+constexpr int POTF2_SMEM = 2 * NB * (NB + 1) * 8;
+
+// Factor diagonal block kb in place (lower) and write its inverse T = L_kk^{-1}.  One CTA per batch element.
+// info[b] = global index (1-based) of the first non-positive pivot, LAPACK potrf style; first failure wins.
+__global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int64_t ld, int64_t sA, int kb,
+                                                     double* __restrict__ T, int64_t sT, int32_t* info) {
+  extern __shared__ __align__(16) unsigned char potf2_smem[];
+  double (*a)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potf2_smem);
+  double (*t)[NB + 1] = a + NB;
+  __shared__ int bad;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double* Ab = A + b * sA + (int64_t)kb * NB * (ld + 1);
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx / NB, c = idx % NB;
+    a[r][c] = (c <= r) ? Ab[(int64_t)r * ld + c] : 0.0;
+  }
+  if (tid == 0) bad = 0;
+  for (int j = 0; j < NB; ++j) {
+    __syncthreads();
+    const double dj = a[j][j];
+    if (!(dj > 0.0) && tid == 0 && bad == 0) bad = j + 1;
+    const double piv = sqrt(dj);
+    __syncthreads();
+    if (tid == 0) a[j][j] = piv;
+    for (int r = j + 1 + tid; r < NB; r += 256) a[r][j] = a[r][j] / piv;
+    __syncthreads();
+    const int w = NB - 1 - j;
+    for (int idx = tid; idx < w * w; idx += 256) {
+      const int r = j + 1 + idx / w, c = j + 1 + idx % w;
+      if (c <= r) a[r][c] = fma(-a[r][j], a[c][j], a[r][c]);
+    }
+  }
+  __syncthreads();
+  // T = inv(L_kk): 4 threads per column split the dot product, fixed combination order
+  {
+    const int c = tid >> 2, part = tid & 3;
+    for (int r = 0; r < NB; ++r) {
+      double s = 0.0;
+      if (r >= c) {
+        for (int k = c + part; k < r; k += 4) s = fma(a[r][k], t[k][c], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0) t[r][c] = (r < c) ? 0.0 : (((r == c) ? 1.0 : 0.0) - s) / a[r][r];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  double* Tb = T + b * sT + (int64_t)kb * NB * NB;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx / NB, c = idx % NB;
+    Ab[(int64_t)r * ld + c] = a[r][c];  // upper part of the block is zero
+    Tb[idx] = t[r][c];
+  }
+  if (tid == 0 && bad && info[b] == 0) info[b] = kb * NB + bad;
+}
+
+// zero the strict upper triangle.  grid (Mp/16, Mp/16, batch), block (16,16)
+__global__ void k_tril(double* __restrict__ A, int Mp, int64_t sA) {
+  const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+  if (i < Mp && j < Mp && j > i) A[blockIdx.z * sA + (int64_t)i * Mp + j] = 0.0;
+}
+
+// Linv = blockdiag(T_0, T_1, ...), zero elsewhere
+__global__ void k_init_blockdiag(double* __restrict__ Linv, int Mp, int64_t sL, const double* __restrict__ T, int64_t sT) {
+  const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+  if (i >= Mp || j >= Mp) return;
+  const int bi = i / NB, bj = j / NB;
+  double v = 0.0;
+  if (bi == bj) v = T[blockIdx.z * sT + (int64_t)bi * NB * NB + (i % NB) * NB + (j % NB)];
+  Linv[blockIdx.z * sL + (int64_t)i * Mp + j] = v;
+}
+
+// out = in^T  (32x32 tiles through shared memory).  grid (Mp/32, Mp/32, batch), block (32, 8)
+__global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, int Mp, int64_t s) {
+  __shared__ double tile[32][33];
+  const double* I = in + blockIdx.z * s;
+  double* O = out + blockIdx.z * s;
+  const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8)
+    if (x < Mp && y0 + r < Mp) tile[r][threadIdx.x] = I[(int64_t)(y0 + r) * Mp + x];
+  __syncthreads();
+  const int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += 8)
+    if (xo < Mp && yo0 + r < Mp) O[(int64_t)(yo0 + r) * Mp + xo] = tile[threadIdx.x][r];
+}
+
+// Bm = I + S/s on the leading M x M (S dense, ld = M, from `partial`), identity on the padding
+__global__ void k_make_B(const double* __restrict__ partial, int64_t sP, int M, int Mp, const double* __restrict__ theta,
+                         int d, double* __restrict__ Bm, int64_t sB) {
+  const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x, b = blockIdx.z;
+  if (i >= Mp || j >= Mp) return;
+  const double s2 = theta[(int64_t)b * (d + 2) + d + 1];
+  double v = (i == j) ? 1.0 : 0.0;
+  if (i < M && j < M) v += partial[b * sP + (int64_t)i * M + j] / s2;
+  Bm[b * sB + (int64_t)i * Mp + j] = v;
+}
+
+// y[i] = alpha * s2^(-spow) * sum_j A[i,j] x[j]   (one warp per row; s2 = noise of batch b)  grid (ceil(M/8), batch), block 256
+__global__ void __launch_bounds__(256) k_gemv(const double* __restrict__ A, int64_t ld, int64_t sA,
+                                              const double* __restrict__ x, int64_t sx, double* __restrict__ y,
+                                              int64_t sy, int M, int ncols, double alpha,
+                                              const double* __restrict__ theta, int d, int spow) {
+  const int b = blockIdx.y, row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const double* a = A + b * sA + (int64_t)row * ld;
+  const double* xv = x + b * sx;
+  double s = 0.0;
+  for (int j = lane; j < ncols; j += 32) s = fma(a[j], xv[j], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    double sc = alpha;
+    if (spow > 0) {
+      const double s2 = theta[(int64_t)b * (d + 2) + d + 1];
+      sc = (spow == 1) ? alpha / s2 : alpha / (s2 * s2);
+    }
+    y[b * sy + row] = sc * s;
+  }
+}
+// y[i] += sum_j A[i,j] x[j]  (accumulating variant used for b += A_chunk y_chunk; x shared across batch)
+__global__ void __launch_bounds__(256) k_gemv_acc(const double* __restrict__ A, int64_t ld, int64_t sA,
+                                                  const double* __restrict__ x, double* __restrict__ y, int64_t sy,
+                                                  int M, int ncols) {
+  const int b = blockIdx.y, row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const double* a = A + b * sA + (int64_t)row * ld;
+  double s = 0.0;
+  for (int j = lane; j < ncols; j += 32) s = fma(a[j], x[j], s);
+  s = warp_sum(s);
+  if (lane == 0) y[b * sy + row] += s;
+}
+
+// out[0] = sum_i y_i^2 over n (single CTA, deterministic)
+__global__ void __launch_bounds__(1024) k_sumsq(const double* __restrict__ y, int64_t n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) s = fma(y[i], y[i], s);
+  s = block_sum<1024>(s, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+// partial[b] = [ S (upper tiles summed over splits, mirrored) | bvec | yty, n*sf2, n ]
+// grid (ceil(M/16), ceil(M/16), batch), block (16,16)
+__global__ void k_finalize_partial(const double* __restrict__ Spart, int64_t ldS, int64_t sSplit, int64_t sSb, int splits,
+                                   const double* __restrict__ bvec, int64_t sbv, const double* __restrict__ yty, int64_t n_local,
+                                   const double* __restrict__ theta, int d, int M, double* __restrict__ partial, int64_t sP) {
+  const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x, b = blockIdx.z;
+  double* out = partial + b * sP;
+  if (i < M && j < M) {
+    // tiles with tile_j >= tile_i were computed: always read the upper element, so S is exactly symmetric
+    const int r = i < j ? i : j, c = i < j ? j : i;
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += Spart[b * sSb + k * sSplit + (int64_t)r * ldS + c];
+    out[(int64_t)i * M + j] = s;
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    const int t = threadIdx.y * 16 + threadIdx.x;
+    for (int k = t; k < M; k += 256) out[(int64_t)M * M + k] = bvec[b * sbv + k];
+    if (t == 0) {
+      out[(int64_t)M * M + M + 0] = yty[0];
+      out[(int64_t)M * M + M + 1] = (double)n_local * theta[(int64_t)b * (d + 2) + d];
+      out[(int64_t)M * M + M + 2] = (double)n_local;
+    }
+  }
+}
+
+// scalars of the bound and of dF/ds2.  One CTA (256 thr) per batch element.
+//   c = LBinv b / s ; beta = Binv b     (given)
+//   F = -N/2 log2pi - N/2 log s - sum log diag L_B - (yty/s - c.c)/2 - (sum_knn - trS)/(2s)
+//   dF/ds = -N/(2s) + (M - tr Binv)/(2s) + yty/(2s^2) - b.beta/s^3 + (b.beta - beta.beta)/(2 s^3) + (sum_knn - trS)/(2s^2)
+__global__ void __launch_bounds__(256) k_bound_scalars(const double* __restrict__ partial, int64_t sP, int M, int Mp,
+                                                       const double* __restrict__ theta, int d,
+                                                       const double* __restrict__ LB, const double* __restrict__ Binv,
+                                                       int64_t sMat, const double* __restrict__ cvec,
+                                                       const double* __restrict__ beta, int64_t sv,
+                                                       double* __restrict__ bound, double* __restrict__ ds2_out) {
+  __shared__ double red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* P = partial + b * sP;
+  const double* bv = P + (int64_t)M * M;
+  const double s2 = theta[(int64_t)b * (d + 2) + d + 1];
+  double logdiag = 0, cc = 0, trS = 0, trBinv = 0, bbeta = 0, betabeta = 0;
+  for (int i = tid; i < M; i += 256) {
+    logdiag += log(LB[b * sMat + (int64_t)i * Mp + i]);
+    const double ci = cvec[b * sv + i], be = beta[b * sv + i];
+    cc = fma(ci, ci, cc);
+    trS += P[(int64_t)i * M + i];
+    trBinv += Binv[b * sMat + (int64_t)i * Mp + i];
+    bbeta = fma(bv[i], be, bbeta);
+    betabeta = fma(be, be, betabeta);
+  }
+  logdiag = block_sum<256>(logdiag, red);
+  cc = block_sum<256>(cc, red);
+  trS = block_sum<256>(trS, red);
+  trBinv = block_sum<256>(trBinv, red);
+  bbeta = block_sum<256>(bbeta, red);
+  betabeta = block_sum<256>(betabeta, red);
+  if (tid == 0) {
+    const double yty = bv[M], sumk = bv[M + 1], N = bv[M + 2];
+    const double LOG2PI = 1.8378770664093453;
+    bound[b] = -0.5 * N * LOG2PI - 0.5 * N * log(s2) - logdiag - 0.5 * (yty / s2 - cc) - 0.5 * (sumk - trS) / s2;
+    if (ds2_out) {
+      const double s3 = s2 * s2 * s2;
+      ds2_out[b] = -0.5 * N / s2 + 0.5 * ((double)M - trBinv) / s2 + 0.5 * yty / (s2 * s2) - bbeta / s3 +
+                   0.5 * (bbeta - betabeta) / s3 + 0.5 * (sumk - trS) / (s2 * s2);
+    }
+  }
+}
+
+// PA = (I - Binv)/s - beta beta^T / s^3 ;  Gbar = (I + S/s) + Binv - 2I + beta beta^T / s^2   (zero on the padding)
+__global__ void k_make_PA_Gbar(const double* __restrict__ partial, int64_t sP, int M, int Mp,
+                               const double* __restrict__ theta, int d, const double* __restrict__ Binv,
+                               const double* __restrict__ beta, int64_t sv, double* __restrict__ PA,
+                               double* __restrict__ Gbar, int64_t sMat) {
+  const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x, b = blockIdx.z;
+  if (i >= Mp || j >= Mp) return;
+  double pa = 0.0, gb = 0.0;
+  if (i < M && j < M) {
+    const double s2 = theta[(int64_t)b * (d + 2) + d + 1];
+    const double bi = Binv[b * sMat + (int64_t)i * Mp + j];
+    const double bb = beta[b * sv + i] * beta[b * sv + j];
+    const double eye = (i == j) ? 1.0 : 0.0;
+    pa = (eye - bi) / s2 - bb / (s2 * s2 * s2);
+    gb = partial[b * sP + (int64_t)i * M + j] / s2 + bi - eye + bb / (s2 * s2);
+  }
+  PA[b * sMat + (int64_t)i * Mp + j] = pa;
+  Gbar[b * sMat + (int64_t)i * Mp + j] = gb;
+}
+
+// Kzz-dependent gradient, one warp per row i:  V = Gzz o Kzz ;
+//   rowacc[i][0..d-1] = sum_j V_ij * dk-factor * (z_i - z_j)^2 ;  rowacc[i][d] = sum_j Gzz_ij k_ij ;
+//   dZ[i][c] = 2 * sum_j Gzz_ij * 2 g_ij (z_i - z_j)_c / ell_c^2      (g = dk/d(d2))
+// grid (ceil(M/8), batch), block 256
+__global__ void __launch_bounds__(256) k_grad_kzz_rows(const double* __restrict__ Gzz, int Mp, int64_t sMat,
+                                                       const double* __restrict__ Z, int M, int d,
+                                                       const double* __restrict__ theta, int kind,
+                                                       double* __restrict__ rowacc /*[batch][M][d+1]*/,
+                                                       double* __restrict__ dZ /*[batch][M][d], stride sG*/, int64_t sG) {
+  const int b = blockIdx.y, i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= M) return;
+  const double* th = theta + (int64_t)b * (d + 2);
+  const double sf2 = th[d];
+  const double* zi = Z + (int64_t)i * d;
+  double ksum = 0.0;
+  for (int j = lane; j < M; j += 32) {
+    double d2 = 0.0;
+    for (int c = 0; c < d; ++c) {
+      const double t = (zi[c] - Z[(int64_t)j * d + c]) / th[c];
+      d2 = fma(t, t, d2);
+    }
+    ksum = fma(Gzz[b * sMat + (int64_t)i * Mp + j], kval(kind, sf2, d2), ksum);
+  }
+  ksum = warp_sum(ksum);
+  if (lane == 0) rowacc[((int64_t)b * M + i) * (d + 1) + d] = ksum;
+  for (int c = 0; c < d; ++c) {
+    double al = 0.0, az = 0.0;
+    for (int j = lane; j < M; j += 32) {
+      double d2 = 0.0;
+      for (int cc = 0; cc < d; ++cc) {
+        const double t = (zi[cc] - Z[(int64_t)j * d + cc]) / th[cc];
+        d2 = fma(t, t, d2);
+      }
+      const double gg = Gzz[b * sMat + (int64_t)i * Mp + j] * kgrad(kind, sf2, d2);
+      const double df = zi[c] - Z[(int64_t)j * d + c];
+      al = fma(gg * df, df, al);
+      az = fma(gg, df, az);
+    }
+    al = warp_sum(al);
+    az = warp_sum(az);
+    if (lane == 0) {
+      // d(d2)/d ell_c = -2 df^2 / ell_c^3 ; d(d2)/d z_ic = 2 df / ell_c^2 (and the symmetric partner doubles it)
+      rowacc[((int64_t)b * M + i) * (d + 1) + c] = -2.0 * al / (th[c] * th[c] * th[c]);
+      dZ[b * sG + (int64_t)i * d + c] = 4.0 * az / (th[c] * th[c]);
+    }
+  }
+}
+
+// grad_mm[b] = [ d_ell (sum rows) , d_sf2 = sum_i rowacc[i][d]/sf2 - N/(2 s) , d_s2 , dZ already written ]
+__global__ void __launch_bounds__(256) k_grad_mm_final(const double* __restrict__ rowacc, int M, int d,
+                                                       const double* __restrict__ theta, const double* __restrict__ partial,
+                                                       int64_t sP, const double* __restrict__ ds2, double* __restrict__ grad,
+                                                       int64_t sG) {
+  __shared__ double red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* th = theta + (int64_t)b * (d + 2);
+  for (int c = 0; c <= d; ++c) {
+    double s = 0.0;
+    for (int i = tid; i < M; i += 256) s += rowacc[((int64_t)b * M + i) * (d + 1) + c];
+    s = block_sum<256>(s, red);
+    if (tid == 0) {
+      if (c < d) grad[b * sG + c] = s;
+      else {
+        const double N = partial[b * sP + (int64_t)M * M + M + 2];
+        grad[b * sG + d] = s / th[d] - 0.5 * N / th[d + 1];
+      }
+    }
+  }
+  if (tid == 0) grad[b * sG + d + 1] = ds2[b];
+}
+
+// mom_acc[b][i][q] += sum_t mom_part[b][t][i][q]   (fixed order over tiles)
+__global__ void k_reduce_moments(const double* __restrict__ part, int64_t sTile, int64_t sB, int ntiles, int64_t count,
+                                 double* __restrict__ acc) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= count) return;
+  double s = 0.0;
+  for (int t = 0; t < ntiles; ++t) s += part[b * sB + t * sTile + idx];
+  acc[(int64_t)b * count + idx] += s;
+}
+
+// moments -> gradient partial.  mom[b][i][0]=r_i, [1..d]=Q_ic, [d+1..2d]=T_ic  with W = G o K (RBF: dk/d(d2) = -K/2)
+//   d_ell_c = sum_i (z^2 r - 2 z Q + T)_ic / ell_c^3 ; d_sf2 = sum_i r_i / sf2 ; dZ_ic = (Q_ic - z_ic r_i)/ell_c^2 ; d_s2 = 0
+__global__ void __launch_bounds__(256) k_grad_from_moments(const double* __restrict__ mom, int M, int d,
+                                                           const double* __restrict__ Z, const double* __restrict__ theta,
+                                                           double* __restrict__ grad, int64_t sG) {
+  __shared__ double red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int nq = 2 * d + 1;
+  const double* th = theta + (int64_t)b * (d + 2);
+  const double* mb = mom + (int64_t)b * M * nq;
+  for (int c = 0; c < d; ++c) {
+    double s = 0.0;
+    for (int i = tid; i < M; i += 256) {
+      const double z = Z[(int64_t)i * d + c], r = mb[(int64_t)i * nq], Q = mb[(int64_t)i * nq + 1 + c],
+                   T = mb[(int64_t)i * nq + 1 + d + c];
+      s += fma(z, fma(z, r, -2.0 * Q), T);
+      grad[b * sG + d + 2 + (int64_t)i * d + c] = (Q - z * r) / (th[c] * th[c]);
+    }
+    s = block_sum<256>(s, red);
+    if (tid == 0) grad[b * sG + c] = s / (th[c] * th[c] * th[c]);
+  }
+  double s = 0.0;
+  for (int i = tid; i < M; i += 256) s += mb[(int64_t)i * nq];
+  s = block_sum<256>(s, red);
+  if (tid == 0) {
+    grad[b * sG + d] = s / th[d];
+    grad[b * sG + d + 1] = 0.0;
+  }
+}
+
+}  // namespace ggp

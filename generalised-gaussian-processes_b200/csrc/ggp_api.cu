@@ -1,0 +1,485 @@
+// C ABI of the B200-native collapsed sparse-GP hot path (see include/ggp_b200.h for the contract and the
+// reference call sites each entry point replaces).  Host orchestration only enqueues kernels on the caller's stream.
+#include "../../include/ggp_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+
+#include "common.cuh"
+#include "dense_mm.cuh"
+#include "gemm_dmma.cuh"
+#include "kernel_tiles.cuh"
+#include "misc.cuh"
+
+using namespace ggp;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      snprintf(g_err, sizeof(g_err), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return (int)e_;                                                                         \
+    }                                                                                         \
+  } while (0)
+#define CKL() CK(cudaGetLastError())
+
+struct ggp_handle {
+  int device = 0, sm_count = 148;
+  // reserved shapes
+  int64_t n_local = 0;
+  int m = 0, d = 0, batch = 0, Mp = 0, nc = 0, splits = 1;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  // m x m (per batch stride Mp*Mp)
+  double *L = 0, *Linv = 0, *LinvT = 0, *Wk = 0, *Bm = 0, *LBinv = 0, *LBinvT = 0, *Binv = 0, *PA = 0, *Gbar = 0, *T1 = 0,
+         *P = 0, *Gzz = 0, *Tblk = 0;
+  // vectors (per batch stride Mp)
+  double *bvec = 0, *cvec = 0, *beta = 0, *u = 0, *yty = 0, *ds2 = 0, *rowacc = 0;
+  // streamed chunk buffers
+  double *Kc = 0, *At = 0, *Spart = 0, *mom_part = 0, *mom_acc = 0;
+};
+
+static int pad_pow2_blocks(int m) {
+  int nb = (m + NB - 1) / NB, p = 1;
+  while (p < nb) p <<= 1;
+  return p * NB;
+}
+
+struct Plan {
+  int Mp, nc, splits;
+  size_t bytes;
+  size_t off[40];
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int batch, int sm_count) {
+  Plan p;
+  p.Mp = pad_pow2_blocks(m);
+  int64_t nmax = std::max<int64_t>(128, (n_local + 127) / 128 * 128);
+  int64_t nc = (cfg && cfg->chunk_rows > 0) ? (cfg->chunk_rows + 127) / 128 * 128 : 16384;
+  // keep the two chunk buffers under ~4 GiB in total
+  const double budget = 4.0 * 1024 * 1024 * 1024;
+  while (nc > 128 && 2.0 * batch * (double)nc * p.Mp * 8.0 > budget) nc /= 2;
+  nc = std::max<int64_t>(128, nc / 128 * 128);
+  p.nc = (int)std::min<int64_t>(nc, nmax);
+  const int T = (m + BM - 1) / BM;
+  const int tiles = T * (T + 1) / 2;
+  int splits = (int)((sm_count + tiles * batch / 2) / std::max(1, tiles * batch));
+  splits = std::max(1, std::min(16, splits));
+  splits = std::min(splits, std::max(1, p.nc / 256));
+  p.splits = splits;
+  const size_t MM = (size_t)p.Mp * p.Mp * 8, V = (size_t)p.Mp * 8;
+  const int nq = 2 * d + 1;
+  size_t o = 0;
+  int k = 0;
+  auto take = [&](size_t bytes) {
+    p.off[k++] = o;
+    o += align_up(bytes, 256);
+  };
+  for (int i = 0; i < 14; ++i) take(MM * batch);       // L, Linv, LinvT, Wk, Bm, LBinv, LBinvT, Binv, PA, Gbar, T1, P, Gzz, Tblk
+  for (int i = 0; i < 4; ++i) take(V * batch);          // bvec, cvec, beta, u
+  take(256);                                            // yty
+  take((size_t)batch * 8);                              // ds2
+  take((size_t)batch * m * (d + 1) * 8);                // rowacc
+  take((size_t)batch * p.nc * p.Mp * 8);                // Kc
+  take((size_t)batch * p.nc * p.Mp * 8);                // At
+  take((size_t)batch * p.splits * MM);                  // Spart
+  take((size_t)batch * (p.nc / 128) * m * nq * 8);      // mom_part
+  take((size_t)batch * m * nq * 8);                     // mom_acc
+  p.bytes = o;
+  return p;
+}
+
+static bool reserved_for(const ggp_handle* h, int64_t n_local, int m, int d, int batch) {
+  return h->arena && h->m == m && h->d == d && batch <= h->batch && n_local <= h->n_local;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+static int launch_gemm(cudaStream_t st, int epi, const GemmP& p, int nbatch) {
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, nbatch * p.nz2 * p.splits);
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
+  if (epi == EPI_STORE)
+    k_gemm_nt<EPI_STORE><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
+  else
+    k_gemm_nt<EPI_MOMENTS><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
+  CKL();
+  return 0;
+}
+
+static GemmP gemm_basic(const double* A, int64_t lda, int64_t sA, const double* B, int64_t ldb, int64_t sB, double* C,
+                        int64_t ldc, int64_t sC, int M, int N, int K, double alpha, double beta, int kmode = 0) {
+  GemmP p;
+  memset(&p, 0, sizeof(p));
+  p.A = A; p.lda = lda; p.sA = sA;
+  p.B = B; p.ldb = ldb; p.sB = sB;
+  p.C = C; p.ldc = ldc; p.sC = sC;
+  p.M = M; p.N = N; p.K = K;
+  p.nz2 = 1; p.splits = 1;
+  p.alpha = alpha; p.beta = beta; p.kmode = kmode;
+  return p;
+}
+
+#define RUN(x)                \
+  do {                        \
+    int rc_ = (x);            \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+// In-place blocked Cholesky of A[batch][Mp][Mp] (lower), explicit inverse -> Linv, Linv^T -> LinvT.
+static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* Linv, double* LinvT, int batch,
+                            int32_t* info) {
+  const int Mp = h->Mp, nblk = Mp / NB;
+  const int64_t sM = (int64_t)Mp * Mp;
+  const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
+  for (int k = 0; k < nblk; ++k) {
+    const int k0 = k * NB;
+    if (k > 0) {  // A[k0:, k0:k0+NB] -= L[k0:, :k0] * L[k0:k0+NB, :k0]^T
+      GemmP p = gemm_basic(A + (int64_t)k0 * Mp, Mp, sM, A + (int64_t)k0 * Mp, Mp, sM, A + (int64_t)k0 * (Mp + 1), Mp, sM,
+                           Mp - k0, NB, k0, -1.0, 1.0);
+      RUN(launch_gemm(st, EPI_STORE, p, batch));
+    }
+    k_potf2_trti2<<<batch, 256, POTF2_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, info);
+    CKL();
+    if (k < nblk - 1) {  // L[k0+NB:, k0:k0+NB] = A[k0+NB:, k0:k0+NB] * T_k^T   (in place; one n-tile, K = NB)
+      double* blk = A + (int64_t)(k0 + NB) * Mp + k0;
+      GemmP p = gemm_basic(blk, Mp, sM, h->Tblk + (int64_t)k * NB * NB, NB, sM, blk, Mp, sM, Mp - k0 - NB, NB, NB, 1.0, 0.0);
+      RUN(launch_gemm(st, EPI_STORE, p, batch));
+    }
+  }
+  k_tril<<<g16, b16, 0, st>>>(A, Mp, sM);
+  CKL();
+  // recursive-doubling triangular inverse
+  k_init_blockdiag<<<g16, b16, 0, st>>>(Linv, Mp, sM, h->Tblk, sM);
+  CKL();
+  const dim3 gt(Mp / 32, Mp / 32, batch), bt(32, 8);
+  for (int s = NB; s < Mp; s *= 2) {
+    k_transpose<<<gt, bt, 0, st>>>(Linv, LinvT, Mp, sM);
+    CKL();
+    const int npairs = Mp / (2 * s);
+    const int64_t sPair = (int64_t)2 * s * (Mp + 1);
+    // C1T = Inv11^T-rows x L21-rows :  Wk[pair upper-right block][j,i] = sum_k Inv11T[j,k] L21[i,k]
+    GemmP p1 = gemm_basic(LinvT, Mp, sM, A + (int64_t)s * Mp, Mp, sM, h->Wk + s, Mp, sM, s, s, s, 1.0, 0.0, KM_A_UPPER);
+    p1.nz2 = npairs; p1.sA2 = sPair; p1.sB2 = sPair; p1.sC2 = sPair;
+    RUN(launch_gemm(st, EPI_STORE, p1, batch));
+    // X = -Inv22 * C1 :  Linv[pair lower-left block][i,j] = -sum_k Inv22[i,k] C1T[j,k]
+    GemmP p2 = gemm_basic(Linv + (int64_t)s * (Mp + 1), Mp, sM, h->Wk + s, Mp, sM, Linv + (int64_t)s * Mp, Mp, sM, s, s, s,
+                          -1.0, 0.0, KM_A_LOWER);
+    p2.nz2 = npairs; p2.sA2 = sPair; p2.sB2 = sPair; p2.sC2 = sPair;
+    RUN(launch_gemm(st, EPI_STORE, p2, batch));
+  }
+  k_transpose<<<gt, bt, 0, st>>>(Linv, LinvT, Mp, sM);
+  CKL();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ggp_version(void) { return 100; }
+const char* ggp_last_error(void) { return g_err; }
+
+int ggp_create(ggp_handle_t** out, int device) {
+  if (!out) return fail(-1, "ggp_create: out is NULL");
+  CK(cudaSetDevice(device));
+  ggp_handle* h = new ggp_handle();
+  h->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  CK(cudaFuncSetAttribute(k_gemm_nt<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  CK(cudaFuncSetAttribute(k_gemm_nt<EPI_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  CK(cudaFuncSetAttribute(k_build_kc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_potf2_trti2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
+  *out = h;
+  return 0;
+}
+
+int ggp_destroy(ggp_handle_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+  return 0;
+}
+
+int ggp_workspace_bytes(const ggp_cfg* cfg, int64_t n_local, int m, int d, int batch, size_t* out) {
+  if (!out || m <= 0 || d <= 0 || batch <= 0 || n_local < 0) return fail(-1, "ggp_workspace_bytes: bad argument");
+  *out = make_plan(cfg, n_local, m, d, batch, 148).bytes;
+  return 0;
+}
+
+int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int d, int batch) {
+  if (!h) return fail(-1, "ggp_reserve: handle is NULL");
+  if (m <= 0 || d <= 0 || batch <= 0 || n_local < 0) return fail(-2, "ggp_reserve: bad shape");
+  if ((size_t)(2 * KT_N * d + d) * 8 > 200 * 1024) return fail(-3, "ggp_reserve: input dimension d too large");
+  CK(cudaSetDevice(h->device));
+  Plan p = make_plan(cfg, n_local, m, d, batch, h->sm_count);
+  if (p.bytes > h->arena_bytes) {
+    if (h->arena) CK(cudaFree(h->arena));
+    h->arena = nullptr;
+    h->arena_bytes = 0;
+    CK(cudaMalloc((void**)&h->arena, p.bytes));
+    h->arena_bytes = p.bytes;
+  }
+  h->n_local = n_local; h->m = m; h->d = d; h->batch = batch;
+  h->Mp = p.Mp; h->nc = p.nc; h->splits = p.splits;
+  double** slots[] = {&h->L, &h->Linv, &h->LinvT, &h->Wk, &h->Bm, &h->LBinv, &h->LBinvT, &h->Binv, &h->PA, &h->Gbar, &h->T1,
+                      &h->P, &h->Gzz, &h->Tblk, &h->bvec, &h->cvec, &h->beta, &h->u, &h->yty, &h->ds2, &h->rowacc, &h->Kc,
+                      &h->At, &h->Spart, &h->mom_part, &h->mom_acc};
+  for (size_t i = 0; i < sizeof(slots) / sizeof(slots[0]); ++i) *slots[i] = reinterpret_cast<double*>(h->arena + p.off[i]);
+  return 0;
+}
+
+int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* Z, const double* theta,
+                    const double* jitter, int m, int d, int batch, int32_t* info) {
+  if (!h || !Z || !theta || !info) return fail(-1, "ggp_sgpr_factor: NULL argument");
+  if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_factor: handle not reserved for this shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kind = cfg ? cfg->kernel : 0;
+  const int Mp = h->Mp;
+  CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
+  k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp);
+  CKL();
+  return chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info);
+}
+
+static int build_chunk(ggp_handle* h, cudaStream_t st, const double* Xc, int nv, int d, const double* Z, int m,
+                       const double* theta, int kind, int batch) {
+  const int Mp = h->Mp;
+  dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
+  const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
+  k_build_kc<<<grid, KT_THREADS, smem, st>>>(Xc, nv, nv, d, Z, m, theta, kind, h->Kc, Mp, (int64_t)h->nc * Mp);
+  CKL();
+  return 0;
+}
+
+int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, const double* y, int64_t n_local,
+                   const double* Z, const double* theta, int m, int d, int batch, double* partial) {
+  if (!h || !Z || !theta || !partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass1: NULL argument");
+  if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_pass1: handle not reserved for this shape");
+  const int kind = cfg ? cfg->kernel : 0;
+  if (cfg && cfg->precision != GGP_PREC_FP64) return fail(-3, "ggp_sgpr_pass1: only GGP_PREC_FP64 is implemented");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = h->Mp, nc = h->nc, splits = h->splits;
+  const int64_t sM = (int64_t)Mp * Mp;
+  CK(cudaMemsetAsync(h->Spart, 0, (size_t)batch * splits * sM * 8, st));
+  CK(cudaMemsetAsync(h->bvec, 0, (size_t)batch * Mp * 8, st));
+  k_sumsq<<<1, 1024, 0, st>>>(y, n_local, h->yty);
+  CKL();
+  for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
+    const int nv = (int)std::min<int64_t>(nc, n_local - c0);
+    RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch));
+    // At[m x nv] = Linv[m x m] * Kc[nv x m]^T   (k clipped to the lower triangle)
+    GemmP t = gemm_basic(h->Linv, Mp, sM, h->Kc, Mp, (int64_t)nc * Mp, h->At, nc, (int64_t)nc * Mp, m, nv, m, 1.0, 0.0,
+                         KM_A_LOWER);
+    t.heavy_first = 1;
+    RUN(launch_gemm(st, EPI_STORE, t, batch));
+    // S_split += At * At^T  (upper tiles)
+    GemmP s = gemm_basic(h->At, nc, (int64_t)nc * Mp, h->At, nc, (int64_t)nc * Mp, h->Spart, Mp, (int64_t)splits * sM, m, m, nv,
+                         1.0, 1.0);
+    s.sym = 1; s.splits = splits; s.sSplit = sM;
+    RUN(launch_gemm(st, EPI_STORE, s, batch));
+    // b += At * y_chunk
+    k_gemv_acc<<<dim3((m + 7) / 8, batch), 256, 0, st>>>(h->At, nc, (int64_t)nc * Mp, y + c0, h->bvec, Mp, m, nv);
+    CKL();
+  }
+  k_finalize_partial<<<dim3((m + 15) / 16, (m + 15) / 16, batch), dim3(16, 16), 0, st>>>(
+      h->Spart, Mp, sM, (int64_t)splits * sM, splits, h->bvec, Mp, h->yty, n_local, theta, d, m, partial,
+      (int64_t)m * m + m + 3);
+  CKL();
+  return 0;
+}
+
+int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* Z, const double* theta, int m, int d,
+                    int batch, const double* partial, int need_grad, double* bound, double* grad_mm, int32_t* info) {
+  if (!h || !Z || !theta || !partial || !bound || !info) return fail(-1, "ggp_sgpr_finish: NULL argument");
+  if (need_grad && !grad_mm) return fail(-1, "ggp_sgpr_finish: grad_mm is NULL");
+  if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_finish: handle not reserved for this shape");
+  const int kind = cfg ? cfg->kernel : 0;
+  if (need_grad && kind != GGP_KERNEL_RBF) return fail(-3, "ggp_sgpr_finish: gradients are implemented for GGP_KERNEL_RBF");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = h->Mp;
+  const int64_t sM = (int64_t)Mp * Mp, sP = (int64_t)m * m + m + 3, sG = (int64_t)d + 2 + (int64_t)m * d;
+  const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
+  const dim3 gv((m + 7) / 8, batch);
+  CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
+  k_make_B<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Bm, sM);
+  CKL();
+  RUN(chol_and_inverse(h, st, h->Bm, h->LBinv, h->LBinvT, batch, info));
+  // Binv = LBinv^T LBinv
+  RUN(launch_gemm(st, EPI_STORE,
+                  gemm_basic(h->LBinvT, Mp, sM, h->LBinvT, Mp, sM, h->Binv, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER | KM_B_UPPER),
+                  batch));
+  const double* bsrc = partial + (int64_t)m * m;
+  // c = LBinv b / s ; beta = Binv b ; u = Linv^T beta / s^2
+  k_gemv<<<gv, 256, 0, st>>>(h->LBinv, Mp, sM, bsrc, sP, h->cvec, Mp, m, m, 1.0, theta, d, 1);
+  CKL();
+  k_gemv<<<gv, 256, 0, st>>>(h->Binv, Mp, sM, bsrc, sP, h->beta, Mp, m, m, 1.0, theta, d, 0);
+  CKL();
+  k_gemv<<<gv, 256, 0, st>>>(h->LinvT, Mp, sM, h->beta, Mp, h->u, Mp, m, m, 1.0, theta, d, 2);
+  CKL();
+  k_bound_scalars<<<batch, 256, 0, st>>>(partial, sP, m, Mp, theta, d, h->Bm, h->Binv, sM, h->cvec, h->beta, Mp, bound,
+                                         need_grad ? h->ds2 : nullptr);
+  CKL();
+  if (!need_grad) return 0;
+  k_make_PA_Gbar<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Binv, h->beta, Mp, h->PA, h->Gbar, sM);
+  CKL();
+  // P = Linv^T PA Linv ;  Gzz = -1/2 Linv^T Gbar Linv
+  RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
+  RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_B_UPPER), batch));
+  RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->Gbar, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
+  RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->Gzz, Mp, sM, m, m, m, -0.5, 0.0, KM_B_UPPER), batch));
+  k_grad_kzz_rows<<<gv, 256, 0, st>>>(h->Gzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, grad_mm + d + 2, sG);
+  CKL();
+  k_grad_mm_final<<<batch, 256, 0, st>>>(h->rowacc, m, d, theta, partial, sP, h->ds2, grad_mm, sG);
+  CKL();
+  return 0;
+}
+
+int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, const double* y, int64_t n_local,
+                   const double* Z, const double* theta, int m, int d, int batch, double* grad_partial) {
+  if (!h || !Z || !theta || !grad_partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass2: NULL argument");
+  if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_pass2: handle not reserved for this shape");
+  const int kind = cfg ? cfg->kernel : 0;
+  if (kind != GGP_KERNEL_RBF) return fail(-3, "ggp_sgpr_pass2: gradients are implemented for GGP_KERNEL_RBF");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = h->Mp, nc = h->nc, nq = 2 * d + 1;
+  const int64_t sM = (int64_t)Mp * Mp, sG = (int64_t)d + 2 + (int64_t)m * d;
+  const int64_t cnt = (int64_t)m * nq;
+  CK(cudaMemsetAsync(h->mom_acc, 0, (size_t)batch * cnt * 8, st));
+  for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
+    const int nv = (int)std::min<int64_t>(nc, n_local - c0);
+    RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch));
+    const int ntiles = (nv + BN - 1) / BN;
+    GemmP g = gemm_basic(h->P, Mp, sM, h->Kc, Mp, (int64_t)nc * Mp, nullptr, 0, 0, m, nv, m, 1.0, 0.0);
+    g.u = h->u; g.su = Mp;
+    g.yv = y + c0;
+    g.Kc = h->Kc; g.ldk = Mp; g.sK = (int64_t)nc * Mp;
+    g.Xc = X + c0 * d; g.d = d;
+    g.mom = h->mom_part; g.sMomTile = cnt; g.sMom = (int64_t)(nc / 128) * cnt;
+    RUN(launch_gemm(st, EPI_MOMENTS, g, batch));
+    k_reduce_moments<<<dim3((unsigned)((cnt + 255) / 256), batch), 256, 0, st>>>(h->mom_part, cnt, (int64_t)(nc / 128) * cnt,
+                                                                                ntiles, cnt, h->mom_acc);
+    CKL();
+  }
+  k_grad_from_moments<<<batch, 256, 0, st>>>(h->mom_acc, m, d, Z, theta, grad_partial, sG);
+  CKL();
+  return 0;
+}
+
+int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* Xs, int64_t ns, const double* Z,
+                     const double* theta, int m, int d, int batch, int add_noise, double* mean, double* var, double* cov) {
+  if (!h || !Xs || !Z || !theta || !mean || !var) return fail(-1, "ggp_sgpr_predict: NULL argument");
+  if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_predict: handle not reserved for this shape");
+  if (cov && ns > h->nc) return fail(-4, "ggp_sgpr_predict: full covariance needs ns <= chunk_rows");
+  const int kind = cfg ? cfg->kernel : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = h->Mp, nc = h->nc;
+  const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nc * Mp;
+  for (int64_t c0 = 0; c0 < ns; c0 += nc) {
+    const int nv = (int)std::min<int64_t>(nc, ns - c0);
+    RUN(build_chunk(h, st, Xs + c0 * d, nv, d, Z, m, theta, kind, batch));
+    // aT[nv x m] = Ks[nv x m] * Linv^T ; tT[nv x m] = aT * LBinv^T
+    RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Linv, Mp, sM, h->At, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->At, Mp, sC, h->LBinv, Mp, sM, h->Kc, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    k_predict_rows<<<dim3((nv + 7) / 8, batch), 256, 0, st>>>(h->At, h->Kc, Mp, sC, h->cvec, Mp, theta, d, m, nv, add_noise,
+                                                              mean + c0, var + c0, ns);
+    CKL();
+    if (cov) {
+      RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Kc, Mp, sC, cov, ns, ns * ns, nv, nv, m, 1.0, 0.0), batch));
+      k_cov_diag<<<dim3((nv + 255) / 256, batch), 256, 0, st>>>(cov, ns, var);
+      CKL();
+    }
+  }
+  return 0;
+}
+
+int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* xb, const double* yb, int64_t nb,
+                  const double* Z, const double* qm, const double* qLs, const double* theta, const double* jitter, int m, int d,
+                  int batch, double num_data, int likelihood, int need_grad, double* elbo, double* grad, int32_t* info) {
+  return fail(-100, "ggp_svgp_elbo: not implemented yet");
+}
+
+int ggp_chol_batched(ggp_handle_t* h, void* stream, double* a, double* linv, int m, int batch, int32_t* info) {
+  if (!h || !a || !info) return fail(-1, "ggp_chol_batched: NULL argument");
+  if (!(h->arena && h->m == m && batch <= h->batch)) RUN(ggp_reserve(h, nullptr, 0, m, std::max(1, h->d), batch));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = h->Mp;
+  const int64_t sM = (int64_t)Mp * Mp;
+  const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
+  CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
+  k_pad_copy<<<g16, b16, 0, st>>>(a, m, h->L, Mp, sM, 1);
+  CKL();
+  RUN(chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info));
+  k_pad_copy<<<g16, b16, 0, st>>>(a, m, h->L, Mp, sM, 0);
+  CKL();
+  if (linv) {
+    k_pad_copy<<<g16, b16, 0, st>>>(linv, m, h->Linv, Mp, sM, 0);
+    CKL();
+  }
+  return 0;
+}
+
+int ggp_gemm_nt(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                int64_t ldc, int mm, int nn, int kk, double alpha, double beta) {
+  if (!h || !A || !B || !C) return fail(-1, "ggp_gemm_nt: NULL argument");
+  if ((lda & 1) || (ldb & 1) || (((uintptr_t)A) & 15) || (((uintptr_t)B) & 15))
+    return fail(-2, "ggp_gemm_nt: operands need 16-byte aligned rows (even leading dimension)");
+  return launch_gemm((cudaStream_t)stream, EPI_STORE, gemm_basic(A, lda, 0, B, ldb, 0, C, ldc, 0, mm, nn, kk, alpha, beta), 1);
+}
+
+int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X1, int64_t n1, const double* X2,
+                      int64_t n2, const double* theta, int d, double* out) {
+  if (!h || !X1 || !X2 || !theta || !out) return fail(-1, "ggp_kernel_matrix: NULL argument");
+  if ((size_t)(2 * KT_N * d + d) * 8 > 200 * 1024) return fail(-3, "ggp_kernel_matrix: d too large");
+  const int kind = cfg ? cfg->kernel : 0;
+  dim3 grid((unsigned)((n2 + KT_M - 1) / KT_M), (unsigned)((n1 + KT_N - 1) / KT_N), 1);
+  const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
+  k_build_kc<<<grid, KT_THREADS, smem, (cudaStream_t)stream>>>(X1, (int)n1, (int)n1, d, X2, (int)n2, theta, kind, out, n2, 0);
+  CKL();
+  return 0;
+}
+
+int ggp_probe_dmma_peak(ggp_handle_t* h, void* stream, int iters, double* tflops_out) {
+  if (!h || !tflops_out) return fail(-1, "ggp_probe_dmma_peak: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* sink;
+  CK(cudaMalloc((void**)&sink, 8 * 1024 * 1024));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int warps_per_sm[3] = {8, 16, 32};
+  double best = 0.0;
+  for (int v = 0; v < 3; ++v) {
+    const int threads = warps_per_sm[v] * 32;
+    double bestv = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+      CK(cudaEventRecord(e0, st));
+      k_dmma_probe<<<h->sm_count, threads, 0, st>>>(sink, iters);
+      CK(cudaEventRecord(e1, st));
+      CK(cudaEventSynchronize(e1));
+      CKL();
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double flops = (double)h->sm_count * warps_per_sm[v] * (double)iters * 32.0 * 512.0;
+      bestv = std::max(bestv, flops / (ms * 1e-3) / 1e12);
+    }
+    tflops_out[1 + v] = bestv;
+    best = std::max(best, bestv);
+  }
+  tflops_out[0] = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return 0;
+}
+
+}  // extern "C"

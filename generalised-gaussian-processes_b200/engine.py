@@ -1,0 +1,220 @@
+"""Host driver of the CUDA hot path: owns a ggp handle per device and sequences
+factor -> pass1 -> [all-reduce] -> finish -> pass2 -> [all-reduce]   (include/ggp_b200.h).
+
+Replaces what gpytorch / pymc3 execute under the reference's calls
+  models/sgpr.py:123-129 (forward, -mll, backward), models/bayesian_sgpr_hmc.py:66-78 (VFE logp/dlogp per leapfrog),
+  models/sgpr.py:150-160 (eval-mode predictive).
+PyTorch is used for device memory, streams and torch.distributed only.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GgpCfg, KERNELS, PRECISIONS, check
+
+
+class NotPSDError(RuntimeError):
+    """Kzz (or I + A A^T / s) not positive definite after the jitter ladder (gpytorch NotPSDError analogue)."""
+
+
+def jitter_ladder(policy, dtype=torch.float64):
+    """gpytorch psd_safe_cholesky ladder / pymc3 stabilize / fixed value."""
+    if policy == "gpytorch":
+        j0 = 1e-8 if dtype == torch.float64 else 1e-6
+        return [0.0, j0, j0 * 10.0, j0 * 100.0]
+    if policy == "pymc3":
+        return [1e-6]
+    return [float(policy)]
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f64c(t, device):
+    return t.detach().to(device=device, dtype=torch.float64).contiguous()
+
+
+class Engine:
+    """One per (device, kernel, precision).  Not thread-safe; one stream at a time."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, device=None, kernel="rbf", precision="fp64", chunk_rows=0):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        key = (device.index, kernel, precision, chunk_rows)
+        if key not in cls._cache:
+            cls._cache[key] = cls(device, kernel, precision, chunk_rows)
+        return cls._cache[key]
+
+    def __init__(self, device, kernel="rbf", precision="fp64", chunk_rows=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("the sparse-GP hot path needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.cfg = GgpCfg(KERNELS[kernel], PRECISIONS[precision], int(chunk_rows), 0)
+        h = ctypes.c_void_p()
+        check(self.lib.ggp_create(ctypes.byref(h), self.device.index), "ggp_create")
+        self.h = h
+        self._shape = None
+        self.launch_count = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.ggp_destroy(self.h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------------
+    def reserve(self, n_local, m, d, batch):
+        s = self._shape
+        if s is not None and s[1] == m and s[2] == d and batch <= s[3] and n_local <= s[0]:
+            return
+        if s is not None and s[1] == m and s[2] == d:
+            n_local, batch = max(n_local, s[0]), max(batch, s[3])
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ggp_reserve(self.h, ctypes.byref(self.cfg), int(n_local), int(m), int(d), int(batch)), "ggp_reserve")
+        self._shape = (int(n_local), int(m), int(d), int(batch))
+
+    def workspace_bytes(self, n_local, m, d, batch):
+        out = ctypes.c_size_t()
+        check(self.lib.ggp_workspace_bytes(ctypes.byref(self.cfg), int(n_local), int(m), int(d), int(batch), ctypes.byref(out)),
+              "ggp_workspace_bytes")
+        return out.value
+
+    # ------------------------------------------------------------------------------------------------------
+    def factor(self, Z, theta, jitter_policy="gpytorch", raise_on_fail=True):
+        """Kzz + jitter I = L L^T with the host-side jitter ladder.  Returns (jitter[batch] tensor, info[batch] cpu)."""
+        m, d = Z.shape
+        batch = theta.shape[0]
+        ladder = jitter_ladder(jitter_policy)
+        level = [0] * batch
+        jit = torch.full((batch,), ladder[0], dtype=torch.float64, device=self.device)
+        info = torch.zeros(batch, dtype=torch.int32, device=self.device)
+        while True:
+            check(self.lib.ggp_sgpr_factor(self.h, ctypes.byref(self.cfg), _stream(), _ptr(Z), _ptr(theta), _ptr(jit),
+                                           m, d, batch, _ptr(info)), "ggp_sgpr_factor")
+            info_h = info.cpu()
+            bad = [b for b in range(batch) if int(info_h[b]) != 0]
+            if not bad:
+                return jit, info_h
+            if any(level[b] + 1 >= len(ladder) for b in bad):
+                if raise_on_fail:
+                    raise NotPSDError(f"Kzz not positive definite after jitter ladder {ladder}; potrf info={info_h.tolist()}")
+                return jit, info_h
+            for b in bad:
+                level[b] += 1
+            jit = torch.tensor([ladder[l] for l in level], dtype=torch.float64, device=self.device)
+
+    def sgpr_eval(self, X, y, Z, theta, jitter_policy="gpytorch", need_grad=True, group=None, raise_on_fail=True):
+        """Collapsed bound F (not divided by N) and dF/d(ell, sf2, s2, Z) for each row of theta.
+
+        X [n_local, d], y [n_local] are THIS rank's rows; with `group` (torch.distributed) the partial sums are
+        all-reduced.  Returns dict(bound[batch], grad[batch, d+2+m*d] | None, jitter, info, n_total).
+        """
+        import torch.distributed as dist
+        dev = self.device
+        X, y, Z, theta = _f64c(X, dev), _f64c(y, dev), _f64c(Z, dev), _f64c(theta, dev)
+        if theta.dim() == 1:
+            theta = theta.unsqueeze(0)
+        n_local, d = X.shape
+        m = Z.shape[0]
+        batch = theta.shape[0]
+        assert theta.shape[1] == d + 2 and Z.shape[1] == d and y.shape[0] == n_local
+        self.reserve(n_local, m, d, batch)
+        with torch.cuda.device(dev):
+            jit, info1 = self.factor(Z, theta, jitter_policy, raise_on_fail)
+            cfgp = ctypes.byref(self.cfg)
+            partial = torch.empty(batch, m * m + m + 3, dtype=torch.float64, device=dev)
+            check(self.lib.ggp_sgpr_pass1(self.h, cfgp, _stream(), _ptr(X), _ptr(y), n_local, _ptr(Z), _ptr(theta), m, d, batch,
+                                          _ptr(partial)), "ggp_sgpr_pass1")
+            # group=None: use the default process group when one is initialised; group=False: never reduce
+            if group is False:
+                distributed, pg = False, None
+            elif group is None:
+                distributed, pg = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1, None
+            else:
+                distributed, pg = True, group
+            if distributed:
+                dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=pg)
+            P = d + 2 + m * d
+            bound = torch.empty(batch, dtype=torch.float64, device=dev)
+            grad_mm = torch.empty(batch, P, dtype=torch.float64, device=dev) if need_grad else None
+            info2 = torch.zeros(batch, dtype=torch.int32, device=dev)
+            check(self.lib.ggp_sgpr_finish(self.h, cfgp, _stream(), _ptr(Z), _ptr(theta), m, d, batch, _ptr(partial),
+                                           1 if need_grad else 0, _ptr(bound), _ptr(grad_mm), _ptr(info2)), "ggp_sgpr_finish")
+            grad = None
+            if need_grad:
+                gp = torch.empty(batch, P, dtype=torch.float64, device=dev)
+                check(self.lib.ggp_sgpr_pass2(self.h, cfgp, _stream(), _ptr(X), _ptr(y), n_local, _ptr(Z), _ptr(theta), m, d,
+                                              batch, _ptr(gp)), "ggp_sgpr_pass2")
+                if distributed:
+                    dist.all_reduce(gp, op=dist.ReduceOp.SUM, group=pg)
+                grad = grad_mm + gp
+        return dict(bound=bound, grad=grad, jitter=jit, info=info1, info_b=info2, n_total=partial[:, -1], partial=partial)
+
+    def sgpr_predict(self, Xs, Z, theta, full_cov=False, add_noise=True):
+        """Predictive at the state left by the last sgpr_eval with the same (Z, theta)."""
+        dev = self.device
+        Xs, Z, theta = _f64c(Xs, dev), _f64c(Z, dev), _f64c(theta, dev)
+        if theta.dim() == 1:
+            theta = theta.unsqueeze(0)
+        ns, d = Xs.shape
+        m = Z.shape[0]
+        batch = theta.shape[0]
+        mean = torch.empty(batch, ns, dtype=torch.float64, device=dev)
+        var = torch.empty(batch, ns, dtype=torch.float64, device=dev)
+        cov = torch.empty(batch, ns, ns, dtype=torch.float64, device=dev) if full_cov else None
+        with torch.cuda.device(dev):
+            check(self.lib.ggp_sgpr_predict(self.h, ctypes.byref(self.cfg), _stream(), _ptr(Xs), ns, _ptr(Z), _ptr(theta), m, d,
+                                            batch, 1 if add_noise else 0, _ptr(mean), _ptr(var), _ptr(cov)), "ggp_sgpr_predict")
+        return mean, var, cov
+
+    # building blocks -----------------------------------------------------------------------------------------
+    def chol(self, a, want_inverse=True):
+        a = a.clone().contiguous()
+        batch, m, _ = a.shape
+        linv = torch.empty_like(a) if want_inverse else None
+        info = torch.zeros(batch, dtype=torch.int32, device=a.device)
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ggp_chol_batched(self.h, _stream(), _ptr(a), _ptr(linv), m, batch, _ptr(info)), "ggp_chol_batched")
+        self._shape = None  # chol may have re-reserved the handle for its own shape
+        return a, linv, info
+
+    def gemm_nt(self, A, B, C=None, alpha=1.0, beta=0.0):
+        mm, kk = A.shape
+        nn = B.shape[0]
+        if C is None:
+            C = torch.zeros(mm, nn, dtype=torch.float64, device=A.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ggp_gemm_nt(self.h, _stream(), _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(C), C.stride(0),
+                                       mm, nn, kk, float(alpha), float(beta)), "ggp_gemm_nt")
+        return C
+
+    def kernel_matrix(self, X1, X2, theta):
+        dev = self.device
+        X1, X2, theta = _f64c(X1, dev), _f64c(X2, dev), _f64c(theta, dev)
+        out = torch.empty(X1.shape[0], X2.shape[0], dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.ggp_kernel_matrix(self.h, ctypes.byref(self.cfg), _stream(), _ptr(X1), X1.shape[0], _ptr(X2),
+                                             X2.shape[0], _ptr(theta), X1.shape[1], _ptr(out)), "ggp_kernel_matrix")
+        return out
+
+    def probe_dmma_peak(self, iters=20000):
+        out = (ctypes.c_double * 4)()
+        with torch.cuda.device(self.device):
+            check(self.lib.ggp_probe_dmma_peak(self.h, _stream(), int(iters), out), "ggp_probe_dmma_peak")
+        return dict(best=out[0], warps8=out[1], warps16=out[2], warps32=out[3])

@@ -1,0 +1,124 @@
+/*
+ * ggp_b200.h -- C ABI of the B200-native collapsed sparse-GP hot path.
+ *
+ * The reference (vr308/Generalised-Gaussian-Processes) has no FFI: its boundary is the Python call its
+ * model wrappers make into gpytorch / pymc3.  Each entry point below names the reference call it replaces
+ * (paths relative to /root/reference).  A maintainer binds these with ctypes.
+ *
+ * Conventions
+ *   - all array arguments are DEVICE pointers to contiguous float64 / int32 unless marked [host]
+ *   - `stream` is a cudaStream_t passed as void*; every call only ENQUEUES work on it (no host sync) unless noted
+ *   - return value: 0 ok; <0 argument -k invalid / handle not reserved; >0 CUDA runtime error code
+ *   - numerical failure is never an abort: per-batch `info[b]` follows LAPACK potrf (k>0: leading minor k
+ *     not positive definite) so the host runs the psd_safe_cholesky jitter ladder
+ *   - theta rows are CONSTRAINED values [ell_0..ell_{d-1}, sf2 (outputscale), s2 (noise variance)]
+ *   - gradient rows are w.r.t. the constrained values, layout [d_ell[d], d_sf2, d_s2, d_Z[m*d]]
+ *   - a handle is bound to one device; one thread / one stream at a time
+ */
+#ifndef GGP_B200_H
+#define GGP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ggp_handle ggp_handle_t;
+
+enum { GGP_KERNEL_RBF = 0, GGP_KERNEL_MATERN32 = 1, GGP_KERNEL_MATERN52 = 2 };
+enum { GGP_PREC_FP64 = 0, GGP_PREC_TF32X3 = 1 };
+enum { GGP_LIK_GAUSSIAN = 0, GGP_LIK_BERNOULLI_PROBIT = 1 };
+
+typedef struct {
+  int32_t kernel;      /* GGP_KERNEL_*   (ScaleKernel(RBFKernel(ard)) at models/sgpr.py:36 is GGP_KERNEL_RBF) */
+  int32_t precision;   /* GGP_PREC_*     contraction arithmetic; everything else is float64 */
+  int32_t chunk_rows;  /* rows of X per streamed chunk; 0 = library default */
+  int32_t reserved;
+} ggp_cfg;
+
+int ggp_version(void);
+const char* ggp_last_error(void);
+
+/* lifetime ------------------------------------------------------------------------------------------------ */
+int ggp_create(ggp_handle_t** out, int device);
+int ggp_destroy(ggp_handle_t* h);
+/* bytes of device workspace ggp_reserve would own for these shapes */
+int ggp_workspace_bytes(const ggp_cfg* cfg, int64_t n_local, int m, int d, int batch, size_t* out);
+/* (re)allocate the handle's workspace; synchronous (cudaMalloc); call once per shape */
+int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int d, int batch);
+
+/* SGPR collapsed bound + gradient --------------------------------------------------------------------------
+ * Replaces, together:  output = self.forward(train_x); loss = -mll(output, train_y); loss.backward()
+ *   (models/sgpr.py:123-129, models/bayesian_sgpr_hmc.py:110-114,128-133)  and the pymc3 logp/dlogp of
+ *   gp.marginal_likelihood (models/bayesian_sgpr_hmc.py:66-71) that NUTS calls per leapfrog step.
+ * Call order per evaluation:  factor -> pass1 -> [allreduce partial over row shards] -> finish
+ *                             -> pass2 -> [allreduce grad_partial]  ; total grad = grad_mm + sum(grad_partial)
+ */
+
+/* Kzz(theta_b) + jitter_b I = L L^T ; L^{-1} kept in the handle.  info[b] device int32.
+ * (InducingPointKernel._inducing_mat / _inducing_inv_root + psd_safe_cholesky, reached from models/sgpr.py:41) */
+int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
+                    const double* Z /*[m,d]*/, const double* theta /*[batch,d+2]*/,
+                    const double* jitter /*[batch]*/, int m, int d, int batch, int32_t* info /*[batch]*/);
+
+/* stream the local rows: partial[b] = [ A A^T (m*m, row-major, symmetric) | A y (m) | y^T y, sum_n k_nn, n_local ]
+ * with A = L^{-1} k(Z, X_local).  Never materialises more than chunk_rows x m of k(X,Z). */
+int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
+                   const double* X /*[n_local,d]*/, const double* y /*[n_local]*/, int64_t n_local,
+                   const double* Z, const double* theta, int m, int d, int batch,
+                   double* partial /*[batch, m*m+m+3]*/);
+
+/* m x m section on the (all-reduced) partial: bound[b] = F (NOT divided by N), grad_mm[b] = the Kzz-, noise- and
+ * k_nn-dependent part of dF/d(ell,sf2,s2,Z); P,u kept in the handle for pass2.  info[b]: chol(I + A A^T / s) status.
+ * (ExactMarginalLogLikelihood.forward, models/sgpr.py:125; MarginalSparse._build_marginal_likelihood_logp) */
+int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
+                    const double* Z, const double* theta, int m, int d, int batch,
+                    const double* partial /*[batch, m*m+m+3]*/, int need_grad,
+                    double* bound /*[batch]*/, double* grad_mm /*[batch, d+2+m*d] or NULL*/, int32_t* info /*[batch]*/);
+
+/* second streaming pass: grad_partial[b] = sum over local rows of (P Kzx + u y^T) o dKzx/d(ell,sf2,Z)
+ * (what loss.backward() propagates into the N x M kernel block; models/sgpr.py:129) */
+int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
+                   const double* X, const double* y, int64_t n_local,
+                   const double* Z, const double* theta, int m, int d, int batch,
+                   double* grad_partial /*[batch, d+2+m*d]*/);
+
+/* Sparse predictive at the state left by factor+pass1+finish  (likelihood(self(test_x)) in eval mode,
+ * models/sgpr.py:150-160; models/bayesian_sgpr_hmc.py:198-231).  mean,var: [batch, ns]; cov: [batch, ns, ns] or NULL.
+ * var/cov include the eval-mode diagonal correction clamp(k** - ||a*||^2, 0) and, if add_noise, + s2. */
+int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
+                     const double* Xs /*[ns,d]*/, int64_t ns,
+                     const double* Z, const double* theta, int m, int d, int batch, int add_noise,
+                     double* mean, double* var, double* cov);
+
+/* Whitened SVGP minibatch ELBO value + gradient  (models/svgp.py:104-110 ; models/bayesian_svgp.py:160-167 with
+ * batch = number of theta draws).  elbo[b] = sum_i E_q[log p(y_i|f_i)] / nb - KL(q||N(0,I)) / num_data.
+ * grad[b] layout: [d_ell[d], d_sf2, d_s2, d_Z[m*d], d_m[m], d_Ls[m*m] (lower triangle, row-major, upper = 0)].
+ * jitter[b] is the TOTAL diagonal jitter added to Kzz (variational_cholesky_jitter 1e-6 + ladder). */
+int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
+                  const double* xb /*[nb,d]*/, const double* yb /*[nb]*/, int64_t nb,
+                  const double* Z, const double* qm /*[m]*/, const double* qLs /*[m,m]*/,
+                  const double* theta /*[batch,d+2]*/, const double* jitter /*[batch]*/,
+                  int m, int d, int batch, double num_data, int likelihood, int need_grad,
+                  double* elbo /*[batch]*/, double* grad /*[batch, d+2+m*d+m+m*m] or NULL*/, int32_t* info);
+
+/* building blocks, exported for the parity tests and the roofline probes ------------------------------------- */
+
+/* in-place batched Cholesky (lower) of a[batch, m, m] row-major + optional explicit inverse of the factor.
+ * (the psd_safe_cholesky call sites; SURVEY 8b ggp_chol_batched) */
+int ggp_chol_batched(ggp_handle_t* h, void* stream, double* a /*[batch,m,m]*/, double* linv /*[batch,m,m] or NULL*/,
+                     int m, int batch, int32_t* info);
+/* C[mm,nn] = alpha * A[mm,kk] * B[nn,kk]^T + beta * C   (row-major, float64, DMMA). ld* in elements. */
+int ggp_gemm_nt(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb,
+                double* C, int64_t ldc, int mm, int nn, int kk, double alpha, double beta);
+/* k(X1, X2)[n1, n2] dense tile (tests) */
+int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X1, int64_t n1,
+                      const double* X2, int64_t n2, const double* theta /*[d+2]*/, int d, double* out /*[n1,n2]*/);
+/* register-resident mma.sync m8n8k4 f64 loop on every SM: measured FP64 tensor-pipe peak [host out, TFLOP/s]; synchronous */
+int ggp_probe_dmma_peak(ggp_handle_t* h, void* stream, int iters, double* tflops_out /*[host]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGP_B200_H */
