@@ -43,6 +43,8 @@ SYMBOLS = {
     "ggp_chol_batched": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "ggp_gemm_nt": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _D, _D]),
     "ggp_kernel_matrix": (_I, [_P, _CFG, _P, _P, _I64, _P, _I64, _P, _I, _P]),
+    "ggp_profile_enable": (_I, [_P, _I]),
+    "ggp_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "ggp_probe_dmma_peak": (_I, [_P, _P, _I, ctypes.POINTER(ctypes.c_double)]),
 }
 

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "dense_mm.cuh"
@@ -28,7 +29,11 @@ static int fail(int code, const char* msg) {
       return (int)e_;                                                                         \
     }                                                                                         \
   } while (0)
-#define CKL() CK(cudaGetLastError())
+#define CKL()            \
+  do {                   \
+    h->launches++;       \
+    CK(cudaGetLastError()); \
+  } while (0)
 
 struct ggp_handle {
   int device = 0, sm_count = 148;
@@ -44,6 +49,45 @@ struct ggp_handle {
   double *bvec = 0, *cvec = 0, *beta = 0, *u = 0, *yty = 0, *ds2 = 0, *rowacc = 0;
   // streamed chunk buffers
   double *Kc = 0, *At = 0, *Spart = 0, *mom_part = 0, *mom_acc = 0;
+  // instrumentation
+  long long launches = 0;
+  bool profiling = false;
+  struct Span { int cat; cudaEvent_t e0, e1; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+  int cur_cat = -1;
+  cudaEvent_t cur_e0 = nullptr;
+};
+
+enum { CAT_BUILD = 0, CAT_TRMM = 1, CAT_SYRK = 2, CAT_BWD = 3, CAT_MM = 4, CAT_OTHER = 5, CAT_COUNT = 6 };
+
+static cudaEvent_t get_event(ggp_handle* h) {
+  if (!h->pool.empty()) {
+    cudaEvent_t e = h->pool.back();
+    h->pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+static void prof_begin(ggp_handle* h, cudaStream_t st, int cat) {
+  if (!h->profiling) return;
+  h->cur_cat = cat;
+  h->cur_e0 = get_event(h);
+  cudaEventRecord(h->cur_e0, st);
+}
+static void prof_end(ggp_handle* h, cudaStream_t st) {
+  if (!h->profiling || h->cur_cat < 0) return;
+  cudaEvent_t e1 = get_event(h);
+  cudaEventRecord(e1, st);
+  h->spans.push_back({h->cur_cat, h->cur_e0, e1});
+  h->cur_cat = -1;
+}
+struct ProfScope {
+  ggp_handle* h; cudaStream_t st;
+  ProfScope(ggp_handle* h_, cudaStream_t st_, int cat) : h(h_), st(st_) { prof_begin(h, st, cat); }
+  ~ProfScope() { prof_end(h, st); }
 };
 
 static int pad_pow2_blocks(int m) {
@@ -103,7 +147,7 @@ static bool reserved_for(const ggp_handle* h, int64_t n_local, int m, int d, int
 }
 
 // ------------------------------------------------------------------------------------------------------------
-static int launch_gemm(cudaStream_t st, int epi, const GemmP& p, int nbatch) {
+static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& p, int nbatch) {
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, nbatch * p.nz2 * p.splits);
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
   if (epi == EPI_STORE)
@@ -144,14 +188,14 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
     if (k > 0) {  // A[k0:, k0:k0+NB] -= L[k0:, :k0] * L[k0:k0+NB, :k0]^T
       GemmP p = gemm_basic(A + (int64_t)k0 * Mp, Mp, sM, A + (int64_t)k0 * Mp, Mp, sM, A + (int64_t)k0 * (Mp + 1), Mp, sM,
                            Mp - k0, NB, k0, -1.0, 1.0);
-      RUN(launch_gemm(st, EPI_STORE, p, batch));
+      RUN(launch_gemm(h, st, EPI_STORE, p, batch));
     }
     k_potf2_trti2<<<batch, 256, POTF2_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, info);
     CKL();
     if (k < nblk - 1) {  // L[k0+NB:, k0:k0+NB] = A[k0+NB:, k0:k0+NB] * T_k^T   (in place; one n-tile, K = NB)
       double* blk = A + (int64_t)(k0 + NB) * Mp + k0;
       GemmP p = gemm_basic(blk, Mp, sM, h->Tblk + (int64_t)k * NB * NB, NB, sM, blk, Mp, sM, Mp - k0 - NB, NB, NB, 1.0, 0.0);
-      RUN(launch_gemm(st, EPI_STORE, p, batch));
+      RUN(launch_gemm(h, st, EPI_STORE, p, batch));
     }
   }
   k_tril<<<g16, b16, 0, st>>>(A, Mp, sM);
@@ -168,12 +212,12 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
     // C1T = Inv11^T-rows x L21-rows :  Wk[pair upper-right block][j,i] = sum_k Inv11T[j,k] L21[i,k]
     GemmP p1 = gemm_basic(LinvT, Mp, sM, A + (int64_t)s * Mp, Mp, sM, h->Wk + s, Mp, sM, s, s, s, 1.0, 0.0, KM_A_UPPER);
     p1.nz2 = npairs; p1.sA2 = sPair; p1.sB2 = sPair; p1.sC2 = sPair;
-    RUN(launch_gemm(st, EPI_STORE, p1, batch));
+    RUN(launch_gemm(h, st, EPI_STORE, p1, batch));
     // X = -Inv22 * C1 :  Linv[pair lower-left block][i,j] = -sum_k Inv22[i,k] C1T[j,k]
     GemmP p2 = gemm_basic(Linv + (int64_t)s * (Mp + 1), Mp, sM, h->Wk + s, Mp, sM, Linv + (int64_t)s * Mp, Mp, sM, s, s, s,
                           -1.0, 0.0, KM_A_LOWER);
     p2.nz2 = npairs; p2.sA2 = sPair; p2.sB2 = sPair; p2.sC2 = sPair;
-    RUN(launch_gemm(st, EPI_STORE, p2, batch));
+    RUN(launch_gemm(h, st, EPI_STORE, p2, batch));
   }
   k_transpose<<<gt, bt, 0, st>>>(Linv, LinvT, Mp, sM);
   CKL();
@@ -245,6 +289,7 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   cudaStream_t st = (cudaStream_t)stream;
   const int kind = cfg ? cfg->kernel : 0;
   const int Mp = h->Mp;
+  ProfScope ps(h, st, CAT_MM);
   CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
   k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp);
   CKL();
@@ -276,17 +321,18 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   CKL();
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
-    RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch));
+    { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch)); }
     // At[m x nv] = Linv[m x m] * Kc[nv x m]^T   (k clipped to the lower triangle)
     GemmP t = gemm_basic(h->Linv, Mp, sM, h->Kc, Mp, (int64_t)nc * Mp, h->At, nc, (int64_t)nc * Mp, m, nv, m, 1.0, 0.0,
                          KM_A_LOWER);
     t.heavy_first = 1;
-    RUN(launch_gemm(st, EPI_STORE, t, batch));
+    { ProfScope ps(h, st, CAT_TRMM); RUN(launch_gemm(h, st, EPI_STORE, t, batch)); }
     // S_split += At * At^T  (upper tiles)
     GemmP s = gemm_basic(h->At, nc, (int64_t)nc * Mp, h->At, nc, (int64_t)nc * Mp, h->Spart, Mp, (int64_t)splits * sM, m, m, nv,
                          1.0, 1.0);
     s.sym = 1; s.splits = splits; s.sSplit = sM;
-    RUN(launch_gemm(st, EPI_STORE, s, batch));
+    { ProfScope ps(h, st, CAT_SYRK); RUN(launch_gemm(h, st, EPI_STORE, s, batch)); }
+    ProfScope ps_o(h, st, CAT_OTHER);
     // b += At * y_chunk
     k_gemv_acc<<<dim3((m + 7) / 8, batch), 256, 0, st>>>(h->At, nc, (int64_t)nc * Mp, y + c0, h->bvec, Mp, m, nv);
     CKL();
@@ -310,12 +356,13 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   const int64_t sM = (int64_t)Mp * Mp, sP = (int64_t)m * m + m + 3, sG = (int64_t)d + 2 + (int64_t)m * d;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
   const dim3 gv((m + 7) / 8, batch);
+  ProfScope ps(h, st, CAT_MM);
   CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
   k_make_B<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Bm, sM);
   CKL();
   RUN(chol_and_inverse(h, st, h->Bm, h->LBinv, h->LBinvT, batch, info));
   // Binv = LBinv^T LBinv
-  RUN(launch_gemm(st, EPI_STORE,
+  RUN(launch_gemm(h, st, EPI_STORE,
                   gemm_basic(h->LBinvT, Mp, sM, h->LBinvT, Mp, sM, h->Binv, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER | KM_B_UPPER),
                   batch));
   const double* bsrc = partial + (int64_t)m * m;
@@ -333,10 +380,10 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   k_make_PA_Gbar<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Binv, h->beta, Mp, h->PA, h->Gbar, sM);
   CKL();
   // P = Linv^T PA Linv ;  Gzz = -1/2 Linv^T Gbar Linv
-  RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
-  RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_B_UPPER), batch));
-  RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->Gbar, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
-  RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->Gzz, Mp, sM, m, m, m, -0.5, 0.0, KM_B_UPPER), batch));
+  RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
+  RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_B_UPPER), batch));
+  RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->Gbar, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
+  RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->Gzz, Mp, sM, m, m, m, -0.5, 0.0, KM_B_UPPER), batch));
   k_grad_kzz_rows<<<gv, 256, 0, st>>>(h->Gzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, grad_mm + d + 2, sG);
   CKL();
   k_grad_mm_final<<<batch, 256, 0, st>>>(h->rowacc, m, d, theta, partial, sP, h->ds2, grad_mm, sG);
@@ -357,7 +404,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   CK(cudaMemsetAsync(h->mom_acc, 0, (size_t)batch * cnt * 8, st));
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
-    RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch));
+    { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch)); }
     const int ntiles = (nv + BN - 1) / BN;
     GemmP g = gemm_basic(h->P, Mp, sM, h->Kc, Mp, (int64_t)nc * Mp, nullptr, 0, 0, m, nv, m, 1.0, 0.0);
     g.u = h->u; g.su = Mp;
@@ -365,7 +412,8 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     g.Kc = h->Kc; g.ldk = Mp; g.sK = (int64_t)nc * Mp;
     g.Xc = X + c0 * d; g.d = d;
     g.mom = h->mom_part; g.sMomTile = cnt; g.sMom = (int64_t)(nc / 128) * cnt;
-    RUN(launch_gemm(st, EPI_MOMENTS, g, batch));
+    { ProfScope ps(h, st, CAT_BWD); RUN(launch_gemm(h, st, EPI_MOMENTS, g, batch)); }
+    ProfScope ps_o(h, st, CAT_OTHER);
     k_reduce_moments<<<dim3((unsigned)((cnt + 255) / 256), batch), 256, 0, st>>>(h->mom_part, cnt, (int64_t)(nc / 128) * cnt,
                                                                                 ntiles, cnt, h->mom_acc);
     CKL();
@@ -388,13 +436,13 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
     const int nv = (int)std::min<int64_t>(nc, ns - c0);
     RUN(build_chunk(h, st, Xs + c0 * d, nv, d, Z, m, theta, kind, batch));
     // aT[nv x m] = Ks[nv x m] * Linv^T ; tT[nv x m] = aT * LBinv^T
-    RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Linv, Mp, sM, h->At, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
-    RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->At, Mp, sC, h->LBinv, Mp, sM, h->Kc, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Linv, Mp, sM, h->At, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->At, Mp, sC, h->LBinv, Mp, sM, h->Kc, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
     k_predict_rows<<<dim3((nv + 7) / 8, batch), 256, 0, st>>>(h->At, h->Kc, Mp, sC, h->cvec, Mp, theta, d, m, nv, add_noise,
                                                               mean + c0, var + c0, ns);
     CKL();
     if (cov) {
-      RUN(launch_gemm(st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Kc, Mp, sC, cov, ns, ns * ns, nv, nv, m, 1.0, 0.0), batch));
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Kc, Mp, sC, cov, ns, ns * ns, nv, nv, m, 1.0, 0.0), batch));
       k_cov_diag<<<dim3((nv + 255) / 256, batch), 256, 0, st>>>(cov, ns, var);
       CKL();
     }
@@ -433,7 +481,7 @@ int ggp_gemm_nt(ggp_handle_t* h, void* stream, const double* A, int64_t lda, con
   if (!h || !A || !B || !C) return fail(-1, "ggp_gemm_nt: NULL argument");
   if ((lda & 1) || (ldb & 1) || (((uintptr_t)A) & 15) || (((uintptr_t)B) & 15))
     return fail(-2, "ggp_gemm_nt: operands need 16-byte aligned rows (even leading dimension)");
-  return launch_gemm((cudaStream_t)stream, EPI_STORE, gemm_basic(A, lda, 0, B, ldb, 0, C, ldc, 0, mm, nn, kk, alpha, beta), 1);
+  return launch_gemm(h, (cudaStream_t)stream, EPI_STORE, gemm_basic(A, lda, 0, B, ldb, 0, C, ldc, 0, mm, nn, kk, alpha, beta), 1);
 }
 
 int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X1, int64_t n1, const double* X2,
@@ -448,6 +496,34 @@ int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const d
   return 0;
 }
 
+int ggp_profile_enable(ggp_handle_t* h, int on) {
+  if (!h) return fail(-1, "ggp_profile_enable: handle is NULL");
+  h->profiling = on != 0;
+  return 0;
+}
+
+int ggp_profile_read(ggp_handle_t* h, double* ms_out, int64_t* spans_out, int64_t* launches_out) {
+  if (!h) return fail(-1, "ggp_profile_read: handle is NULL");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  for (int c = 0; c < CAT_COUNT; ++c) {
+    if (ms_out) ms_out[c] = 0.0;
+    if (spans_out) spans_out[c] = 0;
+  }
+  for (auto& sp : h->spans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sp.e0, sp.e1);
+    if (ms_out) ms_out[sp.cat] += ms;
+    if (spans_out) spans_out[sp.cat] += 1;
+    h->pool.push_back(sp.e0);
+    h->pool.push_back(sp.e1);
+  }
+  h->spans.clear();
+  if (launches_out) *launches_out = h->launches;
+  h->launches = 0;
+  return 0;
+}
+
 int ggp_probe_dmma_peak(ggp_handle_t* h, void* stream, int iters, double* tflops_out) {
   if (!h || !tflops_out) return fail(-1, "ggp_probe_dmma_peak: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -457,19 +533,21 @@ int ggp_probe_dmma_peak(ggp_handle_t* h, void* stream, int iters, double* tflops
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   const int warps_per_sm[3] = {8, 16, 32};
+  const int frag_rows[3] = {8, 4, 2};
   double best = 0.0;
   for (int v = 0; v < 3; ++v) {
-    const int threads = warps_per_sm[v] * 32;
     double bestv = 0.0;
     for (int rep = 0; rep < 3; ++rep) {
       CK(cudaEventRecord(e0, st));
-      k_dmma_probe<<<h->sm_count, threads, 0, st>>>(sink, iters);
+      if (v == 0) k_dmma_probe<8, 256><<<h->sm_count, 256, 0, st>>>(sink, iters);
+      if (v == 1) k_dmma_probe<4, 512><<<h->sm_count, 512, 0, st>>>(sink, iters);
+      if (v == 2) k_dmma_probe<2, 1024><<<h->sm_count, 1024, 0, st>>>(sink, iters);
       CK(cudaEventRecord(e1, st));
       CK(cudaEventSynchronize(e1));
       CKL();
       float ms = 0.f;
       CK(cudaEventElapsedTime(&ms, e0, e1));
-      const double flops = (double)h->sm_count * warps_per_sm[v] * (double)iters * 32.0 * 512.0;
+      const double flops = (double)h->sm_count * warps_per_sm[v] * (double)iters * frag_rows[v] * 4.0 * 512.0;
       bestv = std::max(bestv, flops / (ms * 1e-3) / 1e12);
     }
     tflops_out[1 + v] = bestv;

@@ -50,27 +50,28 @@ __global__ void k_pad_copy(double* __restrict__ a, int m, double* __restrict__ P
   }
 }
 
-// Register-resident DMMA loop with the production fragment shape (8 x 4 independent accumulator pairs per warp).
-__global__ void k_dmma_probe(double* __restrict__ sink, int iters) {
-  double acc[8][4][2];
-  double a[8], b[4];
+// Register-resident DMMA loop (NI x 4 independent accumulator pairs per warp; NI = 8 is the production fragment shape).
+template <int NI, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_dmma_probe(double* __restrict__ sink, int iters) {
+  double acc[NI][4][2];
+  double a[NI], b[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  for (int i = 0; i < NI; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
 #pragma unroll
   for (int j = 0; j < 4; ++j) b[j] = 1.0 - 1e-9 * (threadIdx.x + j);
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < NI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
   double s = 0.0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < NI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) s += acc[i][j][0] + acc[i][j][1];
   if (s == 123.456) sink[blockIdx.x * blockDim.x + threadIdx.x] = s;

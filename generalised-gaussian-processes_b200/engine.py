@@ -213,6 +213,20 @@ class Engine:
                                              X2.shape[0], _ptr(theta), X1.shape[1], _ptr(out)), "ggp_kernel_matrix")
         return out
 
+    PROFILE_CATEGORIES = ("build", "trmm", "syrk", "bwd", "mm", "other")
+
+    def profile_enable(self, on=True):
+        check(self.lib.ggp_profile_enable(self.h, 1 if on else 0), "ggp_profile_enable")
+
+    def profile_read(self):
+        """Synchronise and return ({category: ms}, {category: spans}, kernel launches) since the last read."""
+        ms = (ctypes.c_double * 6)()
+        cnt = (ctypes.c_int64 * 6)()
+        launches = ctypes.c_int64()
+        check(self.lib.ggp_profile_read(self.h, ms, cnt, ctypes.byref(launches)), "ggp_profile_read")
+        cats = self.PROFILE_CATEGORIES
+        return {c: ms[i] for i, c in enumerate(cats)}, {c: cnt[i] for i, c in enumerate(cats)}, launches.value
+
     def probe_dmma_peak(self, iters=20000):
         out = (ctypes.c_double * 4)()
         with torch.cuda.device(self.device):

@@ -118,6 +118,13 @@ int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const d
 /* register-resident mma.sync m8n8k4 f64 loop on every SM: measured FP64 tensor-pipe peak [host out, TFLOP/s]; synchronous */
 int ggp_probe_dmma_peak(ggp_handle_t* h, void* stream, int iters, double* tflops_out /*[host]*/);
 
+/* instrumentation: CUDA-event spans around the kernel categories, on the caller's stream (no host sync until read).
+ * categories: 0 tile build, 1 triangular multiply, 2 SYRK, 3 backward GEMM+moments, 4 m x m section, 5 other.
+ * ggp_profile_read synchronises the device, returns the accumulated milliseconds / span counts per category and the number
+ * of kernels launched since the last read, and resets all three. */
+int ggp_profile_enable(ggp_handle_t* h, int on);
+int ggp_profile_read(ggp_handle_t* h, double* ms_out /*[6] host*/, int64_t* spans_out /*[6] host*/, int64_t* launches_out /*host*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import ggp_b200
 from oracle import sgpr as osgpr
-from tests.helpers import make_problem, relerr
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from helpers import make_problem, relerr
 
 torch.manual_seed(0)
 dev = torch.device("cuda:0")

@@ -1,0 +1,228 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): 1e-8 relative in float64 on the bound, its gradients and the predictive.
+Gradient parity is asserted at moderate conditioning of Kzz; at cond(Kzz) ~ 1e8 the oracle's own two float64 gradient
+evaluations disagree above 1e-9 (tests/test_oracle.py::test_gradient_conditioning_floor_is_inherent), so the
+ill-conditioned case is asserted at 1e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_problem, relerr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import ggp_b200
+    assert os.path.exists(ggp_b200.LIB_PATH), "CUDA extension missing"
+    return ggp_b200.Engine.get(torch.device("cuda:0"))
+
+
+def test_dmma_gemm_matches_torch(eng):
+    dev = eng.device
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for (mm, nn, kk) in [(128, 128, 64), (200, 70, 34), (512, 384, 1000), (1, 1, 2), (130, 257, 18)]:
+        A = torch.randn(mm, kk, dtype=torch.float64, generator=g).to(dev)
+        B = torch.randn(nn, kk, dtype=torch.float64, generator=g).to(dev)
+        C = eng.gemm_nt(A, B)
+        ref = A @ B.T
+        assert relerr(C, ref) < 1e-13, (mm, nn, kk)
+        C2 = eng.gemm_nt(A, B, C=ref.clone(), alpha=-0.5, beta=2.0)
+        assert relerr(C2, 1.5 * ref) < 1e-13
+
+
+def test_batched_cholesky_and_inverse(eng):
+    dev = eng.device
+    g = torch.Generator().manual_seed(1)
+    for m in [1, 20, 64, 65, 100, 500]:
+        R = torch.randn(3, m, m, dtype=torch.float64, generator=g).to(dev)
+        S = R @ R.transpose(1, 2) + m * torch.eye(m, dtype=torch.float64, device=dev)
+        L, Linv, info = eng.chol(S)
+        Lt = torch.linalg.cholesky(S)
+        assert info.tolist() == [0, 0, 0]
+        assert relerr(torch.tril(L), Lt) < 1e-13
+        assert relerr(Linv, torch.linalg.inv(Lt)) < 1e-12
+    # LAPACK-style failure index
+    bad = torch.eye(70, dtype=torch.float64, device=dev).repeat(2, 1, 1)
+    bad[1, 66, 66] = -1.0
+    _, _, info = eng.chol(bad)
+    assert info.tolist() == [0, 67]
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52"])
+def test_kernel_tiles_match_oracle(kind):
+    import ggp_b200
+    from oracle.kernels import ard_kernel
+    e = ggp_b200.Engine.get(torch.device("cuda:0"), kernel=kind)
+    for (n1, n2, d) in [(64, 64, 8), (130, 77, 3), (1, 5, 1), (257, 64, 16)]:
+        g = torch.Generator().manual_seed(n1)
+        X1 = torch.randn(n1, d, dtype=torch.float64, generator=g)
+        X2 = torch.randn(n2, d, dtype=torch.float64, generator=g)
+        th = torch.cat([0.5 + torch.rand(d, dtype=torch.float64, generator=g), torch.tensor([1.7, 0.1], dtype=torch.float64)])
+        K = e.kernel_matrix(X1, X2, th)
+        ref = ard_kernel(X1, X2, th[:d], th[d], kind)
+        assert relerr(K, ref) < 1e-13, (kind, n1, n2, d)
+
+
+@pytest.mark.parametrize("N,M,D,jit", [(300, 20, 1, 1e-4), (1000, 100, 3, 1e-4), (3000, 260, 4, 1e-4), (2500, 129, 8, 1e-4),
+                                       (40000, 300, 8, 1e-4)])
+def test_bound_and_gradient_parity(eng, N, M, D, jit):
+    from oracle import sgpr as osgpr
+    X, y, Z, th = make_problem(N, M, D, seed=N)
+    out = eng.sgpr_eval(X, y, Z, th, jitter_policy=jit)
+    if N <= 5000:
+        Fo, go = osgpr.sgpr_grads_closed_form(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=jit, normalize="none")
+    else:
+        Fo, go, _ = osgpr.sgpr_bound_and_grads_chunked(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=jit, normalize="none")
+    g = out["grad"][0].cpu()
+    assert out["info"].tolist() == [0] and out["info_b"].tolist() == [0]
+    assert relerr(out["bound"], Fo) < TOL
+    assert relerr(g[:D], go["ell"]) < TOL
+    assert relerr(g[D], go["sf2"]) < TOL
+    assert relerr(g[D + 1], go["s2"]) < TOL
+    assert relerr(g[D + 2:].view(M, D), go["Z"]) < TOL
+
+
+def test_ill_conditioned_parity_at_the_float64_floor(eng):
+    from oracle import sgpr as osgpr
+    N, M, D = 3000, 260, 4
+    X, y, Z, th = make_problem(N, M, D, seed=N)
+    out = eng.sgpr_eval(X, y, Z, th, jitter_policy=1e-6)  # cond(Kzz) ~ 1e8
+    Fo, go = osgpr.sgpr_grads_closed_form(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=1e-6, normalize="none")
+    g = out["grad"][0].cpu()
+    assert relerr(out["bound"], Fo) < TOL
+    assert relerr(g[:D], go["ell"]) < 1e-6 and relerr(g[D + 2:].view(M, D), go["Z"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["sgpr_small_1d", "sgpr_small_3d", "sgpr_mid_4d"])
+def test_golden_dense_definition(eng, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+    X, y, Z, th = T(g["X"]), T(g["y"]), T(g["Z"]), T(g["theta"])
+    M, D = Z.shape
+    out = eng.sgpr_eval(X, y, Z, th, jitter_policy=float(g["jitter"]))
+    assert relerr(out["bound"], float(g["F_dense"])) < TOL
+    gr = out["grad"][0].cpu()
+    assert relerr(gr[:D], g["g_ell"]) < 1e-6 and relerr(gr[D + 1], g["g_s2"]) < TOL
+    assert relerr(gr[D + 2:].view(M, D), g["g_Z"]) < 1e-6
+    mean, var, cov = eng.sgpr_predict(T(g["Xs"]), Z, th, full_cov=True)
+    assert relerr(mean[0], g["pred_mean"]) < TOL
+    assert relerr(cov[0], g["pred_cov"]) < TOL
+    assert relerr(var[0], np.diag(g["pred_cov"])) < TOL
+
+
+def test_jitter_ladder_with_duplicate_inducing_rows(eng):
+    """Z drawn WITH replacement (experiments/regression.py:83) makes Kzz exactly singular: the gpytorch ladder must engage
+    and pick the same jitter as the oracle's psd_safe_cholesky."""
+    from oracle import sgpr as osgpr
+    from oracle.linalg import psd_safe_cholesky
+    from oracle.kernels import ard_kernel
+    X, y, Z, th = make_problem(2000, 120, 3, seed=77, without_replacement=False)
+    Z[7] = Z[3]
+    out = eng.sgpr_eval(X, y, Z, th, jitter_policy="gpytorch")
+    _, jit = psd_safe_cholesky(ard_kernel(Z, Z, th[:3], th[3]), "gpytorch")
+    assert jit > 0 and abs(float(out["jitter"][0]) - jit) < 1e-20
+    Fo = osgpr.sgpr_bound(X, y, Z, th[:3], th[3], th[4], "gpytorch", "none")
+    assert relerr(out["bound"], Fo) < 1e-7  # singular-to-jitter regime: cond ~ sf2*M/jitter
+    import ggp_b200
+    with pytest.raises(ggp_b200.NotPSDError):
+        eng.sgpr_eval(X, y, Z, th, jitter_policy=0.0)
+
+
+def test_batched_theta_rows_equal_single_evaluations(eng):
+    N, M, D = 1500, 64, 3
+    X, y, Z, th = make_problem(N, M, D, seed=5)
+    g = torch.Generator().manual_seed(3)
+    thetas = th.unsqueeze(0) * (0.7 + 0.6 * torch.rand(5, D + 2, dtype=torch.float64, generator=g))
+    outb = eng.sgpr_eval(X, y, Z, thetas, jitter_policy=1e-5)
+    for b in range(5):
+        o = eng.sgpr_eval(X, y, Z, thetas[b], jitter_policy=1e-5)
+        assert torch.equal(o["bound"][0], outb["bound"][b])
+        assert torch.equal(o["grad"][0], outb["grad"][b])
+
+
+def test_ragged_and_tiny_shapes(eng):
+    from oracle import sgpr as osgpr
+    for (N, M, D) in [(1, 1, 1), (7, 3, 2), (129, 65, 5), (1025, 17, 2)]:
+        X, y, Z, th = make_problem(max(N, 4), M, D, seed=N + 100)
+        X, y = X[:N], y[:N]
+        out = eng.sgpr_eval(X, y, Z, th, jitter_policy=1e-4)
+        Fo, go = osgpr.sgpr_grads_closed_form(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=1e-4, normalize="none")
+        assert relerr(out["bound"], Fo) < TOL, (N, M, D)
+        assert relerr(out["grad"][0][D + 2:].cpu().view(M, D), go["Z"]) < 1e-7, (N, M, D)
+
+
+def test_shard_additivity_and_determinism_at_scale(eng):
+    """Size-independent properties at a BASELINE-scale M: pass-1 partial sums over two row shards add to the unsharded
+    partial (what the NCCL all-reduce relies on), repeated evaluations are bit-identical, and the analytic gradient
+    matches a central finite difference of the bound along a random direction."""
+    import ctypes
+    N, M, D = 200_000, 1024, 8
+    X, y, Z, th = make_problem(N, M, D, seed=1)
+    dev = eng.device
+    X, y, Z, th = X.to(dev), y.to(dev), Z.to(dev), th.to(dev)
+    full = eng.sgpr_eval(X, y, Z, th, jitter_policy=1e-6)
+    again = eng.sgpr_eval(X, y, Z, th, jitter_policy=1e-6)
+    assert torch.equal(full["bound"], again["bound"]) and torch.equal(full["grad"], again["grad"])
+    h = N // 2 + 37
+    p1 = eng.sgpr_eval(X[:h], y[:h], Z, th, jitter_policy=1e-6, need_grad=False)["partial"]
+    p2 = eng.sgpr_eval(X[h:], y[h:], Z, th, jitter_policy=1e-6, need_grad=False)["partial"]
+    assert relerr(p1 + p2, full["partial"]) < 1e-12
+    # directional finite difference in log-theta
+    g = torch.Generator().manual_seed(2)
+    dirn = torch.randn(D + 2, dtype=torch.float64, generator=g).to(dev) * 0.1
+    eps = 1e-5
+    Fp = eng.sgpr_eval(X, y, Z, th * torch.exp(eps * dirn), jitter_policy=1e-6, need_grad=False)["bound"][0]
+    Fm = eng.sgpr_eval(X, y, Z, th * torch.exp(-eps * dirn), jitter_policy=1e-6, need_grad=False)["bound"][0]
+    fd = (Fp - Fm) / (2 * eps)
+    an = (full["grad"][0][:D + 2] * th * dirn).sum()
+    assert abs(fd - an) < 1e-5 * abs(an)
+
+
+def test_autograd_function_drops_into_a_training_step(eng):
+    """SGPRBound.apply replaces forward + mll + backward of models/sgpr.py:123-129 (gpytorch convention: / N, softplus raws)."""
+    import ggp_b200.functions as F
+    from oracle import sgpr as osgpr
+    N, M, D = 800, 40, 2
+    X, y, Z, th = make_problem(N, M, D, seed=21)
+    dev = eng.device
+    raw_l = torch.zeros(1, D, dtype=torch.float64, device=dev, requires_grad=True)
+    raw_o = torch.zeros((), dtype=torch.float64, device=dev, requires_grad=True)
+    raw_n = torch.zeros(1, dtype=torch.float64, device=dev, requires_grad=True)
+    Zp = Z.to(dev).clone().requires_grad_(True)
+    sp = torch.nn.functional.softplus
+    loss = -F.sgpr_bound(X.to(dev), y.to(dev), Zp, sp(raw_l), sp(raw_o), sp(raw_n) + 1e-4, dict(jitter_policy=1e-5))
+    loss.backward()
+    # oracle: same chain on CPU
+    rl = torch.zeros(1, D, dtype=torch.float64, requires_grad=True)
+    ro = torch.zeros((), dtype=torch.float64, requires_grad=True)
+    rn = torch.zeros(1, dtype=torch.float64, requires_grad=True)
+    Zc = Z.clone().requires_grad_(True)
+    lo = -osgpr.sgpr_bound(X, y, Zc, sp(rl).reshape(-1), sp(ro), (sp(rn) + 1e-4).reshape(()), 1e-5, "n")
+    lo.backward()
+    assert relerr(loss, lo) < TOL
+    assert relerr(raw_l.grad, rl.grad) < TOL and relerr(raw_o.grad, ro.grad) < TOL and relerr(raw_n.grad, rn.grad) < TOL
+    assert relerr(Zp.grad, Zc.grad) < TOL
+
+
+def test_batched_pymc3_logp_dlogp(eng):
+    import ggp_b200.functions as F
+    from oracle import priors
+    N, M, D = 545, 100, 1
+    import ggp_b200.synthetic as syn
+    c = syn.config2_co2_shaped(N, M)
+    X, y, Z = (torch.tensor(c[k]) for k in ("X", "y", "Z"))
+    g = torch.Generator().manual_seed(4)
+    xs = torch.randn(4, D + 2, dtype=torch.float64, generator=g) * 0.3 + torch.tensor([0.0, 0.0, -1.0], dtype=torch.float64)
+    lp, dlp = F.sgpr_vfe_logp_dlogp(xs.to(eng.device), X.to(eng.device), y.to(eng.device), Z.to(eng.device))
+    for cidx in range(4):
+        lo, go = priors.sgpr_vfe_logp_dlogp(xs[cidx], X, y, Z)
+        assert relerr(lp[cidx], lo) < 1e-7   # duplicate Z rows + 1e-6 stabilise jitter: cond(Kzz) ~ 1e8
+        assert relerr(dlp[cidx], go) < 1e-5

@@ -1,0 +1,150 @@
+"""Pins the CPU oracle (oracle/) against definitions that do not share its algebra, and against the committed golden
+vectors.  The reference has no tests / fixtures and its evaluators are not importable here => "parity unpinned" at the
+third-party boundary; these are the known-answer anchors instead."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_problem, relerr
+from oracle import linalg, priors, sgpr, sgpmc, svgp
+from oracle.kernels import ard_kernel
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+
+
+@pytest.mark.parametrize("name", ["sgpr_small_1d", "sgpr_small_3d", "sgpr_mid_4d"])
+def test_oracle_matches_golden_dense_definition(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    X, y, Z, th = T(g["X"]), T(g["y"]), T(g["Z"]), T(g["theta"])
+    D = X.shape[1]
+    jit = float(g["jitter"])
+    F, gr = sgpr.sgpr_grads_closed_form(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=jit, normalize="none")
+    assert abs(F.item() - float(g["F_dense"])) <= 1e-10 * abs(float(g["F_dense"]))
+    # gradients of the dense definition are ill-conditioned through inv(Kzz): 1e-6 relative is what float64 supports here
+    assert relerr(gr["ell"], g["g_ell"]) < 1e-6
+    assert relerr(gr["sf2"], g["g_sf2"]) < 1e-6
+    assert relerr(gr["s2"], g["g_s2"]) < 1e-9
+    assert relerr(gr["Z"], g["g_Z"]) < 1e-6
+    mean, cov = sgpr.sgpr_predict(T(g["Xs"]), X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=jit)
+    assert relerr(mean, g["pred_mean"]) < 1e-8
+    assert relerr(cov, g["pred_cov"]) < 1e-8
+
+
+def test_three_formulations_agree():
+    X, y, Z, th = make_problem(600, 40, 3, seed=5)
+    ell, sf2, s2 = th[:3], th[3], th[4]
+    F = sgpr.sgpr_bound(X, y, Z, ell, sf2, s2, jitter_policy=0.0, normalize="none")
+    Fg = sgpr.sgpr_bound_gpytorch_form(X, y, Z, ell, sf2, s2, jitter_policy=0.0) * 600
+    Fd = sgpr.sgpr_bound_dense(X, y, Z, ell, sf2, s2)
+    assert abs(F - Fg) / abs(F) < 1e-12
+    assert abs(F - Fd) / abs(F) < 1e-11
+
+
+def test_conventions_division_by_n_and_pymc3_jitter():
+    X, y, Z, th = make_problem(600, 40, 3, seed=6)
+    ell, sf2, s2 = th[:3], th[3], th[4]
+    Fn = sgpr.sgpr_bound(X, y, Z, ell, sf2, s2, "gpytorch", "n")
+    F = sgpr.sgpr_bound(X, y, Z, ell, sf2, s2, "gpytorch", "none")
+    assert abs(Fn * 600 - F) < 1e-9 * abs(F)
+    Fp = sgpr.sgpr_bound(X, y, Z, ell, sf2, s2, "pymc3", "none")
+    rel = abs(Fp - F) / abs(F)
+    assert 1e-9 < rel < 1e-3  # the fixed 1e-6 stabilise jitter is a visible convention difference
+
+
+def test_closed_form_and_chunked_match_autograd():
+    X, y, Z, th = make_problem(500, 30, 3, seed=7)
+    ell, sf2, s2 = th[:3], th[3], th[4]
+    Fa, ga = sgpr.sgpr_bound_and_grads_autograd(X, y, Z, ell, sf2, s2, 1e-4, "none")
+    Fc, gc = sgpr.sgpr_grads_closed_form(X, y, Z, ell, sf2, s2, 1e-4, "none")
+    Fk, gk, _ = sgpr.sgpr_bound_and_grads_chunked(X, y, Z, ell, sf2, s2, 1e-4, "none", chunk=128)
+    assert abs(Fa - Fk) < 1e-12 * abs(Fa)
+    for k in ga:
+        assert relerr(gc[k], ga[k]) < 1e-9, k
+        assert relerr(gk[k], ga[k]) < 1e-9, k
+
+
+def test_gradient_conditioning_floor_is_inherent():
+    """At cond(Kzz) ~ 1e8 two float64 evaluations of the SAME oracle gradient (autograd vs closed form) already disagree
+    above 1e-9: the 1e-8 parity budget is only meaningful for moderately conditioned Kzz.  Documented in DESIGN.md."""
+    X, y, Z, th = make_problem(3000, 260, 4, seed=3000)
+    ell, sf2, s2 = th[:4], th[4], th[5]
+    _, ga = sgpr.sgpr_bound_and_grads_autograd(X, y, Z, ell, sf2, s2, 1e-6, "none")
+    _, gc = sgpr.sgpr_grads_closed_form(X, y, Z, ell, sf2, s2, 1e-6, "none")
+    worst = max(relerr(gc[k], ga[k]) for k in ga)
+    assert 1e-11 < worst < 1e-5
+
+
+def test_psd_safe_cholesky_ladder_with_duplicate_inducing_rows():
+    X, y, Z, th = make_problem(400, 30, 2, seed=8, without_replacement=False)
+    Z[5] = Z[2]  # exact duplicate => singular Kzz
+    Kzz = ard_kernel(Z, Z, th[:2], th[2])
+    L, jit = linalg.psd_safe_cholesky(Kzz, "gpytorch")
+    assert jit in (1e-8, 1e-7, 1e-6)
+    with pytest.raises(linalg.NotPSDError):
+        linalg.psd_safe_cholesky(-torch.eye(3, dtype=torch.float64), "gpytorch")
+    assert linalg.jitter_ladder("pymc3") == [1e-6]
+
+
+def test_predictive_matches_dense():
+    X, y, Z, th = make_problem(300, 25, 2, seed=9)
+    Xs = torch.randn(40, 2, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    m1, c1 = sgpr.sgpr_predict(Xs, X, y, Z, th[:2], th[2], th[3], jitter_policy=1e-6)
+    m2, c2 = sgpr.sgpr_predict_dense(Xs, X, y, Z, th[:2], th[2], th[3], jitter=1e-6)
+    assert relerr(m1, m2) < 1e-9 and relerr(c1, c2) < 1e-9
+    m3, v3 = sgpr.sgpr_predict(Xs, X, y, Z, th[:2], th[2], th[3], jitter_policy=1e-6, full_cov=False)
+    assert relerr(v3, torch.diagonal(c1)) < 1e-13
+
+
+def test_pymc3_logp_prior_terms():
+    X, y, Z, th = make_problem(200, 15, 2, seed=10)
+    x = torch.tensor([0.1, -0.3, 0.2, -1.1], dtype=torch.float64)
+    lp, g = priors.sgpr_vfe_logp_dlogp(x, X, y, Z)
+    ell, sf2, s2 = priors.unpack_theta(x, 2)
+    F = sgpr.sgpr_bound(X, y, Z, ell, sf2, s2, "pymc3", "none")
+    from scipy import stats
+    pr = (stats.gamma.logpdf(ell.numpy(), a=2, scale=1).sum() + stats.halfcauchy.logpdf(math.exp(0.2)) + stats.halfcauchy.logpdf(math.exp(-1.1))
+          + x.sum().item())
+    assert abs(lp.item() - (F.item() + pr)) < 1e-9 * abs(lp.item())
+    # finite-difference check of dlogp
+    eps = 1e-6
+    for i in range(4):
+        xp, xm = x.clone(), x.clone()
+        xp[i] += eps; xm[i] -= eps
+        fd = (priors.sgpr_vfe_logp(xp, X, y, Z) - priors.sgpr_vfe_logp(xm, X, y, Z)) / (2 * eps)
+        assert abs(fd - g[i]) < 1e-5 * max(1.0, abs(g[i]))
+
+
+def test_svgp_whitened_equals_unwhitened_and_golden():
+    g = np.load(os.path.join(GOLD, "svgp_small.npz"))
+    xb, yb, Z, th, m, Ls = (T(g[k]) for k in ("xb", "yb", "Z", "theta", "m", "Ls"))
+    D = xb.shape[1]
+    e = svgp.svgp_elbo(xb, yb, Z, m, Ls, th[:D], th[D], th[D + 1], float(g["num_data"]))
+    assert abs(e.item() - float(g["elbo_unwhitened"])) < 1e-9 * abs(e.item())
+    eb = svgp.svgp_elbo(xb, T(g["yb01"]), Z, m, Ls, th[:D], th[D], th[D + 1], float(g["num_data"]), likelihood="bernoulli")
+    assert abs(eb.item() - float(g["elbo_bernoulli_gh20"])) < 1e-12
+
+
+def test_gauss_hermite_20_against_fine_quadrature():
+    mu = torch.tensor([0.3, -1.2, 2.0], dtype=torch.float64)
+    var = torch.tensor([0.5, 1.5, 0.1], dtype=torch.float64)
+    yv = torch.tensor([1.0, 0.0, 1.0], dtype=torch.float64)
+    gh = svgp.bernoulli_probit_expected_log_prob(yv, mu, var)
+    f = torch.linspace(-12, 12, 200001, dtype=torch.float64)
+    for i in range(3):
+        pdf = torch.exp(-0.5 * (f - mu[i]) ** 2 / var[i]) / torch.sqrt(2 * math.pi * var[i])
+        ref = torch.trapz(pdf * svgp.log_ndtr((2 * yv[i] - 1) * f), f)
+        assert abs(ref - gh[i]) < 5e-6
+
+
+def test_sgpmc_density_is_finite_and_differentiable():
+    X, y, Z, th = make_problem(150, 12, 2, seed=12)
+    v = torch.zeros(12, dtype=torch.float64)
+    raw = torch.tensor([0.5, 0.4, 0.3, -0.5], dtype=torch.float64)
+    lp, gv, gr = sgpmc.sgpmc_logp_dlogp(v, raw, X, y, Z)
+    assert torch.isfinite(lp) and torch.isfinite(gv).all() and torch.isfinite(gr).all()
+    lpb, _, _ = sgpmc.sgpmc_logp_dlogp(v, raw, X, (y > 0).double(), Z, likelihood="bernoulli")
+    assert torch.isfinite(lpb)
