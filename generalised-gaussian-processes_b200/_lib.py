@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libggp_b200.so")
+LIB_PATH = os.environ.get("GGP_B200_LIB") or os.path.join(_HERE, "libggp_b200.so")  # env override: developer A/B builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 c_double_p = ctypes.c_void_p  # device pointers are passed as integers
@@ -42,6 +42,7 @@ SYMBOLS = {
     "ggp_svgp_elbo": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I, _I, _I, _D, _I, _I, _P, _P, _P]),
     "ggp_chol_batched": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "ggp_gemm_nt": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _D, _D]),
+    "ggp_gemm_nt_ex": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _D, _D, _I, _I, _I, _I64]),
     "ggp_kernel_matrix": (_I, [_P, _CFG, _P, _P, _I64, _P, _I64, _P, _I, _P]),
     "ggp_profile_enable": (_I, [_P, _I]),
     "ggp_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),

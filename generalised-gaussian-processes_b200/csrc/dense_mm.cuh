@@ -7,60 +7,107 @@
 namespace ggp {
 
 constexpr int NB = 64;  // diagonal block size of the blocked Cholesky / recursive triangular inverse
-constexpr int POTF2_SMEM = 2 * NB * (NB + 1) * 8;
+constexpr int POTF2_SMEM = 0;
 
-// Factor diagonal block kb in place (lower) and write its inverse T = L_kk^{-1}.  One CTA per batch element.
+// Factor diagonal block kb in place (lower) and write its inverse T = L_kk^{-1}.  One CTA (16 x 16 threads) per batch element.
+// Register-resident right-looking sweeps: thread (tx,ty) owns the 4 x 4 elements (ty+16i, tx+16k).  Per column j the owners
+// publish the (unscaled) column through a double-buffered shared vector, ONE barrier, then every thread applies the rank-1
+// update to its registers.  The inverse is the same sweep on T (start from I): T[r,:] -= L[r,j] * T[j,:] / L[j,j].
 // info[b] = global index (1-based) of the first non-positive pivot, LAPACK potrf style; first failure wins.
 __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int64_t ld, int64_t sA, int kb,
                                                      double* __restrict__ T, int64_t sT, int32_t* info) {
-  extern __shared__ __align__(16) unsigned char potf2_smem[];
-  double (*a)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potf2_smem);
-  double (*t)[NB + 1] = a + NB;
+  __shared__ double xch[2][NB];
+  __shared__ double Ls[NB][NB + 1];
   __shared__ int bad;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double* Ab = A + b * sA + (int64_t)kb * NB * (ld + 1);
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx / NB, c = idx % NB;
-    a[r][c] = (c <= r) ? Ab[(int64_t)r * ld + c] : 0.0;
-  }
+  double a[4][4], t[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = ty + 16 * i, c = tx + 16 * k;
+      a[i][k] = (c <= r) ? Ab[(int64_t)r * ld + c] : 0.0;
+      t[i][k] = (r == c) ? 1.0 : 0.0;
+    }
   if (tid == 0) bad = 0;
-  for (int j = 0; j < NB; ++j) {
-    __syncthreads();
-    const double dj = a[j][j];
-    if (!(dj > 0.0) && tid == 0 && bad == 0) bad = j + 1;
-    const double piv = sqrt(dj);
-    __syncthreads();
-    if (tid == 0) a[j][j] = piv;
-    for (int r = j + 1 + tid; r < NB; r += 256) a[r][j] = a[r][j] / piv;
-    __syncthreads();
-    const int w = NB - 1 - j;
-    for (int idx = tid; idx < w * w; idx += 256) {
-      const int r = j + 1 + idx / w, c = j + 1 + idx % w;
-      if (c <= r) a[r][c] = fma(-a[r][j], a[c][j], a[r][c]);
+  // ---- Cholesky sweep ----
+#pragma unroll
+  for (int kj = 0; kj < 4; ++kj) {
+    for (int tj = 0; tj < 16; ++tj) {
+      const int j = kj * 16 + tj;
+      double* x = xch[j & 1];
+      if (tx == tj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[ty + 16 * i] = a[i][kj];
+      }
+      __syncthreads();
+      const double dj = x[j];
+      if (!(dj > 0.0) && tid == 0 && bad == 0) bad = j + 1;
+      const double piv = sqrt(dj), inv = 1.0 / piv, dinv = inv * inv;
+      if (tx == tj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = ty + 16 * i;
+          Ls[r][j] = (r > j) ? a[i][kj] * inv : ((r == j) ? piv : 0.0);
+        }
+      }
+      double xr[4], xc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xr[i] = x[ty + 16 * i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xc[k] = x[tx + 16 * k] * dinv;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < kj) continue;
+        if (tx + 16 * k > j) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i][k] = fma(-xr[i], xc[k], a[i][k]);
+        }
+      }
     }
   }
   __syncthreads();
-  // T = inv(L_kk): 4 threads per column split the dot product, fixed combination order
-  {
-    const int c = tid >> 2, part = tid & 3;
-    for (int r = 0; r < NB; ++r) {
-      double s = 0.0;
-      if (r >= c) {
-        for (int k = c + part; k < r; k += 4) s = fma(a[r][k], t[k][c], s);
+  // ---- inverse sweep:  for j: T[j,:] /= L[j,j];  T[r,:] -= L[r,j] T[j,:] for r > j ----
+#pragma unroll
+  for (int kj = 0; kj < 4; ++kj) {
+    for (int tj = 0; tj < 16; ++tj) {
+      const int j = kj * 16 + tj;
+      double* x = xch[j & 1];
+      if (ty == tj) {
+        const double dinv = 1.0 / Ls[j][j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          t[kj][k] *= dinv;
+          x[tx + 16 * k] = t[kj][k];
+        }
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (part == 0) t[r][c] = (r < c) ? 0.0 : (((r == c) ? 1.0 : 0.0) - s) / a[r][r];
-      __syncwarp();
+      __syncthreads();
+      double xc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xc[k] = x[tx + 16 * k];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < kj) continue;
+        const int r = ty + 16 * i;
+        if (r > j) {
+          const double lrj = Ls[r][j];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t[i][k] = fma(-lrj, xc[k], t[i][k]);
+        }
+      }
     }
   }
   __syncthreads();
   double* Tb = T + b * sT + (int64_t)kb * NB * NB;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx / NB, c = idx % NB;
-    Ab[(int64_t)r * ld + c] = a[r][c];  // upper part of the block is zero
-    Tb[idx] = t[r][c];
-  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = ty + 16 * i, c = tx + 16 * k;
+      Ab[(int64_t)r * ld + c] = (c <= r) ? Ls[r][c] : 0.0;
+      Tb[r * NB + c] = (c <= r) ? t[i][k] : 0.0;
+    }
   if (tid == 0 && bad && info[b] == 0) info[b] = kb * NB + bad;
 }
 
@@ -237,8 +284,9 @@ __global__ void k_make_PA_Gbar(const double* __restrict__ partial, int64_t sP, i
 }
 
 // Kzz-dependent gradient, one warp per row i:  V = Gzz o Kzz ;
-//   rowacc[i][0..d-1] = sum_j V_ij * dk-factor * (z_i - z_j)^2 ;  rowacc[i][d] = sum_j Gzz_ij k_ij ;
-//   dZ[i][c] = 2 * sum_j Gzz_ij * 2 g_ij (z_i - z_j)_c / ell_c^2      (g = dk/d(d2))
+//   rowacc[i][c] = sum_j Gzz_ij g_ij * d(d2)/d ell_c ;  rowacc[i][d] = sum_j Gzz_ij k_ij ;
+//   dZ[i][c] = 2 * sum_j Gzz_ij g_ij * d(d2)/d z_ic                     (g = dk/d(d2); Gzz symmetric)
+// Dimensions are processed in register blocks of 8 (one kernel evaluation per (j, block)).
 // grid (ceil(M/8), batch), block 256
 __global__ void __launch_bounds__(256) k_grad_kzz_rows(const double* __restrict__ Gzz, int Mp, int64_t sMat,
                                                        const double* __restrict__ Z, int M, int d,
@@ -250,36 +298,45 @@ __global__ void __launch_bounds__(256) k_grad_kzz_rows(const double* __restrict_
   const double* th = theta + (int64_t)b * (d + 2);
   const double sf2 = th[d];
   const double* zi = Z + (int64_t)i * d;
-  double ksum = 0.0;
-  for (int j = lane; j < M; j += 32) {
-    double d2 = 0.0;
-    for (int c = 0; c < d; ++c) {
-      const double t = (zi[c] - Z[(int64_t)j * d + c]) / th[c];
-      d2 = fma(t, t, d2);
-    }
-    ksum = fma(Gzz[b * sMat + (int64_t)i * Mp + j], kval(kind, sf2, d2), ksum);
-  }
-  ksum = warp_sum(ksum);
-  if (lane == 0) rowacc[((int64_t)b * M + i) * (d + 1) + d] = ksum;
-  for (int c = 0; c < d; ++c) {
-    double al = 0.0, az = 0.0;
+  const double* grow = Gzz + b * sMat + (int64_t)i * Mp;
+  for (int c0 = 0; c0 < d; c0 += 8) {
+    double al[8], az[8], ksum = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) al[c] = az[c] = 0.0;
     for (int j = lane; j < M; j += 32) {
+      const double* zj = Z + (int64_t)j * d;
       double d2 = 0.0;
       for (int cc = 0; cc < d; ++cc) {
-        const double t = (zi[cc] - Z[(int64_t)j * d + cc]) / th[cc];
+        const double t = (zi[cc] - zj[cc]) / th[cc];
         d2 = fma(t, t, d2);
       }
-      const double gg = Gzz[b * sMat + (int64_t)i * Mp + j] * kgrad(kind, sf2, d2);
-      const double df = zi[c] - Z[(int64_t)j * d + c];
-      al = fma(gg * df, df, al);
-      az = fma(gg, df, az);
+      const double gij = grow[j];
+      if (c0 == 0) ksum = fma(gij, kval(kind, sf2, d2), ksum);
+      const double gg = gij * kgrad(kind, sf2, d2);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c0 + c < d) {
+          const double df = zi[c0 + c] - zj[c0 + c];
+          al[c] = fma(gg * df, df, al[c]);
+          az[c] = fma(gg, df, az[c]);
+        }
+      }
     }
-    al = warp_sum(al);
-    az = warp_sum(az);
-    if (lane == 0) {
-      // d(d2)/d ell_c = -2 df^2 / ell_c^3 ; d(d2)/d z_ic = 2 df / ell_c^2 (and the symmetric partner doubles it)
-      rowacc[((int64_t)b * M + i) * (d + 1) + c] = -2.0 * al / (th[c] * th[c] * th[c]);
-      dZ[b * sG + (int64_t)i * d + c] = 4.0 * az / (th[c] * th[c]);
+    if (c0 == 0) {
+      ksum = warp_sum(ksum);
+      if (lane == 0) rowacc[((int64_t)b * M + i) * (d + 1) + d] = ksum;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c0 + c < d) {
+        const double sl = warp_sum(al[c]), sz = warp_sum(az[c]);
+        if (lane == 0) {
+          const double e = th[c0 + c];
+          // d(d2)/d ell_c = -2 df^2 / ell_c^3 ; d(d2)/d z_ic = 2 df / ell_c^2 (and the symmetric partner doubles it)
+          rowacc[((int64_t)b * M + i) * (d + 1) + c0 + c] = -2.0 * sl / (e * e * e);
+          dZ[b * sG + (int64_t)i * d + c0 + c] = 4.0 * sz / (e * e);
+        }
+      }
     }
   }
 }

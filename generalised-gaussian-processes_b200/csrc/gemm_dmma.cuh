@@ -14,7 +14,15 @@
 
 namespace ggp {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, LDS = BK + 4, GEMM_THREADS = 256;
+#ifndef GGP_BK
+#define GGP_BK 32
+#endif
+#ifndef GGP_STAGES
+#define GGP_STAGES 3
+#endif
+constexpr int BM = 128, BN = 128, BK = GGP_BK, STAGES = GGP_STAGES, LDS = BK + 4, GEMM_THREADS = 256;
+constexpr int LD_TPR = BK / 2;                     // loader threads per tile row (16-byte chunks per row)
+constexpr int LD_RPP = GEMM_THREADS / LD_TPR;      // rows per loader pass
 constexpr int GEMM_SMEM_PIPE = STAGES * (BM + BN) * LDS * 8;  // 163840 B
 constexpr int EPI_LDW = BN + 4;                                // W tile row stride (doubles), == 4 mod 16
 constexpr int MOM_QB = 24;                                     // moment columns per DMMA block (3 n-fragments)
@@ -40,6 +48,8 @@ struct GemmP {
   const double* Kc; int64_t ldk, sK;       // [N x ldk] per batch  (k(x_n, z_i) at Kc[n*ldk + i])
   const double* Xc; int d;                 // [N x d]
   double* mom;      int64_t sMomTile, sMom;  // [batch][tile_n][M][2d+1]
+  // EPI_STORE, optional: per-tile row dots against yv (b = A y)
+  double* rowdot;   int64_t sRowdot;         // [batch][tile_n][M]
 };
 
 template <int EPI>
@@ -50,7 +60,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_nt(const GemmP p) {
 
   const int tn = blockIdx.x;
   const int tm = p.heavy_first ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
-  if (p.sym && tn < tm) return;
+  if ((p.sym == 1 && tn < tm) || (p.sym == 2 && tn > tm)) return;  // 1: upper tiles only, 2: lower tiles only
   int z = blockIdx.z;
   const int split = z % p.splits; z /= p.splits;
   const int pz = z % p.nz2;
@@ -80,31 +90,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_nt(const GemmP p) {
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
   const int g = lane >> 2, q = lane & 3;
 
-  // loader mapping: 8 threads cover one 128-byte row (16 doubles), 32 rows per pass, 4 passes per operand
-  const int ld_row = tid >> 3, ld_chunk = tid & 7;
+  // loader mapping: 8 threads cover one 128-byte row (16 doubles), 32 rows per pass, 4 passes per operand.
+  // Row pointers, validity and shared offsets are computed ONCE; the per-iteration cost is one 64-bit add per row.
+  const int ld_row = tid / LD_TPR, ld_chunk = tid % LD_TPR;
   const int row0_m = tm * BM, row0_n = tn * BN;
+  // one base pointer per operand; rows of later passes are reached with a constant stride
+  const double* gA0 = A + (int64_t)(row0_m + ld_row) * p.lda + ld_chunk * 2;
+  const double* gB0 = B + (int64_t)(row0_n + ld_row) * p.ldb + ld_chunk * 2;
+  const int64_t strA = (int64_t)LD_RPP * p.lda, strB = (int64_t)LD_RPP * p.ldb;
+  unsigned okmask = 0;
+#pragma unroll
+  for (int r = 0; r < BM / LD_RPP; ++r) okmask |= ((row0_m + ld_row + r * LD_RPP < p.M) ? 1u : 0u) << r;
+#pragma unroll
+  for (int r = 0; r < BN / LD_RPP; ++r) okmask |= ((row0_n + ld_row + r * LD_RPP < p.N) ? 1u : 0u) << (16 + r);
+  const int ld_soff = ld_row * LDS + ld_chunk * 2;
+  const int krem0 = p.K - ld_chunk * 2;  // elements left at k = 0 for this thread's 16-byte column
 
   auto load_stage = [&](int stage, int it) {
-    const int k0 = k_lo + it * BK + ld_chunk * 2;
-    int kb = (p.K - k0) * 8;
+    const int k0 = k_lo + it * BK;
+    int kb = (krem0 - k0) * 8;
     kb = kb < 0 ? 0 : (kb > 16 ? 16 : kb);
-    double* dA = sA + stage * BM * LDS;
-    double* dB = sB + stage * BN * LDS;
+    double* dA = sA + stage * BM * LDS + ld_soff;
+    double* dB = sB + stage * BN * LDS + ld_soff;
 #pragma unroll
-    for (int r = 0; r < BM / 32; ++r) {
-      const int row = ld_row + r * 32;
-      const int gr = row0_m + row;
-      const bool ok = gr < p.M;
-      const double* src = ok ? (A + (int64_t)gr * p.lda + k0) : A;
-      cp_async16(dA + row * LDS + ld_chunk * 2, kb > 0 ? src : A, ok ? kb : 0);
+    for (int r = 0; r < BM / LD_RPP; ++r) {
+      const int bytes = ((okmask >> r) & 1u) ? kb : 0;
+      cp_async16(dA + r * LD_RPP * LDS, bytes ? (gA0 + r * strA + k0) : A, bytes);
     }
 #pragma unroll
-    for (int r = 0; r < BN / 32; ++r) {
-      const int row = ld_row + r * 32;
-      const int gr = row0_n + row;
-      const bool ok = gr < p.N;
-      const double* src = ok ? (B + (int64_t)gr * p.ldb + k0) : B;
-      cp_async16(dB + row * LDS + ld_chunk * 2, kb > 0 ? src : B, ok ? kb : 0);
+    for (int r = 0; r < BN / LD_RPP; ++r) {
+      const int bytes = ((okmask >> (16 + r)) & 1u) ? kb : 0;
+      cp_async16(dB + r * LD_RPP * LDS, bytes ? (gB0 + r * strB + k0) : B, bytes);
     }
   };
 
@@ -120,16 +136,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_nt(const GemmP p) {
     cp_async_commit();
   }
 
+  const int frag_a = (wm * 64 + g) * LDS + q, frag_b = (wn * 32 + g) * LDS + q;
+  const bool diag_lower = (p.kmode & KM_A_LOWER) != 0;
   for (int it = 0; it < niter; ++it) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      const int nx = it + STAGES - 1;
-      if (nx < niter) load_stage(nx % STAGES, it_lo + nx);
-      cp_async_commit();
-    }
-    const double* cA = sA + (it % STAGES) * BM * LDS + (wm * 64 + g) * LDS + q;
-    const double* cB = sB + (it % STAGES) * BN * LDS + (wn * 32 + g) * LDS + q;
+    const double* cA = sA + (it % STAGES) * BM * LDS + frag_a;
+    const double* cB = sB + (it % STAGES) * BN * LDS + frag_b;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
       double a[8], b[4];
@@ -137,15 +150,57 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_nt(const GemmP p) {
       for (int i = 0; i < 8; ++i) a[i] = cA[i * 8 * LDS + kk * 4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) b[j] = cB[j * 8 * LDS + kk * 4];
+      if (diag_lower && k_lo + (it_lo + it) * BK + kk * 4 >= row0_m) {
+        // inside the diagonal block of a lower-triangular A: fragment rows [8i, 8i+8) need k <= row only
+        const int kfrag = k_lo + (it_lo + it) * BK + kk * 4 - row0_m - wm * 64;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i)
+          if (kfrag < i * 8 + 8) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      if (kk == 0) {
+        // refill the stage consumed in the previous iteration only after this iteration's first MMAs are in flight
+        const int nx = it + STAGES - 1;
+        if (nx < niter) load_stage(nx % STAGES, it_lo + nx);
+        cp_async_commit();
+      }
     }
   }
   cp_async_wait<0>();
 
   if (EPI == EPI_STORE) {
+    if (p.rowdot) {
+      // fused  rowdot[tile_n][i] = sum_{n in tile} alpha*acc[i,n] * yv[n]   (b = A y, fixed-order reduction)
+      __syncthreads();
+      double* sR = reinterpret_cast<double*>(smem_raw);  // [4][BM]
+      double yv[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gc = row0_n + wn * 32 + j * 8 + 2 * q;
+        yv[j][0] = gc < p.N ? p.yv[gc] : 0.0;
+        yv[j][1] = gc + 1 < p.N ? p.yv[gc + 1] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double sdot = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sdot = fma(acc[i][j][1], yv[j][1], fma(acc[i][j][0], yv[j][0], sdot));
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+        if (q == 0) sR[wn * BM + wm * 64 + i * 8 + g] = sdot;
+      }
+      __syncthreads();
+      if (tid < BM && row0_m + tid < p.M)
+        p.rowdot[bz * p.sRowdot + (int64_t)tn * p.M + row0_m + tid] =
+            p.alpha * (((sR[tid] + sR[BM + tid]) + sR[2 * BM + tid]) + sR[3 * BM + tid]);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int gr = row0_m + wm * 64 + i * 8 + g;

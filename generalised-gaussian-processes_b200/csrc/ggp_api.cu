@@ -57,6 +57,11 @@ struct ggp_handle {
   std::vector<cudaEvent_t> pool;
   int cur_cat = -1;
   cudaEvent_t cur_e0 = nullptr;
+  // CUDA graphs of the blocked Cholesky + inverse
+  struct CholGraph { double *A, *Linv, *LinvT; int batch; long long nodes; cudaGraphExec_t exec; };
+  std::vector<CholGraph> chol_graphs;
+  bool use_graphs = true;
+  int32_t* info_ws = nullptr;
 };
 
 enum { CAT_BUILD = 0, CAT_TRMM = 1, CAT_SYRK = 2, CAT_BWD = 3, CAT_MM = 4, CAT_OTHER = 5, CAT_COUNT = 6 };
@@ -138,6 +143,7 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   take((size_t)batch * p.splits * MM);                  // Spart
   take((size_t)batch * (p.nc / 128) * m * nq * 8);      // mom_part
   take((size_t)batch * m * nq * 8);                     // mom_acc
+  take((size_t)batch * 4 + 256);                        // info_ws
   p.bytes = o;
   return p;
 }
@@ -178,24 +184,25 @@ static GemmP gemm_basic(const double* A, int64_t lda, int64_t sA, const double* 
   } while (0)
 
 // In-place blocked Cholesky of A[batch][Mp][Mp] (lower), explicit inverse -> Linv, Linv^T -> LinvT.
-static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* Linv, double* LinvT, int batch,
-                            int32_t* info) {
+static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, double* Linv, double* LinvT, int batch,
+                                     int32_t* info) {
   const int Mp = h->Mp, nblk = Mp / NB;
   const int64_t sM = (int64_t)Mp * Mp;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
+  // right-looking: factor the diagonal block, form the panel with the block inverse, update the trailing lower tiles
   for (int k = 0; k < nblk; ++k) {
     const int k0 = k * NB;
-    if (k > 0) {  // A[k0:, k0:k0+NB] -= L[k0:, :k0] * L[k0:k0+NB, :k0]^T
-      GemmP p = gemm_basic(A + (int64_t)k0 * Mp, Mp, sM, A + (int64_t)k0 * Mp, Mp, sM, A + (int64_t)k0 * (Mp + 1), Mp, sM,
-                           Mp - k0, NB, k0, -1.0, 1.0);
-      RUN(launch_gemm(h, st, EPI_STORE, p, batch));
-    }
     k_potf2_trti2<<<batch, 256, POTF2_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, info);
     CKL();
-    if (k < nblk - 1) {  // L[k0+NB:, k0:k0+NB] = A[k0+NB:, k0:k0+NB] * T_k^T   (in place; one n-tile, K = NB)
-      double* blk = A + (int64_t)(k0 + NB) * Mp + k0;
-      GemmP p = gemm_basic(blk, Mp, sM, h->Tblk + (int64_t)k * NB * NB, NB, sM, blk, Mp, sM, Mp - k0 - NB, NB, NB, 1.0, 0.0);
+    if (k < nblk - 1) {
+      const int rem = Mp - k0 - NB;
+      double* pan = A + (int64_t)(k0 + NB) * Mp + k0;  // L[k0+NB:, k0:k0+NB] = A[k0+NB:, k0:k0+NB] * T_k^T  (in place, one n-tile)
+      GemmP p = gemm_basic(pan, Mp, sM, h->Tblk + (int64_t)k * NB * NB, NB, sM, pan, Mp, sM, rem, NB, NB, 1.0, 0.0);
       RUN(launch_gemm(h, st, EPI_STORE, p, batch));
+      // A[k0+NB:, k0+NB:] -= panel * panel^T   (lower tiles only)
+      GemmP u = gemm_basic(pan, Mp, sM, pan, Mp, sM, A + (int64_t)(k0 + NB) * (Mp + 1), Mp, sM, rem, rem, NB, -1.0, 1.0);
+      u.sym = 2;
+      RUN(launch_gemm(h, st, EPI_STORE, u, batch));
     }
   }
   k_tril<<<g16, b16, 0, st>>>(A, Mp, sM);
@@ -224,6 +231,42 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
   return 0;
 }
 
+// The blocked factorisation is ~70 short kernels: replay it as a CUDA graph (captured once per operand set) so the m x m
+// section is not launch-latency bound.  info is staged through a handle-owned buffer so the captured pointers stay valid.
+static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* Linv, double* LinvT, int batch, int32_t* info) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  CK(cudaStreamIsCapturing(st, &cs));
+  if (cs != cudaStreamCaptureStatusNone || !h->use_graphs) {
+    CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
+    return chol_and_inverse_launches(h, st, A, Linv, LinvT, batch, info);
+  }
+  ggp_handle::CholGraph* g = nullptr;
+  for (auto& c : h->chol_graphs)
+    if (c.A == A && c.Linv == Linv && c.LinvT == LinvT && c.batch == batch) g = &c;
+  if (!g) {
+    ggp_handle::CholGraph c{};
+    c.A = A; c.Linv = Linv; c.LinvT = LinvT; c.batch = batch;
+    const long long before = h->launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = chol_and_inverse_launches(h, st, A, Linv, LinvT, batch, h->info_ws);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != 0) return rc;
+    CK(e);
+    c.nodes = h->launches - before;
+    h->launches = before;
+    CK(cudaGraphInstantiate(&c.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    h->chol_graphs.push_back(c);
+    g = &h->chol_graphs.back();
+  }
+  CK(cudaMemsetAsync(h->info_ws, 0, sizeof(int32_t) * batch, st));
+  CK(cudaGraphLaunch(g->exec, st));
+  h->launches += g->nodes;
+  CK(cudaMemcpyAsync(info, h->info_ws, sizeof(int32_t) * batch, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -241,7 +284,6 @@ int ggp_create(ggp_handle_t** out, int device) {
   CK(cudaFuncSetAttribute(k_gemm_nt<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   CK(cudaFuncSetAttribute(k_gemm_nt<EPI_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   CK(cudaFuncSetAttribute(k_build_kc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k_potf2_trti2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
   *out = h;
   return 0;
 }
@@ -249,6 +291,7 @@ int ggp_create(ggp_handle_t** out, int device) {
 int ggp_destroy(ggp_handle_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  for (auto& c : h->chol_graphs) cudaGraphExecDestroy(c.exec);
   if (h->arena) cudaFree(h->arena);
   delete h;
   return 0;
@@ -266,6 +309,8 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   if ((size_t)(2 * KT_N * d + d) * 8 > 200 * 1024) return fail(-3, "ggp_reserve: input dimension d too large");
   CK(cudaSetDevice(h->device));
   Plan p = make_plan(cfg, n_local, m, d, batch, h->sm_count);
+  for (auto& c : h->chol_graphs) cudaGraphExecDestroy(c.exec);
+  h->chol_graphs.clear();
   if (p.bytes > h->arena_bytes) {
     if (h->arena) CK(cudaFree(h->arena));
     h->arena = nullptr;
@@ -278,7 +323,9 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   double** slots[] = {&h->L, &h->Linv, &h->LinvT, &h->Wk, &h->Bm, &h->LBinv, &h->LBinvT, &h->Binv, &h->PA, &h->Gbar, &h->T1,
                       &h->P, &h->Gzz, &h->Tblk, &h->bvec, &h->cvec, &h->beta, &h->u, &h->yty, &h->ds2, &h->rowacc, &h->Kc,
                       &h->At, &h->Spart, &h->mom_part, &h->mom_acc};
-  for (size_t i = 0; i < sizeof(slots) / sizeof(slots[0]); ++i) *slots[i] = reinterpret_cast<double*>(h->arena + p.off[i]);
+  const size_t nslots = sizeof(slots) / sizeof(slots[0]);
+  for (size_t i = 0; i < nslots; ++i) *slots[i] = reinterpret_cast<double*>(h->arena + p.off[i]);
+  h->info_ws = reinterpret_cast<int32_t*>(h->arena + p.off[nslots]);
   return 0;
 }
 
@@ -290,7 +337,6 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   const int kind = cfg ? cfg->kernel : 0;
   const int Mp = h->Mp;
   ProfScope ps(h, st, CAT_MM);
-  CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
   k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp);
   CKL();
   return chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info);
@@ -316,7 +362,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   const int Mp = h->Mp, nc = h->nc, splits = h->splits;
   const int64_t sM = (int64_t)Mp * Mp;
   CK(cudaMemsetAsync(h->Spart, 0, (size_t)batch * splits * sM * 8, st));
-  CK(cudaMemsetAsync(h->bvec, 0, (size_t)batch * Mp * 8, st));
+  CK(cudaMemsetAsync(h->bvec, 0, (size_t)batch * m * 8, st));
   k_sumsq<<<1, 1024, 0, st>>>(y, n_local, h->yty);
   CKL();
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
@@ -326,6 +372,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     GemmP t = gemm_basic(h->Linv, Mp, sM, h->Kc, Mp, (int64_t)nc * Mp, h->At, nc, (int64_t)nc * Mp, m, nv, m, 1.0, 0.0,
                          KM_A_LOWER);
     t.heavy_first = 1;
+    t.yv = y + c0; t.rowdot = h->mom_part; t.sRowdot = (int64_t)(nc / 128) * m;   // b partials reuse the moment-partial buffer
     { ProfScope ps(h, st, CAT_TRMM); RUN(launch_gemm(h, st, EPI_STORE, t, batch)); }
     // S_split += At * At^T  (upper tiles)
     GemmP s = gemm_basic(h->At, nc, (int64_t)nc * Mp, h->At, nc, (int64_t)nc * Mp, h->Spart, Mp, (int64_t)splits * sM, m, m, nv,
@@ -333,12 +380,13 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     s.sym = 1; s.splits = splits; s.sSplit = sM;
     { ProfScope ps(h, st, CAT_SYRK); RUN(launch_gemm(h, st, EPI_STORE, s, batch)); }
     ProfScope ps_o(h, st, CAT_OTHER);
-    // b += At * y_chunk
-    k_gemv_acc<<<dim3((m + 7) / 8, batch), 256, 0, st>>>(h->At, nc, (int64_t)nc * Mp, y + c0, h->bvec, Mp, m, nv);
+    // b += sum over n-tiles of the fused row dots (fixed order)
+    k_reduce_moments<<<dim3((unsigned)((m + 255) / 256), batch), 256, 0, st>>>(h->mom_part, m, (int64_t)(nc / 128) * m,
+                                                                              (nv + BN - 1) / BN, m, h->bvec);
     CKL();
   }
   k_finalize_partial<<<dim3((m + 15) / 16, (m + 15) / 16, batch), dim3(16, 16), 0, st>>>(
-      h->Spart, Mp, sM, (int64_t)splits * sM, splits, h->bvec, Mp, h->yty, n_local, theta, d, m, partial,
+      h->Spart, Mp, sM, (int64_t)splits * sM, splits, h->bvec, m, h->yty, n_local, theta, d, m, partial,
       (int64_t)m * m + m + 3);
   CKL();
   return 0;
@@ -357,7 +405,6 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
   const dim3 gv((m + 7) / 8, batch);
   ProfScope ps(h, st, CAT_MM);
-  CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
   k_make_B<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Bm, sM);
   CKL();
   RUN(chol_and_inverse(h, st, h->Bm, h->LBinv, h->LBinvT, batch, info));
@@ -463,7 +510,6 @@ int ggp_chol_batched(ggp_handle_t* h, void* stream, double* a, double* linv, int
   const int Mp = h->Mp;
   const int64_t sM = (int64_t)Mp * Mp;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
-  CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
   k_pad_copy<<<g16, b16, 0, st>>>(a, m, h->L, Mp, sM, 1);
   CKL();
   RUN(chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info));
@@ -482,6 +528,20 @@ int ggp_gemm_nt(ggp_handle_t* h, void* stream, const double* A, int64_t lda, con
   if ((lda & 1) || (ldb & 1) || (((uintptr_t)A) & 15) || (((uintptr_t)B) & 15))
     return fail(-2, "ggp_gemm_nt: operands need 16-byte aligned rows (even leading dimension)");
   return launch_gemm(h, (cudaStream_t)stream, EPI_STORE, gemm_basic(A, lda, 0, B, ldb, 0, C, ldc, 0, mm, nn, kk, alpha, beta), 1);
+}
+
+int ggp_gemm_nt_ex(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                   int64_t ldc, int mm, int nn, int kk, double alpha, double beta, int kmode, int sym, int splits,
+                   int64_t split_stride) {
+  if (!h || !A || !B || !C) return fail(-1, "ggp_gemm_nt_ex: NULL argument");
+  if ((lda & 1) || (ldb & 1) || (((uintptr_t)A) & 15) || (((uintptr_t)B) & 15))
+    return fail(-2, "ggp_gemm_nt_ex: operands need 16-byte aligned rows (even leading dimension)");
+  GemmP p = gemm_basic(A, lda, 0, B, ldb, 0, C, ldc, 0, mm, nn, kk, alpha, beta, kmode);
+  p.sym = sym;
+  p.splits = splits < 1 ? 1 : splits;
+  p.sSplit = split_stride;
+  p.heavy_first = (kmode & KM_A_LOWER) ? 1 : 0;
+  return launch_gemm(h, (cudaStream_t)stream, EPI_STORE, p, 1);
 }
 
 int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X1, int64_t n1, const double* X2,

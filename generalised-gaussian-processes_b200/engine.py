@@ -204,6 +204,15 @@ class Engine:
                                        mm, nn, kk, float(alpha), float(beta)), "ggp_gemm_nt")
         return C
 
+    def gemm_nt_ex(self, A, B, C, alpha=1.0, beta=0.0, kmode=0, sym=0, splits=1, split_stride=0):
+        mm, kk = A.shape
+        nn = B.shape[0]
+        with torch.cuda.device(self.device):
+            check(self.lib.ggp_gemm_nt_ex(self.h, _stream(), _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(C), C.stride(-2),
+                                          mm, nn, kk, float(alpha), float(beta), int(kmode), int(sym), int(splits),
+                                          int(split_stride)), "ggp_gemm_nt_ex")
+        return C
+
     def kernel_matrix(self, X1, X2, theta):
         dev = self.device
         X1, X2, theta = _f64c(X1, dev), _f64c(X2, dev), _f64c(theta, dev)

@@ -112,6 +112,12 @@ int ggp_chol_batched(ggp_handle_t* h, void* stream, double* a /*[batch,m,m]*/, d
 /* C[mm,nn] = alpha * A[mm,kk] * B[nn,kk]^T + beta * C   (row-major, float64, DMMA). ld* in elements. */
 int ggp_gemm_nt(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb,
                 double* C, int64_t ldc, int mm, int nn, int kk, double alpha, double beta);
+/* same with the structure switches the streamed passes use: kmode bit0/1 = A lower/upper triangular, bit2/3 = B lower/upper
+ * triangular (k-range clipped per tile); sym 1/2 = only upper/lower 128x128 output tiles; splits > 1 = split-K, split s
+ * accumulates into C + s*split_stride (beta must be 1, buffers pre-zeroed). */
+int ggp_gemm_nt_ex(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb,
+                   double* C, int64_t ldc, int mm, int nn, int kk, double alpha, double beta, int kmode, int sym,
+                   int splits, int64_t split_stride);
 /* k(X1, X2)[n1, n2] dense tile (tests) */
 int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X1, int64_t n1,
                       const double* X2, int64_t n2, const double* theta /*[d+2]*/, int d, double* out /*[n1,n2]*/);
