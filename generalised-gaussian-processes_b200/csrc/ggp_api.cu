@@ -13,6 +13,7 @@
 #include "gemm_dmma.cuh"
 #include "kernel_tiles.cuh"
 #include "misc.cuh"
+#include "svgp.cuh"
 
 using namespace ggp;
 
@@ -49,6 +50,8 @@ struct ggp_handle {
   double *bvec = 0, *cvec = 0, *beta = 0, *u = 0, *yty = 0, *ds2 = 0, *rowacc = 0;
   // streamed chunk buffers
   double *Kc = 0, *At = 0, *Spart = 0, *mom_part = 0, *mom_acc = 0;
+  double *sv[5] = {0, 0, 0, 0, 0}, *rowout = 0;
+  int nsv = 0;
   // instrumentation
   long long launches = 0;
   bool profiling = false;
@@ -102,7 +105,7 @@ static int pad_pow2_blocks(int m) {
 }
 
 struct Plan {
-  int Mp, nc, splits;
+  int Mp, nc, splits, nsv;
   size_t bytes;
   size_t off[40];
 };
@@ -144,6 +147,9 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   take((size_t)batch * (p.nc / 128) * m * nq * 8);      // mom_part
   take((size_t)batch * m * nq * 8);                     // mom_acc
   take((size_t)batch * 4 + 256);                        // info_ws
+  p.nsv = std::min(p.nc, 4096);
+  for (int i = 0; i < 5; ++i) take((size_t)batch * p.nsv * p.Mp * 8);   // SVGP / SGPMC row and transposed buffers
+  take((size_t)batch * 4 * p.nsv * 8);                  // rowout
   p.bytes = o;
   return p;
 }
@@ -326,6 +332,9 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   const size_t nslots = sizeof(slots) / sizeof(slots[0]);
   for (size_t i = 0; i < nslots; ++i) *slots[i] = reinterpret_cast<double*>(h->arena + p.off[i]);
   h->info_ws = reinterpret_cast<int32_t*>(h->arena + p.off[nslots]);
+  for (int i = 0; i < 5; ++i) h->sv[i] = reinterpret_cast<double*>(h->arena + p.off[nslots + 1 + i]);
+  h->rowout = reinterpret_cast<double*>(h->arena + p.off[nslots + 6]);
+  h->nsv = p.nsv;
   return 0;
 }
 
@@ -499,8 +508,108 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
 
 int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* xb, const double* yb, int64_t nb,
                   const double* Z, const double* qm, const double* qLs, const double* theta, const double* jitter, int m, int d,
-                  int batch, double num_data, int likelihood, int need_grad, double* elbo, double* grad, int32_t* info) {
-  return fail(-100, "ggp_svgp_elbo: not implemented yet");
+                  int batch, double data_jitter, double lik_scale, double kl_scale, int likelihood, int need_grad, double* elbo,
+                  double* grad, int32_t* info) {
+  if (!h || !xb || !yb || !Z || !qm || !theta || !jitter || !elbo || !info) return fail(-1, "ggp_svgp_elbo: NULL argument");
+  if (need_grad && !grad) return fail(-1, "ggp_svgp_elbo: grad is NULL");
+  if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_svgp_elbo: handle not reserved for this shape");
+  const int kind = cfg ? cfg->kernel : 0;
+  if (need_grad && kind != GGP_KERNEL_RBF) return fail(-3, "ggp_svgp_elbo: gradients are implemented for GGP_KERNEL_RBF");
+  const int nq = 2 * d + 1;
+  if (nq > h->Mp) return fail(-3, "ggp_svgp_elbo: 2d+1 must not exceed the padded inducing count");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = h->Mp, nsv = h->nsv;
+  const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nsv * Mp, sG = (int64_t)d + 2 + (int64_t)m * d + m + (int64_t)m * m;
+  const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16), g16one(Mp / 16, Mp / 16, 1);
+  const bool hasS = qLs != nullptr;
+  double *Kc = h->sv[0], *aT = h->sv[1], *wT = h->sv[2], *SL = h->sv[3], *tA = h->sv[4], *tB = h->Kc, *tC = h->At;
+  double *LsP = h->Bm, *LsT = h->LBinv, *dLsraw = h->Binv, *Gb = h->PA, *Hm = h->Gbar, *dKzz = h->Gzz, *gk = h->P,
+         *dZzz = h->LBinvT, *dm = h->bvec, *scal = h->cvec, *mom = h->mom_acc;
+  // note: h->Kc / h->At hold at least nsv x Mp per batch element (nc >= nsv) and are used here as transposed scratch
+  {
+    ProfScope ps(h, st, CAT_MM);
+    k_build_kzz<<<g16, b16, 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, sM);
+    CKL();
+    RUN(chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info));
+  }
+  ProfScope ps(h, st, CAT_OTHER);
+  if (hasS) {
+    k_pad_tril<<<g16one, b16, 0, st>>>(qLs, m, LsP, Mp);
+    CKL();
+    k_transpose<<<dim3(Mp / 32, Mp / 32, 1), dim3(32, 8), 0, st>>>(LsP, LsT, Mp, sM);
+    CKL();
+  }
+  CK(cudaMemsetAsync(scal, 0, (size_t)batch * 4 * 8, st));
+  if (need_grad) {
+    CK(cudaMemsetAsync(dm, 0, (size_t)batch * Mp * 8, st));
+    CK(cudaMemsetAsync(dLsraw, 0, (size_t)batch * sM * 8, st));
+    CK(cudaMemsetAsync(Gb, 0, (size_t)batch * sM * 8, st));
+    CK(cudaMemsetAsync(mom, 0, (size_t)batch * m * nq * 8, st));
+  }
+  for (int64_t c0 = 0; c0 < nb; c0 += nsv) {
+    const int nv = (int)std::min<int64_t>(nsv, nb - c0);
+    const int nvp = (nv + 15) / 16 * 16;  // padded row count of the transposed buffers (zero filled)
+    const double* Xc = xb + c0 * d;
+    {
+      dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
+      const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
+      k_build_kc<<<grid, KT_THREADS, smem, st>>>(Xc, nv, nv, d, Z, m, theta, kind, Kc, Mp, sC);
+      CKL();
+    }
+    // aT[nv x m] = Kc * Linv^T ; wT = aT * Ls
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(Kc, Mp, sC, h->Linv, Mp, sM, aT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    if (hasS)
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(aT, Mp, sC, LsT, Mp, 0, wT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_UPPER), batch));
+    k_svgp_rows<<<dim3((nv + 7) / 8, batch), 256, 0, st>>>(aT, hasS ? wT : nullptr, Mp, sC, qm, yb + c0, theta, d, m, nv, likelihood,
+                                                          data_jitter, lik_scale, h->rowout, nsv);
+    CKL();
+    k_svgp_reduce_rows<<<batch, 256, 0, st>>>(h->rowout, nsv, nv, scal);
+    CKL();
+    if (!need_grad) continue;
+    // SL = wT * Ls^T = (S a)^T ;  GAT = gmu m^T + 2 gv (SL - aT)
+    if (hasS)
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(wT, Mp, sC, LsP, Mp, 0, SL, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    k_svgp_gat<<<dim3((Mp + 255) / 256, nv, batch), 256, 0, st>>>(SL, aT, Mp, sC, qm, h->rowout, nsv, m, Mp, hasS ? 1 : 0);
+    CKL();
+    k_svgp_dm<<<dim3((m + 255) / 256, batch), 256, 0, st>>>(aT, Mp, sC, h->rowout, nsv, m, nv, dm, Mp);
+    CKL();
+    const dim3 gT((nvp + 31) / 32, Mp / 32, batch), bT(32, 8);
+    if (hasS) {  // dLsraw += (aT o gv)^T wT
+      k_transpose_rect<<<gT, bT, 0, st>>>(aT, nullptr, Mp, sC, h->rowout + 2 * nsv, (int64_t)4 * nsv, nv, Mp, tB, nvp, sC);
+      CKL();
+      k_transpose_rect<<<gT, bT, 0, st>>>(wT, nullptr, Mp, sC, nullptr, 0, nv, Mp, tC, nvp, sC);
+      CKL();
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(tB, nvp, sC, tC, nvp, sC, dLsraw, Mp, sM, m, m, nv, 1.0, 1.0), batch));
+    }
+    // Gbar += GAT^T aT
+    k_transpose_rect<<<gT, bT, 0, st>>>(aT, nullptr, Mp, sC, nullptr, 0, nv, Mp, tA, nvp, sC);
+    CKL();
+    k_transpose_rect<<<gT, bT, 0, st>>>(SL, nullptr, Mp, sC, nullptr, 0, nv, Mp, tB, nvp, sC);
+    CKL();
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(tB, nvp, sC, tA, nvp, sC, Gb, Mp, sM, m, m, nv, 1.0, 1.0), batch));
+    // dKc = GAT * Linv  (into wT's buffer) ;  mom += (dKc o Kc)^T [1, x, x^2]
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(SL, Mp, sC, h->LinvT, Mp, sM, wT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_UPPER), batch));
+    k_transpose_rect<<<gT, bT, 0, st>>>(wT, Kc, Mp, sC, nullptr, 0, nv, Mp, tC, nvp, sC);
+    CKL();
+    k_phiT<<<dim3((nvp + 255) / 256, nq), 256, 0, st>>>(Xc, nv, d, tA, nvp);
+    CKL();
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(tC, nvp, sC, tA, nvp, 0, mom, nq, (int64_t)m * nq, m, nq, nv, 1.0, 1.0), batch));
+  }
+  if (need_grad) {
+    // dKzz = -Linv^T sym(Phi(Gbar)) Linv
+    k_sym_phi<<<g16, b16, 0, st>>>(Gb, Hm, m, Mp, sM);
+    CKL();
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, Hm, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, dKzz, Mp, sM, m, m, m, -1.0, 0.0, KM_B_UPPER), batch));
+    k_grad_kzz_rows<<<dim3((m + 7) / 8, batch), 256, 0, st>>>(dKzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, dZzz + d + 2, sM);
+    CKL();
+    k_grad_from_moments<<<batch, 256, 0, st>>>(mom, m, d, Z, theta, gk, sM);
+    CKL();
+  }
+  k_svgp_final<<<batch, 256, 0, st>>>(scal, gk, sM, h->rowacc, dZzz, dm, Mp, dLsraw, sM, Mp, qm, qLs, theta, m, d, kl_scale, need_grad,
+                                      elbo, grad, sG);
+  CKL();
+  return 0;
 }
 
 int ggp_chol_batched(ggp_handle_t* h, void* stream, double* a, double* linv, int m, int batch, int32_t* info) {

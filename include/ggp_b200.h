@@ -92,16 +92,22 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
                      const double* Z, const double* theta, int m, int d, int batch, int add_noise,
                      double* mean, double* var, double* cov);
 
-/* Whitened SVGP minibatch ELBO value + gradient  (models/svgp.py:104-110 ; models/bayesian_svgp.py:160-167 with
- * batch = number of theta draws).  elbo[b] = sum_i E_q[log p(y_i|f_i)] / nb - KL(q||N(0,I)) / num_data.
+/* Whitened sparse-GP marginals + expected log-likelihood, value and gradient.  One routine serves
+ *   - the SVGP minibatch ELBO (models/svgp.py:104-110 ; models/bayesian_svgp.py:160-167 with batch = number of theta draws):
+ *       data_jitter = 1e-4, lik_scale = 1/nb, kl_scale = 1/num_data
+ *   - the SGPMC whitened-conditional log-likelihood tfp-HMC differentiates per leapfrog (models/sgp_hmc.py:63-69):
+ *       qLs = NULL (S = 0), qm = v, data_jitter = 0, lik_scale = 1, kl_scale = 0, nb = N (streamed in chunks)
+ * out[b] = lik_scale * sum_i E_q[log p(y_i|f_i)] - kl_scale * KL(N(m, Ls Ls^T) || N(0, I)),
+ *   mu_i = a_i^T m, var_i = k_ii + data_jitter + ||Ls^T a_i||^2 - ||a_i||^2, a = L^{-1} k(Z, x_i), L L^T = Kzz + jitter_b I.
  * grad[b] layout: [d_ell[d], d_sf2, d_s2, d_Z[m*d], d_m[m], d_Ls[m*m] (lower triangle, row-major, upper = 0)].
- * jitter[b] is the TOTAL diagonal jitter added to Kzz (variational_cholesky_jitter 1e-6 + ladder). */
+ * jitter[b] is the TOTAL diagonal jitter added to Kzz (variational_cholesky_jitter 1e-6 + ladder, or gpflow's 1e-5).
+ * likelihood: GGP_LIK_GAUSSIAN (noise s2 from theta) or GGP_LIK_BERNOULLI_PROBIT (20-point Gauss-Hermite). */
 int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
                   const double* xb /*[nb,d]*/, const double* yb /*[nb]*/, int64_t nb,
-                  const double* Z, const double* qm /*[m]*/, const double* qLs /*[m,m]*/,
+                  const double* Z, const double* qm /*[m]*/, const double* qLs /*[m,m] or NULL*/,
                   const double* theta /*[batch,d+2]*/, const double* jitter /*[batch]*/,
-                  int m, int d, int batch, double num_data, int likelihood, int need_grad,
-                  double* elbo /*[batch]*/, double* grad /*[batch, d+2+m*d+m+m*m] or NULL*/, int32_t* info);
+                  int m, int d, int batch, double data_jitter, double lik_scale, double kl_scale, int likelihood,
+                  int need_grad, double* elbo /*[batch]*/, double* grad /*[batch, d+2+m*d+m+m*m] or NULL*/, int32_t* info);
 
 /* building blocks, exported for the parity tests and the roofline probes ------------------------------------- */
 
