@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import GgpCfg, KERNELS, PRECISIONS, check
+from ._lib import GgpCfg, KERNELS, LIKELIHOODS, PRECISIONS, check
 
 
 class NotPSDError(RuntimeError):
@@ -181,6 +181,51 @@ class Engine:
             check(self.lib.ggp_sgpr_predict(self.h, ctypes.byref(self.cfg), _stream(), _ptr(Xs), ns, _ptr(Z), _ptr(theta), m, d,
                                             batch, 1 if add_noise else 0, _ptr(mean), _ptr(var), _ptr(cov)), "ggp_sgpr_predict")
         return mean, var, cov
+
+    def svgp_eval(self, xb, yb, Z, qm, qLs, theta, num_data=None, likelihood="gaussian", jitter_policy="gpytorch",
+                  base_jitter=1e-6, data_jitter=1e-4, lik_scale=None, kl_scale=None, need_grad=True, raise_on_fail=True):
+        """Whitened SVGP ELBO (models/svgp.py:104-106) or, with qLs=None, the SGPMC conditional log-likelihood
+        (models/sgp_hmc.py:63).  Returns dict(value[batch], grad[batch, d+2+m*d+m+m*m] | None, jitter, info).
+
+        jitter: total Kzz jitter = base_jitter (gpytorch variational_cholesky_jitter 1e-6 / gpflow 1e-5) + ladder level.
+        Defaults follow gpytorch: lik_scale = 1/nb, kl_scale = 1/num_data, data_jitter = 1e-4."""
+        dev = self.device
+        xb, yb, Z, qm, theta = (_f64c(t, dev) for t in (xb, yb, Z, qm, theta))
+        qLs = _f64c(qLs, dev) if qLs is not None else None
+        if theta.dim() == 1:
+            theta = theta.unsqueeze(0)
+        nb, d = xb.shape
+        m = Z.shape[0]
+        batch = theta.shape[0]
+        if lik_scale is None:
+            lik_scale = 1.0 / nb
+        if kl_scale is None:
+            kl_scale = 0.0 if (qLs is None or num_data is None) else 1.0 / float(num_data)
+        self.reserve(min(nb, 4096), m, d, batch)
+        ladder = [base_jitter + float(j) for j in jitter_ladder(jitter_policy)]
+        level = [0] * batch
+        P = d + 2 + m * d + m + m * m
+        value = torch.empty(batch, dtype=torch.float64, device=dev)
+        grad = torch.empty(batch, P, dtype=torch.float64, device=dev) if need_grad else None
+        info = torch.zeros(batch, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            while True:
+                jit = torch.tensor([ladder[l] for l in level], dtype=torch.float64, device=dev)
+                check(self.lib.ggp_svgp_elbo(self.h, ctypes.byref(self.cfg), _stream(), _ptr(xb), _ptr(yb), nb, _ptr(Z), _ptr(qm),
+                                             _ptr(qLs), _ptr(theta), _ptr(jit), m, d, batch, float(data_jitter), float(lik_scale),
+                                             float(kl_scale), LIKELIHOODS[likelihood], 1 if need_grad else 0, _ptr(value),
+                                             _ptr(grad), _ptr(info)), "ggp_svgp_elbo")
+                info_h = info.cpu()
+                bad = [b for b in range(batch) if int(info_h[b]) != 0]
+                if not bad:
+                    break
+                if any(level[b] + 1 >= len(ladder) for b in bad):
+                    if raise_on_fail:
+                        raise NotPSDError(f"Kzz not positive definite after jitter ladder {ladder}; potrf info={info_h.tolist()}")
+                    break
+                for b in bad:
+                    level[b] += 1
+        return dict(value=value, grad=grad, jitter=jit, info=info_h)
 
     # building blocks -----------------------------------------------------------------------------------------
     def chol(self, a, want_inverse=True):

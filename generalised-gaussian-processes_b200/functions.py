@@ -95,3 +95,84 @@ def sgpr_vfe_logp_dlogp(x, X, y, Z, jitter_policy="pymc3", engine=None, group=Fa
     lp = torch.where(bad, torch.full_like(lp, -float("inf")), lp)
     dx = torch.where(bad.unsqueeze(1), torch.zeros_like(dx), dx)
     return lp, dx
+
+
+class SVGPElbo(torch.autograd.Function):
+    """Whitened SVGP minibatch ELBO: drop-in for  output = self(x_batch); -mll(output, y_batch)  (models/svgp.py:104-106).
+    Differentiable in Z, q_mean, q_chol (lower triangle), lengthscale, outputscale, noise (constrained values)."""
+
+    @staticmethod
+    def forward(ctx, xb, yb, Z, q_mean, q_chol, lengthscale, outputscale, noise, num_data, cfg=None):
+        c = _cfg(cfg)
+        eng = Engine.get(xb.device, c["kernel"], c["precision"], c["chunk_rows"])
+        theta = torch.cat([lengthscale.reshape(-1), outputscale.reshape(-1), noise.reshape(-1)]).to(torch.float64)
+        need = any(ctx.needs_input_grad[2:8])
+        out = eng.svgp_eval(xb, yb, Z, q_mean, q_chol, theta, num_data=num_data, likelihood=c.get("likelihood", "gaussian"),
+                            jitter_policy=c["jitter_policy"], need_grad=need)
+        ctx.dims = (xb.shape[1], Z.shape[0])
+        ctx.shapes = tuple(t.shape for t in (Z, q_mean, q_chol, lengthscale, outputscale, noise))
+        ctx.dtypes = tuple(t.dtype for t in (Z, q_mean, q_chol, lengthscale, outputscale, noise))
+        ctx.save_for_backward(out["grad"][0] if need else torch.empty(0, device=xb.device))
+        return out["value"][0].to(xb.dtype)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (g,) = ctx.saved_tensors
+        D, M = ctx.dims
+        sh, dt = ctx.shapes, ctx.dtypes
+        gout = gout.to(torch.float64)
+        o = D + 2
+        pick = lambda i, t, k: (gout * t).reshape(sh[k]).to(dt[k]) if ctx.needs_input_grad[i] else None
+        gZ = pick(2, g[o:o + M * D], 0)
+        gm = pick(3, g[o + M * D:o + M * D + M], 1)
+        gL = pick(4, g[o + M * D + M:], 2)
+        gl = pick(5, g[:D], 3)
+        go = pick(6, g[D], 4)
+        gn = pick(7, g[D + 1], 5)
+        return None, None, gZ, gm, gL, gl, go, gn, None, None
+
+
+def svgp_elbo(xb, yb, Z, q_mean, q_chol, lengthscale, outputscale, noise, num_data, cfg=None):
+    return SVGPElbo.apply(xb, yb, Z, q_mean, q_chol, lengthscale, outputscale, noise, num_data, cfg)
+
+
+def sgpmc_logp_dlogp(v, raw, X, y, Z, likelihood="gaussian", jitter=1e-5, engine=None, with_priors=True):
+    """gpflow SGPMC log_posterior_density and gradient, batched over chains (models/sgp_hmc.py:38-83).
+
+    v [C, M] whitened inducing values, raw [C, D+2] softplus-unconstrained (ell[D], sf2, s2).  Returns (logp[C], d/dv[C,M],
+    d/draw[C,D+2]).  The streamed N x M work (a = L^{-1}k(Z,x), mu = a^T v, var = k - |a|^2, likelihood, backward) runs on
+    the GPU for each chain; priors Gamma(2,1) on the constrained values + softplus log-Jacobians are added here."""
+    import torch.nn.functional as Fnn
+    eng = engine or Engine.get(X.device)
+    dev = eng.device
+    v = v.to(device=dev, dtype=torch.float64)
+    raw = raw.to(device=dev, dtype=torch.float64)
+    if v.dim() == 1:
+        v, raw = v.unsqueeze(0), raw.unsqueeze(0)
+    C, M = v.shape
+    D = X.shape[1]
+    pos = Fnn.softplus(raw)
+    theta = pos.clone()
+    if likelihood != "gaussian":
+        theta[:, D + 1] = 1.0  # unused by the Bernoulli likelihood
+    lps, gvs, grs = [], [], []
+    for c in range(C):  # v differs per chain (it occupies the variational-mean slot), so chains are sequenced on one engine
+        out = eng.svgp_eval(X, y, Z, v[c], None, theta[c], likelihood=likelihood, jitter_policy=0.0, base_jitter=jitter,
+                            data_jitter=0.0, lik_scale=1.0, kl_scale=0.0, need_grad=True, raise_on_fail=False)
+        g = out["grad"][0]
+        lp = out["value"][0] - 0.5 * (v[c] @ v[c]) - 0.5 * M * math.log(2.0 * math.pi)
+        gv = g[D + 2 + M * D:D + 2 + M * D + M] - v[c]
+        gpos = g[:D + 2].clone()
+        npos = D + 2 if likelihood == "gaussian" else D + 1
+        if likelihood != "gaussian":
+            gpos[D + 1] = 0.0
+        sig = torch.sigmoid(raw[c])
+        graw = gpos * sig
+        if with_priors:
+            lp = lp + (torch.log(pos[c, :npos]) - pos[c, :npos]).sum() + Fnn.logsigmoid(raw[c, :npos]).sum()
+            graw[:npos] = graw[:npos] + (1.0 / pos[c, :npos] - 1.0) * sig[:npos] + (1.0 - sig[:npos])
+        if int(out["info"][0]) != 0 or not torch.isfinite(lp):
+            lp = torch.full_like(lp, -float("inf"))
+            gv, graw = torch.zeros_like(gv), torch.zeros_like(graw)
+        lps.append(lp); gvs.append(gv); grs.append(graw)
+    return torch.stack(lps), torch.stack(gvs), torch.stack(grs)
