@@ -64,6 +64,7 @@ struct ggp_handle {
   struct CholGraph { double *A, *Linv, *LinvT; int batch; long long nodes; cudaGraphExec_t exec; };
   std::vector<CholGraph> chol_graphs;
   bool use_graphs = true;
+  cudaStream_t cap_stream = nullptr;
   int32_t* info_ws = nullptr;
 };
 
@@ -254,9 +255,11 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
     c.A = A; c.Linv = Linv; c.LinvT = LinvT; c.batch = batch;
     const long long before = h->launches;
     cudaGraph_t graph = nullptr;
-    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = chol_and_inverse_launches(h, st, A, Linv, LinvT, batch, h->info_ws);
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    // capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured
+    if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = chol_and_inverse_launches(h, h->cap_stream, A, Linv, LinvT, batch, h->info_ws);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
     if (rc != 0) return rc;
     CK(e);
     c.nodes = h->launches - before;
@@ -298,6 +301,7 @@ int ggp_destroy(ggp_handle_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   for (auto& c : h->chol_graphs) cudaGraphExecDestroy(c.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->arena) cudaFree(h->arena);
   delete h;
   return 0;
@@ -609,6 +613,43 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
   k_svgp_final<<<batch, 256, 0, st>>>(scal, gk, sM, h->rowacc, dZzz, dm, Mp, dLsraw, sM, Mp, qm, qLs, theta, m, d, kl_scale, need_grad,
                                       elbo, grad, sG);
   CKL();
+  return 0;
+}
+
+int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* xs, int64_t ns, const double* Z,
+                     const double* qm, const double* qLs, const double* theta, const double* jitter, int m, int d, int batch,
+                     double data_jitter, int add_noise, double* mean, double* var, int32_t* info) {
+  if (!h || !xs || !Z || !qm || !theta || !jitter || !mean || !var || !info) return fail(-1, "ggp_svgp_predict: NULL argument");
+  if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_svgp_predict: handle not reserved for this shape");
+  const int kind = cfg ? cfg->kernel : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = h->Mp, nsv = h->nsv;
+  const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nsv * Mp;
+  const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
+  const bool hasS = qLs != nullptr;
+  double *Kc = h->sv[0], *aT = h->sv[1], *wT = h->sv[2], *LsP = h->Bm, *LsT = h->LBinv;
+  k_build_kzz<<<g16, b16, 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, sM);
+  CKL();
+  RUN(chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info));
+  if (hasS) {
+    k_pad_tril<<<dim3(Mp / 16, Mp / 16, 1), b16, 0, st>>>(qLs, m, LsP, Mp);
+    CKL();
+    k_transpose<<<dim3(Mp / 32, Mp / 32, 1), dim3(32, 8), 0, st>>>(LsP, LsT, Mp, sM);
+    CKL();
+  }
+  for (int64_t c0 = 0; c0 < ns; c0 += nsv) {
+    const int nv = (int)std::min<int64_t>(nsv, ns - c0);
+    dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
+    const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
+    k_build_kc<<<grid, KT_THREADS, smem, st>>>(xs + c0 * d, nv, nv, d, Z, m, theta, kind, Kc, Mp, sC);
+    CKL();
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(Kc, Mp, sC, h->Linv, Mp, sM, aT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    if (hasS)
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(aT, Mp, sC, LsT, Mp, 0, wT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_UPPER), batch));
+    k_svgp_marginals<<<dim3((nv + 7) / 8, batch), 256, 0, st>>>(aT, hasS ? wT : nullptr, Mp, sC, qm, theta, d, m, nv, data_jitter,
+                                                               add_noise, mean + c0, var + c0, ns);
+    CKL();
+  }
   return 0;
 }
 

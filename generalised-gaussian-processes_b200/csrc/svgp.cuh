@@ -99,6 +99,34 @@ __global__ void __launch_bounds__(256) k_svgp_rows(const double* __restrict__ aT
   ro[3 * ldr + n] = lik_scale * gs;
 }
 
+// Predictive marginals only: mean[b][n] = aT[n,:].m ; var[b][n] = sf2 + data_jitter + ||wT[n]||^2 - ||aT[n]||^2 (+ s2)
+__global__ void __launch_bounds__(256) k_svgp_marginals(const double* __restrict__ aT, const double* __restrict__ wT, int64_t ld,
+                                                        int64_t sC, const double* __restrict__ qm, const double* __restrict__ theta,
+                                                        int d, int M, int nv, double data_jitter, int add_noise,
+                                                        double* __restrict__ mean, double* __restrict__ var, int64_t sOut) {
+  const int b = blockIdx.y, n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= nv) return;
+  const double* a = aT + b * sC + (int64_t)n * ld;
+  double mu = 0.0, v1 = 0.0, v2 = 0.0;
+  for (int j = lane; j < M; j += 32) {
+    const double aj = a[j];
+    mu = fma(aj, qm[j], mu);
+    v2 = fma(aj, aj, v2);
+  }
+  if (wT) {
+    const double* w = wT + b * sC + (int64_t)n * ld;
+    for (int j = lane; j < M; j += 32) v1 = fma(w[j], w[j], v1);
+  }
+  mu = warp_sum(mu);
+  v1 = warp_sum(v1);
+  v2 = warp_sum(v2);
+  if (lane == 0) {
+    const double sf2 = theta[(int64_t)b * (d + 2) + d], s2 = theta[(int64_t)b * (d + 2) + d + 1];
+    mean[b * sOut + n] = mu;
+    var[b * sOut + n] = sf2 + data_jitter + v1 - v2 + (add_noise ? s2 : 0.0);
+  }
+}
+
 // scal[b][0] += sum_n ell_n ; [1] += sum_n gv_n (direct d/dsf2 through k_nn) ; [2] += sum_n gs_n   (one CTA per batch)
 __global__ void __launch_bounds__(256) k_svgp_reduce_rows(const double* __restrict__ rowout, int64_t ldr, int nv,
                                                           double* __restrict__ scal) {

@@ -227,6 +227,29 @@ class Engine:
                     level[b] += 1
         return dict(value=value, grad=grad, jitter=jit, info=info_h)
 
+    def svgp_predict(self, xs, Z, qm, qLs, theta, base_jitter=1e-6, data_jitter=1e-4, add_noise=True):
+        """Predictive marginals of the whitened strategy (models/svgp.py:132-141): (mean[batch,ns], var[batch,ns])."""
+        dev = self.device
+        xs, Z, qm, theta = (_f64c(t, dev) for t in (xs, Z, qm, theta))
+        qLs = _f64c(qLs, dev) if qLs is not None else None
+        if theta.dim() == 1:
+            theta = theta.unsqueeze(0)
+        ns, d = xs.shape
+        m, batch = Z.shape[0], theta.shape[0]
+        self.reserve(min(ns, 4096), m, d, batch)
+        mean = torch.empty(batch, ns, dtype=torch.float64, device=dev)
+        var = torch.empty(batch, ns, dtype=torch.float64, device=dev)
+        info = torch.zeros(batch, dtype=torch.int32, device=dev)
+        for j in jitter_ladder("gpytorch"):
+            jit = torch.full((batch,), base_jitter + j, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                check(self.lib.ggp_svgp_predict(self.h, ctypes.byref(self.cfg), _stream(), _ptr(xs), ns, _ptr(Z), _ptr(qm), _ptr(qLs),
+                                                _ptr(theta), _ptr(jit), m, d, batch, float(data_jitter), 1 if add_noise else 0,
+                                                _ptr(mean), _ptr(var), _ptr(info)), "ggp_svgp_predict")
+            if not bool((info != 0).any()):
+                return mean, var
+        raise NotPSDError("Kzz not positive definite after the jitter ladder")
+
     # building blocks -----------------------------------------------------------------------------------------
     def chol(self, a, want_inverse=True):
         a = a.clone().contiguous()

@@ -109,6 +109,13 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
                   int m, int d, int batch, double data_jitter, double lik_scale, double kl_scale, int likelihood,
                   int need_grad, double* elbo /*[batch]*/, double* grad /*[batch, d+2+m*d+m+m*m] or NULL*/, int32_t* info);
 
+/* SVGP predictive marginals at test inputs (posterior_predictive, models/svgp.py:132-141; diagonal only -- the exact
+ * expression, see SURVEY A.7 on fast_pred_var):  mean[b][n] = a^T m ; var[b][n] = k** + data_jitter + ||Ls^T a||^2 - ||a||^2 (+ s2) */
+int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* xs /*[ns,d]*/, int64_t ns,
+                     const double* Z, const double* qm, const double* qLs /*or NULL*/, const double* theta,
+                     const double* jitter /*[batch]*/, int m, int d, int batch, double data_jitter, int add_noise,
+                     double* mean /*[batch,ns]*/, double* var /*[batch,ns]*/, int32_t* info);
+
 /* building blocks, exported for the parity tests and the roofline probes ------------------------------------- */
 
 /* in-place batched Cholesky (lower) of a[batch, m, m] row-major + optional explicit inverse of the factor.

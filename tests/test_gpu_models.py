@@ -1,0 +1,143 @@
+"""GPU tests of the host layer that mirrors the reference's model classes (models.py, hmc.py, utils.py): the reference's
+training / sampling / prediction loops run against the CUDA path and are checked against the CPU oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_problem, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_sparse_gpr_training_matches_oracle_trajectory():
+    """models/sgpr.py:110-137: 5 Adam steps on -mll/N from gpytorch's initial values; same losses as the oracle trained on CPU."""
+    import ggp_b200.models as mdl
+    import ggp_b200.synthetic as syn
+    from oracle import sgpr as osgpr
+    c = syn.config1_demo_1d()
+    X, y, Z = (torch.tensor(c[k]) for k in ("X", "y", "Z"))
+    lik = mdl.GaussianLikelihood()
+    model = mdl.SparseGPR(X.to(DEV), y.to(DEV), lik, Z).to(DEV)
+    assert abs(model.base_covar_module.outputscale.item() - math.log(2)) < 1e-12      # gpytorch init
+    assert abs(model.likelihood.noise.item() - (math.log(2) + 1e-4)) < 1e-12
+    opt = torch.optim.Adam(model.parameters(), lr=0.05)
+    losses = model.train_model(opt, max_steps=5)
+    # oracle replica
+    sp = torch.nn.functional.softplus
+    rl = torch.zeros(1, 1, dtype=torch.float64, requires_grad=True)
+    ro = torch.zeros((), dtype=torch.float64, requires_grad=True)
+    rn = torch.zeros(1, dtype=torch.float64, requires_grad=True)
+    Zc = Z.clone().requires_grad_(True)
+    opt2 = torch.optim.Adam([rl, ro, rn, Zc], lr=0.05)
+    ref = []
+    for _ in range(5):
+        opt2.zero_grad()
+        lo = -osgpr.sgpr_bound(X, y, Zc, sp(rl).reshape(-1), sp(ro), (sp(rn) + 1e-4).reshape(()), "gpytorch", "n")
+        ref.append(lo.item())
+        lo.backward()
+        opt2.step()
+    assert max(abs(a - b) / abs(b) for a, b in zip(losses, ref)) < 1e-8
+    assert relerr(model.covar_module.inducing_points, Zc) < 1e-7
+    # predictive
+    xs = torch.linspace(-3, 3, 50, dtype=torch.float64)
+    pred = model.posterior_predictive(xs.to(DEV))
+    mo, co = osgpr.sgpr_predict(xs[:, None], X, y, Zc.detach(), sp(rl).detach().reshape(-1), sp(ro).detach(),
+                                (sp(rn) + 1e-4).detach().reshape(()), "gpytorch")
+    assert relerr(pred.loc, mo) < 1e-7 and relerr(pred.covariance_matrix, co) < 1e-7
+    from ggp_b200 import utils
+    ytest = torch.sin(3 * xs).to(DEV)
+    assert math.isfinite(float(utils.nlpd(pred, ytest, 1.0))) and math.isfinite(float(utils.rmse(pred.loc, ytest, 1.0)))
+
+
+def test_attribute_surface_used_by_update_model_to_hyper():
+    """models/bayesian_sgpr_hmc.py:82-86 assigns noise / outputscale / lengthscale through the property setters."""
+    import ggp_b200.models as mdl
+    X, y, Z, th = make_problem(200, 10, 3, seed=1)
+    model = mdl.BayesianSparseGPR_HMC(X.to(DEV), y.to(DEV), mdl.GaussianLikelihood(), Z).to(DEV)
+    hs = {"ls": np.array([0.5, 1.5, 2.5]), "sig_f": 1.3, "sig_n": 0.4}
+    model.update_model_to_hyper(None, hs)
+    assert relerr(model.base_covar_module.base_kernel.lengthscale.reshape(-1), hs["ls"]) < 1e-12
+    assert abs(model.base_covar_module.outputscale.item() - 1.69) < 1e-12
+    assert abs(model.likelihood.noise.item() - 0.16) < 1e-12 and abs(model.likelihood.noise_covar.noise.item() - 0.16) < 1e-12
+    model.freeze_kernel_hyperparameters()
+    assert [n for n, p in model.named_parameters() if p.requires_grad] == ["covar_module.inducing_points"]
+
+
+def test_hmc_on_the_collapsed_bound_recovers_the_posterior_mode_region():
+    """models/bayesian_sgpr_hmc.py:58-80 on config 2's shape: 4 chains in lock-step, one batched logp/dlogp per leapfrog."""
+    import ggp_b200
+    import ggp_b200.synthetic as syn
+    from ggp_b200.hmc import sample_hyper
+    from oracle import priors
+    c = syn.config2_co2_shaped()
+    X, y, Z = (torch.tensor(c[k]).to(DEV) for k in ("X", "y", "Z"))
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    traces, res = sample_hyper(X, y, Z, n_samples=60, tune=120, chains=4, n_leapfrog=8, step_size=0.02, generator=gen)
+    assert len(traces) == 4 and len(traces[0]) == 60
+    assert float(res["accept_rate"].mean()) > 0.4
+    assert set(traces[0][0]) == {"ls", "sig_f", "sig_n"}
+    # the sampler's logp bookkeeping is the oracle's logp at the sampled points
+    xs = res["samples"][-1].cpu()
+    for ch in range(4):
+        lo = priors.sgpr_vfe_logp(xs[ch], X.cpu(), y.cpu(), Z.cpu())
+        assert abs(res["logp"][-1, ch].item() - lo.item()) < 1e-6 * abs(lo.item())
+    # chains end up far above the log-density of the jittered starting points, and in a region of small noise
+    assert res["logp"][-1].min().item() > -400
+    assert all(t[len(t) - 1]["sig_n"] < 0.5 for t in traces)
+    # batched stochastic bound over the draws (models/bayesian_sgpr_hmc.py:121-131) == mean of single evaluations
+    import ggp_b200.models as mdl
+    model = mdl.BayesianSparseGPR_HMC(X, y, mdl.GaussianLikelihood(), Z.cpu()).to(DEV)
+    val = model.stochastic_bound(traces[0])
+    eng = ggp_b200.Engine.get(torch.device(DEV))
+    th = traces[0].thetas().to(DEV)
+    singles = [eng.sgpr_eval(X, y, model.covar_module.inducing_points, th[i], need_grad=False)["bound"][0] / X.shape[0] for i in range(60)]
+    assert abs(val.item() - torch.stack(singles).mean().item()) < 1e-10 * abs(val.item())
+    preds = mdl.mixture_posterior_predictive(model, X[:40], traces[0], full_cov=True)
+    assert 1 <= len(preds) <= 60
+    from ggp_b200 import utils
+    mu, sd = utils.get_posterior_predictive_means_stds(preds)
+    lo_, hi_ = utils.get_posterior_predictive_uncertainty_intervals(mu, sd)
+    assert mu.shape == (len(preds), 40) and (hi_ > lo_).all()
+
+
+def test_svgp_model_minibatch_training_and_prediction():
+    """models/svgp.py:88-141 with the DataLoader the reference builds (experiments/regression.py:107-108)."""
+    import ggp_b200.models as mdl
+    from torch.utils.data import DataLoader, TensorDataset
+    from oracle import svgp as osv
+    X, y, Z, th = make_problem(1200, 32, 2, seed=4)
+    torch.manual_seed(11)
+    model = mdl.StochasticVariationalGP(X.to(DEV), y.to(DEV), mdl.GaussianLikelihood(), Z).to(DEV)
+    loader = DataLoader(TensorDataset(X, y), batch_size=256, shuffle=True)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    losses = model.train_model(opt, loader, num_epochs=2)
+    assert len(losses) == 2 * 5 and losses[-1] < losses[0]
+    # the value of one more ELBO equals the oracle's at the trained parameters
+    xb, yb = X[:256], y[:256]
+    e = model.elbo(xb.to(DEV), yb.to(DEV))
+    k = model.covar_module
+    eo = osv.svgp_elbo(xb, yb, model.inducing_inputs.detach().cpu(), model.variational_mean.detach().cpu(),
+                       model.chol_variational_covar.detach().cpu(), k.base_kernel.lengthscale.detach().cpu().reshape(-1),
+                       k.outputscale.detach().cpu(), model.likelihood.noise.detach().cpu().reshape(()), 1200)
+    assert relerr(e, eo) < 1e-8
+    pred = model.posterior_predictive(X[:100].to(DEV))
+    mo, vo = osv.svgp_predict(X[:100], model.inducing_inputs.detach().cpu(), model.variational_mean.detach().cpu(),
+                              model.chol_variational_covar.detach().cpu(), k.base_kernel.lengthscale.detach().cpu().reshape(-1),
+                              k.outputscale.detach().cpu(), model.likelihood.noise.detach().cpu().reshape(()))
+    assert relerr(pred.loc, mo) < 1e-8 and relerr(pred.variance, vo) < 1e-8
+
+
+def test_bayesian_svgp_five_draws_per_batch():
+    import ggp_b200.models as mdl
+    X, y, Z, th = make_problem(600, 24, 2, seed=6)
+    torch.manual_seed(5)
+    model = mdl.BayesianStochasticVariationalGP(X.to(DEV), y.to(DEV), mdl.GaussianLikelihood(), Z).to(DEV)
+    loss = model.train_step_loss(X[:128].to(DEV), y[:128].to(DEV))
+    loss.backward()
+    assert torch.isfinite(loss)
+    assert model.inducing_inputs.grad is not None and torch.isfinite(model.inducing_inputs.grad).all()
+    assert model.log_theta.q_mu.grad is not None          # through the KL term
+    assert model.variational_mean.grad.abs().sum() > 0
