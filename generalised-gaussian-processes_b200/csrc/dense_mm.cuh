@@ -364,15 +364,33 @@ __global__ void __launch_bounds__(256) k_grad_mm_final(const double* __restrict_
   if (tid == 0) grad[b * sG + d + 1] = ds2[b];
 }
 
-// mom_acc[b][i][q] += sum_t mom_part[b][t][i][q]   (fixed order over tiles)
-__global__ void k_reduce_moments(const double* __restrict__ part, int64_t sTile, int64_t sB, int ntiles, int64_t count,
-                                 double* __restrict__ acc) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  if (idx >= count) return;
-  double s = 0.0;
-  for (int t = 0; t < ntiles; ++t) s += part[b * sB + t * sTile + idx];
-  acc[(int64_t)b * count + idx] += s;
+// acc[b][idx] += sum_t part[b][t][idx]   (fixed order: 8 interleaved tile groups per index, combined 0..7)
+// block 256 = 32 consecutive indices x 8 tile groups; grid (ceil(count/32), batch)
+__global__ void __launch_bounds__(256) k_reduce_moments(const double* __restrict__ part, int64_t sTile, int64_t sB, int ntiles,
+                                                        int64_t count, double* __restrict__ acc) {
+  __shared__ double red[8][33];
+  const int li = threadIdx.x & 31, grp = threadIdx.x >> 5, b = blockIdx.y;
+  const int64_t idx = (int64_t)blockIdx.x * 32 + li;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (idx < count) {
+    const double* src = part + b * sB + idx;
+    int t = grp;
+    for (; t + 24 < ntiles; t += 32) {
+      s0 += src[(int64_t)t * sTile];
+      s1 += src[(int64_t)(t + 8) * sTile];
+      s2 += src[(int64_t)(t + 16) * sTile];
+      s3 += src[(int64_t)(t + 24) * sTile];
+    }
+    for (; t < ntiles; t += 8) s0 += src[(int64_t)t * sTile];
+  }
+  red[grp][li] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (grp == 0 && idx < count) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][li];
+    acc[(int64_t)b * count + idx] += s;
+  }
 }
 
 // moments -> gradient partial.  mom[b][i][0]=r_i, [1..d]=Q_ic, [d+1..2d]=T_ic  with W = G o K (RBF: dk/d(d2) = -K/2)

@@ -145,7 +145,7 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   take((size_t)batch * p.nc * p.Mp * 8);                // Kc
   take((size_t)batch * p.nc * p.Mp * 8);                // At
   take((size_t)batch * p.splits * MM);                  // Spart
-  take((size_t)batch * (p.nc / 128) * m * nq * 8);      // mom_part
+  take((size_t)batch * (p.nc / 128) * 4 * m * nq * 8);  // mom_part (one slab per 128-column tile and warp column)
   take((size_t)batch * m * nq * 8);                     // mom_acc
   take((size_t)batch * 4 + 256);                        // info_ws
   p.nsv = std::min(p.nc, 4096);
@@ -160,9 +160,14 @@ static bool reserved_for(const ggp_handle* h, int64_t n_local, int m, int d, int
 }
 
 // ------------------------------------------------------------------------------------------------------------
-static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& p, int nbatch) {
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, nbatch * p.nz2 * p.splits);
-  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
+static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& pin, int nbatch) {
+  GemmP p = pin;
+  p.ntm = (p.M + BM - 1) / BM;
+  p.ntn = (p.N + BN - 1) / BN;
+  if (p.ntm == 0 || p.ntn == 0 || nbatch == 0) return 0;
+  p.tiles_per_z = p.sym == 1 ? p.ntn * (p.ntn + 1) / 2 : (p.sym == 2 ? p.ntm * (p.ntm + 1) / 2 : p.ntm * p.ntn);
+  p.total = p.tiles_per_z * nbatch * p.nz2 * p.splits;
+  const int grid = std::min(p.total, h->sm_count);   // persistent: one CTA per SM, static round-robin over the work items
   if (epi == EPI_STORE)
     k_gemm_nt<EPI_STORE><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
   else
@@ -394,7 +399,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     { ProfScope ps(h, st, CAT_SYRK); RUN(launch_gemm(h, st, EPI_STORE, s, batch)); }
     ProfScope ps_o(h, st, CAT_OTHER);
     // b += sum over n-tiles of the fused row dots (fixed order)
-    k_reduce_moments<<<dim3((unsigned)((m + 255) / 256), batch), 256, 0, st>>>(h->mom_part, m, (int64_t)(nc / 128) * m,
+    k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, (int64_t)(nc / 128) * m,
                                                                               (nv + BN - 1) / BN, m, h->bvec);
     CKL();
   }
@@ -471,11 +476,11 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     g.yv = y + c0;
     g.Kc = h->Kc; g.ldk = Mp; g.sK = (int64_t)nc * Mp;
     g.Xc = X + c0 * d; g.d = d;
-    g.mom = h->mom_part; g.sMomTile = cnt; g.sMom = (int64_t)(nc / 128) * cnt;
+    g.mom = h->mom_part; g.sMomTile = cnt; g.sMom = (int64_t)(nc / 128) * 4 * cnt;
     { ProfScope ps(h, st, CAT_BWD); RUN(launch_gemm(h, st, EPI_MOMENTS, g, batch)); }
     ProfScope ps_o(h, st, CAT_OTHER);
-    k_reduce_moments<<<dim3((unsigned)((cnt + 255) / 256), batch), 256, 0, st>>>(h->mom_part, cnt, (int64_t)(nc / 128) * cnt,
-                                                                                ntiles, cnt, h->mom_acc);
+    k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, (int64_t)(nc / 128) * 4 * cnt,
+                                                                                ntiles * 4, cnt, h->mom_acc);
     CKL();
   }
   k_grad_from_moments<<<batch, 256, 0, st>>>(h->mom_acc, m, d, Z, theta, grad_partial, sG);
