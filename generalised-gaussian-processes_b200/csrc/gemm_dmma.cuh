@@ -26,11 +26,33 @@ namespace ggp {
 #ifndef GGP_STAGES
 #define GGP_STAGES 3
 #endif
-constexpr int BM = 128, BN = 128, BK = GGP_BK, STAGES = GGP_STAGES, LDS = BK + 4, GEMM_THREADS = 256;
+#ifndef GGP_BN
+#define GGP_BN 128
+#endif
+#ifndef GGP_CTAS_PER_SM
+#define GGP_CTAS_PER_SM 1
+#endif
+constexpr int BM = 128, BN = GGP_BN, BK = GGP_BK, STAGES = GGP_STAGES, LDS = BK + 4;
+constexpr int WARPS_M = BM / 64, WARPS_N = BN / 32, GEMM_THREADS = WARPS_M * WARPS_N * 32;
+constexpr int CTAS_PER_SM = GGP_CTAS_PER_SM;       // co-resident CTAs: one CTA's epilogue / barrier drain overlaps the other's mainloop
 constexpr int LD_TPR = BK / 2;                     // loader threads per tile row (16-byte chunks per row)
 constexpr int LD_RPP = GEMM_THREADS / LD_TPR;      // rows per loader pass
 constexpr int GEMM_SMEM_PIPE = STAGES * (BM + BN) * LDS * 8;
-constexpr int GEMM_SMEM = GEMM_SMEM_PIPE + 4 * BM * 8;   // + row-dot exchange [4][BM]
+constexpr int GEMM_SMEM = GEMM_SMEM_PIPE + WARPS_N * BM * 8;   // + row-dot exchange [WARPS_N][BM]
+static_assert(BM == 128 && (BN == 64 || BN == 128), "tile shapes: 128x128 (8 warps) or 128x64 (4 warps)");
+static_assert(BM / LD_RPP <= 16 && BN / LD_RPP <= 16, "okmask layout");
+// symmetric outputs with rectangular tiles: tile (tm, tn) touches the upper triangle iff tn >= tm * (BM / BN)
+constexpr int TRATIO = BM / BN;
+__host__ __device__ inline int sym_upper_tiles(int ntm, int ntn) {
+  int t = 0;
+  for (int tm = 0; tm < ntm; ++tm) t += max(0, ntn - tm * TRATIO);
+  return t;
+}
+__host__ __device__ inline int sym_lower_tiles(int ntm, int ntn) {
+  int t = 0;
+  for (int tm = 0; tm < ntm; ++tm) t += min(ntn, (tm + 1) * TRATIO);
+  return t;
+}
 
 enum { KM_A_LOWER = 1, KM_A_UPPER = 2, KM_B_LOWER = 4, KM_B_UPPER = 8 };
 enum { EPI_STORE = 0, EPI_MOMENTS = 1 };
@@ -47,6 +69,8 @@ struct GemmP {
   int kmode, sym, heavy_first;
   // work decomposition (filled by launch_gemm)
   int ntm, ntn, tiles_per_z, total;
+  // TMA path: 0/1 multipliers of the (inner, outer) batch coordinates per operand (0 = broadcast operand, stride 0)
+  int tmA_pz, tmA_bz, tmB_pz, tmB_bz;
   // EPI_MOMENTS only
   const double* u;  int64_t su;            // [M] per batch
   const double* yv;                        // [N]
@@ -61,15 +85,16 @@ struct WorkItem {
   int tm, tn, bz, pz, split, k_lo, it_lo, niter;
 };
 
+template <int KS>
 __device__ __forceinline__ void decode_work(const GemmP& p, int w, WorkItem& o) {
   int z = w / p.tiles_per_z, t = w - z * p.tiles_per_z;
-  if (p.sym == 1) {  // upper tiles, row tm has ntn - tm of them
+  if (p.sym == 1) {  // upper tiles, row tm has ntn - tm*TRATIO of them
     int tm = 0;
-    while (t >= p.ntn - tm) { t -= p.ntn - tm; ++tm; }
-    o.tm = tm; o.tn = tm + t;
-  } else if (p.sym == 2) {  // lower tiles, row tm has tm + 1
+    while (t >= p.ntn - tm * TRATIO) { t -= p.ntn - tm * TRATIO; ++tm; }
+    o.tm = tm; o.tn = tm * TRATIO + t;
+  } else if (p.sym == 2) {  // lower tiles, row tm has min(ntn, (tm+1)*TRATIO)
     int tm = 0;
-    while (t >= tm + 1) { t -= tm + 1; ++tm; }
+    while (t >= min(p.ntn, (tm + 1) * TRATIO)) { t -= min(p.ntn, (tm + 1) * TRATIO); ++tm; }
     o.tm = tm; o.tn = t;
   } else {
     const int y = t / p.ntn;
@@ -84,7 +109,7 @@ __device__ __forceinline__ void decode_work(const GemmP& p, int w, WorkItem& o) 
   if (p.kmode & KM_B_LOWER) k_hi = min(k_hi, (o.tn + 1) * BN);
   if (p.kmode & KM_A_UPPER) k_lo = max(k_lo, o.tm * BM);
   if (p.kmode & KM_B_UPPER) k_lo = max(k_lo, o.tn * BN);
-  const int nkt = (k_hi > k_lo) ? (k_hi - k_lo + BK - 1) / BK : 0;
+  const int nkt = (k_hi > k_lo) ? (k_hi - k_lo + KS - 1) / KS : 0;
   int it_lo = 0, it_hi = nkt;
   if (p.splits > 1) {
     const int per = (nkt + p.splits - 1) / p.splits;
@@ -96,15 +121,149 @@ __device__ __forceinline__ void decode_work(const GemmP& p, int w, WorkItem& o) 
   o.niter = it_hi > it_lo ? it_hi - it_lo : 0;
 }
 
+// Epilogues work on the accumulator registers and global memory only (the operand pipeline keeps streaming the next tile).
+// NAMED_BAR: the CTA has a producer warp, so the consumer warps meet on named barrier 1 instead of __syncthreads().
+template <bool NAMED_BAR>
+__device__ __forceinline__ void epi_sync() {
+  if (NAMED_BAR) asm volatile("bar.sync 1, 256;\n" ::: "memory");
+  else __syncthreads();
+}
+
+template <int EPI, bool NAMED_BAR>
+__device__ __forceinline__ void gemm_epilogue(const GemmP& p, const WorkItem& wi, double (&acc)[8][4][2], double* sR, int tid,
+                                              int wm, int wn, int g, int q) {
+  const int row0_m = wi.tm * BM, row0_n = wi.tn * BN;
+  // ---------------- epilogue (registers + global only; the pipeline keeps streaming the next tile) ----------------
+  if (EPI == EPI_STORE) {
+    double* __restrict__ C = p.C + wi.bz * p.sC + wi.pz * p.sC2 + wi.split * p.sSplit;
+    const bool vec16 = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    if (p.rowdot) {
+      // fused  rowdot[tile_n][i] = sum_{n in tile} alpha*acc[i,n] * yv[n]   (b = A y, fixed-order reduction)
+      double yv[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gc = row0_n + wn * 32 + j * 8 + 2 * q;
+        yv[j][0] = gc < p.N ? p.yv[gc] : 0.0;
+        yv[j][1] = gc + 1 < p.N ? p.yv[gc + 1] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double sdot = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sdot = fma(acc[i][j][1], yv[j][1], fma(acc[i][j][0], yv[j][0], sdot));
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+        if (q == 0) sR[wn * BM + wm * 64 + i * 8 + g] = sdot;
+      }
+      epi_sync<NAMED_BAR>();
+      if (tid < BM && row0_m + tid < p.M)
+        p.rowdot[wi.bz * p.sRowdot + (int64_t)wi.tn * p.M + row0_m + tid] =
+            p.alpha * (WARPS_N == 4 ? (((sR[tid] + sR[BM + tid]) + sR[2 * BM + tid]) + sR[3 * BM + tid]) : (sR[tid] + sR[BM + tid]));
+      epi_sync<NAMED_BAR>();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gr = row0_m + wm * 64 + i * 8 + g;
+      if (gr >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gc = row0_n + wn * 32 + j * 8 + 2 * q;
+        double* dst = C + (int64_t)gr * p.ldc + gc;
+        double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+#ifdef GGP_EXP_NOSTORE
+        if (v0 == 1.2345e-300) dst[0] = v0;
+        continue;
+#endif
+        if (gc + 1 < p.N) {
+          if (vec16) {  // 16-byte accesses: the 4 lanes of a quad cover 2 full 32-B sectors per row
+            double2* d2 = reinterpret_cast<double2*>(dst);
+            if (p.beta != 0.0) { const double2 o = *d2; v0 += p.beta * o.x; v1 += p.beta * o.y; }
+            *d2 = make_double2(v0, v1);
+          } else {
+            if (p.beta != 0.0) { v0 += p.beta * dst[0]; v1 += p.beta * dst[1]; }
+            dst[0] = v0; dst[1] = v1;
+          }
+        } else if (gc < p.N) {
+          if (p.beta != 0.0) v0 += p.beta * dst[0];
+          dst[0] = v0;
+        }
+      }
+    }
+  } else {
+    // ---- fused backward epilogue:  W = (alpha*acc + u y^T) o K ;  mom[i, :] = sum_n W[i,n] * [1, x_n, x_n^2] ----
+    // W stays in the accumulator registers and is fed back to the tensor pipe as the A operand: the C fragment holds
+    // W[g][2q+e], so taking k' = q with column n = 2q+e (e = 0,1) is a valid k-permutation as long as the B operand uses
+    // the same one: lane (g,q) supplies Phi[n = 2q+e][moment column g].
+    const double* __restrict__ Kc = p.Kc + wi.bz * p.sK;
+    const double* __restrict__ uu = p.u + wi.bz * p.su;
+    double yv[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = row0_n + wn * 32 + j * 8 + 2 * q;
+      yv[j][0] = gc < p.N ? p.yv[gc] : 0.0;
+      yv[j][1] = gc + 1 < p.N ? p.yv[gc + 1] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gr = row0_m + wm * 64 + i * 8 + g;
+      const bool rok = gr < p.M;
+      const double ui = rok ? uu[gr] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gc = row0_n + wn * 32 + j * 8 + 2 * q;
+        const double k0 = (rok && gc < p.N) ? Kc[(int64_t)gc * p.ldk + gr] : 0.0;
+        const double k1 = (rok && gc + 1 < p.N) ? Kc[(int64_t)(gc + 1) * p.ldk + gr] : 0.0;
+        acc[i][j][0] = fma(ui, yv[j][0], p.alpha * acc[i][j][0]) * k0;
+        acc[i][j][1] = fma(ui, yv[j][1], p.alpha * acc[i][j][1]) * k1;
+      }
+    }
+    const int nq = 2 * p.d + 1;
+    double* mom = p.mom + wi.bz * p.sMom + (int64_t)(wi.tn * WARPS_N + wn) * p.sMomTile;   // one slab per 32 columns of n
+    for (int q0 = 0; q0 < nq; q0 += 8) {
+      // B fragments for this block of 8 moment columns: phi[j][e] = Phi[n(j,q,e)][q0 + g]
+      const int qa = q0 + g;
+      double phi[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gn = row0_n + wn * 32 + j * 8 + 2 * q + e;
+          double v = 0.0;
+          if (qa < nq && gn < p.N) {
+            if (qa == 0) v = 1.0;
+            else if (qa <= p.d) v = p.Xc[(int64_t)gn * p.d + (qa - 1)];
+            else { const double x = p.Xc[(int64_t)gn * p.d + (qa - 1 - p.d)]; v = x * x; }
+          }
+          phi[j][e] = v;
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dmma884(m0, m1, acc[i][j][0], phi[j][0]);
+          dmma884(m0, m1, acc[i][j][1], phi[j][1]);
+        }
+        const int gr = row0_m + wm * 64 + i * 8 + g;
+        const int qc = q0 + 2 * q;
+        if (gr < p.M) {
+          if (qc < nq) mom[(int64_t)gr * nq + qc] = m0;
+          if (qc + 1 < nq) mom[(int64_t)gr * nq + qc + 1] = m1;
+        }
+      }
+    }
+  }
+}
+
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_nt(const GemmP p) {
+__global__ void __launch_bounds__(GEMM_THREADS, CTAS_PER_SM) k_gemm_nt(const GemmP p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sA = reinterpret_cast<double*>(smem_raw);
   double* sB = sA + STAGES * BM * LDS;
-  double* sR = sB + STAGES * BN * LDS;  // [4][BM] row-dot exchange (never aliased with the pipeline)
+  double* sR = sB + STAGES * BN * LDS;  // [WARPS_N][BM] row-dot exchange (never aliased with the pipeline)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;  // WARPS_M x WARPS_N warps
   const int g = lane >> 2, q = lane & 3;
   const int ld_row = tid / LD_TPR, ld_chunk = tid % LD_TPR;
   const int ld_soff = ld_row * LDS + ld_chunk * 2;
@@ -127,7 +286,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_nt(const GemmP p) {
     while (rL < nrounds) {
       const int w = item_of(rL);
       if (w < p.total) {
-        decode_work(p, w, wi);
+        decode_work<BK>(p, w, wi);
         if (wi.niter > 0) break;
       }
       ++rL;
@@ -184,7 +343,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_nt(const GemmP p) {
     const int wC = item_of(rC);
     if (wC >= p.total) continue;
     WorkItem wi;
-    decode_work(p, wC, wi);
+    decode_work<BK>(p, wC, wi);
     if (wi.niter == 0) continue;
     const int row0_m = wi.tm * BM, row0_n = wi.tn * BN;
     const int kbaseC = wi.k_lo + wi.it_lo * BK;
@@ -209,13 +368,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_nt(const GemmP p) {
         for (int j = 0; j < 4; ++j) b[j] = cB[j * 8 * LDS + kk * 4];
         if (diag_lower && kbaseC + it * BK + kk * 4 >= row0_m) {
           // inside the diagonal block of a lower-triangular A: fragment rows [8i, 8i+8) need k <= row only
+          // (a predicated-off DMMA still occupies the tensor pipe for its full 16 cycles - measured with ncu - so the staircase
+          //  must be real control flow: jump into the fragment-row sequence at the first row that needs this k-step)
           const int kfrag = kbaseC + it * BK + kk * 4 - row0_m - wm * 64;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (kfrag < i * 8 + 8) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
+          const int i_lo = kfrag < 0 ? 0 : (kfrag >> 3);
+#define GGP_FRAG_ROW(i)                                                          \
+  _Pragma("unroll") for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          switch (i_lo) {
+            case 0: GGP_FRAG_ROW(0)  // fallthrough
+            case 1: GGP_FRAG_ROW(1)
+            case 2: GGP_FRAG_ROW(2)
+            case 3: GGP_FRAG_ROW(3)
+            case 4: GGP_FRAG_ROW(4)
+            case 5: GGP_FRAG_ROW(5)
+            case 6: GGP_FRAG_ROW(6)
+            case 7: GGP_FRAG_ROW(7)
+            default: break;
+          }
+#undef GGP_FRAG_ROW
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -227,119 +397,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_nt(const GemmP p) {
       }
     }
 
-    // ---------------- epilogue (registers + global only; the pipeline keeps streaming the next tile) ----------------
-    if (EPI == EPI_STORE) {
-      double* __restrict__ C = p.C + wi.bz * p.sC + wi.pz * p.sC2 + wi.split * p.sSplit;
-      if (p.rowdot) {
-        // fused  rowdot[tile_n][i] = sum_{n in tile} alpha*acc[i,n] * yv[n]   (b = A y, fixed-order reduction)
-        double yv[4][2];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int gc = row0_n + wn * 32 + j * 8 + 2 * q;
-          yv[j][0] = gc < p.N ? p.yv[gc] : 0.0;
-          yv[j][1] = gc + 1 < p.N ? p.yv[gc + 1] : 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          double sdot = 0.0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sdot = fma(acc[i][j][1], yv[j][1], fma(acc[i][j][0], yv[j][0], sdot));
-          sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-          sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-          if (q == 0) sR[wn * BM + wm * 64 + i * 8 + g] = sdot;
-        }
-        __syncthreads();
-        if (tid < BM && row0_m + tid < p.M)
-          p.rowdot[wi.bz * p.sRowdot + (int64_t)wi.tn * p.M + row0_m + tid] =
-              p.alpha * (((sR[tid] + sR[BM + tid]) + sR[2 * BM + tid]) + sR[3 * BM + tid]);
-        __syncthreads();
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int gr = row0_m + wm * 64 + i * 8 + g;
-        if (gr >= p.M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int gc = row0_n + wn * 32 + j * 8 + 2 * q;
-          double* dst = C + (int64_t)gr * p.ldc + gc;
-          double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-#ifdef GGP_EXP_NOSTORE
-          if (v0 == 1.2345e-300) dst[0] = v0;
-          continue;
-#endif
-          if (gc + 1 < p.N) {
-            if (p.beta != 0.0) { v0 += p.beta * dst[0]; v1 += p.beta * dst[1]; }
-            dst[0] = v0; dst[1] = v1;
-          } else if (gc < p.N) {
-            if (p.beta != 0.0) v0 += p.beta * dst[0];
-            dst[0] = v0;
-          }
-        }
-      }
-    } else {
-      // ---- fused backward epilogue:  W = (alpha*acc + u y^T) o K ;  mom[i, :] = sum_n W[i,n] * [1, x_n, x_n^2] ----
-      // W stays in the accumulator registers and is fed back to the tensor pipe as the A operand: the C fragment holds
-      // W[g][2q+e], so taking k' = q with column n = 2q+e (e = 0,1) is a valid k-permutation as long as the B operand uses
-      // the same one: lane (g,q) supplies Phi[n = 2q+e][moment column g].
-      const double* __restrict__ Kc = p.Kc + wi.bz * p.sK;
-      const double* __restrict__ uu = p.u + wi.bz * p.su;
-      double yv[4][2];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gc = row0_n + wn * 32 + j * 8 + 2 * q;
-        yv[j][0] = gc < p.N ? p.yv[gc] : 0.0;
-        yv[j][1] = gc + 1 < p.N ? p.yv[gc + 1] : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int gr = row0_m + wm * 64 + i * 8 + g;
-        const bool rok = gr < p.M;
-        const double ui = rok ? uu[gr] : 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int gc = row0_n + wn * 32 + j * 8 + 2 * q;
-          const double k0 = (rok && gc < p.N) ? Kc[(int64_t)gc * p.ldk + gr] : 0.0;
-          const double k1 = (rok && gc + 1 < p.N) ? Kc[(int64_t)(gc + 1) * p.ldk + gr] : 0.0;
-          acc[i][j][0] = fma(ui, yv[j][0], p.alpha * acc[i][j][0]) * k0;
-          acc[i][j][1] = fma(ui, yv[j][1], p.alpha * acc[i][j][1]) * k1;
-        }
-      }
-      const int nq = 2 * p.d + 1;
-      double* mom = p.mom + wi.bz * p.sMom + (int64_t)(wi.tn * 4 + wn) * p.sMomTile;
-      for (int q0 = 0; q0 < nq; q0 += 8) {
-        // B fragments for this block of 8 moment columns: phi[j][e] = Phi[n(j,q,e)][q0 + g]
-        const int qa = q0 + g;
-        double phi[4][2];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int gn = row0_n + wn * 32 + j * 8 + 2 * q + e;
-            double v = 0.0;
-            if (qa < nq && gn < p.N) {
-              if (qa == 0) v = 1.0;
-              else if (qa <= p.d) v = p.Xc[(int64_t)gn * p.d + (qa - 1)];
-              else { const double x = p.Xc[(int64_t)gn * p.d + (qa - 1 - p.d)]; v = x * x; }
-            }
-            phi[j][e] = v;
-          }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          double m0 = 0.0, m1 = 0.0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            dmma884(m0, m1, acc[i][j][0], phi[j][0]);
-            dmma884(m0, m1, acc[i][j][1], phi[j][1]);
-          }
-          const int gr = row0_m + wm * 64 + i * 8 + g;
-          const int qc = q0 + 2 * q;
-          if (gr < p.M) {
-            if (qc < nq) mom[(int64_t)gr * nq + qc] = m0;
-            if (qc + 1 < nq) mom[(int64_t)gr * nq + qc + 1] = m1;
-          }
-        }
-      }
-    }
+    gemm_epilogue<EPI, false>(p, wi, acc, sR, tid, wm, wn, g, q);
   }
   cp_async_wait<0>();
 }

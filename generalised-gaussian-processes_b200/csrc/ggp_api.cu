@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -11,6 +12,7 @@
 #include "common.cuh"
 #include "dense_mm.cuh"
 #include "gemm_dmma.cuh"
+#include "gemm_tma.cuh"
 #include "kernel_tiles.cuh"
 #include "misc.cuh"
 #include "svgp.cuh"
@@ -123,9 +125,9 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   while (nc > 128 && 2.0 * batch * (double)nc * p.Mp * 8.0 > budget) nc /= 2;
   nc = std::max<int64_t>(128, nc / 128 * 128);
   p.nc = (int)std::min<int64_t>(nc, nmax);
-  const int T = (m + BM - 1) / BM;
-  const int tiles = T * (T + 1) / 2;
-  int splits = (int)((sm_count + tiles * batch / 2) / std::max(1, tiles * batch));
+  const int tiles = sym_upper_tiles((m + BM - 1) / BM, (m + BN - 1) / BN);
+  const int ctas = sm_count * CTAS_PER_SM;
+  int splits = (int)((ctas + tiles * batch / 2) / std::max(1, tiles * batch));
   splits = std::max(1, std::min(16, splits));
   splits = std::min(splits, std::max(1, p.nc / 256));
   p.splits = splits;
@@ -145,7 +147,7 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   take((size_t)batch * p.nc * p.Mp * 8);                // Kc
   take((size_t)batch * p.nc * p.Mp * 8);                // At
   take((size_t)batch * p.splits * MM);                  // Spart
-  take((size_t)batch * (p.nc / 128) * 4 * m * nq * 8);  // mom_part (one slab per 128-column tile and warp column)
+  take((size_t)batch * (p.nc / 32) * m * nq * 8);       // mom_part (one slab per 32 rows of the chunk = tile x warp column)
   take((size_t)batch * m * nq * 8);                     // mom_acc
   take((size_t)batch * 4 + 256);                        // info_ws
   p.nsv = std::min(p.nc, 4096);
@@ -160,14 +162,75 @@ static bool reserved_for(const ggp_handle* h, int64_t n_local, int m, int d, int
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// ---- TMA tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda) ----
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn get_tmap_encode() {
+  static tmap_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (tmap_encode_fn)ptr;
+  }
+  return fn;
+}
+static int g_use_tma = -1;   // GGP_GEMM_TMA=0 forces the LDGSTS mainloop (developer A/B)
+
+// operand [count_outer][count_inner][rows x K] (row-major, leading dimension ld, element strides s_inner / s_outer) as a 4-D map
+// (k, row, inner, outer) with a 16 x 128 box and the 128-byte swizzle.  Returns false when the layout cannot be described.
+static bool make_operand_map(CUtensorMap* tm, const double* ptr, int rows, int K, int64_t ld, int cnt_inner, int64_t s_inner,
+                             int cnt_outer, int64_t s_outer, int* mul_inner, int* mul_outer) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc || !ptr || rows < 1 || K < 1) return false;
+  // a batch stride of 0 is a broadcast operand: describe one instance and pin that coordinate to 0
+  *mul_inner = (cnt_inner > 1 && s_inner != 0) ? 1 : 0;
+  *mul_outer = (cnt_outer > 1 && s_outer != 0) ? 1 : 0;
+  if (!*mul_inner) cnt_inner = 1;
+  if (!*mul_outer) cnt_outer = 1;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 1) || ld < K) return false;
+  if (cnt_inner > 1 && (s_inner <= 0 || (s_inner & 1))) return false;
+  if (cnt_outer > 1 && (s_outer <= 0 || (s_outer & 1))) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)std::max(1, cnt_inner), (cuuint64_t)std::max(1, cnt_outer)};
+  const cuuint64_t row_b = (cuuint64_t)ld * 8;
+  const cuuint64_t strides[3] = {row_b, cnt_inner > 1 ? (cuuint64_t)s_inner * 8 : row_b, cnt_outer > 1 ? (cuuint64_t)s_outer * 8 : row_b};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] >= ((cuuint64_t)1 << 40)) return false;
+  const cuuint32_t box[4] = {(cuuint32_t)TK, 128u, 1u, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& pin, int nbatch) {
   GemmP p = pin;
   p.ntm = (p.M + BM - 1) / BM;
   p.ntn = (p.N + BN - 1) / BN;
   if (p.ntm == 0 || p.ntn == 0 || nbatch == 0) return 0;
-  p.tiles_per_z = p.sym == 1 ? p.ntn * (p.ntn + 1) / 2 : (p.sym == 2 ? p.ntm * (p.ntm + 1) / 2 : p.ntm * p.ntn);
+  p.tiles_per_z = p.sym == 1 ? sym_upper_tiles(p.ntm, p.ntn) : (p.sym == 2 ? sym_lower_tiles(p.ntm, p.ntn) : p.ntm * p.ntn);
   p.total = p.tiles_per_z * nbatch * p.nz2 * p.splits;
-  const int grid = std::min(p.total, h->sm_count);   // persistent: one CTA per SM, static round-robin over the work items
+  const int grid = std::min(p.total, h->sm_count * CTAS_PER_SM);   // persistent CTAs, static snake order over the work items
+  if (g_use_tma < 0) {
+    const char* e = getenv("GGP_GEMM_TMA");
+    g_use_tma = (e && e[0] == '0') ? 0 : 1;
+  }
+  CUtensorMap tmA, tmB;
+  // in-place products (C aliases an operand) stay on the LDGSTS kernel: its loads of a tile are complete before its epilogue,
+  // whereas the TMA producer prefetches the next tiles while this tile's C is being written
+  const bool alias = (p.C == p.A || p.C == p.B);
+  if (g_use_tma && !alias && make_operand_map(&tmA, p.A, p.M, p.K, p.lda, p.nz2, p.sA2, nbatch, p.sA, &p.tmA_pz, &p.tmA_bz) &&
+      make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.nz2, p.sB2, nbatch, p.sB, &p.tmB_pz, &p.tmB_bz)) {
+    if (epi == EPI_STORE)
+      k_gemm_tma<EPI_STORE><<<grid, T_THREADS, T_SMEM, st>>>(tmA, tmB, p);
+    else
+      k_gemm_tma<EPI_MOMENTS><<<grid, T_THREADS, T_SMEM, st>>>(tmA, tmB, p);
+    CKL();
+    return 0;
+  }
   if (epi == EPI_STORE)
     k_gemm_nt<EPI_STORE><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
   else
@@ -297,6 +360,8 @@ int ggp_create(ggp_handle_t** out, int device) {
   h->sm_count = prop.multiProcessorCount;
   CK(cudaFuncSetAttribute(k_gemm_nt<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   CK(cudaFuncSetAttribute(k_gemm_nt<EPI_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  CK(cudaFuncSetAttribute(k_gemm_tma<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+  CK(cudaFuncSetAttribute(k_gemm_tma<EPI_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
   CK(cudaFuncSetAttribute(k_build_kc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   *out = h;
   return 0;
@@ -390,7 +455,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     GemmP t = gemm_basic(h->Linv, Mp, sM, h->Kc, Mp, (int64_t)nc * Mp, h->At, nc, (int64_t)nc * Mp, m, nv, m, 1.0, 0.0,
                          KM_A_LOWER);
     t.heavy_first = 1;
-    t.yv = y + c0; t.rowdot = h->mom_part; t.sRowdot = (int64_t)(nc / 128) * m;   // b partials reuse the moment-partial buffer
+    t.yv = y + c0; t.rowdot = h->mom_part; t.sRowdot = (int64_t)(nc / BN) * m;   // b partials reuse the moment-partial buffer
     { ProfScope ps(h, st, CAT_TRMM); RUN(launch_gemm(h, st, EPI_STORE, t, batch)); }
     // S_split += At * At^T  (upper tiles)
     GemmP s = gemm_basic(h->At, nc, (int64_t)nc * Mp, h->At, nc, (int64_t)nc * Mp, h->Spart, Mp, (int64_t)splits * sM, m, m, nv,
@@ -399,7 +464,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     { ProfScope ps(h, st, CAT_SYRK); RUN(launch_gemm(h, st, EPI_STORE, s, batch)); }
     ProfScope ps_o(h, st, CAT_OTHER);
     // b += sum over n-tiles of the fused row dots (fixed order)
-    k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, (int64_t)(nc / 128) * m,
+    k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, (int64_t)(nc / BN) * m,
                                                                               (nv + BN - 1) / BN, m, h->bvec);
     CKL();
   }
@@ -476,11 +541,11 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     g.yv = y + c0;
     g.Kc = h->Kc; g.ldk = Mp; g.sK = (int64_t)nc * Mp;
     g.Xc = X + c0 * d; g.d = d;
-    g.mom = h->mom_part; g.sMomTile = cnt; g.sMom = (int64_t)(nc / 128) * 4 * cnt;
+    g.mom = h->mom_part; g.sMomTile = cnt; g.sMom = (int64_t)(nc / 32) * cnt;
     { ProfScope ps(h, st, CAT_BWD); RUN(launch_gemm(h, st, EPI_MOMENTS, g, batch)); }
     ProfScope ps_o(h, st, CAT_OTHER);
-    k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, (int64_t)(nc / 128) * 4 * cnt,
-                                                                                ntiles * 4, cnt, h->mom_acc);
+    k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, (int64_t)(nc / 32) * cnt,
+                                                                                ntiles * WARPS_N, cnt, h->mom_acc);
     CKL();
   }
   k_grad_from_moments<<<batch, 256, 0, st>>>(h->mom_acc, m, d, Z, theta, grad_partial, sG);
