@@ -232,7 +232,7 @@ def main():
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "k_gemm_nt (DMMA.8x8x4: triangular multiply + SYRK + backward GEMM)",
+            "roofline": {"bound": "tensor", "kernel": "k_gemm_tma (TMA-fed DMMA.8x8x4 mainloop: triangular multiply + SYRK + backward GEMM)",
                          "achieved": achieved, "peak": peak["best"], "unit": "TFLOP/s", "frac": (achieved / peak["best"]) if achieved else None,
                          "traffic": None, "peak_source": "measured live: register-resident mma.sync m8n8k4 f64 loop on all SMs "
                          "(MEASURED_PEAKS.json holds no FP64 figure)", "launches_per_step": gemm_launches,

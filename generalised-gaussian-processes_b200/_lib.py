@@ -17,7 +17,7 @@ c_int_p = ctypes.c_void_p
 
 class GgpCfg(ctypes.Structure):
     _fields_ = [("kernel", ctypes.c_int32), ("precision", ctypes.c_int32),
-                ("chunk_rows", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("chunk_rows", ctypes.c_int32), ("tile_cache_mib", ctypes.c_int32)]
 
 
 KERNELS = {"rbf": 0, "matern32": 1, "matern52": 2}

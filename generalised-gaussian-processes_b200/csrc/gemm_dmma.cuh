@@ -67,6 +67,7 @@ struct GemmP {
   int64_t sSplit;
   double alpha, beta;
   int kmode, sym, heavy_first;
+  int n_major;      // non-symmetric outputs: enumerate all row tiles (tm) of one column tile (tn) consecutively
   // work decomposition (filled by launch_gemm)
   int ntm, ntn, tiles_per_z, total;
   // TMA path: 0/1 multipliers of the (inner, outer) batch coordinates per operand (0 = broadcast operand, stride 0)
@@ -97,9 +98,14 @@ __device__ __forceinline__ void decode_work(const GemmP& p, int w, WorkItem& o) 
     while (t >= min(p.ntn, (tm + 1) * TRATIO)) { t -= min(p.ntn, (tm + 1) * TRATIO); ++tm; }
     o.tm = tm; o.tn = t;
   } else {
-    const int y = t / p.ntn;
-    o.tn = t - y * p.ntn;
-    o.tm = p.heavy_first ? (p.ntm - 1 - y) : y;
+    if (p.n_major) {
+      o.tn = t / p.ntm;
+      o.tm = t - o.tn * p.ntm;
+    } else {
+      const int y = t / p.ntn;
+      o.tn = t - y * p.ntn;
+      o.tm = p.heavy_first ? (p.ntm - 1 - y) : y;
+    }
   }
   o.split = z % p.splits; z /= p.splits;
   o.pz = z % p.nz2;

@@ -52,6 +52,14 @@ struct ggp_handle {
   double *bvec = 0, *cvec = 0, *beta = 0, *u = 0, *yty = 0, *ds2 = 0, *rowacc = 0;
   // streamed chunk buffers
   double *Kc = 0, *At = 0, *Spart = 0, *mom_part = 0, *mom_acc = 0;
+  // optional HBM cache of the k(X_local, Z) tiles built in pass 1, reused by pass 2 of the same evaluation (cfg.tile_cache_mib)
+  double* kc_all = nullptr;
+  size_t kc_all_bytes = 0;
+  int64_t kc_rows = 0;          // rows per batch element in kc_all
+  bool kc_valid = false;
+  const void *kc_X = nullptr, *kc_Z = nullptr, *kc_theta = nullptr;
+  int64_t kc_n = 0;
+  int kc_batch = 0, kc_kind = 0;
   double *sv[5] = {0, 0, 0, 0, 0}, *rowout = 0;
   int nsv = 0;
   // instrumentation
@@ -373,13 +381,17 @@ int ggp_destroy(ggp_handle_t* h) {
   for (auto& c : h->chol_graphs) cudaGraphExecDestroy(c.exec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->arena) cudaFree(h->arena);
+  if (h->kc_all) cudaFree(h->kc_all);
   delete h;
   return 0;
 }
 
 int ggp_workspace_bytes(const ggp_cfg* cfg, int64_t n_local, int m, int d, int batch, size_t* out) {
   if (!out || m <= 0 || d <= 0 || batch <= 0 || n_local < 0) return fail(-1, "ggp_workspace_bytes: bad argument");
-  *out = make_plan(cfg, n_local, m, d, batch, 148).bytes;
+  const Plan p = make_plan(cfg, n_local, m, d, batch, 148);
+  *out = p.bytes;
+  const size_t cache = (size_t)batch * ((n_local + 127) / 128 * 128) * p.Mp * 8;
+  if (cfg && cfg->tile_cache_mib > 0 && n_local > 0 && cache <= (size_t)cfg->tile_cache_mib * 1024 * 1024) *out += cache;
   return 0;
 }
 
@@ -400,6 +412,30 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   }
   h->n_local = n_local; h->m = m; h->d = d; h->batch = batch;
   h->Mp = p.Mp; h->nc = p.nc; h->splits = p.splits;
+  h->kc_valid = false;
+  {
+    const int64_t rows = (n_local + 127) / 128 * 128;
+    const size_t need = (size_t)batch * rows * p.Mp * 8;
+    const size_t budget = (cfg && cfg->tile_cache_mib > 0) ? (size_t)cfg->tile_cache_mib * 1024 * 1024 : 0;
+    if (n_local > 0 && need <= budget) {
+      if (need > h->kc_all_bytes) {
+        if (h->kc_all) CK(cudaFree(h->kc_all));
+        h->kc_all = nullptr;
+        h->kc_all_bytes = 0;
+        if (cudaMalloc((void**)&h->kc_all, need) == cudaSuccess) {
+          h->kc_all_bytes = need;
+        } else {   // not enough memory for the cache: fall back to rebuilding the tiles in pass 2
+          (void)cudaGetLastError();
+          h->kc_all = nullptr;
+        }
+      }
+      h->kc_rows = rows;
+    } else if (h->kc_all) {
+      CK(cudaFree(h->kc_all));
+      h->kc_all = nullptr;
+      h->kc_all_bytes = 0;
+    }
+  }
   double** slots[] = {&h->L, &h->Linv, &h->LinvT, &h->Wk, &h->Bm, &h->LBinv, &h->LBinvT, &h->Binv, &h->PA, &h->Gbar, &h->T1,
                       &h->P, &h->Gzz, &h->Tblk, &h->bvec, &h->cvec, &h->beta, &h->u, &h->yty, &h->ds2, &h->rowacc, &h->Kc,
                       &h->At, &h->Spart, &h->mom_part, &h->mom_acc};
@@ -419,6 +455,7 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   cudaStream_t st = (cudaStream_t)stream;
   const int kind = cfg ? cfg->kernel : 0;
   const int Mp = h->Mp;
+  h->kc_valid = false;
   ProfScope ps(h, st, CAT_MM);
   k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp);
   CKL();
@@ -426,11 +463,11 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
 }
 
 static int build_chunk(ggp_handle* h, cudaStream_t st, const double* Xc, int nv, int d, const double* Z, int m,
-                       const double* theta, int kind, int batch) {
+                       const double* theta, int kind, int batch, double* dst, int64_t sK) {
   const int Mp = h->Mp;
   dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
   const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
-  k_build_kc<<<grid, KT_THREADS, smem, st>>>(Xc, nv, nv, d, Z, m, theta, kind, h->Kc, Mp, (int64_t)h->nc * Mp);
+  k_build_kc<<<grid, KT_THREADS, smem, st>>>(Xc, nv, nv, d, Z, m, theta, kind, dst, Mp, sK);
   CKL();
   return 0;
 }
@@ -450,9 +487,11 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   CKL();
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
-    { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch)); }
+    double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
+    const int64_t sK = h->kc_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
+    { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
     // At[m x nv] = Linv[m x m] * Kc[nv x m]^T   (k clipped to the lower triangle)
-    GemmP t = gemm_basic(h->Linv, Mp, sM, h->Kc, Mp, (int64_t)nc * Mp, h->At, nc, (int64_t)nc * Mp, m, nv, m, 1.0, 0.0,
+    GemmP t = gemm_basic(h->Linv, Mp, sM, Kc_c, Mp, sK, h->At, nc, (int64_t)nc * Mp, m, nv, m, 1.0, 0.0,
                          KM_A_LOWER);
     t.heavy_first = 1;
     t.yv = y + c0; t.rowdot = h->mom_part; t.sRowdot = (int64_t)(nc / BN) * m;   // b partials reuse the moment-partial buffer
@@ -467,6 +506,10 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, (int64_t)(nc / BN) * m,
                                                                               (nv + BN - 1) / BN, m, h->bvec);
     CKL();
+  }
+  if (h->kc_all) {
+    h->kc_valid = true;
+    h->kc_X = X; h->kc_Z = Z; h->kc_theta = theta; h->kc_n = n_local; h->kc_batch = batch; h->kc_kind = kind;
   }
   k_finalize_partial<<<dim3((m + 15) / 16, (m + 15) / 16, batch), dim3(16, 16), 0, st>>>(
       h->Spart, Mp, sM, (int64_t)splits * sM, splits, h->bvec, m, h->yty, n_local, theta, d, m, partial,
@@ -532,14 +575,20 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   const int64_t sM = (int64_t)Mp * Mp, sG = (int64_t)d + 2 + (int64_t)m * d;
   const int64_t cnt = (int64_t)m * nq;
   CK(cudaMemsetAsync(h->mom_acc, 0, (size_t)batch * cnt * 8, st));
+  // the tiles cached by the pass 1 of this evaluation (same operands, same handle, no factor() since) are reused as they are
+  const bool cached = h->kc_all && h->kc_valid && h->kc_X == X && h->kc_Z == Z && h->kc_theta == theta && h->kc_n == n_local &&
+                      h->kc_batch == batch && h->kc_kind == kind;
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
-    { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch)); }
+    double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
+    const int64_t sK = h->kc_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
+    if (!cached) { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
     const int ntiles = (nv + BN - 1) / BN;
-    GemmP g = gemm_basic(h->P, Mp, sM, h->Kc, Mp, (int64_t)nc * Mp, nullptr, 0, 0, m, nv, m, 1.0, 0.0);
+    GemmP g = gemm_basic(h->P, Mp, sM, Kc_c, Mp, sK, nullptr, 0, 0, m, nv, m, 1.0, 0.0);
+    g.n_major = 1;   // all row tiles of one chunk-row tile back to back: each k(X,Z) tile comes from HBM once, then from L2
     g.u = h->u; g.su = Mp;
     g.yv = y + c0;
-    g.Kc = h->Kc; g.ldk = Mp; g.sK = (int64_t)nc * Mp;
+    g.Kc = Kc_c; g.ldk = Mp; g.sK = sK;
     g.Xc = X + c0 * d; g.d = d;
     g.mom = h->mom_part; g.sMomTile = cnt; g.sMom = (int64_t)(nc / 32) * cnt;
     { ProfScope ps(h, st, CAT_BWD); RUN(launch_gemm(h, st, EPI_MOMENTS, g, batch)); }
@@ -564,7 +613,7 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nc * Mp;
   for (int64_t c0 = 0; c0 < ns; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, ns - c0);
-    RUN(build_chunk(h, st, Xs + c0 * d, nv, d, Z, m, theta, kind, batch));
+    RUN(build_chunk(h, st, Xs + c0 * d, nv, d, Z, m, theta, kind, batch, h->Kc, (int64_t)h->nc * h->Mp));
     // aT[nv x m] = Ks[nv x m] * Linv^T ; tT[nv x m] = aT * LBinv^T
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Linv, Mp, sM, h->At, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->At, Mp, sC, h->LBinv, Mp, sM, h->Kc, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));

@@ -46,23 +46,28 @@ class Engine:
     _cache = {}
 
     @classmethod
-    def get(cls, device=None, kernel="rbf", precision="fp64", chunk_rows=0):
+    def get(cls, device=None, kernel="rbf", precision="fp64", chunk_rows=0, tile_cache_mib=None):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         device = torch.device(device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        key = (device.index, kernel, precision, chunk_rows)
+        key = (device.index, kernel, precision, chunk_rows, tile_cache_mib)
         if key not in cls._cache:
-            cls._cache[key] = cls(device, kernel, precision, chunk_rows)
+            cls._cache[key] = cls(device, kernel, precision, chunk_rows, tile_cache_mib)
         return cls._cache[key]
 
-    def __init__(self, device, kernel="rbf", precision="fp64", chunk_rows=0):
+    def __init__(self, device, kernel="rbf", precision="fp64", chunk_rows=0, tile_cache_mib=None):
         if not torch.cuda.is_available():
             raise RuntimeError("the sparse-GP hot path needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device(device)
-        self.cfg = GgpCfg(KERNELS[kernel], PRECISIONS[precision], int(chunk_rows), 0)
+        if tile_cache_mib is None:
+            # keep the k(X,Z) tiles of pass 1 in HBM for pass 2 when they fit in a quarter of the free device memory (<= 32 GiB);
+            # tile_cache_mib=0 restores the strictly streaming behaviour (never more than chunk_rows x m of k(X,Z) alive)
+            free_b, _ = torch.cuda.mem_get_info(torch.device(device))
+            tile_cache_mib = int(min(32 * 1024, free_b // (4 * 1024 * 1024)))
+        self.cfg = GgpCfg(KERNELS[kernel], PRECISIONS[precision], int(chunk_rows), int(tile_cache_mib))
         h = ctypes.c_void_p()
         check(self.lib.ggp_create(ctypes.byref(h), self.device.index), "ggp_create")
         self.h = h

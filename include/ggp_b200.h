@@ -34,7 +34,8 @@ typedef struct {
   int32_t kernel;      /* GGP_KERNEL_*   (ScaleKernel(RBFKernel(ard)) at models/sgpr.py:36 is GGP_KERNEL_RBF) */
   int32_t precision;   /* GGP_PREC_*     contraction arithmetic; everything else is float64 */
   int32_t chunk_rows;  /* rows of X per streamed chunk; 0 = library default */
-  int32_t reserved;
+  int32_t tile_cache_mib; /* MiB of device memory the handle may use to keep the k(X_local,Z) tiles of pass1 for the pass2 of the
+                             same evaluation (saves the second tile build); 0 = never materialise more than chunk_rows x m */
 } ggp_cfg;
 
 int ggp_version(void);

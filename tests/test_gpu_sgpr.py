@@ -186,6 +186,25 @@ def test_shard_additivity_and_determinism_at_scale(eng):
     assert abs(fd - an) < 1e-5 * abs(an)
 
 
+def test_tile_cache_equals_streaming_rebuild(eng):
+    """cfg.tile_cache_mib: keeping the k(X,Z) tiles of pass 1 in HBM for pass 2 must be bit-identical to rebuilding them
+    (strictly streaming mode), for one and for several theta rows, and must not leak across evaluations with a new theta."""
+    import ggp_b200
+    N, M, D = 40_000, 200, 5
+    X, y, Z, th = make_problem(N, M, D, seed=4)
+    stream_eng = ggp_b200.Engine.get(eng.device, tile_cache_mib=0)
+    cache_eng = ggp_b200.Engine.get(eng.device, tile_cache_mib=4096)
+    ths = torch.stack([th, th * 1.3, th * 0.8])
+    for t in (th, ths):
+        a = stream_eng.sgpr_eval(X, y, Z, t, jitter_policy=1e-6)
+        b = cache_eng.sgpr_eval(X, y, Z, t, jitter_policy=1e-6)
+        assert torch.equal(a["bound"], b["bound"]) and torch.equal(a["grad"], b["grad"])
+    th2 = th * 1.1
+    b2 = cache_eng.sgpr_eval(X, y, Z, th2, jitter_policy=1e-6)
+    a2 = stream_eng.sgpr_eval(X, y, Z, th2, jitter_policy=1e-6)
+    assert torch.equal(a2["grad"], b2["grad"])
+
+
 def test_autograd_function_drops_into_a_training_step(eng):
     """SGPRBound.apply replaces forward + mll + backward of models/sgpr.py:123-129 (gpytorch convention: / N, softplus raws)."""
     import ggp_b200.functions as F
