@@ -92,6 +92,37 @@ def cpu_oracle_rate(sample_rows, threads, repeats=1):
     return best * (N_FULL / sample_rows), best
 
 
+def hmc_rate(dev, eng_cls, iters=12, warm=4, chains=4, n_leapfrog=10):
+    """HMC samples/s on BASELINE configs[1] (co2-shaped N=545, M=100, 4 chains): lock-step fixed-L HMC over theta on the collapsed
+    bound with pymc3's priors/transforms (models/bayesian_sgpr_hmc.py:60-78); every leapfrog is ONE batched bound+grad evaluation of
+    all chains.  Timed over `iters` post-warm-up HMC iterations with CUDA events."""
+    import torch
+    import ggp_b200.synthetic as syn
+    from ggp_b200.functions import sgpr_vfe_logp_dlogp
+    from ggp_b200.hmc import hmc_sample
+    c = syn.config2_co2_shaped()
+    X, y, Z = (torch.tensor(c[k], device=dev) for k in ("X", "y", "Z"))
+    eng = eng_cls.get(dev)
+    D = X.shape[1]
+    g = torch.Generator(device=dev).manual_seed(173)
+    x0 = torch.zeros(chains, D + 2, dtype=torch.float64, device=dev)
+    x0[:, :D] = 0.6931471805599453
+    f = lambda xx: sgpr_vfe_logp_dlogp(xx, X, y, Z, engine=eng, group=False)
+    ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
+    def progress(it):
+        if it == warm - 1:
+            ev[0].record()
+    res = hmc_sample(f, x0, iters, tune=warm, n_leapfrog=n_leapfrog, step_size=0.02, adapt_mass=False, generator=g, progress=progress)
+    ev[1].record()
+    torch.cuda.synchronize()
+    sec = ev[0].elapsed_time(ev[1]) * 1e-3
+    return {"workload": "configs[1]: co2-shaped N=545 D=1 M=100, 4 chains in lock-step, fixed-length HMC (L=10) on the VFE bound + pymc3 priors",
+            "samples_per_s": chains * iters / sec, "chains": chains, "leapfrogs_per_sample": n_leapfrog,
+            "bound_grad_evals_per_s": chains * iters * n_leapfrog / sec, "ms_per_batched_leapfrog": 1e3 * sec / (iters * n_leapfrog),
+            "accept_rate": float(res["accept_rate"].mean().item())}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -121,6 +152,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_FULL, help="override N (debug only; the headline number needs the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hmc", action="store_true")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -242,6 +274,10 @@ def main():
             "breakdown_ms_per_step": {k: v / args.steps for k, v in cat_ms.items()},
             "bound_value": float(out["bound"][0].item()),
         }
+        line["hmc_at_headline_config"] = {"leapfrogs_per_sample": 10, "samples_per_s": value / 10.0,
+                                          "note": "one HMC sample = L leapfrogs x one bound+grad evaluation (models/sgp_hmc.py:67-69 uses L=10)"}
+        if world == 1 and not args.no_hmc:
+            line["hmc"] = hmc_rate(dev, ggp_b200.Engine)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = 196608 if N >= 196608 else N
