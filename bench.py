@@ -250,6 +250,12 @@ def main():
     d2h = (1 + P) * 8
 
     if rank == 0:
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1b_ncu_traffic.json")) as fh:
+                traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
+        except Exception:
+            pass
         gemm_ms = (cat_ms["trmm"] + cat_ms["syrk"] + cat_ms["bwd"]) / args.steps
         gemm_launches = (cat_n["trmm"] + cat_n["syrk"] + cat_n["bwd"]) / args.steps
         flops_local = 4.0 * n_local * M_IND * M_IND  # N M^2 (tri) + N M^2 (syrk) + 2 N M^2 (backward)
@@ -266,7 +272,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "k_gemm_tma (TMA-fed DMMA.8x8x4 mainloop: triangular multiply + SYRK + backward GEMM)",
                          "achieved": achieved, "peak": peak["best"], "unit": "TFLOP/s", "frac": (achieved / peak["best"]) if achieved else None,
-                         "traffic": None, "peak_source": "measured live: register-resident mma.sync m8n8k4 f64 loop on all SMs "
+                         "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full, avg of the 3 GEMM roles on a "
+                         "16384-row chunk; profiles/r1b_ncu_traffic.json)", "peak_source": "measured live: register-resident mma.sync m8n8k4 f64 loop on all SMs "
                          "(MEASURED_PEAKS.json holds no FP64 figure)", "launches_per_step": gemm_launches,
                          "avg_launch_ms": gemm_ms / gemm_launches if gemm_launches else None,
                          "algorithmic_flops_per_step_per_rank": flops_local,
