@@ -92,7 +92,7 @@ def cpu_oracle_rate(sample_rows, threads, repeats=1):
     return best * (N_FULL / sample_rows), best
 
 
-def hmc_rate(dev, eng_cls, iters=12, warm=4, chains=4, n_leapfrog=10):
+def hmc_rate(dev, eng_cls, iters=40, warm=5, chains=4, n_leapfrog=10):
     """HMC samples/s on BASELINE configs[1] (co2-shaped N=545, M=100, 4 chains): lock-step fixed-L HMC over theta on the collapsed
     bound with pymc3's priors/transforms (models/bayesian_sgpr_hmc.py:60-78); every leapfrog is ONE batched bound+grad evaluation of
     all chains.  Timed over `iters` post-warm-up HMC iterations with CUDA events."""
@@ -108,19 +108,25 @@ def hmc_rate(dev, eng_cls, iters=12, warm=4, chains=4, n_leapfrog=10):
     x0 = torch.zeros(chains, D + 2, dtype=torch.float64, device=dev)
     x0[:, :D] = 0.6931471805599453
     f = lambda xx: sgpr_vfe_logp_dlogp(xx, X, y, Z, engine=eng, group=False)
-    ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    out = {"workload": "configs[1]: co2-shaped N=545 D=1 M=100, 4 chains in lock-step, fixed-length HMC (L=10) on the VFE bound + pymc3 priors",
+           "chains": chains, "leapfrogs_per_sample": n_leapfrog}
+    for mode in ("eager", "cuda_graph"):
+        ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
 
-    def progress(it):
-        if it == warm - 1:
-            ev[0].record()
-    res = hmc_sample(f, x0, iters, tune=warm, n_leapfrog=n_leapfrog, step_size=0.02, adapt_mass=False, generator=g, progress=progress)
-    ev[1].record()
-    torch.cuda.synchronize()
-    sec = ev[0].elapsed_time(ev[1]) * 1e-3
-    return {"workload": "configs[1]: co2-shaped N=545 D=1 M=100, 4 chains in lock-step, fixed-length HMC (L=10) on the VFE bound + pymc3 priors",
-            "samples_per_s": chains * iters / sec, "chains": chains, "leapfrogs_per_sample": n_leapfrog,
-            "bound_grad_evals_per_s": chains * iters * n_leapfrog / sec, "ms_per_batched_leapfrog": 1e3 * sec / (iters * n_leapfrog),
-            "accept_rate": float(res["accept_rate"].mean().item())}
+        def progress(it):
+            if it == warm - 1:
+                ev[0].record()
+        g.manual_seed(173)
+        res = hmc_sample(f, x0, iters, tune=warm, n_leapfrog=n_leapfrog, step_size=0.02, adapt_mass=False, generator=g,
+                         progress=progress, cuda_graph=(mode == "cuda_graph"))
+        ev[1].record()
+        torch.cuda.synchronize()
+        sec = ev[0].elapsed_time(ev[1]) * 1e-3
+        out[mode] = {"samples_per_s": chains * iters / sec, "bound_grad_evals_per_s": chains * iters * n_leapfrog / sec,
+                     "ms_per_batched_leapfrog": 1e3 * sec / (iters * n_leapfrog), "accept_rate": float(res["accept_rate"].mean().item())}
+    out["samples_per_s"] = out["cuda_graph"]["samples_per_s"]
+    out["note"] = "cuda_graph: the L-leapfrog trajectory (L bound+grad evaluations of all chains) is one CUDA graph replay"
+    return out
 
 
 def run_reference(args, rank):

@@ -393,34 +393,62 @@ __global__ void __launch_bounds__(256) k_reduce_moments(const double* __restrict
   }
 }
 
-// moments -> gradient partial.  mom[b][i][0]=r_i, [1..d]=Q_ic, [d+1..2d]=T_ic  with W = G o K (RBF: dk/d(d2) = -K/2)
-//   d_ell_c = sum_i (z^2 r - 2 z Q + T)_ic / ell_c^3 ; d_sf2 = sum_i r_i / sf2 ; dZ_ic = (Q_ic - z_ic r_i)/ell_c^2 ; d_s2 = 0
+// moments -> gradient partial.  mom[b][i][0]=r_i, [1..d]=Q_ic, [d+1..2d]=T_ic are the moments of W against [1, x, x^2].
+//   RBF (rk == NULL): W = G o K and dk/d(d2) = -K/2:
+//     d_ell_c = sum_i (z^2 r - 2 z Q + T)_ic / ell_c^3 ; d_sf2 = sum_i r_i / sf2 ; dZ_ic = (Q_ic - z_ic r_i)/ell_c^2
+//   other stationary kernels (rk != NULL): W = G o dk/d(d2):
+//     d_ell_c = -2 sum_i (z^2 r - 2 z Q + T)_ic / ell_c^3 ; dZ_ic = 2 (z_ic r_i - Q_ic)/ell_c^2 ;
+//     d_sf2 = rk / sf2 with rk = sum(G o K) = tr(P_A S) + beta^T b / s^2 from the m x m section (k_rk_from_mm)
+//   d_s2 = 0 in both cases.
 __global__ void __launch_bounds__(256) k_grad_from_moments(const double* __restrict__ mom, int M, int d,
                                                            const double* __restrict__ Z, const double* __restrict__ theta,
-                                                           double* __restrict__ grad, int64_t sG) {
+                                                           double* __restrict__ grad, int64_t sG, const double* __restrict__ rk) {
   __shared__ double red[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int nq = 2 * d + 1;
   const double* th = theta + (int64_t)b * (d + 2);
   const double* mb = mom + (int64_t)b * M * nq;
+  const double fl = rk ? -2.0 : 1.0, fz = rk ? -2.0 : 1.0;
   for (int c = 0; c < d; ++c) {
     double s = 0.0;
     for (int i = tid; i < M; i += 256) {
       const double z = Z[(int64_t)i * d + c], r = mb[(int64_t)i * nq], Q = mb[(int64_t)i * nq + 1 + c],
                    T = mb[(int64_t)i * nq + 1 + d + c];
       s += fma(z, fma(z, r, -2.0 * Q), T);
-      grad[b * sG + d + 2 + (int64_t)i * d + c] = (Q - z * r) / (th[c] * th[c]);
+      grad[b * sG + d + 2 + (int64_t)i * d + c] = fz * (Q - z * r) / (th[c] * th[c]);
     }
     s = block_sum<256>(s, red);
-    if (tid == 0) grad[b * sG + c] = s / (th[c] * th[c] * th[c]);
+    if (tid == 0) grad[b * sG + c] = fl * s / (th[c] * th[c] * th[c]);
   }
   double s = 0.0;
   for (int i = tid; i < M; i += 256) s += mb[(int64_t)i * nq];
   s = block_sum<256>(s, red);
   if (tid == 0) {
-    grad[b * sG + d] = s / th[d];
+    grad[b * sG + d] = (rk ? rk[b] : s) / th[d];
     grad[b * sG + d + 1] = 0.0;
   }
+}
+
+// rk[b] = sum_{i,n} G_in K_in = tr(P_A S) + beta^T b / s^2   (G = P Kzx + u y^T, Kzx Kxz = L S L^T, Kzx y = L b)
+// -- the k-weighted total needed for dF/d sf2 when the streamed moments are weighted by dk/d(d2) instead of k.
+__global__ void __launch_bounds__(256) k_rk_from_mm(const double* __restrict__ partial, int64_t sP, int M, int Mp,
+                                                    const double* __restrict__ theta, int d, const double* __restrict__ PA,
+                                                    int64_t sMat, const double* __restrict__ beta, double* __restrict__ rk) {
+  __shared__ double red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* S = partial + b * sP;
+  const double* bv = S + (int64_t)M * M;
+  const double s2 = theta[(int64_t)b * (d + 2) + d + 1];
+  double acc = 0.0;
+  for (int64_t e = tid; e < (int64_t)M * M; e += 256) {
+    const int i = (int)(e / M), j = (int)(e - (int64_t)i * M);
+    acc = fma(PA[b * sMat + (int64_t)i * Mp + j], S[e], acc);
+  }
+  double acc2 = 0.0;
+  for (int i = tid; i < M; i += 256) acc2 = fma(beta[(int64_t)b * Mp + i], bv[i], acc2);
+  acc += acc2 / (s2 * s2);
+  acc = block_sum<256>(acc, red);
+  if (tid == 0) rk[b] = acc;
 }
 
 }  // namespace ggp

@@ -49,7 +49,7 @@ struct ggp_handle {
   double *L = 0, *Linv = 0, *LinvT = 0, *Wk = 0, *Bm = 0, *LBinv = 0, *LBinvT = 0, *Binv = 0, *PA = 0, *Gbar = 0, *T1 = 0,
          *P = 0, *Gzz = 0, *Tblk = 0;
   // vectors (per batch stride Mp)
-  double *bvec = 0, *cvec = 0, *beta = 0, *u = 0, *yty = 0, *ds2 = 0, *rowacc = 0;
+  double *bvec = 0, *cvec = 0, *beta = 0, *u = 0, *yty = 0, *ds2 = 0, *rowacc = 0, *rk = 0;
   // streamed chunk buffers
   double *Kc = 0, *At = 0, *Spart = 0, *mom_part = 0, *mom_acc = 0;
   // optional HBM cache of the k(X_local, Z) tiles built in pass 1, reused by pass 2 of the same evaluation (cfg.tile_cache_mib)
@@ -157,6 +157,7 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   take((size_t)batch * p.splits * MM);                  // Spart
   take((size_t)batch * (p.nc / 32) * m * nq * 8);       // mom_part (one slab per 32 rows of the chunk = tile x warp column)
   take((size_t)batch * m * nq * 8);                     // mom_acc
+  take((size_t)batch * 8);                              // rk
   take((size_t)batch * 4 + 256);                        // info_ws
   p.nsv = std::min(p.nc, 4096);
   for (int i = 0; i < 5; ++i) take((size_t)batch * p.nsv * p.Mp * 8);   // SVGP / SGPMC row and transposed buffers
@@ -438,7 +439,7 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   }
   double** slots[] = {&h->L, &h->Linv, &h->LinvT, &h->Wk, &h->Bm, &h->LBinv, &h->LBinvT, &h->Binv, &h->PA, &h->Gbar, &h->T1,
                       &h->P, &h->Gzz, &h->Tblk, &h->bvec, &h->cvec, &h->beta, &h->u, &h->yty, &h->ds2, &h->rowacc, &h->Kc,
-                      &h->At, &h->Spart, &h->mom_part, &h->mom_acc};
+                      &h->At, &h->Spart, &h->mom_part, &h->mom_acc, &h->rk};
   const size_t nslots = sizeof(slots) / sizeof(slots[0]);
   for (size_t i = 0; i < nslots; ++i) *slots[i] = reinterpret_cast<double*>(h->arena + p.off[i]);
   h->info_ws = reinterpret_cast<int32_t*>(h->arena + p.off[nslots]);
@@ -524,7 +525,7 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   if (need_grad && !grad_mm) return fail(-1, "ggp_sgpr_finish: grad_mm is NULL");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_finish: handle not reserved for this shape");
   const int kind = cfg ? cfg->kernel : 0;
-  if (need_grad && kind != GGP_KERNEL_RBF) return fail(-3, "ggp_sgpr_finish: gradients are implemented for GGP_KERNEL_RBF");
+  if (kind < GGP_KERNEL_RBF || kind > GGP_KERNEL_MATERN52) return fail(-3, "ggp_sgpr_finish: unknown kernel");
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp;
   const int64_t sM = (int64_t)Mp * Mp, sP = (int64_t)m * m + m + 3, sG = (int64_t)d + 2 + (int64_t)m * d;
@@ -552,6 +553,10 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   if (!need_grad) return 0;
   k_make_PA_Gbar<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Binv, h->beta, Mp, h->PA, h->Gbar, sM);
   CKL();
+  if (kind != GGP_KERNEL_RBF) {
+    k_rk_from_mm<<<batch, 256, 0, st>>>(partial, sP, m, Mp, theta, d, h->PA, sM, h->beta, h->rk);
+    CKL();
+  }
   // P = Linv^T PA Linv ;  Gzz = -1/2 Linv^T Gbar Linv
   RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
   RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_B_UPPER), batch));
@@ -569,7 +574,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   if (!h || !Z || !theta || !grad_partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass2: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_pass2: handle not reserved for this shape");
   const int kind = cfg ? cfg->kernel : 0;
-  if (kind != GGP_KERNEL_RBF) return fail(-3, "ggp_sgpr_pass2: gradients are implemented for GGP_KERNEL_RBF");
+  if (kind < GGP_KERNEL_RBF || kind > GGP_KERNEL_MATERN52) return fail(-3, "ggp_sgpr_pass2: unknown kernel");
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc, nq = 2 * d + 1;
   const int64_t sM = (int64_t)Mp * Mp, sG = (int64_t)d + 2 + (int64_t)m * d;
@@ -589,6 +594,15 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     g.u = h->u; g.su = Mp;
     g.yv = y + c0;
     g.Kc = Kc_c; g.ldk = Mp; g.sK = sK;
+    if (kind != GGP_KERNEL_RBF) {
+      // Matern: the epilogue multiplier is dk/d(d2), not k (RBF: -k/2, folded into k_grad_from_moments); built into the At buffer
+      ProfScope ps(h, st, CAT_BUILD);
+      dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
+      const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
+      k_build_kc<<<grid, KT_THREADS, smem, st>>>(X + c0 * d, nv, nv, d, Z, m, theta, kind, h->At, Mp, (int64_t)nc * Mp, 1);
+      CKL();
+      g.Kc = h->At; g.ldk = Mp; g.sK = (int64_t)nc * Mp;
+    }
     g.Xc = X + c0 * d; g.d = d;
     g.mom = h->mom_part; g.sMomTile = cnt; g.sMom = (int64_t)(nc / 32) * cnt;
     { ProfScope ps(h, st, CAT_BWD); RUN(launch_gemm(h, st, EPI_MOMENTS, g, batch)); }
@@ -597,7 +611,8 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
                                                                                 ntiles * WARPS_N, cnt, h->mom_acc);
     CKL();
   }
-  k_grad_from_moments<<<batch, 256, 0, st>>>(h->mom_acc, m, d, Z, theta, grad_partial, sG);
+  k_grad_from_moments<<<batch, 256, 0, st>>>(h->mom_acc, m, d, Z, theta, grad_partial, sG,
+                                             kind != GGP_KERNEL_RBF ? h->rk : nullptr);
   CKL();
   return 0;
 }
@@ -726,7 +741,7 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, dKzz, Mp, sM, m, m, m, -1.0, 0.0, KM_B_UPPER), batch));
     k_grad_kzz_rows<<<dim3((m + 7) / 8, batch), 256, 0, st>>>(dKzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, dZzz + d + 2, sM);
     CKL();
-    k_grad_from_moments<<<batch, 256, 0, st>>>(mom, m, d, Z, theta, gk, sM);
+    k_grad_from_moments<<<batch, 256, 0, st>>>(mom, m, d, Z, theta, gk, sM, nullptr);
     CKL();
   }
   k_svgp_final<<<batch, 256, 0, st>>>(scal, gk, sM, h->rowacc, dZzz, dm, Mp, dLsraw, sM, Mp, qm, qLs, theta, m, d, kl_scale, need_grad,

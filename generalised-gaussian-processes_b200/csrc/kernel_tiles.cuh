@@ -30,11 +30,12 @@ __device__ __forceinline__ double kgrad(int kind, double sf2, double d2) {
 }
 
 // Kc[b][n][m] = k(x_n, z_m; theta_b) for n in [0, n_fill): rows >= n_valid and columns >= M are written as zero.
+// deriv = 1 emits dk/d(d2) instead (the multiplier of the backward epilogue for the non-RBF kernels).
 // grid: (ceil(ldk/KT_M), ceil(n_fill/KT_N), batch)
 __global__ void __launch_bounds__(KT_THREADS) k_build_kc(const double* __restrict__ X, int n_valid, int n_fill, int d,
                                                         const double* __restrict__ Z, int M,
                                                         const double* __restrict__ theta, int kind,
-                                                        double* __restrict__ Kc, int64_t ldk, int64_t sK) {
+                                                        double* __restrict__ Kc, int64_t ldk, int64_t sK, int deriv = 0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* xs = reinterpret_cast<double*>(smem_raw);   // [KT_N][d]
   double* zs = xs + KT_N * d;                          // [d][KT_M]   (z / ell, transposed: conflict-free)
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc(const double* __restric
     for (int j = 0; j < 4; ++j) {
       const int m = m0 + tx + 16 * j;
       if (m >= ldk) continue;
-      out[(int64_t)n * ldk + m] = (nv && m < M) ? kval(kind, sf2, d2[i][j]) : 0.0;
+      out[(int64_t)n * ldk + m] = (nv && m < M) ? (deriv ? kgrad(kind, sf2, d2[i][j]) : kval(kind, sf2, d2[i][j])) : 0.0;
     }
   }
 }

@@ -111,6 +111,10 @@ class Engine:
         while True:
             check(self.lib.ggp_sgpr_factor(self.h, ctypes.byref(self.cfg), _stream(), _ptr(Z), _ptr(theta), _ptr(jit),
                                            m, d, batch, _ptr(info)), "ggp_sgpr_factor")
+            if len(ladder) == 1 and not raise_on_fail:
+                # fixed jitter (pymc3 stabilize / gpflow default) and the caller handles info[b] != 0 itself: nothing to retry, so
+                # no host read-back -- the evaluation stays asynchronous and can be captured in a CUDA graph (hmc.GraphedTrajectory)
+                return jit, info
             info_h = info.cpu()
             bad = [b for b in range(batch) if int(info_h[b]) != 0]
             if not bad:

@@ -65,6 +65,29 @@ LOG2 = math.log(2.0)
 LOGPI = math.log(math.pi)
 
 
+def _vfe_eval(x, X, y, Z, jitter_policy, eng, group, with_prior):
+    """Shared core of the pymc3 targets: x[C, D+2] unconstrained, one Z for all rows.  Returns (lp[C], dx[C, D+2], dZ[C, M, D], bad[C])."""
+    D = X.shape[1]
+    M = Z.shape[0]
+    ell = torch.exp(x[:, :D])
+    sig_f = torch.exp(x[:, D])
+    sig_n = torch.exp(x[:, D + 1])
+    theta = torch.cat([ell, (sig_f ** 2).unsqueeze(1), (sig_n ** 2).unsqueeze(1)], dim=1)
+    out = eng.sgpr_eval(X, y, Z, theta, jitter_policy=jitter_policy, need_grad=True, group=group, raise_on_fail=False)
+    g = out["grad"]
+    dx = torch.cat([g[:, :D] * ell, (g[:, D] * 2.0 * sig_f ** 2).unsqueeze(1), (g[:, D + 1] * 2.0 * sig_n ** 2).unsqueeze(1)], dim=1)
+    dZ = g[:, D + 2:].reshape(-1, M, D)
+    lp = out["bound"].clone()
+    if with_prior:
+        lp = lp + (torch.log(ell) - ell).sum(1) + (LOG2 - LOGPI - torch.log1p(sig_f ** 2)) + (LOG2 - LOGPI - torch.log1p(sig_n ** 2)) \
+            + x.sum(1)
+        dpr = torch.cat([(1.0 - ell), (-2.0 * sig_f ** 2 / (1.0 + sig_f ** 2)).unsqueeze(1),
+                         (-2.0 * sig_n ** 2 / (1.0 + sig_n ** 2)).unsqueeze(1)], dim=1) + 1.0
+        dx = dx + dpr
+    bad = (out["info"].to(eng.device) != 0) | (out["info_b"] != 0) | ~torch.isfinite(lp)
+    return lp, dx, dZ, bad
+
+
 def sgpr_vfe_logp_dlogp(x, X, y, Z, jitter_policy="pymc3", engine=None, group=False, with_prior=True):
     """pymc3 log-posterior of models/bayesian_sgpr_hmc.py:60-71 and its gradient, batched over the rows of x.
 
@@ -76,25 +99,35 @@ def sgpr_vfe_logp_dlogp(x, X, y, Z, jitter_policy="pymc3", engine=None, group=Fa
     x = x.to(device=eng.device, dtype=torch.float64)
     if x.dim() == 1:
         x = x.unsqueeze(0)
-    D = X.shape[1]
-    ell = torch.exp(x[:, :D])
-    sig_f = torch.exp(x[:, D])
-    sig_n = torch.exp(x[:, D + 1])
-    theta = torch.cat([ell, (sig_f ** 2).unsqueeze(1), (sig_n ** 2).unsqueeze(1)], dim=1)
-    out = eng.sgpr_eval(X, y, Z, theta, jitter_policy=jitter_policy, need_grad=True, group=group, raise_on_fail=False)
-    g = out["grad"]
-    dx = torch.cat([g[:, :D] * ell, (g[:, D] * 2.0 * sig_f ** 2).unsqueeze(1), (g[:, D + 1] * 2.0 * sig_n ** 2).unsqueeze(1)], dim=1)
-    lp = out["bound"].clone()
-    if with_prior:
-        lp = lp + (torch.log(ell) - ell).sum(1) + (LOG2 - LOGPI - torch.log1p(sig_f ** 2)) + (LOG2 - LOGPI - torch.log1p(sig_n ** 2)) \
-            + x.sum(1)
-        dpr = torch.cat([(1.0 - ell), (-2.0 * sig_f ** 2 / (1.0 + sig_f ** 2)).unsqueeze(1),
-                         (-2.0 * sig_n ** 2 / (1.0 + sig_n ** 2)).unsqueeze(1)], dim=1) + 1.0
-        dx = dx + dpr
-    bad = (out["info"].to(eng.device) != 0) | (out["info_b"] != 0) | ~torch.isfinite(lp)
+    lp, dx, _, bad = _vfe_eval(x, X, y, Z, jitter_policy, eng, group, with_prior)
     lp = torch.where(bad, torch.full_like(lp, -float("inf")), lp)
     dx = torch.where(bad.unsqueeze(1), torch.zeros_like(dx), dx)
     return lp, dx
+
+
+def all_in_hmc_logp_dlogp(x, X, y, num_inducing, jitter_policy="pymc3", engine=None, group=False):
+    """Log-posterior of models/all_in_HMC.py:47-60 (Rossi et al. baseline): theta AND the inducing inputs Z are sampled.
+
+    x[C, D+2+M*D] = (ls_log__[D], sig_f_log__, sig_n_log__, Z[M*D] row-major); Z ~ Normal(0,1) elementwise (:57), untransformed.
+    dF/dZ is the analytic inducing-input gradient of the same bound+gradient evaluation.  Every chain carries its
+    own Z, so chains are evaluated one after another (the reference runs chains=1, :60)."""
+    eng = engine or Engine.get(X.device)
+    x = x.to(device=eng.device, dtype=torch.float64)
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    D = X.shape[1]
+    M = int(num_inducing)
+    assert x.shape[1] == D + 2 + M * D
+    lps, gs = [], []
+    for c in range(x.shape[0]):
+        Zc = x[c, D + 2:].reshape(M, D).contiguous()
+        lp, dx, dZ, bad = _vfe_eval(x[c:c + 1, :D + 2], X, y, Zc, jitter_policy, eng, group, True)
+        lp = lp[0] + (-0.5 * Zc * Zc).sum() - 0.5 * M * D * math.log(2.0 * math.pi)
+        g = torch.cat([dx[0], (dZ[0] - Zc).reshape(-1)])
+        b = bad[0] | ~torch.isfinite(lp)
+        lps.append(torch.where(b, torch.full_like(lp, -float("inf")), lp))
+        gs.append(torch.where(b, torch.zeros_like(g), g))
+    return torch.stack(lps), torch.stack(gs)
 
 
 class SVGPElbo(torch.autograd.Function):

@@ -3,9 +3,10 @@
 Replaces the samplers the reference calls:
   * pm.sample(n, tune, chains=1, step=pm.NUTS())             models/bayesian_sgpr_hmc.py:73-78   (target: sgpr_vfe_logp_dlogp)
   * tfp.mcmc.HamiltonianMonteCarlo(L=10, step 0.01) + SimpleStepSizeAdaptation   models/sgp_hmc.py:67-83 (target: sgpmc)
-This round ships fixed-length HMC (it batches trivially: every chain takes the same number of leapfrogs, so C chains cost one
-launch sequence per leapfrog) with per-chain dual-averaging step sizes (target accept 0.8, pymc3/Stan constants) and windowed
-diagonal mass adaptation.  NUTS with per-chain tree masking is the next row; DESIGN.md says so.
+Two samplers: fixed-length HMC (`hmc_sample`; every chain takes the same number of leapfrogs, so C chains cost one launch sequence
+per leapfrog, and the whole trajectory can be replayed as one CUDA graph) and multinomial NUTS with pymc3's defaults
+(`nuts_sample`; lock-step tree doubling with per-chain masking).  Both use per-chain dual-averaging step sizes (target accept 0.8,
+pymc3/Stan constants) and windowed diagonal mass adaptation.
 """
 import math
 
@@ -35,8 +36,54 @@ class DualAveraging:
         return torch.exp(self.log_eps_bar)
 
 
+class GraphedTrajectory:
+    """L leapfrog steps of C lock-step chains replayed as ONE CUDA graph.
+
+    At the reference's own sizes (co2: N=545, M=100) a bound+gradient evaluation is ~90 short kernels: the arithmetic is
+    microseconds, the launch/host latency a millisecond.  Capturing the whole trajectory (L evaluations + the leapfrog updates)
+    removes the host from the inner loop.  Needs a sync-free target: a fixed jitter policy (pymc3's 1e-6, gpflow's 1e-5), for which
+    Engine.factor does no host read-back, and static shapes.  Inputs/outputs live in static buffers (copied in / cloned out)."""
+
+    def __init__(self, logp_dlogp, C, P, n_leapfrog, device, dtype=torch.float64):
+        self.f, self.L = logp_dlogp, int(n_leapfrog)
+        z = lambda *sh: torch.zeros(*sh, dtype=dtype, device=device)
+        self.x, self.p, self.g, self.eps, self.inv_mass = z(C, P), z(C, P), z(C, P), z(C), torch.ones(C, P, dtype=dtype, device=device)
+        self.graph, self.out = None, None
+
+    def _run(self):
+        xn, pn, gn, e = self.x, self.p, self.g, self.eps.unsqueeze(1)
+        lpn = None
+        for _ in range(self.L):
+            pn = pn + 0.5 * e * gn
+            xn = xn + e * pn * self.inv_mass
+            lpn, gn = self.f(xn)
+            pn = pn + 0.5 * e * gn
+        return xn, pn, lpn, gn
+
+    def capture(self, x, g):
+        """Warm up on a side stream at a valid point (x, g), then capture."""
+        self.x.copy_(x); self.g.copy_(g); self.p.zero_(); self.eps.fill_(1e-3)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+        return self
+
+    def __call__(self, x, p, g, eps, inv_mass):
+        self.x.copy_(x); self.p.copy_(p); self.g.copy_(g); self.eps.copy_(eps); self.inv_mass.copy_(inv_mass)
+        self.graph.replay()
+        return tuple(t.clone() for t in self.out)
+
+
 def hmc_sample(logp_dlogp, x0, n_samples, tune=500, n_leapfrog=10, step_size=0.01, target_accept=0.8, adapt_mass=True,
-               adaptation="dual_averaging", num_adaptation_steps=None, generator=None, progress=None):
+               adaptation="dual_averaging", num_adaptation_steps=None, generator=None, progress=None, cuda_graph=False):
     """Run C chains in lock-step.  logp_dlogp(x[C,P]) -> (logp[C], grad[C,P]) (rows with logp=-inf are rejected).
 
     Returns dict(samples[n_samples, C, P], logp[n_samples, C], accept_rate[C], step_size[C], n_evals, inv_mass[C,P]).
@@ -47,6 +94,7 @@ def hmc_sample(logp_dlogp, x0, n_samples, tune=500, n_leapfrog=10, step_size=0.0
     dev, dt = x.device, x.dtype
     lp, g = logp_dlogp(x)
     n_evals = 1
+    traj = GraphedTrajectory(logp_dlogp, C, P, n_leapfrog, dev, dt).capture(x, g) if (cuda_graph and x.is_cuda) else None
     eps = torch.full((C,), float(step_size), dtype=dt, device=dev)
     inv_mass = torch.ones(C, P, dtype=dt, device=dev)          # diagonal inverse metric (= posterior variance estimate)
     da = DualAveraging(eps, target_accept)
@@ -58,14 +106,18 @@ def hmc_sample(logp_dlogp, x0, n_samples, tune=500, n_leapfrog=10, step_size=0.0
     for it in range(tune + n_samples):
         p = torch.randn(C, P, dtype=dt, device=dev, generator=generator) / torch.sqrt(inv_mass)
         h0 = -lp + 0.5 * (p * p * inv_mass).sum(1)
-        xn, pn, lpn, gn = x, p, lp, g
-        e = eps.unsqueeze(1)
-        for _ in range(n_leapfrog):
-            pn = pn + 0.5 * e * gn
-            xn = xn + e * pn * inv_mass
-            lpn, gn = logp_dlogp(xn)
-            n_evals += 1
-            pn = pn + 0.5 * e * gn
+        if traj is not None:
+            xn, pn, lpn, gn = traj(x, p, g, eps, inv_mass)
+            n_evals += n_leapfrog
+        else:
+            xn, pn, lpn, gn = x, p, lp, g
+            e = eps.unsqueeze(1)
+            for _ in range(n_leapfrog):
+                pn = pn + 0.5 * e * gn
+                xn = xn + e * pn * inv_mass
+                lpn, gn = logp_dlogp(xn)
+                n_evals += 1
+                pn = pn + 0.5 * e * gn
         h1 = -lpn + 0.5 * (pn * pn * inv_mass).sum(1)
         dh = h0 - h1
         acc_prob = torch.where(torch.isfinite(dh), torch.exp(dh.clamp(max=0.0)), torch.zeros_like(dh))
@@ -102,6 +154,153 @@ def hmc_sample(logp_dlogp, x0, n_samples, tune=500, n_leapfrog=10, step_size=0.0
                 inv_mass=inv_mass, n_leapfrog=n_leapfrog)
 
 
+def _ckpt_range(n):
+    """Checkpoint slots of the iterative U-turn scheme for leaf n of a subtree built left-to-right: every balanced
+    sub-subtree that ENDS at an odd leaf n starts at an even leaf whose (momentum, running sum) was saved in slot
+    popcount(start >> 1).  Returns (idx_min, idx_max): save into idx_max when n is even, check idx_max..idx_min when n is odd."""
+    idx_max = bin(n >> 1).count("1")
+    t, m = 0, n
+    while m & 1:
+        t, m = t + 1, m >> 1
+    return idx_max - t + 1, idx_max
+
+
+def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_treedepth=10, step_size=None, adapt_mass=True,
+                max_energy_error=1000.0, generator=None, progress=None):
+    """No-U-turn sampler, C chains in lock-step, with the defaults of the sampler the reference calls: `pm.sample(n, tune=tune,
+    chains=1)` with `pm.NUTS()` (models/bayesian_sgpr_hmc.py:73-78, models/all_in_HMC.py:60): multinomial NUTS, uniform progressive
+    sampling inside a subtree and biased progressive sampling between the old tree and the new subtree, U-turn test
+    p_sum . v_edge <= 0 at both edges of every balanced subtree, divergence at |energy change| > 1000, max_treedepth 10,
+    step size by dual averaging to target_accept 0.8 from 0.25 / P^(1/4), statistic = mean over tree leaves of min(1, exp(-dE)).
+    The mass matrix is diagonal, adapted in windows (pymc3 adapts it with a running estimator; the window schedule differs).
+
+    Batching: one tree doubling = 2^j leapfrogs = 2^j BATCHED logp/dlogp calls shared by every chain; a chain whose tree has
+    stopped is masked out (its rows are still evaluated, which is what lock-step costs).  The U-turn checks inside a subtree use
+    the iterative checkpoint scheme (no recursion), so the leaf index - and hence the control flow - is identical for all chains.
+    Returns the hmc_sample dict plus tree_depth[n_samples, C], n_leapfrog[n_samples, C], diverging[n_samples, C]."""
+    x = x0.clone()
+    C, P = x.shape
+    dev, dt = x.device, x.dtype
+    U = lambda *sh: torch.rand(*sh, dtype=dt, device=dev, generator=generator)
+    lp, g = logp_dlogp(x)
+    n_evals = 1
+    eps0 = float(step_size) if step_size is not None else 0.25 / P ** 0.25
+    eps = torch.full((C,), eps0, dtype=dt, device=dev)
+    inv_mass = torch.ones(C, P, dtype=dt, device=dev)
+    da = DualAveraging(eps, target_accept)
+    samples = torch.empty(n_samples, C, P, dtype=dt, device=dev)
+    lps = torch.empty(n_samples, C, dtype=dt, device=dev)
+    depths = torch.zeros(n_samples, C, dtype=torch.int32, device=dev)
+    nleap = torch.zeros(n_samples, C, dtype=torch.int32, device=dev)
+    divs = torch.zeros(n_samples, C, dtype=torch.bool, device=dev)
+    acc_sum = torch.zeros(C, dtype=dt, device=dev)
+    windows = sorted({int(tune * f) for f in (0.25, 0.5, 0.75)} - {0}) if adapt_mass and tune >= 40 else []
+    win_start, buf = 0, []
+    ninf = torch.full((C,), -float("inf"), dtype=dt, device=dev)
+    K = max(max_treedepth, 1)
+
+    def turning(p_left, p_right, p_sum):
+        return ((p_sum * p_left * inv_mass).sum(1) <= 0) | ((p_sum * p_right * inv_mass).sum(1) <= 0)
+
+    for it in range(tune + n_samples):
+        p0 = torch.randn(C, P, dtype=dt, device=dev, generator=generator) / torch.sqrt(inv_mass)
+        e0 = -lp + 0.5 * (p0 * p0 * inv_mass).sum(1)
+        xl, pl, gl = x, p0, g
+        xr, pr, gr = x, p0, g
+        x_prop, lp_prop, g_prop = x, lp, g
+        log_w = torch.zeros(C, dtype=dt, device=dev)
+        p_sum = p0.clone()
+        sum_acc = torch.zeros(C, dtype=dt, device=dev)
+        n_leaf = torch.zeros(C, dtype=dt, device=dev)
+        depth = torch.zeros(C, dtype=torch.int32, device=dev)
+        diverged = torch.zeros(C, dtype=torch.bool, device=dev)
+        active = torch.ones(C, dtype=torch.bool, device=dev)
+        for j in range(max_treedepth):
+            if not bool(active.any()):
+                break
+            right = U(C) < 0.5
+            sgn = torch.where(right, torch.ones_like(eps), -torch.ones_like(eps))
+            e = (eps * sgn).unsqueeze(1)
+            r1 = right.unsqueeze(1)
+            xe, pe, ge = torch.where(r1, xr, xl), torch.where(r1, pr, pl), torch.where(r1, gr, gl)
+            s_log_w, s_p_sum = ninf.clone(), torch.zeros(C, P, dtype=dt, device=dev)
+            s_x, s_lp, s_g = xe, lp, ge
+            s_turn = torch.zeros(C, dtype=torch.bool, device=dev)
+            s_div = torch.zeros(C, dtype=torch.bool, device=dev)
+            building = active.clone()
+            p_ck = torch.zeros(K, C, P, dtype=dt, device=dev)
+            ps_ck = torch.zeros(K, C, P, dtype=dt, device=dev)
+            for n in range(2 ** j):
+                pn = pe + 0.5 * e * ge
+                xn = xe + e * pn * inv_mass
+                lpn, gn = logp_dlogp(xn)
+                n_evals += 1
+                pn = pn + 0.5 * e * gn
+                en = -lpn + 0.5 * (pn * pn * inv_mass).sum(1)
+                dlt = e0 - en                                              # log weight of the leaf
+                bad = ~torch.isfinite(dlt) | (dlt.abs() > max_energy_error)
+                s_div = s_div | (building & bad)
+                dlt = torch.where(bad, ninf, dlt)
+                good = building & ~bad
+                sum_acc = sum_acc + torch.where(building, torch.exp(dlt.clamp(max=0.0)), torch.zeros_like(dlt))
+                n_leaf = n_leaf + building.to(dt)
+                new_w = torch.logaddexp(s_log_w, dlt)
+                take = good & (torch.log(U(C)) < dlt - new_w)
+                t1 = take.unsqueeze(1)
+                s_x, s_lp, s_g = torch.where(t1, xn, s_x), torch.where(take, lpn, s_lp), torch.where(t1, gn, s_g)
+                s_log_w = torch.where(good, new_w, s_log_w)
+                g1 = good.unsqueeze(1)
+                s_p_sum = torch.where(g1, s_p_sum + pn, s_p_sum)
+                xe, pe, ge = torch.where(g1, xn, xe), torch.where(g1, pn, pe), torch.where(g1, gn, ge)
+                building = good
+                lo, hi = _ckpt_range(n)
+                if n % 2 == 0:
+                    p_ck[hi], ps_ck[hi] = pe, s_p_sum
+                else:
+                    tn = torch.zeros(C, dtype=torch.bool, device=dev)
+                    for i in range(hi, lo - 1, -1):
+                        tn = tn | turning(p_ck[i], pe, s_p_sum - ps_ck[i] + p_ck[i])
+                    s_turn = s_turn | (building & tn)
+                    building = building & ~tn
+            diverged = diverged | (active & s_div)
+            ok = active & ~s_turn & ~s_div
+            take = ok & (torch.log(U(C)) < s_log_w - log_w)
+            t1 = take.unsqueeze(1)
+            x_prop, lp_prop, g_prop = torch.where(t1, s_x, x_prop), torch.where(take, s_lp, lp_prop), torch.where(t1, s_g, g_prop)
+            log_w = torch.where(ok, torch.logaddexp(log_w, s_log_w), log_w)
+            o1 = ok.unsqueeze(1)
+            p_sum = torch.where(o1, p_sum + s_p_sum, p_sum)
+            okr, okl = (ok & right).unsqueeze(1), (ok & ~right).unsqueeze(1)
+            xr, pr, gr = torch.where(okr, xe, xr), torch.where(okr, pe, pr), torch.where(okr, ge, gr)
+            xl, pl, gl = torch.where(okl, xe, xl), torch.where(okl, pe, pl), torch.where(okl, ge, gl)
+            depth = depth + ok.to(torch.int32)
+            active = ok & ~turning(pl, pr, p_sum)
+        x, lp, g = x_prop, lp_prop, g_prop
+        acc_prob = sum_acc / n_leaf.clamp(min=1.0)
+        if it < tune:
+            eps = da.update(acc_prob)
+            if it == tune - 1:
+                eps = da.final()
+            if windows:
+                buf.append(x.clone())
+                if it + 1 in windows:
+                    S = torch.stack(buf[win_start:])
+                    if S.shape[0] >= 10:
+                        var = S.var(0, unbiased=True)
+                        nn_ = S.shape[0]
+                        inv_mass = (nn_ / (nn_ + 5.0)) * var + 1e-3 * (5.0 / (nn_ + 5.0))
+                        da = DualAveraging(eps, target_accept)
+                    win_start = len(buf)
+        else:
+            k = it - tune
+            samples[k], lps[k], depths[k], nleap[k], divs[k] = x, lp, depth, n_leaf.to(torch.int32), diverged
+            acc_sum += acc_prob
+        if progress is not None:
+            progress(it)
+    return dict(samples=samples, logp=lps, accept_rate=acc_sum / max(n_samples, 1), step_size=eps, n_evals=n_evals,
+                inv_mass=inv_mass, tree_depth=depths, n_leapfrog=nleap, diverging=divs)
+
+
 class HyperTrace:
     """Minimal pymc3-MultiTrace look-alike: len(trace), trace[i] -> {'ls', 'sig_f', 'sig_n'} (numpy, float64),
     trace.get_sampler_stats('step_size').  Built from unconstrained log-space draws x[n, D+2] of ONE chain."""
@@ -128,7 +327,8 @@ class HyperTrace:
         return torch.cat([v[:, :self.D], v[:, self.D:] ** 2], dim=1)
 
 
-def sample_hyper(X, y, Z, n_samples, tune, chains=1, n_leapfrog=10, step_size=0.02, engine=None, generator=None, seed_jitter=True):
+def sample_hyper(X, y, Z, n_samples, tune, chains=1, n_leapfrog=10, step_size=0.02, engine=None, generator=None, seed_jitter=True,
+                 cuda_graph=False, sampler="hmc", max_treedepth=10):
     """HMC over theta = (ls, sig_f, sig_n) on the collapsed VFE bound with pymc3's priors and transforms
     (models/bayesian_sgpr_hmc.py:58-80).  Start = prior test value (Gamma mean 2, HalfCauchy beta 1) + U(-1,1) jitter
     in unconstrained space (pymc3 init='jitter+adapt_diag').  Returns (list of HyperTrace per chain, raw result)."""
@@ -142,7 +342,11 @@ def sample_hyper(X, y, Z, n_samples, tune, chains=1, n_leapfrog=10, step_size=0.
         x0 = x0 + (torch.rand(chains, D + 2, dtype=torch.float64, device=dev, generator=generator) * 2.0 - 1.0)
     f = lambda xx: sgpr_vfe_logp_dlogp(xx, X, y, Z, engine=engine)
     t0 = time.perf_counter()
-    res = hmc_sample(f, x0, n_samples, tune=tune, n_leapfrog=n_leapfrog, step_size=step_size, generator=generator)
+    if sampler == "nuts":   # pm.NUTS() defaults (models/bayesian_sgpr_hmc.py:73-78)
+        res = nuts_sample(f, x0, n_samples, tune=tune, max_treedepth=max_treedepth, generator=generator)
+    else:
+        res = hmc_sample(f, x0, n_samples, tune=tune, n_leapfrog=n_leapfrog, step_size=step_size, generator=generator,
+                         cuda_graph=cuda_graph)
     dt = time.perf_counter() - t0
     res["seconds"] = dt
     traces = [HyperTrace(res["samples"][:, c], res["step_size"][c], dt) for c in range(chains)]

@@ -52,3 +52,19 @@ def sgpr_vfe_logp_dlogp(x, X, y, Z, jitter_policy="pymc3"):
     lp = sgpr_vfe_logp(x, X, y, Z, jitter_policy)
     (g,) = torch.autograd.grad(lp, x)
     return lp.detach(), g
+
+
+def all_in_hmc_logp(x, X, y, M, jitter_policy="pymc3"):
+    """models/all_in_HMC.py:47-60: theta AND the inducing inputs are sampled.  Free variables in declaration order:
+    ls_log__[D], sig_f_log__, sig_n_log__, Z[M, D] (untransformed, Normal(0, 1) elementwise, :57).  x = [D + 2 + M*D]."""
+    D = X.shape[1]
+    Z = x[D + 2:].reshape(M, D)
+    lpz = (-0.5 * Z * Z - 0.5 * math.log(2.0 * math.pi)).sum()
+    return sgpr_vfe_logp(x[:D + 2], X, y, Z, jitter_policy) + lpz
+
+
+def all_in_hmc_logp_dlogp(x, X, y, M, jitter_policy="pymc3"):
+    x = x.detach().clone().requires_grad_(True)
+    lp = all_in_hmc_logp(x, X, y, M, jitter_policy)
+    (g,) = torch.autograd.grad(lp, x)
+    return lp.detach(), g

@@ -141,3 +141,56 @@ def test_bayesian_svgp_five_draws_per_batch():
     assert model.inducing_inputs.grad is not None and torch.isfinite(model.inducing_inputs.grad).all()
     assert model.log_theta.q_mu.grad is not None          # through the KL term
     assert model.variational_mean.grad.abs().sum() > 0
+
+
+def test_hmc_cuda_graph_trajectory_is_identical_to_eager():
+    """hmc.GraphedTrajectory: the L-leapfrog trajectory replayed as one CUDA graph runs the same kernels in the same order as the
+    eager loop, so with the same RNG stream the chains are bit-identical (fixed pymc3 jitter -> no host read-back in factor)."""
+    import ggp_b200
+    from ggp_b200.functions import sgpr_vfe_logp_dlogp
+    from ggp_b200.hmc import hmc_sample
+    X, y, Z, th = make_problem(300, 24, 2, seed=11)
+    X, y, Z = X.to(DEV), y.to(DEV), Z.to(DEV)
+    eng = ggp_b200.Engine.get(torch.device(DEV))
+    f = lambda xx: sgpr_vfe_logp_dlogp(xx, X, y, Z, engine=eng, group=False)
+    x0 = torch.zeros(3, 4, dtype=torch.float64, device=DEV)
+    x0[:, 2:] = torch.tensor([0.0, -1.0], dtype=torch.float64, device=DEV)
+    runs = []
+    for use_graph in (False, True):
+        g = torch.Generator(device=DEV).manual_seed(5)
+        runs.append(hmc_sample(f, x0, 6, tune=6, n_leapfrog=4, step_size=0.02, adapt_mass=False, generator=g, cuda_graph=use_graph))
+    assert torch.equal(runs[0]["samples"], runs[1]["samples"]) and torch.equal(runs[0]["logp"], runs[1]["logp"])
+    assert torch.isfinite(runs[1]["logp"]).all() and runs[1]["n_evals"] == runs[0]["n_evals"]
+
+
+def test_all_in_hmc_target_matches_oracle():
+    """models/all_in_HMC.py:47-60: theta and Z sampled together; logp and its gradient w.r.t. (log theta, Z) vs oracle autograd."""
+    import ggp_b200
+    from ggp_b200.functions import all_in_hmc_logp_dlogp
+    from oracle import priors
+    N, M, D = 400, 30, 2
+    X, y, _, _ = make_problem(N, M, D, seed=3)
+    g = torch.Generator().manual_seed(9)
+    xs = torch.cat([0.3 * torch.randn(2, D + 2, dtype=torch.float64, generator=g), torch.randn(2, M * D, dtype=torch.float64, generator=g)], 1)
+    lp, dlp = all_in_hmc_logp_dlogp(xs.to(DEV), X.to(DEV), y.to(DEV), M)
+    for c in range(2):
+        lo, go = priors.all_in_hmc_logp_dlogp(xs[c], X, y, M)
+        assert relerr(lp[c], lo) < 1e-8
+        assert relerr(dlp[c, :D + 2], go[:D + 2]) < 1e-7 and relerr(dlp[c, D + 2:], go[D + 2:]) < 1e-7
+
+
+def test_nuts_on_the_collapsed_bound_agrees_with_fixed_length_hmc():
+    """pm.NUTS() on the VFE target (models/bayesian_sgpr_hmc.py:73-78): the batched lock-step NUTS and the fixed-length HMC sample
+    the same posterior over (log ell, log sig_f, log sig_n); their posterior means agree within Monte-Carlo error."""
+    from ggp_b200.hmc import sample_hyper
+    X, y, Z, th = make_problem(250, 16, 1, seed=21, noise=0.3)
+    X, y, Z = X.to(DEV), y.to(DEV), Z.to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(8)
+    _, rn = sample_hyper(X, y, Z, n_samples=150, tune=150, chains=6, generator=gen, sampler="nuts", max_treedepth=6)
+    _, rh = sample_hyper(X, y, Z, n_samples=150, tune=150, chains=6, n_leapfrog=12, step_size=0.05, generator=gen, cuda_graph=True)
+    assert torch.isfinite(rn["logp"]).all() and float(rn["diverging"].float().mean()) < 0.05
+    assert 1 <= int(rn["tree_depth"].min()) and int(rn["tree_depth"].max()) <= 6
+    mn, mh = rn["samples"].reshape(-1, 3).mean(0), rh["samples"].reshape(-1, 3).mean(0)
+    sd = rh["samples"].reshape(-1, 3).std(0)
+    assert ((mn - mh).abs() < 0.5 * sd + 0.05).all(), (mn, mh, sd)
+    assert 0.55 < float(rn["accept_rate"].mean()) < 0.98

@@ -148,3 +148,18 @@ def test_sgpmc_density_is_finite_and_differentiable():
     assert torch.isfinite(lp) and torch.isfinite(gv).all() and torch.isfinite(gr).all()
     lpb, _, _ = sgpmc.sgpmc_logp_dlogp(v, raw, X, (y > 0).double(), Z, likelihood="bernoulli")
     assert torch.isfinite(lpb)
+
+
+def test_all_in_hmc_logp_is_vfe_logp_plus_standard_normal_on_Z():
+    """models/all_in_HMC.py:57: Z ~ Normal(0, 1) elementwise on top of the theta target; gradient by finite differences."""
+    from oracle import priors
+    X, y, Z, th = make_problem(120, 7, 2, seed=2)
+    D, M = 2, 7
+    x = torch.cat([torch.tensor([0.1, -0.2, 0.05, -0.8], dtype=torch.float64), Z.reshape(-1)])
+    lp, g = priors.all_in_hmc_logp_dlogp(x, X, y, M)
+    base = priors.sgpr_vfe_logp(x[:D + 2], X, y, Z)
+    assert abs(float(lp - base - (-0.5 * Z * Z - 0.5 * math.log(2 * math.pi)).sum())) < 1e-9
+    for i in [0, 3, 5, 11]:
+        e = torch.zeros_like(x); e[i] = 1e-6
+        fd = (priors.all_in_hmc_logp(x + e, X, y, M) - priors.all_in_hmc_logp(x - e, X, y, M)) / 2e-6
+        assert abs(float(fd - g[i])) < 1e-5 * max(1.0, abs(float(g[i])))
