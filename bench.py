@@ -159,6 +159,8 @@ def main():
     ap.add_argument("--rows", type=int, default=N_FULL, help="override N (debug only; the headline number needs the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hmc", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("GGP_BENCH_PRECISION", "fp64"), choices=["fp64", "fp64_i8"],
+                    help="fp64: FP64 DMMA tensor path; fp64_i8: FP64-class exact int8 slicing on tcgen05 (csrc/gemm_i8.cuh)")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -186,7 +188,7 @@ def main():
     thh = torch.tensor(syn.theta_trained_like(D_IN)).pin_memory()
     X, y, Z, th = Xh.to(dev), yh.to(dev), Zh.to(dev), thh.to(dev)
     n_local = hi - lo
-    eng = ggp_b200.Engine.get(dev)
+    eng = ggp_b200.Engine.get(dev, precision=args.precision)
     group = None if world > 1 else False
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 

@@ -21,7 +21,7 @@ class GgpCfg(ctypes.Structure):
 
 
 KERNELS = {"rbf": 0, "matern32": 1, "matern52": 2}
-PRECISIONS = {"fp64": 0, "tf32x3": 1}
+PRECISIONS = {"fp64": 0, "tf32x3": 1, "fp64_i8": 2}
 LIKELIHOODS = {"gaussian": 0, "bernoulli": 1}
 
 # every symbol include/ggp_b200.h declares: name -> (restype, argtypes)
@@ -44,6 +44,7 @@ SYMBOLS = {
     "ggp_chol_batched": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "ggp_gemm_nt": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _D, _D]),
     "ggp_gemm_nt_ex": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _D, _D, _I, _I, _I, _I64]),
+    "ggp_gemm_nt_i8": (_I, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I]),
     "ggp_kernel_matrix": (_I, [_P, _CFG, _P, _P, _I64, _P, _I64, _P, _I, _P]),
     "ggp_profile_enable": (_I, [_P, _I]),
     "ggp_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),

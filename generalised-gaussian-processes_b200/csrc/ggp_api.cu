@@ -13,6 +13,7 @@
 #include "dense_mm.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_tma.cuh"
+#include "gemm_i8.cuh"
 #include "kernel_tiles.cuh"
 #include "misc.cuh"
 #include "svgp.cuh"
@@ -61,6 +62,13 @@ struct ggp_handle {
   int64_t kc_n = 0;
   int kc_batch = 0, kc_kind = 0;
   double *sv[5] = {0, 0, 0, 0, 0}, *rowout = 0;
+  // int8 digit planes of the sliced-integer path (GGP_PREC_FP64_I8; gemm_i8.cuh)
+  char* arena_i8 = nullptr;
+  size_t arena_i8_bytes = 0;
+  int8_t *Lq = 0, *Pq = 0, *Atq = 0, *Kq = 0;
+  int *eL = 0, *eP = 0;
+  int8_t* kq_all = nullptr;
+  size_t kq_all_bytes = 0;
   int nsv = 0;
   // instrumentation
   long long launches = 0;
@@ -353,6 +361,51 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
   return 0;
 }
 
+
+// ---- sliced-integer (tcgen05 kind::i8) GEMM: host side -----------------------------------------------------------------
+// digit planes [I8_NS][rows][ld bytes] (plane stride in bytes) as a 3-D map (k, row, plane), 64-byte swizzle, box 64 x box_rows x 1;
+// rows / k beyond the extents given here are zero-filled by the TMA unit
+static bool make_i8_map(CUtensorMap* tm, const int8_t* ptr, int64_t rows, int64_t kbytes, int64_t ld, int64_t plane, int box_rows) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc || !ptr || rows < 1 || kbytes < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 15) || (plane & 15)) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)kbytes, (cuuint64_t)rows, (cuuint64_t)I8_NS};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)plane};
+  const cuuint32_t box[3] = {(cuuint32_t)I8_BKB, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct I8Operand { const int8_t* q; int64_t rows, ld, plane; };
+
+static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Operand& A, const I8Operand& B) {
+  if (p.K < 1 || p.M < 1 || p.N < 1) return 0;
+  if (p.K > I8_MAX_K) return fail(-4, "launch_i8: k extent exceeds the exact int32 accumulation bound (65536)");
+  p.tiles_m = (p.M + I8_BM - 1) / I8_BM;
+  p.tiles_n = (p.N + I8_BN - 1) / I8_BN;
+  int tiles = p.tiles_m * p.tiles_n;
+  if (p.sym) {
+    tiles = 0;
+    for (int tm = 0; tm < p.tiles_m; ++tm) tiles += std::max(0, p.tiles_n - 2 * tm);
+  }
+  if (p.splits < 1) p.splits = 1;
+  p.total = tiles * p.splits;
+  CUtensorMap tmA, tmB;
+  if (!make_i8_map(&tmA, A.q, A.rows, p.K, A.ld, A.plane, I8_BM) || !make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN))
+    return fail(-4, "launch_i8: operand planes cannot be described by a tensor map (alignment)");
+  const int grid = std::min(p.total, h->sm_count);
+  if (epi == I8_EPI_F64) k_gemm_i8<I8_EPI_F64><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
+  else if (epi == I8_EPI_SLICE) k_gemm_i8<I8_EPI_SLICE><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
+  else k_gemm_i8<I8_EPI_MOMENTS><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
+  CKL();
+  return 0;
+}
+
+static bool use_i8(const ggp_handle* h, const ggp_cfg* cfg, int d, int batch) {
+  return cfg && cfg->precision == GGP_PREC_FP64_I8 && batch == 1 && h->Mp >= I8_BM && d <= I8_MAX_D && h->arena_i8 != nullptr;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -372,6 +425,9 @@ int ggp_create(ggp_handle_t** out, int device) {
   CK(cudaFuncSetAttribute(k_gemm_tma<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
   CK(cudaFuncSetAttribute(k_gemm_tma<EPI_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
   CK(cudaFuncSetAttribute(k_build_kc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_SLICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
   *out = h;
   return 0;
 }
@@ -383,6 +439,8 @@ int ggp_destroy(ggp_handle_t* h) {
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->arena) cudaFree(h->arena);
   if (h->kc_all) cudaFree(h->kc_all);
+  if (h->kq_all) cudaFree(h->kq_all);
+  if (h->arena_i8) cudaFree(h->arena_i8);
   delete h;
   return 0;
 }
@@ -437,6 +495,44 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
       h->kc_all_bytes = 0;
     }
   }
+  // sliced-integer path: digit planes of L^{-1}, P, one chunk of A^T and one chunk of k(X,Z) (+ the whole-N cache next to kc_all)
+  if (cfg && cfg->precision == GGP_PREC_FP64_I8 && batch == 1 && p.Mp >= I8_BM) {
+    const size_t MMq = align_up((size_t)I8_NS * p.Mp * p.Mp, 256), CHq = align_up((size_t)I8_NS * p.Mp * p.nc, 256),
+                 EX = align_up((size_t)p.Mp * 4, 256);
+    const size_t need = 2 * MMq + 2 * CHq + 2 * EX;
+    if (need > h->arena_i8_bytes) {
+      if (h->arena_i8) CK(cudaFree(h->arena_i8));
+      h->arena_i8 = nullptr;
+      h->arena_i8_bytes = 0;
+      CK(cudaMalloc((void**)&h->arena_i8, need));
+      h->arena_i8_bytes = need;
+    }
+    char* q = h->arena_i8;
+    h->Lq = (int8_t*)q; q += MMq;
+    h->Pq = (int8_t*)q; q += MMq;
+    h->Atq = (int8_t*)q; q += CHq;
+    h->Kq = (int8_t*)q; q += CHq;
+    h->eL = (int*)q; q += EX;
+    h->eP = (int*)q;
+    if (h->kc_all) {
+      const size_t needq = (size_t)h->kc_rows * p.Mp * I8_NS;
+      const size_t budget = (size_t)cfg->tile_cache_mib * 1024 * 1024;
+      bool ok = 2 * needq <= budget;
+      if (ok && needq > h->kq_all_bytes) {
+        if (h->kq_all) CK(cudaFree(h->kq_all));
+        h->kq_all = nullptr;
+        h->kq_all_bytes = 0;
+        if (cudaMalloc((void**)&h->kq_all, needq) == cudaSuccess) h->kq_all_bytes = needq;
+        else { (void)cudaGetLastError(); ok = false; }
+      }
+      if (!ok) {   // the cache must hold both the FP64 tiles and their digit planes, or neither
+        CK(cudaFree(h->kc_all));
+        h->kc_all = nullptr;
+        h->kc_all_bytes = 0;
+        if (h->kq_all) { CK(cudaFree(h->kq_all)); h->kq_all = nullptr; h->kq_all_bytes = 0; }
+      }
+    }
+  }
   double** slots[] = {&h->L, &h->Linv, &h->LinvT, &h->Wk, &h->Bm, &h->LBinv, &h->LBinvT, &h->Binv, &h->PA, &h->Gbar, &h->T1,
                       &h->P, &h->Gzz, &h->Tblk, &h->bvec, &h->cvec, &h->beta, &h->u, &h->yty, &h->ds2, &h->rowacc, &h->Kc,
                       &h->At, &h->Spart, &h->mom_part, &h->mom_acc, &h->rk};
@@ -478,7 +574,9 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   if (!h || !Z || !theta || !partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass1: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_pass1: handle not reserved for this shape");
   const int kind = cfg ? cfg->kernel : 0;
-  if (cfg && cfg->precision != GGP_PREC_FP64) return fail(-3, "ggp_sgpr_pass1: only GGP_PREC_FP64 is implemented");
+  if (cfg && cfg->precision == GGP_PREC_TF32X3)
+    return fail(-3, "ggp_sgpr_pass1: GGP_PREC_TF32X3 is not offered: it cannot meet the gradient tolerance (DESIGN.md 4b); use "
+                    "GGP_PREC_FP64 (DMMA) or GGP_PREC_FP64_I8 (exact int8 slicing on tcgen05)");
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc, splits = h->splits;
   const int64_t sM = (int64_t)Mp * Mp;
@@ -486,11 +584,64 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   CK(cudaMemsetAsync(h->bvec, 0, (size_t)batch * m * 8, st));
   k_sumsq<<<1, 1024, 0, st>>>(y, n_local, h->yty);
   CKL();
+  const bool i8 = use_i8(h, cfg, d, batch);
+  int eK = 0, eA = 0;
+  if (i8) {
+    // fixed exponents of the bounded operands: k(x,z) <= sf2 and |A[m,n]| <= sqrt(k_nn) = sqrt(sf2) (theta is read on the host: one
+    // scalar; the evaluation is synchronous w.r.t. theta anyway through the jitter ladder) -- see gemm_i8.cuh
+    double sf2 = 1.0;
+    CK(cudaMemcpyAsync(&sf2, theta + d, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    eK = ilogb(sf2) + 2;
+    eA = ilogb(sqrt(sf2)) + 3;
+    ProfScope ps(h, st, CAT_BUILD);
+    k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->Linv, Mp, Mp, Mp, h->Lq, Mp, (int64_t)Mp * Mp, Mp, h->eL);
+    CKL();
+  }
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
     double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
     const int64_t sK = h->kc_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
     { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
+    if (i8) {
+      int8_t* Kq_c = h->kq_all ? h->kq_all + c0 * Mp : h->Kq;
+      const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
+      {
+        ProfScope ps(h, st, CAT_BUILD);
+        const int64_t nthr = (int64_t)nv * (Mp / 16);
+        k_slice_fixed<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Kc_c, nv, Mp, Mp, Kq_c, Mp, plK, theta, d);
+        CKL();
+      }
+      const int ntn = (nv + I8_BN - 1) / I8_BN;
+      {   // A^T digits [m x nv] = L^{-1} (lower) x Kc^T, fused b-partials = A y
+        I8P t;
+        memset(&t, 0, sizeof(t));
+        t.M = m; t.N = nv; t.K = Mp; t.lower_a = 1; t.splits = 1;
+        t.ea = h->eL; t.eb0 = eK; t.alpha = 1.0;
+        t.Oq = h->Atq; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo = eA;
+        t.yv = y + c0; t.rowdot = h->mom_part;
+        ProfScope ps(h, st, CAT_TRMM);
+        RUN(launch_i8(h, st, I8_EPI_SLICE, t, {h->Lq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK}));
+      }
+      {   // S_split += A A^T (tiles touching the upper triangle)
+        I8P sy;
+        memset(&sy, 0, sizeof(sy));
+        sy.M = m; sy.N = m; sy.K = nv; sy.sym = 1;
+        int tiles = 0;
+        const int tmn = (m + I8_BM - 1) / I8_BM, tnn = (m + I8_BN - 1) / I8_BN;
+        for (int tm = 0; tm < tmn; ++tm) tiles += std::max(0, tnn - 2 * tm);
+        sy.splits = std::max(1, std::min(std::min(splits, h->sm_count / std::max(1, tiles)), (nv + 4 * I8_BKB - 1) / (4 * I8_BKB)));
+        sy.ea0 = eA; sy.eb0 = eA; sy.alpha = 1.0; sy.beta = 1.0;
+        sy.C = h->Spart; sy.ldc = Mp; sy.sSplit = sM;
+        const I8Operand A{h->Atq, m, nc, (int64_t)Mp * nc};
+        ProfScope ps(h, st, CAT_SYRK);
+        RUN(launch_i8(h, st, I8_EPI_F64, sy, A, A));
+      }
+      ProfScope ps_o(h, st, CAT_OTHER);
+      k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, 0, ntn, m, h->bvec);
+      CKL();
+      continue;
+    }
     // At[m x nv] = Linv[m x m] * Kc[nv x m]^T   (k clipped to the lower triangle)
     GemmP t = gemm_basic(h->Linv, Mp, sM, Kc_c, Mp, sK, h->At, nc, (int64_t)nc * Mp, m, nv, m, 1.0, 0.0,
                          KM_A_LOWER);
@@ -583,11 +734,53 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   // the tiles cached by the pass 1 of this evaluation (same operands, same handle, no factor() since) are reused as they are
   const bool cached = h->kc_all && h->kc_valid && h->kc_X == X && h->kc_Z == Z && h->kc_theta == theta && h->kc_n == n_local &&
                       h->kc_batch == batch && h->kc_kind == kind;
+  const bool i8 = use_i8(h, cfg, d, batch);
+  int eK = 0;
+  if (i8) {
+    double sf2 = 1.0;
+    CK(cudaMemcpyAsync(&sf2, theta + d, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    eK = ilogb(sf2) + 2;
+    ProfScope ps(h, st, CAT_BUILD);
+    k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->P, Mp, Mp, Mp, h->Pq, Mp, (int64_t)Mp * Mp, Mp, h->eP);
+    CKL();
+  }
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
     double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
     const int64_t sK = h->kc_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
     if (!cached) { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
+    if (i8) {
+      int8_t* Kq_c = h->kq_all ? h->kq_all + c0 * Mp : h->Kq;
+      const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
+      if (!cached) {
+        ProfScope ps(h, st, CAT_BUILD);
+        const int64_t nthr = (int64_t)nv * (Mp / 16);
+        k_slice_fixed<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Kc_c, nv, Mp, Mp, Kq_c, Mp, plK, theta, d);
+        CKL();
+      }
+      const double* Kmul = Kc_c;
+      if (kind != GGP_KERNEL_RBF) {
+        ProfScope ps(h, st, CAT_BUILD);
+        dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
+        const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
+        k_build_kc<<<grid, KT_THREADS, smem, st>>>(X + c0 * d, nv, nv, d, Z, m, theta, kind, h->At, Mp, (int64_t)nc * Mp, 1);
+        CKL();
+        Kmul = h->At;
+      }
+      I8P g8;
+      memset(&g8, 0, sizeof(g8));
+      g8.M = m; g8.N = nv; g8.K = Mp; g8.n_major = 1; g8.splits = 1;
+      g8.ea = h->eP; g8.eb0 = eK; g8.alpha = 1.0;
+      g8.u = h->u; g8.yv = y + c0; g8.Kmul = Kmul; g8.ldk = Mp; g8.Xc = X + c0 * d; g8.d = d;
+      g8.mom = h->mom_part; g8.sMomTile = cnt;
+      { ProfScope ps(h, st, CAT_BWD); RUN(launch_i8(h, st, I8_EPI_MOMENTS, g8, {h->Pq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK})); }
+      ProfScope ps_o(h, st, CAT_OTHER);
+      k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, 0, (nv + I8_BN - 1) / I8_BN, cnt,
+                                                                                  h->mom_acc);
+      CKL();
+      continue;
+    }
     const int ntiles = (nv + BN - 1) / BN;
     GemmP g = gemm_basic(h->P, Mp, sM, Kc_c, Mp, sK, nullptr, 0, 0, m, nv, m, 1.0, 0.0);
     g.n_major = 1;   // all row tiles of one chunk-row tile back to back: each k(X,Z) tile comes from HBM once, then from L2
@@ -826,6 +1019,35 @@ int ggp_gemm_nt_ex(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
   p.sSplit = split_stride;
   p.heavy_first = (kmode & KM_A_LOWER) ? 1 : 0;
   return launch_gemm(h, (cudaStream_t)stream, EPI_STORE, p, 1);
+}
+
+int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                   int64_t ldc, int mm, int nn, int kk) {
+  if (!h || !A || !B || !C) return fail(-1, "ggp_gemm_nt_i8: NULL argument");
+  if (mm < 1 || nn < 1 || kk < 1 || kk > I8_MAX_K) return fail(-2, "ggp_gemm_nt_i8: bad shape (1 <= kk <= 65536)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t kp = (kk + 63) / 64 * 64;
+  int8_t *qa = nullptr, *qb = nullptr;
+  int *ea = nullptr, *eb = nullptr;
+  CK(cudaMalloc((void**)&qa, (size_t)I8_NS * mm * kp));
+  CK(cudaMalloc((void**)&qb, (size_t)I8_NS * nn * kp));
+  CK(cudaMalloc((void**)&ea, (size_t)mm * 4));
+  CK(cudaMalloc((void**)&eb, (size_t)nn * 4));
+  k_slice_rows<<<(mm + 7) / 8, 256, 0, st>>>(A, mm, kk, lda, qa, kp, (int64_t)mm * kp, (int)kp, ea);
+  CKL();
+  k_slice_rows<<<(nn + 7) / 8, 256, 0, st>>>(B, nn, kk, ldb, qb, kp, (int64_t)nn * kp, (int)kp, eb);
+  CKL();
+  I8P p;
+  memset(&p, 0, sizeof(p));
+  p.M = mm; p.N = nn; p.K = (int)kp; p.splits = 1;
+  p.ea = ea; p.eb = eb; p.alpha = 1.0; p.beta = 0.0;
+  p.C = C; p.ldc = ldc;
+  int rc = launch_i8(h, st, I8_EPI_F64, p, {qa, mm, kp, (int64_t)mm * kp}, {qb, nn, kp, (int64_t)nn * kp});
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(qa); cudaFree(qb); cudaFree(ea); cudaFree(eb);
+  if (rc != 0) return rc;
+  CK(e);
+  return 0;
 }
 
 int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X1, int64_t n1, const double* X2,

@@ -290,6 +290,15 @@ class Engine:
                                           int(split_stride)), "ggp_gemm_nt_ex")
         return C
 
+    def gemm_nt_i8(self, A, B):
+        """C = A B^T through the sliced-integer tcgen05 path (FP64-class accuracy; tests / probes)."""
+        A, B = _f64c(A, self.device), _f64c(B, self.device)
+        C = torch.empty(A.shape[0], B.shape[0], dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ggp_gemm_nt_i8(self.h, _stream(), _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(C), C.stride(0),
+                                          A.shape[0], B.shape[0], A.shape[1]), "ggp_gemm_nt_i8")
+        return C
+
     def kernel_matrix(self, X1, X2, theta):
         dev = self.device
         X1, X2, theta = _f64c(X1, dev), _f64c(X2, dev), _f64c(theta, dev)
