@@ -2,10 +2,11 @@
 //     C[i,j] = sum_k A[i,k] * B[j,k]
 // tcgen05.mma has no f64 kind, and the DMMA path (gemm_tma.cuh) already keeps the FP64 tensor pipe 88-94 % busy; this is the route
 // past that roofline that still meets the 1e-8 parity budget.
-//   * operands: I8_NS signed 7-bit digits of a row-scaled fixed-point value, x = 2^e * sum_i d_i 2^(-7 (i+1)), |d_i| <= 64, stored as
+//   * operands: I8_NS balanced 7-bit digits (|d_i| <= 64) of a row-scaled fixed-point value,
+//     x = 2^e * sum_i d_i 2^(-7 (i+1)), stored as
 //     digit PLANES [I8_NS][rows][K] of int8, K contiguous (k_slice_rows / k_build_kc_i8 / the EPI_SLICE epilogue below);
 //   * tcgen05.mma kind::i8 (SASS UTCIMMA): 128 x N x 32 products, int32 accumulators in TMEM.  All digit pairs (i, j) of one
-//     significance level l = i + j are accumulated EXACTLY in one accumulator (|d|^2 (l+1) K <= 4096 * 8 * K < 2^31 for K <= 2^16),
+//     significance level l = i + j are accumulated EXACTLY in one accumulator (|d|^2 (l+1) K <= 4096 * 8 * K < 2^31 for K < 2^16),
 //     so a 128 x 64 output tile owns I8_NS accumulators = 512 TMEM columns;
 //   * digit i of A is multiplied against digits 0..NS-1-i of B in ONE wide MMA: the B digit tiles are consecutive K-major tiles in
 //     shared memory (= one tall tile) and their products belong to consecutive levels (= consecutive accumulator columns), which
@@ -31,9 +32,12 @@ constexpr int I8_STAGE_BYTES = I8_NS * (I8_A_BYTES + I8_B_BYTES);
 constexpr int I8_THREADS = 192;
 constexpr int I8_MAX_D = 32;                   // input dimension limit of the moments epilogue (shared-memory staging of X)
 constexpr int I8_EPI_SMEM = I8_BN * (I8_MAX_D + 1) * 8;
-constexpr int I8_SMEM = I8_STAGES * I8_STAGE_BYTES + 1024 + 256 + I8_EPI_SMEM;
+constexpr int I8_WSTAGE_LD = 12;               // doubles per staged W row (8 used): 24-word stride = conflict-free DMMA fragment loads
+constexpr int I8_WSTAGE_BYTES = 128 * I8_WSTAGE_LD * 8;
+constexpr int I8_SMEM = I8_STAGES * I8_STAGE_BYTES + 1024 + 256 + I8_EPI_SMEM + I8_WSTAGE_BYTES;
+static_assert(I8_SMEM <= 232448, "shared memory budget (227 KB)");
 constexpr int I8_TMEM_COLS = 512;
-constexpr int I8_MAX_K = 65536;                // exact int32 accumulation bound
+constexpr int I8_MAX_K = 32768;                // exact int32 accumulation bound (see i8_digits)
 static_assert(I8_NS * I8_BN <= 512, "level accumulators must fit TMEM");
 
 enum { I8_EPI_F64 = 0, I8_EPI_SLICE = 1, I8_EPI_MOMENTS = 2 };
@@ -55,7 +59,15 @@ struct I8P {
   const double* yv; double* rowdot;      // rowdot[tn][M]
   // I8_EPI_MOMENTS: W = (alpha * acc + u[row] * yv[col]) * Kmul[col][row];  mom[tn][row][:] = sum_col W * [1, x_col, x_col^2]
   const double* u; const double* Kmul; int64_t ldk; const double* Xc; int d; double* mom; int64_t sMomTile;
+  int serial_epi;                        // 1: hand TMEM back only after the whole epilogue (FP64 epilogue math and the running
+                                         // UTCIMMA stream throttle each other on the tensor / FP64 pipe: measured 10x slower when overlapped)
+  long long* dbg;                        // developer timeline (CTA 0): [role][item][4] clock64 stamps, or NULL
 };
+constexpr int I8_DBG_ITEMS = 16;
+#define I8_STAMP(role, item, slot)                                                                              \
+  do {                                                                                                          \
+    if (p.dbg && blockIdx.x == 0 && (item) < I8_DBG_ITEMS) p.dbg[((role) * I8_DBG_ITEMS + (item)) * 4 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void i8_mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -129,28 +141,42 @@ __device__ __forceinline__ void i8_decode(const I8P& p, int w, I8Item& o) {
   o.kb_hi = min(nkb, o.kb_lo + per);
 }
 
-// signed 7-bit digits of v (|v| < 1/2), most significant first
+// Balanced 7-bit digits of v (|v| < 1/2), most significant first: t = rn(v 2^56) = sum_i d_i 2^(7 (7-i)) with d_1..d_7 in
+// [-64, 63] and |d_0| <= 64.  Adding C = sum_{i>=1} 64 * 2^(7 (7-i)) first turns the balanced recoding (carries) into plain bit
+// fields: d_i = field_i(t + C) - 64, d_0 = (t + C) >> 49.  One conversion, one 64-bit add, three integer ops per digit.
+// Balanced digits matter: the digit pairs with i + j >= NS are dropped, and with zero-mean digits what is dropped is zero-mean
+// (with unsigned fields it is a one-sided bias that grows linearly in K: measured 50x worse).
+// Exactness of the level sums: |d_i d_j| <= 4096, at most 8 pairs per level -> K < 2^31 / 2^15 = 65536 (I8_MAX_K = 32768).
 __device__ __forceinline__ void i8_digits(double v, int8_t (&dg)[I8_NS]) {
-#pragma unroll
-  for (int i = 0; i < I8_NS; ++i) {
-    v *= 128.0;
-    const double r = rint(v);
-    v -= r;
-    dg[i] = (int8_t)(int)r;
-  }
+  static_assert(I8_NS == 8, "56-bit fixed point");
+  const long long t = __double2ll_rn(v * 72057594037927936.0) + 283691315109952ll;   // v * 2^56 + C, C = 64 (2^49 - 1) / 127
+  const unsigned lo = (unsigned)((unsigned long long)t & 0x0FFFFFFFull);   // bits 0..27  -> digits 7..4
+  const int hi = (int)(t >> 28);                                            // bits 28..55 -> digits 3..0
+  dg[7] = (int8_t)((int)(lo & 127u) - 64);
+  dg[6] = (int8_t)((int)((lo >> 7) & 127u) - 64);
+  dg[5] = (int8_t)((int)((lo >> 14) & 127u) - 64);
+  dg[4] = (int8_t)((int)((lo >> 21) & 127u) - 64);
+  dg[3] = (int8_t)((hi & 127) - 64);
+  dg[2] = (int8_t)(((hi >> 7) & 127) - 64);
+  dg[1] = (int8_t)(((hi >> 14) & 127) - 64);
+  dg[0] = (int8_t)(hi >> 21);
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const I8P p) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round-trip would turn every later access into
+  // a generic load that the compiler must order against the global stores of the epilogue)
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(base + I8_STAGES * I8_STAGE_BYTES);
   uint64_t* empty = full + I8_STAGES;
   uint64_t* tmem_full = empty + I8_STAGES;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  double* xs = reinterpret_cast<double*>(base + I8_STAGES * I8_STAGE_BYTES + 256);   // [I8_BN][d + 1]: x rows and y of the tile
+  double* xs = reinterpret_cast<double*>(base + I8_STAGES * I8_STAGE_BYTES + 256);   // [I8_BN][d]: x rows of the tile
+  double* ys = xs + I8_BN * I8_MAX_D;                                                  // [I8_BN]
+  double* wstage = xs + I8_EPI_SMEM / 8;                                              // [4 warps][32 rows][I8_WSTAGE_LD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
@@ -200,8 +226,10 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       I8Item it;
       i8_decode(p, w, it);
       if (it.kb_hi <= it.kb_lo) continue;
+      if (lane == 0) I8_STAMP(0, item, 0);
       if (item > 0) i8_mbar_wait(tmem_empty, (item - 1) & 1);   // the epilogue has drained the previous tile's accumulators
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+      if (lane == 0) I8_STAMP(0, item, 1);
       for (int kb = it.kb_lo; kb < it.kb_hi; ++kb, ++n) {
         const int s = n % I8_STAGES;
         i8_mbar_wait(&full[s], (n / I8_STAGES) & 1);
@@ -226,9 +254,11 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           i8_umma_commit(&empty[s]);                            // frees the stage once the MMAs that read it are done
           if (kb == it.kb_hi - 1) i8_umma_commit(tmem_full);    // accumulators of this tile complete
+          if (kb == it.kb_lo) I8_STAMP(0, item, 2);
         }
         __syncwarp();
       }
+      if (lane == 0) I8_STAMP(0, item, 3);
       ++item;
     }
   } else {
@@ -242,40 +272,70 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (it.kb_hi <= it.kb_lo) continue;
       const int row = it.tm * I8_BM + quarter * 32 + lane;
       const int col0 = it.tn * I8_BN;
+      double kv0[16], kv1[16];   // I8_EPI_MOMENTS: Kmul values of column groups, loaded ahead of their use (HBM latency)
+      auto load_kv = [&](double (&kv)[16], int g) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int gc = col0 + g * 16 + c;
+          kv[c] = (row < p.M && gc < p.N) ? __ldg(p.Kmul + (int64_t)gc * p.ldk + row) : 0.0;
+        }
+      };
       if (EPI == I8_EPI_MOMENTS) {
         // stage the tile's x rows and y into shared memory (previous tile's readers are past their last read: barrier below)
         asm volatile("bar.sync 1, 128;\n" ::: "memory");
         const int d = p.d;
-        for (int i = et; i < I8_BN * (d + 1); i += 128) {
-          const int c = i / (d + 1), q = i - c * (d + 1);
-          const int gc = col0 + c;
-          double v = 0.0;
-          if (gc < p.N) v = (q < d) ? p.Xc[(int64_t)gc * d + q] : p.yv[gc];
-          xs[i] = v;
+        {   // the tile's x rows are one contiguous block of 64 d doubles: coalesced copy, 4 independent loads in flight per thread
+          const double* src = p.Xc + (int64_t)col0 * d;
+          const int cnt = I8_BN * d, lim = max(0, min(cnt, (p.N - col0) * d));
+          for (int i0 = et; i0 < cnt; i0 += 4 * 128) {
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int i = i0 + j * 128; v[j] = (i < lim) ? __ldg(src + i) : 0.0; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int i = i0 + j * 128; if (i < cnt) xs[i] = v[j]; }
+          }
+          if (et < I8_BN) ys[et] = (col0 + et < p.N) ? __ldg(p.yv + col0 + et) : 0.0;
         }
+        load_kv(kv0, 0);   // in flight while the MMAs of this tile run
+        load_kv(kv1, 1);
         asm volatile("bar.sync 1, 128;\n" ::: "memory");
       }
+      if (et == 0) I8_STAMP(1, item, 0);
       i8_mbar_wait(tmem_full, item & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+      if (et == 0) I8_STAMP(1, item, 1);
       double acc[I8_BN];
 #pragma unroll
       for (int c = 0; c < I8_BN; ++c) acc[c] = 0.0;
 #pragma unroll
       for (int c0 = 0; c0 < I8_BN; c0 += 16) {
+        // four levels per TMEM round trip, combined exactly in int64 (|sum| < 2^53) before ONE int->double conversion:
+        // levels l0..l0+3 -> t = ((a0 * 128 + a1) * 128 + a2) * 128 + a3, value = t * 2^(-7 (l0 + 5))
+        static_assert(I8_NS == 8, "two groups of four levels");
 #pragma unroll
-        for (int l = I8_NS - 1; l >= 0; --l) {
-          uint32_t v[16];
-          i8_tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(l * I8_BN + c0), v);
+        for (int l0 = 4; l0 >= 0; l0 -= 4) {
+          uint32_t v0[16], v1[16], v2[16], v3[16];
+          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(l0 * I8_BN + c0);
+          i8_tmem_ld16(ta, v0);
+          i8_tmem_ld16(ta + I8_BN, v1);
+          i8_tmem_ld16(ta + 2 * I8_BN, v2);
+          i8_tmem_ld16(ta + 3 * I8_BN, v3);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-          const double wl = exp2(-7.0 * (l + 2));
+          const double wl = (l0 == 4) ? 1.0842021724855044e-19 /* 2^-63 */ : 2.9103830456733704e-11 /* 2^-35 */;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) acc[c0 + c] = fma((double)(int)v[c], wl, acc[c0 + c]);
+          for (int c = 0; c < 16; ++c) {
+            const long long t = ((long long)(int)v0[c] << 21) + ((long long)(int)v1[c] << 14) + ((long long)(int)v2[c] << 7) +
+                                (long long)(int)v3[c];
+            acc[c0 + c] = fma((double)t, wl, acc[c0 + c]);
+          }
         }
       }
       // accumulators are in registers: hand TMEM back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
       __syncwarp();
-      if (lane == 0) i8_mbar_arrive(tmem_empty);
+      if (lane == 0 && !p.serial_epi) i8_mbar_arrive(tmem_empty);
+      if (et == 0) I8_STAMP(1, item, 2);
+      const int item_done = item;
       ++item;
 
       const int e_r = p.ea ? p.ea[min(row, p.M - 1)] : p.ea0;
@@ -293,12 +353,20 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (rok) {
           double* dst = p.C + (int64_t)it.split * p.sSplit + (int64_t)row * p.ldc + col0;
           if (col0 + I8_BN <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            if (p.beta != 0.0) {   // read-modify-write in groups of 8 independent 16-byte loads (not one latency per element pair)
 #pragma unroll
-            for (int c = 0; c < I8_BN; c += 2) {
-              double2* d2 = reinterpret_cast<double2*>(dst + c);
-              double v0 = acc[c], v1 = acc[c + 1];
-              if (p.beta != 0.0) { const double2 o = *d2; v0 += p.beta * o.x; v1 += p.beta * o.y; }
-              *d2 = make_double2(v0, v1);
+              for (int c0 = 0; c0 < I8_BN; c0 += 16) {
+                double2 o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = *reinterpret_cast<const double2*>(dst + c0 + 2 * j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<double2*>(dst + c0 + 2 * j) =
+                      make_double2(fma(p.beta, o[j].x, acc[c0 + 2 * j]), fma(p.beta, o[j].y, acc[c0 + 2 * j + 1]));
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < I8_BN; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(acc[c], acc[c + 1]);
             }
           } else {
 #pragma unroll
@@ -308,10 +376,15 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       } else if (EPI == I8_EPI_SLICE) {
         if (p.rowdot) {
-          double sdot = 0.0;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-          for (int c = 0; c < I8_BN; ++c) sdot = fma(acc[c], (col0 + c < p.N) ? p.yv[col0 + c] : 0.0, sdot);
-          if (rok) p.rowdot[(int64_t)it.tn * p.M + row] = sdot;
+          for (int c = 0; c < I8_BN; c += 4) {
+            s0 = fma(acc[c], (col0 + c < p.N) ? __ldg(p.yv + col0 + c) : 0.0, s0);
+            s1 = fma(acc[c + 1], (col0 + c + 1 < p.N) ? __ldg(p.yv + col0 + c + 1) : 0.0, s1);
+            s2 = fma(acc[c + 2], (col0 + c + 2 < p.N) ? __ldg(p.yv + col0 + c + 2) : 0.0, s2);
+            s3 = fma(acc[c + 3], (col0 + c + 3 < p.N) ? __ldg(p.yv + col0 + c + 3) : 0.0, s3);
+          }
+          if (rok) p.rowdot[(int64_t)it.tn * p.M + row] = (s0 + s1) + (s2 + s3);
         }
         // digit planes of the tile row: 64 consecutive bytes per plane (columns beyond N are zero because their B rows are zero)
         const double si = exp2((double)-p.eo);
@@ -338,31 +411,73 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // W = (G + u y^T) o Kmul, then the moments against [1, x, x^2] of the tile's 64 columns
         const int d = p.d, nq = 2 * d + 1;
         const double ui = rok ? p.u[row] : 0.0;
-        double r0 = 0.0;
+        auto apply_kv = [&](const double (&kv)[16], int g) {
 #pragma unroll
-        for (int c = 0; c < I8_BN; ++c) {
-          const int gc = col0 + c;
-          const double kv = (rok && gc < p.N) ? p.Kmul[(int64_t)gc * p.ldk + row] : 0.0;
-          acc[c] = fma(ui, xs[c * (d + 1) + d], acc[c]) * kv;
-          r0 += acc[c];
-        }
-        double* mo = p.mom + (int64_t)it.tn * p.sMomTile + (int64_t)row * nq;
-        if (rok) mo[0] = r0;
-        for (int q = 0; q < d; ++q) {
-          double m1 = 0.0, m2 = 0.0;
+          for (int c = 0; c < 16; ++c) acc[g * 16 + c] = fma(ui, ys[g * 16 + c], acc[g * 16 + c]) * kv[c];
+        };
+        apply_kv(kv0, 0);
+        load_kv(kv0, 2);
+        apply_kv(kv1, 1);
+        load_kv(kv1, 3);
+        apply_kv(kv0, 2);
+        apply_kv(kv1, 3);
+        // mom[row][:] = sum_c W[row][c] * Phi[c][:], Phi = [1, x, x^2]: a 128 x 64 x (2d+1) product.  The vector FP64 pipe is far too
+        // slow for it (ncu: math-pipe throttle, the epilogue took longer than the MMAs of the next tile), so it goes to the FP64
+        // tensor pipe, idle in this kernel: W is staged 8 columns at a time through a private 32 x 8 shared-memory patch per warp
+        // (row stride 12 doubles: conflict-free 64-bit fragment loads) and fed to DMMA.8x8x4 as the A operand.
+        // lane = 4g + q:  a = W[8G + g][4kq + q],  b = Phi[4kq + q][8B + g],  (c0, c1) = mom[8G + g][8B + 2q, + 1]
+        const int g = lane >> 2, q4 = lane & 3;
+        double* wsm = wstage + (warp - 2) * 32 * I8_WSTAGE_LD;
+        for (int b0 = 0; b0 * 8 < nq; b0 += 3) {   // three blocks of 8 moments per sweep (one sweep for d <= 11)
+          double cm[4][3][2];
 #pragma unroll
-          for (int c = 0; c < I8_BN; ++c) {
-            const double x = xs[c * (d + 1) + q];
-            const double wx = acc[c] * x;
-            m1 += wx;
-            m2 = fma(wx, x, m2);
+          for (int G = 0; G < 4; ++G)
+#pragma unroll
+            for (int B = 0; B < 3; ++B) cm[G][B][0] = cm[G][B][1] = 0.0;
+#pragma unroll
+          for (int pc = 0; pc < I8_BN / 8; ++pc) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; j += 2)
+              *reinterpret_cast<double2*>(wsm + lane * I8_WSTAGE_LD + j) = make_double2(acc[pc * 8 + j], acc[pc * 8 + j + 1]);
+            __syncwarp();
+#pragma unroll
+            for (int kq = 0; kq < 2; ++kq) {
+              double a[4];
+#pragma unroll
+              for (int G = 0; G < 4; ++G) a[G] = wsm[(8 * G + g) * I8_WSTAGE_LD + 4 * kq + q4];
+              const double* xr = xs + (pc * 8 + 4 * kq + q4) * d;
+#pragma unroll
+              for (int B = 0; B < 3; ++B) {
+                const int m = (b0 + B) * 8 + g;
+                double b = 0.0;
+                if (m == 0) b = 1.0;
+                else if (m <= d) b = xr[m - 1];
+                else if (m <= 2 * d) { const double x = xr[m - 1 - d]; b = x * x; }
+#pragma unroll
+                for (int G = 0; G < 4; ++G) dmma884(cm[G][B][0], cm[G][B][1], a[G], b);
+              }
+            }
           }
-          if (rok) {
-            mo[1 + q] = m1;
-            mo[1 + d + q] = m2;
+#pragma unroll
+          for (int G = 0; G < 4; ++G) {
+            const int rr = it.tm * I8_BM + quarter * 32 + 8 * G + g;
+            if (rr >= p.M) continue;
+            double* mo = p.mom + (int64_t)it.tn * p.sMomTile + (int64_t)rr * nq;
+#pragma unroll
+            for (int B = 0; B < 3; ++B) {
+              const int m = (b0 + B) * 8 + 2 * q4;
+              if (m < nq) mo[m] = cm[G][B][0];
+              if (m + 1 < nq) mo[m + 1] = cm[G][B][1];
+            }
           }
         }
       }
+      if (p.serial_epi) {
+        __syncwarp();
+        if (lane == 0) i8_mbar_arrive(tmem_empty);
+      }
+      if (et == 0) I8_STAMP(1, item_done, 3);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
@@ -391,30 +506,32 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
 }
 
 // digit planes of an existing k(X,Z) tile Kc[n][m] (FP64, leading dimension ldk) with the fixed exponent e (k <= sf2 < 2^(e-1)):
-// Kq[i][n][m].  Each thread converts 16 consecutive m of one row: 16-byte stores per plane.
+// Kq[i][n][m].  Each thread converts 4 consecutive m of one row: the warp reads 1 KB contiguous and writes 128 B per plane.
 __global__ void __launch_bounds__(256) k_slice_fixed(const double* __restrict__ Kc, int64_t rows, int cols, int64_t ldk,
                                                      int8_t* __restrict__ Kq, int64_t ldq, int64_t plane, const double* __restrict__ theta,
                                                      int d) {
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const int cpr = cols / 16;
+  const int cpr = cols / 4;
   const int64_t row = t / cpr;
-  const int c0 = (int)(t - row * cpr) * 16;
+  const int c0 = (int)(t - row * cpr) * 4;
   if (row >= rows) return;
   const int e = ilogb(theta[d]) + 2;
   const double si = exp2((double)-e);
-  uint32_t pk[I8_NS][4];
+  const double2 a = *reinterpret_cast<const double2*>(Kc + row * ldk + c0);
+  const double2 b = *reinterpret_cast<const double2*>(Kc + row * ldk + c0 + 2);
+  const double x[4] = {a.x, a.y, b.x, b.y};
+  uint32_t pk[I8_NS];
 #pragma unroll
-  for (int i = 0; i < I8_NS; ++i) pk[i][0] = pk[i][1] = pk[i][2] = pk[i][3] = 0u;
+  for (int i = 0; i < I8_NS; ++i) pk[i] = 0u;
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
+  for (int c = 0; c < 4; ++c) {
     int8_t dg[I8_NS];
-    i8_digits(Kc[row * ldk + c0 + c] * si, dg);
+    i8_digits(x[c] * si, dg);
 #pragma unroll
-    for (int i = 0; i < I8_NS; ++i) pk[i][c >> 2] |= ((uint32_t)(uint8_t)dg[i]) << (8 * (c & 3));
+    for (int i = 0; i < I8_NS; ++i) pk[i] |= ((uint32_t)(uint8_t)dg[i]) << (8 * c);
   }
 #pragma unroll
-  for (int i = 0; i < I8_NS; ++i)
-    *reinterpret_cast<uint4*>(Kq + (int64_t)i * plane + row * ldq + c0) = make_uint4(pk[i][0], pk[i][1], pk[i][2], pk[i][3]);
+  for (int i = 0; i < I8_NS; ++i) *reinterpret_cast<uint32_t*>(Kq + (int64_t)i * plane + row * ldq + c0) = pk[i];
 }
 
 }  // namespace ggp

@@ -69,6 +69,8 @@ struct ggp_handle {
   int *eL = 0, *eP = 0;
   int8_t* kq_all = nullptr;
   size_t kq_all_bytes = 0;
+  long long* i8_dbg = nullptr;   // developer timeline buffer (GGP_I8_TIMELINE=2)
+  int i8_dbg_prints = 0;
   int nsv = 0;
   // instrumentation
   long long launches = 0;
@@ -381,7 +383,7 @@ struct I8Operand { const int8_t* q; int64_t rows, ld, plane; };
 
 static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Operand& A, const I8Operand& B) {
   if (p.K < 1 || p.M < 1 || p.N < 1) return 0;
-  if (p.K > I8_MAX_K) return fail(-4, "launch_i8: k extent exceeds the exact int32 accumulation bound (65536)");
+  if (p.K > I8_MAX_K) return fail(-4, "launch_i8: k extent exceeds the exact int32 accumulation bound (32768)");
   p.tiles_m = (p.M + I8_BM - 1) / I8_BM;
   p.tiles_n = (p.N + I8_BN - 1) / I8_BN;
   int tiles = p.tiles_m * p.tiles_n;
@@ -395,10 +397,31 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
   if (!make_i8_map(&tmA, A.q, A.rows, p.K, A.ld, A.plane, I8_BM) || !make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN))
     return fail(-4, "launch_i8: operand planes cannot be described by a tensor map (alignment)");
   const int grid = std::min(p.total, h->sm_count);
+  const char* tl = getenv("GGP_I8_TIMELINE");
+  const bool dbg = tl && tl[0] == '2' && h->i8_dbg_prints < 9 && !p.dbg;
+  if (dbg) {
+    if (!h->i8_dbg) CK(cudaMalloc((void**)&h->i8_dbg, 2 * I8_DBG_ITEMS * 4 * sizeof(long long)));
+    CK(cudaMemsetAsync(h->i8_dbg, 0, 2 * I8_DBG_ITEMS * 4 * sizeof(long long), st));
+    p.dbg = h->i8_dbg;
+  }
   if (epi == I8_EPI_F64) k_gemm_i8<I8_EPI_F64><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
   else if (epi == I8_EPI_SLICE) k_gemm_i8<I8_EPI_SLICE><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
   else k_gemm_i8<I8_EPI_MOMENTS><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
   CKL();
+  if (dbg) {
+    CK(cudaStreamSynchronize(st));
+    long long hb[2 * I8_DBG_ITEMS * 4];
+    CK(cudaMemcpy(hb, h->i8_dbg, sizeof(hb), cudaMemcpyDeviceToHost));
+    const long long t0 = hb[0];
+    fprintf(stderr, "== i8 timeline, epilogue %d, M=%d N=%d K=%d lower=%d sym=%d splits=%d\n", epi, p.M, p.N, p.K, p.lower_a, p.sym, p.splits);
+    for (int it = 0; it < 8; ++it) {
+      const long long* m = hb + it * 4;
+      const long long* ep = hb + (I8_DBG_ITEMS + it) * 4;
+      fprintf(stderr, "tile %2d  mma: start %8lld tmem_free %8lld first_kb %8lld all_issued %8lld | epi: wait %8lld full %8lld drained %8lld done %8lld\n",
+              it, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, ep[0] - t0, ep[1] - t0, ep[2] - t0, ep[3] - t0);
+    }
+    h->i8_dbg_prints++;
+  }
   return 0;
 }
 
@@ -608,7 +631,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
       {
         ProfScope ps(h, st, CAT_BUILD);
-        const int64_t nthr = (int64_t)nv * (Mp / 16);
+        const int64_t nthr = (int64_t)nv * (Mp / 4);
         k_slice_fixed<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Kc_c, nv, Mp, Mp, Kq_c, Mp, plK, theta, d);
         CKL();
       }
@@ -755,7 +778,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
       if (!cached) {
         ProfScope ps(h, st, CAT_BUILD);
-        const int64_t nthr = (int64_t)nv * (Mp / 16);
+        const int64_t nthr = (int64_t)nv * (Mp / 4);
         k_slice_fixed<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Kc_c, nv, Mp, Mp, Kq_c, Mp, plK, theta, d);
         CKL();
       }
@@ -774,6 +797,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       g8.ea = h->eP; g8.eb0 = eK; g8.alpha = 1.0;
       g8.u = h->u; g8.yv = y + c0; g8.Kmul = Kmul; g8.ldk = Mp; g8.Xc = X + c0 * d; g8.d = d;
       g8.mom = h->mom_part; g8.sMomTile = cnt;
+      { const char* e = getenv("GGP_I8_SERIAL_EPI"); g8.serial_epi = (e && e[0] == '0') ? 0 : 1; }
       { ProfScope ps(h, st, CAT_BWD); RUN(launch_i8(h, st, I8_EPI_MOMENTS, g8, {h->Pq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK})); }
       ProfScope ps_o(h, st, CAT_OTHER);
       k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, 0, (nv + I8_BN - 1) / I8_BN, cnt,
@@ -1024,7 +1048,7 @@ int ggp_gemm_nt_ex(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
 int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                    int64_t ldc, int mm, int nn, int kk) {
   if (!h || !A || !B || !C) return fail(-1, "ggp_gemm_nt_i8: NULL argument");
-  if (mm < 1 || nn < 1 || kk < 1 || kk > I8_MAX_K) return fail(-2, "ggp_gemm_nt_i8: bad shape (1 <= kk <= 65536)");
+  if (mm < 1 || nn < 1 || kk < 1 || kk > I8_MAX_K) return fail(-2, "ggp_gemm_nt_i8: bad shape (1 <= kk <= 32768)");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t kp = (kk + 63) / 64 * 64;
   int8_t *qa = nullptr, *qb = nullptr;
@@ -1042,8 +1066,27 @@ int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
   p.M = mm; p.N = nn; p.K = (int)kp; p.splits = 1;
   p.ea = ea; p.eb = eb; p.alpha = 1.0; p.beta = 0.0;
   p.C = C; p.ldc = ldc;
+  long long* dbg = nullptr;
+  const char* tl = getenv("GGP_I8_TIMELINE");   // developer switch: print CTA 0's clock64 timeline of the first tiles to stderr
+  if (tl && tl[0] == '1') {
+    CK(cudaMalloc((void**)&dbg, 2 * I8_DBG_ITEMS * 4 * sizeof(long long)));
+    CK(cudaMemsetAsync(dbg, 0, 2 * I8_DBG_ITEMS * 4 * sizeof(long long), st));
+    p.dbg = dbg;
+  }
   int rc = launch_i8(h, st, I8_EPI_F64, p, {qa, mm, kp, (int64_t)mm * kp}, {qb, nn, kp, (int64_t)nn * kp});
   cudaError_t e = cudaStreamSynchronize(st);
+  if (dbg) {
+    long long hb[2 * I8_DBG_ITEMS * 4];
+    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    const long long t0 = hb[0];
+    for (int it = 0; it < I8_DBG_ITEMS; ++it) {
+      const long long* m = hb + it * 4;
+      const long long* ep = hb + (I8_DBG_ITEMS + it) * 4;
+      fprintf(stderr, "tile %2d  mma: start %8lld  tmem_free %8lld  first_kb_issued %8lld  all_issued %8lld | epi: wait %8lld  full %8lld  drained %8lld  done %8lld\n",
+              it, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, ep[0] - t0, ep[1] - t0, ep[2] - t0, ep[3] - t0);
+    }
+    cudaFree(dbg);
+  }
   cudaFree(qa); cudaFree(qb); cudaFree(ea); cudaFree(eb);
   if (rc != 0) return rc;
   CK(e);

@@ -137,7 +137,7 @@ int ggp_gemm_nt_ex(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
                    double* C, int64_t ldc, int mm, int nn, int kk, double alpha, double beta, int kmode, int sym,
                    int splits, int64_t split_stride);
 /* C[mm,nn] = A[mm,kk] * B[nn,kk]^T evaluated by the sliced-integer tcgen05 path (row-scaled 8 x 7-bit digits, exact int32
- * accumulation, kk <= 65536).  Allocates and frees its digit planes (synchronous): a test / probe entry, not a hot-path one. */
+ * accumulation, kk <= 32768).  Allocates and frees its digit planes (synchronous): a test / probe entry, not a hot-path one. */
 int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb,
                    double* C, int64_t ldc, int mm, int nn, int kk);
 /* k(X1, X2)[n1, n2] dense tile (tests) */

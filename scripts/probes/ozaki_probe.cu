@@ -23,8 +23,12 @@
 #define BN 64           // tile columns; NS * BN <= 512 TMEM columns
 #endif
 constexpr int BM = 128;
-constexpr int BKB = 64;           // bytes (= int8 elements) of K per stage row: one 64-byte swizzle row
-constexpr int STAGES = 2;
+#ifndef BKB
+#define BKB 64                    // bytes (= int8 elements) of K per stage row: one swizzle row (64 -> SWIZZLE_64B, 32 -> SWIZZLE_32B)
+#endif
+#ifndef STAGES
+#define STAGES 2
+#endif
 constexpr int A_SLICE_BYTES = BM * BKB, B_SLICE_BYTES = BN * BKB;
 constexpr int STAGE_BYTES = NS * (A_SLICE_BYTES + B_SLICE_BYTES);
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
@@ -49,9 +53,9 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), canonical value 1
-  d |= (uint64_t)(512 >> 4) << 32;           // stride byte offset between 8-row groups
+  d |= (uint64_t)((8 * BKB) >> 4) << 32;     // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                    // version
-  d |= (uint64_t)4 << 61;                    // SWIZZLE_64B
+  d |= (uint64_t)(BKB == 64 ? 4 : 6) << 61;  // SWIZZLE_64B / SWIZZLE_32B
   return d;
 }
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -71,7 +75,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // C[m][n] = 2^(ea[m] + eb[n]) * sum_l 2^(-7 (l + 2)) * acc_l[m][n]
 __global__ void __launch_bounds__(THREADS, 1)
 k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const int* __restrict__ ea,
-             const int* __restrict__ eb, double* __restrict__ C, int M, int N, int K, int64_t ldc) {
+             const int* __restrict__ eb, double* __restrict__ C, int M, int N, int K, int64_t ldc, int mode) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
@@ -100,22 +104,21 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = 0; kb < (mode == 1 ? (nkb < STAGES ? nkb : STAGES) : nkb); ++kb) {   // mode 1 (diagnostic): fill the ring once, MMAs re-read it
         const int s = kb % STAGES;
         if (kb >= STAGES) mbar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
         mbar_expect_tx(&full[s], STAGE_BYTES);
         unsigned char* st = base + s * STAGE_BYTES;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) tma_load_3d(st + i * A_SLICE_BYTES, &tmA, kb * BKB, tm * BM, i, &full[s]);
-#pragma unroll
-        for (int j = 0; j < NS; ++j) tma_load_3d(st + NS * A_SLICE_BYTES + j * B_SLICE_BYTES, &tmB, kb * BKB, tn * BN, j, &full[s]);
+        // one box per operand covers all NS digit planes (k x rows x planes): 2 TMA instructions per stage
+        tma_load_3d(st, &tmA, kb * BKB, tm * BM, 0, &full[s]);
+        tma_load_3d(st + NS * A_SLICE_BYTES, &tmB, kb * BKB, tn * BN, 0, &full[s]);
       }
     }
   } else if (warp == 1) {
     // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
-      mbar_wait(&full[s], (kb / STAGES) & 1);
+      if (mode != 1 || kb < STAGES) mbar_wait(&full[s], (kb / STAGES) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
       if (lane == 0) {
         const uint32_t sa = smem_u32(base + s * STAGE_BYTES), sb = sa + NS * A_SLICE_BYTES;
@@ -204,14 +207,16 @@ static bool make_map(CUtensorMap* tm, int8_t* ptr, int R, int K, int box_rows) {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)NS};
   const cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)R * K};
-  const cuuint32_t box[3] = {(cuuint32_t)BKB, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)BKB, (cuuint32_t)box_rows, (cuuint32_t)NS};
   const cuuint32_t es[3] = {1u, 1u, 1u};
   return ((tmap_encode_fn)fp)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                              BKB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int main(int argc, char** argv) {
   int M = argc > 3 ? atoi(argv[1]) : 1024, N = argc > 3 ? atoi(argv[2]) : 16384, K = argc > 3 ? atoi(argv[3]) : 1024;
+  const int mode = argc > 4 ? atoi(argv[4]) : 0;
+  if (mode) printf("DIAGNOSTIC mode %d: results are NOT a GEMM\n", mode);
   if (M % BM || N % BN || K % BKB || K > 65536) { printf("shape must be a multiple of the tile (128, %d, %d), K <= 65536\n", BN, BKB); return 1; }
   printf("ozaki probe: M=%d N=%d K=%d  NS=%d digits (%d bits), tile 128x%d, %d products per k-step\n", M, N, K, NS, 7 * NS, BN, NS * (NS + 1) / 2);
   std::vector<double> hA((size_t)M * K), hB((size_t)N * K);
@@ -244,12 +249,12 @@ int main(int argc, char** argv) {
   CK(cudaDeviceSynchronize());
   CK(cudaEventElapsedTime(&ms_slice, e0, e1));
   const int grid = (M / BM) * (N / BN);
-  k_ozaki_gemm<<<grid, THREADS, SMEM_BYTES>>>(tmA, tmB, eA, eB, dC, M, N, K, N);
+  k_ozaki_gemm<<<grid, THREADS, SMEM_BYTES>>>(tmA, tmB, eA, eB, dC, M, N, K, N, mode);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   const int reps = 5;
   CK(cudaEventRecord(e0));
-  for (int r = 0; r < reps; ++r) k_ozaki_gemm<<<grid, THREADS, SMEM_BYTES>>>(tmA, tmB, eA, eB, dC, M, N, K, N);
+  for (int r = 0; r < reps; ++r) k_ozaki_gemm<<<grid, THREADS, SMEM_BYTES>>>(tmA, tmB, eA, eB, dC, M, N, K, N, mode);
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   CK(cudaEventElapsedTime(&ms, e0, e1));
