@@ -159,8 +159,9 @@ def main():
     ap.add_argument("--rows", type=int, default=N_FULL, help="override N (debug only; the headline number needs the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hmc", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("GGP_BENCH_PRECISION", "fp64"), choices=["fp64", "fp64_i8"],
-                    help="fp64: FP64 DMMA tensor path; fp64_i8: FP64-class exact int8 slicing on tcgen05 (csrc/gemm_i8.cuh)")
+    ap.add_argument("--precision", default=os.environ.get("GGP_BENCH_PRECISION", "fp64_i8"), choices=["fp64", "fp64_i8"],
+                    help="fp64_i8 (default): FP64-class exact int8 slicing on tcgen05 (csrc/gemm_i8.cuh); fp64: FP64 DMMA tensor path")
+    ap.add_argument("--no-dmma-leg", action="store_true", help="skip the secondary measurement of the FP64 DMMA path")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -227,6 +228,38 @@ def main():
     ms_step = float(t.item()) / args.steps
     value = 1e3 / ms_step
 
+    # ---- secondary leg: the same step on the FP64 DMMA path (mma.sync m8n8k4 f64), for comparison with the sliced-integer path
+    dmma = None
+    if args.precision != "fp64" and not args.no_dmma_leg:
+        eng2 = ggp_b200.Engine.get(dev, precision="fp64")
+        def step_dmma():
+            flush.zero_()
+            return eng2.sgpr_eval(X, y, Z, th, jitter_policy="gpytorch", need_grad=True, group=group)
+        for _ in range(2):
+            o2 = step_dmma()
+        torch.cuda.synchronize()
+        eng2.profile_read(); eng2.profile_enable(True)
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for _ in range(args.steps):
+            o2 = step_dmma()
+        e1.record()
+        torch.cuda.synchronize()
+        c2, n2, _ = eng2.profile_read(); eng2.profile_enable(False)
+        t3 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        ms2 = float(t3.item()) / args.steps
+        g2 = (c2["trmm"] + c2["syrk"] + c2["bwd"]) / args.steps
+        dmma = {"value": 1e3 / ms2, "unit": "evals/s", "ms_per_step": ms2, "kernel": "k_gemm_tma (TMA-fed DMMA.8x8x4)",
+                "gemm_tflops": 4.0 * n_local * M_IND * M_IND / (g2 * 1e-3) / 1e12 if g2 > 0 else None,
+                "frac_of_dmma_peak": (4.0 * n_local * M_IND * M_IND / (g2 * 1e-3) / 1e12 / peak["best"]) if g2 > 0 else None,
+                "bound_value": float(o2["bound"][0].item()),
+                "rel_diff_of_bound_vs_headline_path": abs(float(o2["bound"][0].item()) - float(out["bound"][0].item())) / abs(float(o2["bound"][0].item())),
+                "rel_diff_of_grad_vs_headline_path": float(((o2["grad"] - out["grad"]).abs().max() / o2["grad"].abs().max()).item())}
+        del eng2
+
     # ---- end to end through the public API with HOST buffers: H2D of the step's inputs and D2H of its result inside the timed region
     P = D_IN + 2 + M_IND * D_IN
     res_h = torch.empty(1 + P, dtype=torch.float64).pin_memory()
@@ -258,37 +291,68 @@ def main():
     d2h = (1 + P) * 8
 
     if rank == 0:
-        traffic = None
+        traffic = traffic_i8 = None
         try:
             with open(os.path.join(ROOT, "profiles", "r1b_ncu_traffic.json")) as fh:
                 traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
+            with open(os.path.join(ROOT, "profiles", "r1c_ncu_traffic_i8.json")) as fh:
+                traffic_i8 = json.load(fh)["traffic_bytes_per_launch_avg"]
         except Exception:
             pass
         gemm_ms = (cat_ms["trmm"] + cat_ms["syrk"] + cat_ms["bwd"]) / args.steps
         gemm_launches = (cat_n["trmm"] + cat_n["syrk"] + cat_n["bwd"]) / args.steps
         flops_local = 4.0 * n_local * M_IND * M_IND  # N M^2 (tri) + N M^2 (syrk) + 2 N M^2 (backward)
         achieved = flops_local / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        if args.precision == "fp64_i8":
+            # sliced-integer path: 36 int8 digit-pair products per FP64 product; int8 dense tensor peak = 2 x the bf16 dense peak (nominal
+            # ratio); the bf16 figure is the cuBLAS burst number the driver measured on this pool (MEASURED_PEAKS.json), else the
+            # profiling recipe's fallback 1590 TFLOP/s
+            bf16 = float(peaks.get("bf16_tflops", 1590.0))
+            src = "measured (MEASURED_PEAKS.json bf16_tflops x 2)" if "bf16_tflops" in peaks else "fallback (1590 bf16 TFLOP/s x 2)"
+            tops = 36.0 * flops_local / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+            roof = {"bound": "tensor", "kernel": "k_gemm_i8 (TMA-fed tcgen05.mma kind::i8, int32 TMEM accumulators: triangular multiply + SYRK + backward GEMM)",
+                    "achieved": tops, "peak": 2.0 * bf16, "unit": "TOP/s (int8)", "frac": tops / (2.0 * bf16) if tops else None,
+                    "peak_source": src, "fp64_equivalent_tflops": achieved,
+                    "fp64_equivalent_vs_dmma_peak": (achieved / peak["best"]) if achieved else None, "dmma_peak_tflops": peak["best"],
+                    "digit_products_per_fp64_product": 36, "launches_per_step": gemm_launches,
+                    "avg_launch_ms": gemm_ms / gemm_launches if gemm_launches else None,
+                    "algorithmic_flops_per_step_per_rank": flops_local, "traffic": traffic_i8,
+                    "traffic_unit": "bytes per launch (dram read+write, ncu --set full, avg of the 3 GEMM roles on a 16384-row chunk)",
+                    "whole_step_fp64_equivalent_tflops": flops_local / (ms_step * 1e-3) / 1e12}
+            dtype = "f64 via 8x7-bit int8 digits (exact int32 accumulation on tcgen05, f64 recombination); parity 1e-8 as the DMMA path"
+        else:
+            roof = {"bound": "tensor", "kernel": "k_gemm_tma (TMA-fed DMMA.8x8x4 mainloop: triangular multiply + SYRK + backward GEMM)",
+                    "achieved": achieved, "peak": peak["best"], "unit": "TFLOP/s", "frac": (achieved / peak["best"]) if achieved else None,
+                    "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full, avg of the 3 GEMM roles on a "
+                    "16384-row chunk; profiles/r1b_ncu_traffic.json)", "peak_source": "measured live: register-resident mma.sync m8n8k4 f64 loop on all SMs "
+                    "(MEASURED_PEAKS.json holds no FP64 figure)", "launches_per_step": gemm_launches,
+                    "avg_launch_ms": gemm_ms / gemm_launches if gemm_launches else None,
+                    "algorithmic_flops_per_step_per_rank": flops_local,
+                    "whole_step_frac": flops_local / (ms_step * 1e-3) / 1e12 / peak["best"]}
+            dtype = "f64"
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "N": N, "M": M_IND, "D": D_IN, "rows_per_rank": n_local, "theta": "trained-like (ell=sqrt(D), sf2=1, s2=0.1)",
-                       "jitter_policy": "gpytorch", "l2": "256 MB buffer written between steps (inside the timed region)"},
+                       "jitter_policy": "gpytorch", "precision": args.precision,
+                       "l2": "256 MB buffer written between steps (inside the timed region)"},
             "e2e": {"value": 1e3 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "k_gemm_tma (TMA-fed DMMA.8x8x4 mainloop: triangular multiply + SYRK + backward GEMM)",
-                         "achieved": achieved, "peak": peak["best"], "unit": "TFLOP/s", "frac": (achieved / peak["best"]) if achieved else None,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full, avg of the 3 GEMM roles on a "
-                         "16384-row chunk; profiles/r1b_ncu_traffic.json)", "peak_source": "measured live: register-resident mma.sync m8n8k4 f64 loop on all SMs "
-                         "(MEASURED_PEAKS.json holds no FP64 figure)", "launches_per_step": gemm_launches,
-                         "avg_launch_ms": gemm_ms / gemm_launches if gemm_launches else None,
-                         "algorithmic_flops_per_step_per_rank": flops_local,
-                         "whole_step_frac": flops_local / (ms_step * 1e-3) / 1e12 / peak["best"]},
+            "roofline": roof,
             "breakdown_ms_per_step": {k: v / args.steps for k, v in cat_ms.items()},
             "bound_value": float(out["bound"][0].item()),
         }
+        if dmma is not None:
+            line["fp64_dmma_path"] = dmma
         line["hmc_at_headline_config"] = {"leapfrogs_per_sample": 10, "samples_per_s": value / 10.0,
                                           "note": "one HMC sample = L leapfrogs x one bound+grad evaluation (models/sgp_hmc.py:67-69 uses L=10)"}
         if world == 1 and not args.no_hmc:
