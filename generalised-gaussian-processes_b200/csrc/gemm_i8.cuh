@@ -12,8 +12,8 @@
 //     shared memory (= one tall tile) and their products belong to consecutive levels (= consecutive accumulator columns), which
 //     keeps the shared-memory operand reads below the 128 B/clk limit (12 MMAs per 32-byte k-step instead of 36);
 //   * TMA (cp.async.bulk.tensor, 64-byte swizzle) stages 8 + 8 digit tiles per 64-byte k-block into a 2-stage mbarrier ring;
-//   * persistent CTAs, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and TMEM owner, warps 2..5 =
-//     epilogue (TMEM lane quarters 2,3,0,1).  The epilogue first drains the accumulators to FP64 registers (levels combined from
+//   * persistent CTAs, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and TMEM owner, warps 2..9 =
+//     epilogue (TMEM lane quarter w % 4, column half (w - 2) / 4).  The epilogue first drains the accumulators to FP64 registers (levels combined from
 //     the least significant up), releases TMEM so the next tile's MMAs start, then runs its role-specific part.
 // Measured by scripts/probes/ozaki_probe.cu on a B200: |err| / sum|a||b| = 1.7e-16 (an FP64 FMA chain: ~3e-15), 64 TF/s
 // FP64-equivalent at K = 1024 and 88 TF/s at K = 16384 (the DMMA peak is 37.2).
@@ -29,11 +29,13 @@ constexpr int I8_BKB = 64;                     // bytes of k per stage row (one 
 constexpr int I8_STAGES = 2;
 constexpr int I8_A_BYTES = I8_BM * I8_BKB, I8_B_BYTES = I8_BN * I8_BKB;
 constexpr int I8_STAGE_BYTES = I8_NS * (I8_A_BYTES + I8_B_BYTES);
-constexpr int I8_THREADS = 192;
-constexpr int I8_MAX_D = 32;                   // input dimension limit of the moments epilogue (shared-memory staging of X)
+constexpr int I8_EPI_WARPS = 8;                // two per TMEM lane quarter, 32 of the 64 tile columns each
+constexpr int I8_EC = I8_BN / 2;               // columns per epilogue warp
+constexpr int I8_THREADS = 64 + 32 * I8_EPI_WARPS;
+constexpr int I8_MAX_D = 16;                   // input dimension limit of the moments epilogue (shared-memory staging of X)
 constexpr int I8_EPI_SMEM = I8_BN * (I8_MAX_D + 1) * 8;
 constexpr int I8_WSTAGE_LD = 12;               // doubles per staged W row (8 used): 24-word stride = conflict-free DMMA fragment loads
-constexpr int I8_WSTAGE_BYTES = 128 * I8_WSTAGE_LD * 8;
+constexpr int I8_WSTAGE_BYTES = I8_EPI_WARPS * 32 * I8_WSTAGE_LD * 8;
 constexpr int I8_SMEM = I8_STAGES * I8_STAGE_BYTES + 1024 + 256 + I8_EPI_SMEM + I8_WSTAGE_BYTES;
 static_assert(I8_SMEM <= 232448, "shared memory budget (227 KB)");
 constexpr int I8_TMEM_COLS = 512;
@@ -187,7 +189,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_init(&empty[s], 1);
     }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    mbar_init(tmem_empty, I8_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -262,16 +264,18 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       ++item;
     }
   } else {
-    // ================= epilogue (4 warps; warp w owns TMEM lanes [32 (w % 4), +32)) =================
+    // ================= epilogue (8 warps; warp w owns TMEM lanes [32 (w % 4), +32) and 32 of the 64 tile columns) =================
     const int quarter = warp & 3;
-    const int et = threadIdx.x - 64;   // 0..127
+    const int half = (warp - 2) >> 2;  // column half of the tile handled by this warp
+    const int et = threadIdx.x - 64;   // 0..255
     int item = 0;
     for (int w = blockIdx.x; w < p.total; w += G) {
       I8Item it;
       i8_decode(p, w, it);
       if (it.kb_hi <= it.kb_lo) continue;
       const int row = it.tm * I8_BM + quarter * 32 + lane;
-      const int col0 = it.tn * I8_BN;
+      const int col0 = it.tn * I8_BN + half * I8_EC;   // first column of this warp's half
+      const int colt = it.tn * I8_BN;                  // first column of the tile
       double kv0[16], kv1[16];   // I8_EPI_MOMENTS: Kmul values of column groups, loaded ahead of their use (HBM latency)
       auto load_kv = [&](double (&kv)[16], int g) {
 #pragma unroll
@@ -282,40 +286,40 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       };
       if (EPI == I8_EPI_MOMENTS) {
         // stage the tile's x rows and y into shared memory (previous tile's readers are past their last read: barrier below)
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
         const int d = p.d;
         {   // the tile's x rows are one contiguous block of 64 d doubles: coalesced copy, 4 independent loads in flight per thread
-          const double* src = p.Xc + (int64_t)col0 * d;
-          const int cnt = I8_BN * d, lim = max(0, min(cnt, (p.N - col0) * d));
-          for (int i0 = et; i0 < cnt; i0 += 4 * 128) {
+          const double* src = p.Xc + (int64_t)colt * d;
+          const int cnt = I8_BN * d, lim = max(0, min(cnt, (p.N - colt) * d));
+          for (int i0 = et; i0 < cnt; i0 += 4 * 256) {
             double v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const int i = i0 + j * 128; v[j] = (i < lim) ? __ldg(src + i) : 0.0; }
+            for (int j = 0; j < 4; ++j) { const int i = i0 + j * 256; v[j] = (i < lim) ? __ldg(src + i) : 0.0; }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const int i = i0 + j * 128; if (i < cnt) xs[i] = v[j]; }
+            for (int j = 0; j < 4; ++j) { const int i = i0 + j * 256; if (i < cnt) xs[i] = v[j]; }
           }
-          if (et < I8_BN) ys[et] = (col0 + et < p.N) ? __ldg(p.yv + col0 + et) : 0.0;
+          if (et < I8_BN) ys[et] = (colt + et < p.N) ? __ldg(p.yv + colt + et) : 0.0;
         }
-        load_kv(kv0, 0);   // in flight while the MMAs of this tile run
+        load_kv(kv0, 0);   // both groups of this warp's 32 columns are in flight while the MMAs of this tile run
         load_kv(kv1, 1);
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
       }
       if (et == 0) I8_STAMP(1, item, 0);
       i8_mbar_wait(tmem_full, item & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
       if (et == 0) I8_STAMP(1, item, 1);
-      double acc[I8_BN];
+      double acc[I8_EC];
 #pragma unroll
-      for (int c = 0; c < I8_BN; ++c) acc[c] = 0.0;
+      for (int c = 0; c < I8_EC; ++c) acc[c] = 0.0;
 #pragma unroll
-      for (int c0 = 0; c0 < I8_BN; c0 += 16) {
+      for (int c0 = 0; c0 < I8_EC; c0 += 16) {
         // four levels per TMEM round trip, combined exactly in int64 (|sum| < 2^53) before ONE int->double conversion:
         // levels l0..l0+3 -> t = ((a0 * 128 + a1) * 128 + a2) * 128 + a3, value = t * 2^(-7 (l0 + 5))
         static_assert(I8_NS == 8, "two groups of four levels");
 #pragma unroll
         for (int l0 = 4; l0 >= 0; l0 -= 4) {
           uint32_t v0[16], v1[16], v2[16], v3[16];
-          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(l0 * I8_BN + c0);
+          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(l0 * I8_BN + half * I8_EC + c0);
           i8_tmem_ld16(ta, v0);
           i8_tmem_ld16(ta + I8_BN, v1);
           i8_tmem_ld16(ta + 2 * I8_BN, v2);
@@ -342,20 +346,20 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool rok = row < p.M;
       if (p.eb) {
 #pragma unroll
-        for (int c = 0; c < I8_BN; ++c) acc[c] = p.alpha * ldexp(acc[c], e_r + p.eb[min(col0 + c, p.N - 1)]);
+        for (int c = 0; c < I8_EC; ++c) acc[c] = p.alpha * ldexp(acc[c], e_r + p.eb[min(col0 + c, p.N - 1)]);
       } else {
         const double sc = p.alpha * exp2((double)(e_r + p.eb0));
 #pragma unroll
-        for (int c = 0; c < I8_BN; ++c) acc[c] *= sc;
+        for (int c = 0; c < I8_EC; ++c) acc[c] *= sc;
       }
 
       if (EPI == I8_EPI_F64) {
         if (rok) {
           double* dst = p.C + (int64_t)it.split * p.sSplit + (int64_t)row * p.ldc + col0;
-          if (col0 + I8_BN <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          if (col0 + I8_EC <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
             if (p.beta != 0.0) {   // read-modify-write in groups of 8 independent 16-byte loads (not one latency per element pair)
 #pragma unroll
-              for (int c0 = 0; c0 < I8_BN; c0 += 16) {
+              for (int c0 = 0; c0 < I8_EC; c0 += 16) {
                 double2 o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = *reinterpret_cast<const double2*>(dst + c0 + 2 * j);
@@ -366,11 +370,11 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               }
             } else {
 #pragma unroll
-              for (int c = 0; c < I8_BN; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(acc[c], acc[c + 1]);
+              for (int c = 0; c < I8_EC; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(acc[c], acc[c + 1]);
             }
           } else {
 #pragma unroll
-            for (int c = 0; c < I8_BN; ++c)
+            for (int c = 0; c < I8_EC; ++c)
               if (col0 + c < p.N) dst[c] = acc[c] + (p.beta != 0.0 ? p.beta * dst[c] : 0.0);
           }
         }
@@ -378,18 +382,18 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (p.rowdot) {
           double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-          for (int c = 0; c < I8_BN; c += 4) {
+          for (int c = 0; c < I8_EC; c += 4) {
             s0 = fma(acc[c], (col0 + c < p.N) ? __ldg(p.yv + col0 + c) : 0.0, s0);
             s1 = fma(acc[c + 1], (col0 + c + 1 < p.N) ? __ldg(p.yv + col0 + c + 1) : 0.0, s1);
             s2 = fma(acc[c + 2], (col0 + c + 2 < p.N) ? __ldg(p.yv + col0 + c + 2) : 0.0, s2);
             s3 = fma(acc[c + 3], (col0 + c + 3 < p.N) ? __ldg(p.yv + col0 + c + 3) : 0.0, s3);
           }
-          if (rok) p.rowdot[(int64_t)it.tn * p.M + row] = (s0 + s1) + (s2 + s3);
+          if (rok) p.rowdot[(int64_t)(it.tn * 2 + half) * p.M + row] = (s0 + s1) + (s2 + s3);   // one slab per 32 columns
         }
         // digit planes of the tile row: 64 consecutive bytes per plane (columns beyond N are zero because their B rows are zero)
         const double si = exp2((double)-p.eo);
 #pragma unroll
-        for (int c0 = 0; c0 < I8_BN; c0 += 16) {
+        for (int c0 = 0; c0 < I8_EC; c0 += 16) {
           uint32_t pk[I8_NS][4];
 #pragma unroll
           for (int i = 0; i < I8_NS; ++i) pk[i][0] = pk[i][1] = pk[i][2] = pk[i][3] = 0u;
@@ -413,21 +417,17 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const double ui = rok ? p.u[row] : 0.0;
         auto apply_kv = [&](const double (&kv)[16], int g) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) acc[g * 16 + c] = fma(ui, ys[g * 16 + c], acc[g * 16 + c]) * kv[c];
+          for (int c = 0; c < 16; ++c) acc[g * 16 + c] = fma(ui, ys[half * I8_EC + g * 16 + c], acc[g * 16 + c]) * kv[c];
         };
         apply_kv(kv0, 0);
-        load_kv(kv0, 2);
         apply_kv(kv1, 1);
-        load_kv(kv1, 3);
-        apply_kv(kv0, 2);
-        apply_kv(kv1, 3);
         // mom[row][:] = sum_c W[row][c] * Phi[c][:], Phi = [1, x, x^2]: a 128 x 64 x (2d+1) product.  The vector FP64 pipe is far too
         // slow for it (ncu: math-pipe throttle, the epilogue took longer than the MMAs of the next tile), so it goes to the FP64
         // tensor pipe, idle in this kernel: W is staged 8 columns at a time through a private 32 x 8 shared-memory patch per warp
         // (row stride 12 doubles: conflict-free 64-bit fragment loads) and fed to DMMA.8x8x4 as the A operand.
         // lane = 4g + q:  a = W[8G + g][4kq + q],  b = Phi[4kq + q][8B + g],  (c0, c1) = mom[8G + g][8B + 2q, + 1]
         const int g = lane >> 2, q4 = lane & 3;
-        double* wsm = wstage + (warp - 2) * 32 * I8_WSTAGE_LD;
+        double* wsm = wstage + (warp - 2) * 32 * I8_WSTAGE_LD;   // private patch of this warp
         for (int b0 = 0; b0 * 8 < nq; b0 += 3) {   // three blocks of 8 moments per sweep (one sweep for d <= 11)
           double cm[4][3][2];
 #pragma unroll
@@ -435,7 +435,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int B = 0; B < 3; ++B) cm[G][B][0] = cm[G][B][1] = 0.0;
 #pragma unroll
-          for (int pc = 0; pc < I8_BN / 8; ++pc) {
+          for (int pc = 0; pc < I8_EC / 8; ++pc) {
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; j += 2)
@@ -446,7 +446,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               double a[4];
 #pragma unroll
               for (int G = 0; G < 4; ++G) a[G] = wsm[(8 * G + g) * I8_WSTAGE_LD + 4 * kq + q4];
-              const double* xr = xs + (pc * 8 + 4 * kq + q4) * d;
+              const double* xr = xs + (half * I8_EC + pc * 8 + 4 * kq + q4) * d;
 #pragma unroll
               for (int B = 0; B < 3; ++B) {
                 const int m = (b0 + B) * 8 + g;
@@ -463,7 +463,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int G = 0; G < 4; ++G) {
             const int rr = it.tm * I8_BM + quarter * 32 + 8 * G + g;
             if (rr >= p.M) continue;
-            double* mo = p.mom + (int64_t)it.tn * p.sMomTile + (int64_t)rr * nq;
+            double* mo = p.mom + (int64_t)(it.tn * 2 + half) * p.sMomTile + (int64_t)rr * nq;   // one slab per 32 columns
 #pragma unroll
             for (int B = 0; B < 3; ++B) {
               const int m = (b0 + B) * 8 + 2 * q4;

@@ -661,7 +661,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
         RUN(launch_i8(h, st, I8_EPI_F64, sy, A, A));
       }
       ProfScope ps_o(h, st, CAT_OTHER);
-      k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, 0, ntn, m, h->bvec);
+      k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, 0, 2 * ntn, m, h->bvec);   // one slab per 32 columns
       CKL();
       continue;
     }
@@ -800,7 +800,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       { const char* e = getenv("GGP_I8_SERIAL_EPI"); g8.serial_epi = (e && e[0] == '0') ? 0 : 1; }
       { ProfScope ps(h, st, CAT_BWD); RUN(launch_i8(h, st, I8_EPI_MOMENTS, g8, {h->Pq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK})); }
       ProfScope ps_o(h, st, CAT_OTHER);
-      k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, 0, (nv + I8_BN - 1) / I8_BN, cnt,
+      k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, 0, 2 * ((nv + I8_BN - 1) / I8_BN), cnt,
                                                                                   h->mom_acc);
       CKL();
       continue;

@@ -24,7 +24,8 @@ def test_gemm_i8_matches_float64_matmul(mm, nn, kk):
     assert float(((C - ref).abs() / scale).max()) < 2e-15
 
 
-@pytest.mark.parametrize("N,M,D,jit", [(3000, 260, 4, 1e-4), (2500, 129, 8, 1e-4), (40000, 300, 8, 1e-4), (20000, 1024, 8, 1e-4)])
+@pytest.mark.parametrize("N,M,D,jit", [(3000, 260, 4, 1e-4), (2500, 129, 8, 1e-4), (40000, 300, 8, 1e-4), (20000, 1024, 8, 1e-4),
+                                       (5000, 200, 16, 1e-4), (1777, 100, 1, 1e-4), (16385, 128, 3, 1e-4)])
 def test_i8_bound_and_gradient_parity(N, M, D, jit):
     import ggp_b200
     from oracle import sgpr as osgpr
@@ -61,3 +62,16 @@ def test_i8_matern_gradient_parity():
     Fo, go = osgpr.sgpr_bound_and_grads_autograd(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=1e-4, normalize="none", kind="matern32")
     g = out["grad"][0].cpu()
     assert relerr(out["bound"], Fo) < TOL and relerr(g[:D], go["ell"]) < TOL and relerr(g[D + 2:].view(M, D), go["Z"]) < TOL
+
+
+def test_i8_row_shard_additivity_and_determinism():
+    """Row shards add up (what the NCCL all-reduce does across ranks) and repeated evaluations are bit-identical."""
+    import ggp_b200
+    eng = ggp_b200.Engine.get(torch.device("cuda:0"), precision="fp64_i8")
+    X, y, Z, th = make_problem(30000, 256, 6, seed=12)
+    full = eng.sgpr_eval(X, y, Z, th, jitter_policy=1e-4)
+    again = eng.sgpr_eval(X, y, Z, th, jitter_policy=1e-4)
+    assert torch.equal(full["bound"], again["bound"]) and torch.equal(full["grad"], again["grad"])
+    p1 = eng.sgpr_eval(X[:13000], y[:13000], Z, th, jitter_policy=1e-4)["partial"].clone()
+    p2 = eng.sgpr_eval(X[13000:], y[13000:], Z, th, jitter_policy=1e-4)["partial"].clone()
+    assert relerr(p1 + p2, full["partial"]) < 1e-13
