@@ -19,6 +19,7 @@
 // FP64-equivalent at K = 1024 and 88 TF/s at K = 16384 (the DMMA peak is 37.2).
 #pragma once
 #include <cuda.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace ggp {
@@ -50,6 +51,8 @@ struct I8P {
   int lower_a;                           // A lower triangular: k range of row tile tm clipped to (tm + 1) * 128
   int sym;                               // only tiles that touch the upper triangle (tn * 64 + 63 >= tm * 128)
   int n_major;                           // enumerate the row tiles of one column tile consecutively
+  int snake;                             // CTA b takes item b of even rounds and item G-1-b of odd rounds (work list sorted by weight:
+                                         // the triangular multiply's k range grows with tm, plain round-robin is 6 % off balance)
   int M, N;                              // valid rows of A / rows of B (stores are clipped to them)
   const int* ea; int ea0;                // exponents of the A rows (array or scalar)
   const int* eb; int eb0;                // exponents of the B rows
@@ -61,6 +64,9 @@ struct I8P {
   const double* yv; double* rowdot;      // rowdot[tn][M]
   // I8_EPI_MOMENTS: W = (alpha * acc + u[row] * yv[col]) * Kmul[col][row];  mom[tn][row][:] = sum_col W * [1, x_col, x_col^2]
   const double* u; const double* Kmul; int64_t ldk; const double* Xc; int d; double* mom; int64_t sMomTile;
+  int mom_accum;                         // I8_EPI_MOMENTS, 2 d + 1 <= 24: grid = tiles_m x ng, CTA b owns row tile b % tiles_m and the column tiles
+                                         // b / tiles_m + ng k; its moments stay in registers over all its tiles and are written once:
+                                         // mom[(b / tiles_m) * 2 + half][row][:]  (2 ng slabs instead of one per 32 columns)
   int serial_epi;                        // 1: hand TMEM back only after the whole epilogue (FP64 epilogue math and the running
                                          // UTCIMMA stream throttle each other on the tensor / FP64 pipe: measured 10x slower when overlapped)
   long long* dbg;                        // developer timeline (CTA 0): [role][item][4] clock64 stamps, or NULL
@@ -143,15 +149,29 @@ __device__ __forceinline__ void i8_decode(const I8P& p, int w, I8Item& o) {
   o.kb_hi = min(nkb, o.kb_lo + per);
 }
 
+// work item of CTA b in round k (all three warp roles enumerate the same list)
+__device__ __forceinline__ int i8_item(const I8P& p, int k, int b, int G) {
+  if (p.mom_accum) {   // n-major encoding of (tm = b % tiles_m, tn = b / tiles_m + ng k); beyond the last column tile -> >= total
+    const int ng = G / p.tiles_m, tn = b / p.tiles_m + ng * k;
+    return tn < p.tiles_n ? tn * p.tiles_m + b % p.tiles_m : p.total;
+  }
+  return k * G + ((p.snake && (k & 1)) ? (G - 1 - b) : b);
+}
+__device__ __forceinline__ int i8_rounds(const I8P& p, int G) {
+  if (p.mom_accum) { const int ng = G / p.tiles_m; return (p.tiles_n + ng - 1) / ng; }
+  return (p.total + G - 1) / G;
+}
+
 // Balanced 7-bit digits of v (|v| < 1/2), most significant first: t = rn(v 2^56) = sum_i d_i 2^(7 (7-i)) with d_1..d_7 in
 // [-64, 63] and |d_0| <= 64.  Adding C = sum_{i>=1} 64 * 2^(7 (7-i)) first turns the balanced recoding (carries) into plain bit
 // fields: d_i = field_i(t + C) - 64, d_0 = (t + C) >> 49.  One conversion, one 64-bit add, three integer ops per digit.
 // Balanced digits matter: the digit pairs with i + j >= NS are dropped, and with zero-mean digits what is dropped is zero-mean
 // (with unsigned fields it is a one-sided bias that grows linearly in K: measured 50x worse).
 // Exactness of the level sums: |d_i d_j| <= 4096, at most 8 pairs per level -> K < 2^31 / 2^15 = 65536 (I8_MAX_K = 32768).
-__device__ __forceinline__ void i8_digits(double v, int8_t (&dg)[I8_NS]) {
+// T = rn(v 2^56) already in hand (the all-integer epilogue of the triangular multiply)
+__device__ __forceinline__ void i8_digits_fixed(long long T, int8_t (&dg)[I8_NS]) {
   static_assert(I8_NS == 8, "56-bit fixed point");
-  const long long t = __double2ll_rn(v * 72057594037927936.0) + 283691315109952ll;   // v * 2^56 + C, C = 64 (2^49 - 1) / 127
+  const long long t = T + 283691315109952ll;   // + C, C = 64 (2^49 - 1) / 127
   const unsigned lo = (unsigned)((unsigned long long)t & 0x0FFFFFFFull);   // bits 0..27  -> digits 7..4
   const int hi = (int)(t >> 28);                                            // bits 28..55 -> digits 3..0
   dg[7] = (int8_t)((int)(lo & 127u) - 64);
@@ -162,6 +182,47 @@ __device__ __forceinline__ void i8_digits(double v, int8_t (&dg)[I8_NS]) {
   dg[2] = (int8_t)(((hi >> 7) & 127) - 64);
   dg[1] = (int8_t)(((hi >> 14) & 127) - 64);
   dg[0] = (int8_t)(hi >> 21);
+}
+__device__ __forceinline__ void i8_digits(double v, int8_t (&dg)[I8_NS]) { i8_digits_fixed(__double2ll_rn(v * 72057594037927936.0), dg); }
+
+// I8_EPI_SLICE builds its output digits without touching the FP64 pipe (FP64 instructions issued while the UTCIMMA stream runs are
+// throttled and slow the MMAs down in turn: the mainloop ran at 2830 clk per k-block next to the FP64 epilogue, 2470 alone).
+// The product value is (t_hi 2^28 + t_lo) 2^(-63 + e_row + e_col) with t_hi / t_lo the combined level sums 0..3 / 4..7, the output
+// fixed point is rn(value 2^(56 - eo)) = rn((t_hi 2^28 + t_lo) / 2^sh), sh = 7 + eo - e_row - e_col: two shifts and an add.
+__device__ __forceinline__ long long i8_fx_lo(long long t, int sh) {
+  if (sh <= 0) return (long long)((unsigned long long)t << min(-sh, 63));
+  if (sh <= 28) return (t + (1ll << (sh - 1))) >> sh;
+  return (t + (1ll << 27)) >> 28;   // in units of 2^28: joins t_hi before the final shift
+}
+__device__ __forceinline__ long long i8_fx_hi(long long t, long long lo, int sh) {
+  if (sh <= 28) return (long long)((unsigned long long)t << min(28 - sh, 63)) + lo;
+  const int s = min(sh - 28, 62);
+  return (t + lo + (1ll << (s - 1))) >> s;
+}
+// the common case 1 <= sh <= 28 (whole warp) with 32-bit funnel shifts: (t + 2^(sh-1)) >> sh and (t << (28 - sh)) + lo
+__device__ __forceinline__ long long i8_fx_lo_fast(long long t, int sh, long long rnd) {
+  const long long r = t + rnd;
+  const uint32_t rl = (uint32_t)r, rh = (uint32_t)((unsigned long long)r >> 32);
+  const uint32_t ol = __funnelshift_r(rl, rh, sh);
+  const int oh = (int)rh >> sh;
+  return (long long)(((unsigned long long)(uint32_t)oh << 32) | ol);
+}
+__device__ __forceinline__ long long i8_fx_hi_fast(long long t, long long lo, int s2) {
+  const uint32_t tl = (uint32_t)t, th = (uint32_t)((unsigned long long)t >> 32);
+  const uint32_t oh = __funnelshift_l(tl, th, s2), ol = tl << s2;
+  return (long long)(((unsigned long long)oh << 32) | ol) + lo;
+}
+// four level sums -> one exact 64-bit integer, t = a0 2^21 + a1 2^14 + a2 2^7 + a3 (three IMAD.WIDE)
+__device__ __forceinline__ long long i8_mad_wide(int a, int b, long long c) {
+  long long d;
+  asm("mad.wide.s32 %0, %1, %2, %3;\n" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ long long i8_comb4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
+  long long t = (long long)(int)a3;
+  t = i8_mad_wide((int)a2, 128, t);
+  t = i8_mad_wide((int)a1, 16384, t);
+  return i8_mad_wide((int)a0, 2097152, t);
 }
 
 template <int EPI>
@@ -182,6 +243,11 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
+  if (p.dbg && threadIdx.x == 0) {   // developer timeline: wall-clock span of every CTA
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.dbg[2 * I8_DBG_ITEMS * 4 + 2 * blockIdx.x] = (long long)gt;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < I8_STAGES; ++s) {
@@ -205,7 +271,9 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // ================= TMA producer =================
     if (lane == 0) {
       int n = 0;
-      for (int w = blockIdx.x; w < p.total; w += G) {
+      for (int rnd = 0, nrnd = i8_rounds(p, G); rnd < nrnd; ++rnd) {
+        const int w = i8_item(p, rnd, blockIdx.x, G);
+        if (w >= p.total) continue;
         I8Item it;
         i8_decode(p, w, it);
         for (int kb = it.kb_lo; kb < it.kb_hi; ++kb, ++n) {
@@ -224,7 +292,9 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   } else if (warp == 1) {
     // ================= MMA issuer =================
     int n = 0, item = 0;
-    for (int w = blockIdx.x; w < p.total; w += G) {
+    for (int rnd = 0, nrnd = i8_rounds(p, G); rnd < nrnd; ++rnd) {
+      const int w = i8_item(p, rnd, blockIdx.x, G);
+      if (w >= p.total) continue;
       I8Item it;
       i8_decode(p, w, it);
       if (it.kb_hi <= it.kb_lo) continue;
@@ -268,8 +338,15 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;  // column half of the tile handled by this warp
     const int et = threadIdx.x - 64;   // 0..255
+    double cmA[4][3][2];               // I8_EPI_MOMENTS with mom_accum: moments of this warp's rows over all tiles of the CTA
+#pragma unroll
+    for (int G4 = 0; G4 < 4; ++G4)
+#pragma unroll
+      for (int B = 0; B < 3; ++B) cmA[G4][B][0] = cmA[G4][B][1] = 0.0;
     int item = 0;
-    for (int w = blockIdx.x; w < p.total; w += G) {
+    for (int rnd = 0, nrnd = i8_rounds(p, G); rnd < nrnd; ++rnd) {
+      const int w = i8_item(p, rnd, blockIdx.x, G);
+      if (w >= p.total) continue;
       I8Item it;
       i8_decode(p, w, it);
       if (it.kb_hi <= it.kb_lo) continue;
@@ -304,36 +381,50 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         load_kv(kv1, 1);
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
       }
+      const int e_r = p.ea ? p.ea[min(row, p.M - 1)] : p.ea0;
+      const int sh = 7 + p.eo - e_r - p.eb0;   // I8_EPI_SLICE (scalar column exponent, alpha = 1: checked on the host)
+      const bool fx_fast = (EPI == I8_EPI_SLICE) && __all_sync(0xffffffffu, sh >= 1 && sh <= 28);
+      const long long fx_rnd = 1ll << ((sh - 1) & 63);
       if (et == 0) I8_STAMP(1, item, 0);
       i8_mbar_wait(tmem_full, item & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
       if (et == 0) I8_STAMP(1, item, 1);
       double acc[I8_EC];
+      long long fx[I8_EC];   // I8_EPI_SLICE: rn(value 2^(56 - eo)), integer arithmetic only
 #pragma unroll
-      for (int c = 0; c < I8_EC; ++c) acc[c] = 0.0;
+      for (int c = 0; c < I8_EC; ++c) { acc[c] = 0.0; fx[c] = 0; }
+      // four levels per TMEM round trip, combined exactly in int64 (|sum| < 2^53) before ONE int->double conversion (or, in the
+      // all-integer epilogue, two shifts): levels l0..l0+3 -> t = ((a0 * 128 + a1) * 128 + a2) * 128 + a3, value = t * 2^(-7 (l0 + 5))
+      static_assert(I8_NS == 8, "two groups of four levels");
+      auto drain = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
-      for (int c0 = 0; c0 < I8_EC; c0 += 16) {
-        // four levels per TMEM round trip, combined exactly in int64 (|sum| < 2^53) before ONE int->double conversion:
-        // levels l0..l0+3 -> t = ((a0 * 128 + a1) * 128 + a2) * 128 + a3, value = t * 2^(-7 (l0 + 5))
-        static_assert(I8_NS == 8, "two groups of four levels");
+        for (int c0 = 0; c0 < I8_EC; c0 += 16) {
 #pragma unroll
-        for (int l0 = 4; l0 >= 0; l0 -= 4) {
-          uint32_t v0[16], v1[16], v2[16], v3[16];
-          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(l0 * I8_BN + half * I8_EC + c0);
-          i8_tmem_ld16(ta, v0);
-          i8_tmem_ld16(ta + I8_BN, v1);
-          i8_tmem_ld16(ta + 2 * I8_BN, v2);
-          i8_tmem_ld16(ta + 3 * I8_BN, v3);
-          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-          const double wl = (l0 == 4) ? 1.0842021724855044e-19 /* 2^-63 */ : 2.9103830456733704e-11 /* 2^-35 */;
+          for (int l0 = 4; l0 >= 0; l0 -= 4) {
+            uint32_t v0[16], v1[16], v2[16], v3[16];
+            const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(l0 * I8_BN + half * I8_EC + c0);
+            i8_tmem_ld16(ta, v0);
+            i8_tmem_ld16(ta + I8_BN, v1);
+            i8_tmem_ld16(ta + 2 * I8_BN, v2);
+            i8_tmem_ld16(ta + 3 * I8_BN, v3);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            const double wl = (l0 == 4) ? 1.0842021724855044e-19 /* 2^-63 */ : 2.9103830456733704e-11 /* 2^-35 */;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const long long t = ((long long)(int)v0[c] << 21) + ((long long)(int)v1[c] << 14) + ((long long)(int)v2[c] << 7) +
-                                (long long)(int)v3[c];
-            acc[c0 + c] = fma((double)t, wl, acc[c0 + c]);
+            for (int c = 0; c < 16; ++c) {
+              const long long t = i8_comb4(v0[c], v1[c], v2[c], v3[c]);
+              if (EPI == I8_EPI_SLICE) {
+                if (FAST) fx[c0 + c] = (l0 == 4) ? i8_fx_lo_fast(t, sh, fx_rnd) : i8_fx_hi_fast(t, fx[c0 + c], 28 - sh);
+                else fx[c0 + c] = (l0 == 4) ? i8_fx_lo(t, sh) : i8_fx_hi(t, fx[c0 + c], sh);
+              } else {
+                acc[c0 + c] = fma((double)t, wl, acc[c0 + c]);
+              }
+            }
           }
         }
-      }
+      };
+      if (fx_fast) drain(std::true_type{});
+      else drain(std::false_type{});
       // accumulators are in registers: hand TMEM back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
       __syncwarp();
@@ -342,9 +433,9 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int item_done = item;
       ++item;
 
-      const int e_r = p.ea ? p.ea[min(row, p.M - 1)] : p.ea0;
       const bool rok = row < p.M;
-      if (p.eb) {
+      if (EPI == I8_EPI_SLICE) {
+      } else if (p.eb) {
 #pragma unroll
         for (int c = 0; c < I8_EC; ++c) acc[c] = p.alpha * ldexp(acc[c], e_r + p.eb[min(col0 + c, p.N - 1)]);
       } else {
@@ -379,7 +470,10 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
       } else if (EPI == I8_EPI_SLICE) {
-        if (p.rowdot) {
+        if (p.rowdot) {   // (not used by the streamed pass any more: b = L^{-1} (Kzx y) comes from the tile build)
+          const double so = exp2((double)(p.eo - 56));
+#pragma unroll
+          for (int c = 0; c < I8_EC; ++c) acc[c] = (double)fx[c] * so;
           double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
           for (int c = 0; c < I8_EC; c += 4) {
@@ -390,25 +484,38 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           if (rok) p.rowdot[(int64_t)(it.tn * 2 + half) * p.M + row] = (s0 + s1) + (s2 + s3);   // one slab per 32 columns
         }
-        // digit planes of the tile row: 64 consecutive bytes per plane (columns beyond N are zero because their B rows are zero)
-        const double si = exp2((double)-p.eo);
+        // digit planes of the tile row: this thread's 32 columns are 32 consecutive bytes per plane = one full sector, written with one
+        // 256-bit store (two 16-byte stores made every sector a pair of partial writes; the kernel runs at the L2 throughput cap).
+        // Columns beyond N are zero because their B rows are zero.
+        {
+          uint32_t pk[I8_NS][I8_EC / 4];
 #pragma unroll
-        for (int c0 = 0; c0 < I8_EC; c0 += 16) {
-          uint32_t pk[I8_NS][4];
+          for (int i = 0; i < I8_NS; ++i)
 #pragma unroll
-          for (int i = 0; i < I8_NS; ++i) pk[i][0] = pk[i][1] = pk[i][2] = pk[i][3] = 0u;
+            for (int j = 0; j < I8_EC / 4; ++j) pk[i][j] = 0u;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
+          for (int c = 0; c < I8_EC; ++c) {
             int8_t dg[I8_NS];
-            i8_digits(acc[c0 + c] * si, dg);
+            i8_digits_fixed(fx[c], dg);
 #pragma unroll
             for (int i = 0; i < I8_NS; ++i) pk[i][c >> 2] |= ((uint32_t)(uint8_t)dg[i]) << (8 * (c & 3));
           }
+          static_assert(I8_EC == 32, "one 32-byte sector per thread and plane");
           if (rok) {
+            int8_t* dst = p.Oq + (int64_t)row * p.o_ld + col0;
+            if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0 && (p.o_plane & 31) == 0) {
 #pragma unroll
-            for (int i = 0; i < I8_NS; ++i)
-              *reinterpret_cast<uint4*>(p.Oq + (int64_t)i * p.o_plane + (int64_t)row * p.o_ld + col0 + c0) =
-                  make_uint4(pk[i][0], pk[i][1], pk[i][2], pk[i][3]);
+              for (int i = 0; i < I8_NS; ++i)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst + (int64_t)i * p.o_plane), "r"(pk[i][0]),
+                             "r"(pk[i][1]), "r"(pk[i][2]), "r"(pk[i][3]), "r"(pk[i][4]), "r"(pk[i][5]), "r"(pk[i][6]), "r"(pk[i][7])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < I8_NS; ++i) {
+                *reinterpret_cast<uint4*>(dst + (int64_t)i * p.o_plane) = make_uint4(pk[i][0], pk[i][1], pk[i][2], pk[i][3]);
+                *reinterpret_cast<uint4*>(dst + (int64_t)i * p.o_plane + 16) = make_uint4(pk[i][4], pk[i][5], pk[i][6], pk[i][7]);
+              }
+            }
           }
         }
       } else {
@@ -428,12 +535,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // lane = 4g + q:  a = W[8G + g][4kq + q],  b = Phi[4kq + q][8B + g],  (c0, c1) = mom[8G + g][8B + 2q, + 1]
         const int g = lane >> 2, q4 = lane & 3;
         double* wsm = wstage + (warp - 2) * 32 * I8_WSTAGE_LD;   // private patch of this warp
-        for (int b0 = 0; b0 * 8 < nq; b0 += 3) {   // three blocks of 8 moments per sweep (one sweep for d <= 11)
-          double cm[4][3][2];
-#pragma unroll
-          for (int G = 0; G < 4; ++G)
-#pragma unroll
-            for (int B = 0; B < 3; ++B) cm[G][B][0] = cm[G][B][1] = 0.0;
+        auto sweep = [&](int b0, double (&cm)[4][3][2]) {   // cm += W (this warp's 32 x 32 patch) x Phi[:, 8 b0 .. 8 b0 + 24)
 #pragma unroll
           for (int pc = 0; pc < I8_EC / 8; ++pc) {
             __syncwarp();
@@ -459,16 +561,28 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               }
             }
           }
+        };
+        if (p.mom_accum) {
+          sweep(0, cmA);   // one sweep covers all 2 d + 1 <= 24 moments; written after the CTA's last tile
+        } else {
+          for (int b0 = 0; b0 * 8 < nq; b0 += 3) {   // three blocks of 8 moments per sweep (one sweep for d <= 11)
+            double cm[4][3][2];
 #pragma unroll
-          for (int G = 0; G < 4; ++G) {
-            const int rr = it.tm * I8_BM + quarter * 32 + 8 * G + g;
-            if (rr >= p.M) continue;
-            double* mo = p.mom + (int64_t)(it.tn * 2 + half) * p.sMomTile + (int64_t)rr * nq;   // one slab per 32 columns
+            for (int G = 0; G < 4; ++G)
 #pragma unroll
-            for (int B = 0; B < 3; ++B) {
-              const int m = (b0 + B) * 8 + 2 * q4;
-              if (m < nq) mo[m] = cm[G][B][0];
-              if (m + 1 < nq) mo[m + 1] = cm[G][B][1];
+              for (int B = 0; B < 3; ++B) cm[G][B][0] = cm[G][B][1] = 0.0;
+            sweep(b0, cm);
+#pragma unroll
+            for (int G = 0; G < 4; ++G) {
+              const int rr = it.tm * I8_BM + quarter * 32 + 8 * G + g;
+              if (rr >= p.M) continue;
+              double* mo = p.mom + (int64_t)(it.tn * 2 + half) * p.sMomTile + (int64_t)rr * nq;   // one slab per 32 columns
+#pragma unroll
+              for (int B = 0; B < 3; ++B) {
+                const int m = (b0 + B) * 8 + 2 * q4;
+                if (m < nq) mo[m] = cm[G][B][0];
+                if (m + 1 < nq) mo[m + 1] = cm[G][B][1];
+              }
             }
           }
         }
@@ -479,9 +593,30 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       if (et == 0) I8_STAMP(1, item_done, 3);
     }
+    if (EPI == I8_EPI_MOMENTS && p.mom_accum) {
+      const int nq = 2 * p.d + 1, g = lane >> 2, q4 = lane & 3;
+      const int tm = blockIdx.x % p.tiles_m, slab = (blockIdx.x / p.tiles_m) * 2 + half;
+#pragma unroll
+      for (int G4 = 0; G4 < 4; ++G4) {
+        const int rr = tm * I8_BM + quarter * 32 + 8 * G4 + g;
+        if (rr >= p.M) continue;
+        double* mo = p.mom + (int64_t)slab * p.sMomTile + (int64_t)rr * nq;
+#pragma unroll
+        for (int B = 0; B < 3; ++B) {
+          const int m = B * 8 + 2 * q4;
+          if (m < nq) mo[m] = cmA[G4][B][0];
+          if (m + 1 < nq) mo[m + 1] = cmA[G4][B][1];
+        }
+      }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.dbg[2 * I8_DBG_ITEMS * 4 + 2 * blockIdx.x + 1] = (long long)gt;
+  }
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(I8_TMEM_COLS));
 }
 

@@ -67,6 +67,7 @@ struct ggp_handle {
   size_t arena_i8_bytes = 0;
   int8_t *Lq = 0, *Pq = 0, *Atq = 0, *Kq = 0;
   int *eL = 0, *eP = 0;
+  double* kzy = nullptr;   // Kzx y accumulated over the chunks (b = L^{-1} Kzx y)
   int8_t* kq_all = nullptr;
   size_t kq_all_bytes = 0;
   long long* i8_dbg = nullptr;   // developer timeline buffer (GGP_I8_TIMELINE=2)
@@ -384,6 +385,8 @@ struct I8Operand { const int8_t* q; int64_t rows, ld, plane; };
 static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Operand& A, const I8Operand& B) {
   if (p.K < 1 || p.M < 1 || p.N < 1) return 0;
   if (p.K > I8_MAX_K) return fail(-4, "launch_i8: k extent exceeds the exact int32 accumulation bound (32768)");
+  if (epi == I8_EPI_SLICE && (p.eb || p.alpha != 1.0))
+    return fail(-4, "launch_i8: the digit-plane epilogue takes a scalar column exponent and alpha = 1");
   p.tiles_m = (p.M + I8_BM - 1) / I8_BM;
   p.tiles_n = (p.N + I8_BN - 1) / I8_BN;
   int tiles = p.tiles_m * p.tiles_n;
@@ -396,12 +399,17 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
   CUtensorMap tmA, tmB;
   if (!make_i8_map(&tmA, A.q, A.rows, p.K, A.ld, A.plane, I8_BM) || !make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN))
     return fail(-4, "launch_i8: operand planes cannot be described by a tensor map (alignment)");
-  const int grid = std::min(p.total, h->sm_count);
+  int grid = std::min(p.total, h->sm_count);
+  if (epi == I8_EPI_MOMENTS && p.mom_accum) {
+    if (p.tiles_m > h->sm_count || 2 * p.d + 1 > 24 || p.sym || p.splits != 1)
+      return fail(-4, "launch_i8: mom_accum needs tiles_m <= SM count, 2 d + 1 <= 24, no symmetry and no split-K");
+    grid = p.tiles_m * std::max(1, std::min(h->sm_count / p.tiles_m, p.tiles_n));
+  }
   const char* tl = getenv("GGP_I8_TIMELINE");
   const bool dbg = tl && tl[0] == '2' && h->i8_dbg_prints < 9 && !p.dbg;
   if (dbg) {
-    if (!h->i8_dbg) CK(cudaMalloc((void**)&h->i8_dbg, 2 * I8_DBG_ITEMS * 4 * sizeof(long long)));
-    CK(cudaMemsetAsync(h->i8_dbg, 0, 2 * I8_DBG_ITEMS * 4 * sizeof(long long), st));
+    if (!h->i8_dbg) CK(cudaMalloc((void**)&h->i8_dbg, (2 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long)));
+    CK(cudaMemsetAsync(h->i8_dbg, 0, (2 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long), st));
     p.dbg = h->i8_dbg;
   }
   if (epi == I8_EPI_F64) k_gemm_i8<I8_EPI_F64><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
@@ -410,11 +418,21 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
   CKL();
   if (dbg) {
     CK(cudaStreamSynchronize(st));
-    long long hb[2 * I8_DBG_ITEMS * 4];
+    long long hb[2 * I8_DBG_ITEMS * 4 + 2 * 256];
     CK(cudaMemcpy(hb, h->i8_dbg, sizeof(hb), cudaMemcpyDeviceToHost));
+    {
+      const long long* g = hb + 2 * I8_DBG_ITEMS * 4;
+      long long s0 = g[0], s1 = g[0], e0 = g[1], e1 = g[1];
+      for (int b = 0; b < grid && b < 256; ++b) {
+        s0 = std::min(s0, g[2 * b]); s1 = std::max(s1, g[2 * b]);
+        e0 = std::min(e0, g[2 * b + 1]); e1 = std::max(e1, g[2 * b + 1]);
+      }
+      fprintf(stderr, "== CTA spans (ns): starts within %lld, first end +%lld, last end +%lld; CTA0 %lld..%lld\n", s1 - s0, e0 - s0, e1 - s0,
+              g[0] - s0, g[1] - s0);
+    }
     const long long t0 = hb[0];
     fprintf(stderr, "== i8 timeline, epilogue %d, M=%d N=%d K=%d lower=%d sym=%d splits=%d\n", epi, p.M, p.N, p.K, p.lower_a, p.sym, p.splits);
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < I8_DBG_ITEMS; ++it) {
       const long long* m = hb + it * 4;
       const long long* ep = hb + (I8_DBG_ITEMS + it) * 4;
       fprintf(stderr, "tile %2d  mma: start %8lld tmem_free %8lld first_kb %8lld all_issued %8lld | epi: wait %8lld full %8lld drained %8lld done %8lld\n",
@@ -522,7 +540,7 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   if (cfg && cfg->precision == GGP_PREC_FP64_I8 && batch == 1 && p.Mp >= I8_BM) {
     const size_t MMq = align_up((size_t)I8_NS * p.Mp * p.Mp, 256), CHq = align_up((size_t)I8_NS * p.Mp * p.nc, 256),
                  EX = align_up((size_t)p.Mp * 4, 256);
-    const size_t need = 2 * MMq + 2 * CHq + 2 * EX;
+    const size_t need = 2 * MMq + 2 * CHq + 2 * EX + align_up((size_t)p.Mp * 8, 256);
     if (need > h->arena_i8_bytes) {
       if (h->arena_i8) CK(cudaFree(h->arena_i8));
       h->arena_i8 = nullptr;
@@ -536,7 +554,8 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
     h->Atq = (int8_t*)q; q += CHq;
     h->Kq = (int8_t*)q; q += CHq;
     h->eL = (int*)q; q += EX;
-    h->eP = (int*)q;
+    h->eP = (int*)q; q += EX;
+    h->kzy = (double*)q;
     if (h->kc_all) {
       const size_t needq = (size_t)h->kc_rows * p.Mp * I8_NS;
       const size_t budget = (size_t)cfg->tile_cache_mib * 1024 * 1024;
@@ -592,6 +611,17 @@ static int build_chunk(ggp_handle* h, cudaStream_t st, const double* Xc, int nv,
   return 0;
 }
 
+// sliced-integer path: FP64 tile + digit planes + (optionally) the Kzx y partials of the chunk in one kernel
+static int build_chunk_i8(ggp_handle* h, cudaStream_t st, const double* Xc, const double* yc, int nv, int d, const double* Z, int m,
+                          const double* theta, int kind, double* Kc, int8_t* Kq, int64_t plane, double* kty_part) {
+  const int Mp = h->Mp;
+  dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N);
+  const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
+  k_build_kc_i8<<<grid, KT_THREADS, smem, st>>>(Xc, yc, nv, d, Z, m, theta, kind, Kc, Mp, Kq, Mp, plane, kty_part);
+  CKL();
+  return 0;
+}
+
 int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, const double* y, int64_t n_local,
                    const double* Z, const double* theta, int m, int d, int batch, double* partial) {
   if (!h || !Z || !theta || !partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass1: NULL argument");
@@ -620,29 +650,31 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     ProfScope ps(h, st, CAT_BUILD);
     k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->Linv, Mp, Mp, Mp, h->Lq, Mp, (int64_t)Mp * Mp, Mp, h->eL);
     CKL();
+    CK(cudaMemsetAsync(h->kzy, 0, (size_t)Mp * 8, st));
   }
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
     double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
     const int64_t sK = h->kc_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
-    { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
     if (i8) {
       int8_t* Kq_c = h->kq_all ? h->kq_all + c0 * Mp : h->Kq;
       const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
-      {
+      const int ntb = (nv + KT_N - 1) / KT_N;
+      {   // k(X,Z) tile, its digit planes and the Kzx y partials of the chunk (one slab per 64 rows)
         ProfScope ps(h, st, CAT_BUILD);
-        const int64_t nthr = (int64_t)nv * (Mp / 4);
-        k_slice_fixed<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Kc_c, nv, Mp, Mp, Kq_c, Mp, plK, theta, d);
+        RUN(build_chunk_i8(h, st, X + c0 * d, y + c0, nv, d, Z, m, theta, kind, Kc_c, Kq_c, plK, h->mom_part));
+        k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), 1), 256, 0, st>>>(h->mom_part, Mp, 0, ntb, m, h->kzy);
         CKL();
       }
-      const int ntn = (nv + I8_BN - 1) / I8_BN;
-      {   // A^T digits [m x nv] = L^{-1} (lower) x Kc^T, fused b-partials = A y
+      {   // A^T digits [m x nv] = L^{-1} (lower) x Kc^T; all-integer epilogue
         I8P t;
         memset(&t, 0, sizeof(t));
-        t.M = m; t.N = nv; t.K = Mp; t.lower_a = 1; t.splits = 1;
+        t.M = m; t.N = nv; t.K = Mp; t.lower_a = 1; t.splits = 1; t.snake = 1;
+        { const char* e = getenv("GGP_I8_TRMM_ORDER"); t.n_major = (e && e[0] == '0') ? 0 : 1; }
+        if (getenv("GGP_I8_ROWDOT")) { t.yv = y + c0; t.rowdot = h->mom_part; }
+        if (getenv("GGP_I8_TRMM_SERIAL")) t.serial_epi = 1;
         t.ea = h->eL; t.eb0 = eK; t.alpha = 1.0;
         t.Oq = h->Atq; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo = eA;
-        t.yv = y + c0; t.rowdot = h->mom_part;
         ProfScope ps(h, st, CAT_TRMM);
         RUN(launch_i8(h, st, I8_EPI_SLICE, t, {h->Lq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK}));
       }
@@ -660,11 +692,14 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
         ProfScope ps(h, st, CAT_SYRK);
         RUN(launch_i8(h, st, I8_EPI_F64, sy, A, A));
       }
-      ProfScope ps_o(h, st, CAT_OTHER);
-      k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, 0, 2 * ntn, m, h->bvec);   // one slab per 32 columns
-      CKL();
+      if (getenv("GGP_I8_ROWDOT")) {
+        ProfScope ps_o(h, st, CAT_OTHER);
+        k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, 0, 2 * ((nv + I8_BN - 1) / I8_BN), m, h->bvec);
+        CKL();
+      }
       continue;
     }
+    { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
     // At[m x nv] = Linv[m x m] * Kc[nv x m]^T   (k clipped to the lower triangle)
     GemmP t = gemm_basic(h->Linv, Mp, sM, Kc_c, Mp, sK, h->At, nc, (int64_t)nc * Mp, m, nv, m, 1.0, 0.0,
                          KM_A_LOWER);
@@ -680,6 +715,11 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     // b += sum over n-tiles of the fused row dots (fixed order)
     k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, (int64_t)(nc / BN) * m,
                                                                               (nv + BN - 1) / BN, m, h->bvec);
+    CKL();
+  }
+  if (i8 && n_local > 0 && !getenv("GGP_I8_ROWDOT")) {   // b = A y = L^{-1} (Kzx y)
+    ProfScope ps(h, st, CAT_OTHER);
+    k_gemv<<<dim3((m + 7) / 8, 1), 256, 0, st>>>(h->Linv, Mp, (int64_t)Mp * Mp, h->kzy, 0, h->bvec, m, m, m, 1.0, theta, d, 0);
     CKL();
   }
   if (h->kc_all) {
@@ -768,19 +808,21 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->P, Mp, Mp, Mp, h->Pq, Mp, (int64_t)Mp * Mp, Mp, h->eP);
     CKL();
   }
-  for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
-    const int nv = (int)std::min<int64_t>(nc, n_local - c0);
+  // sliced-integer path: the moments stay in the registers of the CTA that produced them over all its tiles (2 d + 1 <= 24), and
+  // with the cached RBF tiles of pass 1 the whole local row range is ONE launch (no per-chunk tails, 2 x 18 slabs to reduce)
+  const bool i8_accum = i8 && nq <= 24 && (Mp / I8_BM) <= h->sm_count && !getenv("GGP_I8_NO_ACCUM");
+  const int64_t step = (i8_accum && cached && kind == GGP_KERNEL_RBF && n_local < (int64_t)1 << 30) ? std::max<int64_t>(n_local, 1) : nc;
+  for (int64_t c0 = 0; c0 < n_local; c0 += step) {
+    const int nv = (int)std::min<int64_t>(step, n_local - c0);
     double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
     const int64_t sK = h->kc_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
-    if (!cached) { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
+    if (!cached && !i8) { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
     if (i8) {
       int8_t* Kq_c = h->kq_all ? h->kq_all + c0 * Mp : h->Kq;
       const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
       if (!cached) {
         ProfScope ps(h, st, CAT_BUILD);
-        const int64_t nthr = (int64_t)nv * (Mp / 4);
-        k_slice_fixed<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Kc_c, nv, Mp, Mp, Kq_c, Mp, plK, theta, d);
-        CKL();
+        RUN(build_chunk_i8(h, st, X + c0 * d, nullptr, nv, d, Z, m, theta, kind, Kc_c, Kq_c, plK, nullptr));
       }
       const double* Kmul = Kc_c;
       if (kind != GGP_KERNEL_RBF) {
@@ -797,11 +839,13 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       g8.ea = h->eP; g8.eb0 = eK; g8.alpha = 1.0;
       g8.u = h->u; g8.yv = y + c0; g8.Kmul = Kmul; g8.ldk = Mp; g8.Xc = X + c0 * d; g8.d = d;
       g8.mom = h->mom_part; g8.sMomTile = cnt;
+      g8.mom_accum = i8_accum ? 1 : 0;
       { const char* e = getenv("GGP_I8_SERIAL_EPI"); g8.serial_epi = (e && e[0] == '0') ? 0 : 1; }
       { ProfScope ps(h, st, CAT_BWD); RUN(launch_i8(h, st, I8_EPI_MOMENTS, g8, {h->Pq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK})); }
       ProfScope ps_o(h, st, CAT_OTHER);
-      k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, 0, 2 * ((nv + I8_BN - 1) / I8_BN), cnt,
-                                                                                  h->mom_acc);
+      const int tiles_m = (m + I8_BM - 1) / I8_BM, tiles_n = (nv + I8_BN - 1) / I8_BN;
+      const int nslabs = i8_accum ? 2 * std::max(1, std::min(h->sm_count / tiles_m, tiles_n)) : 2 * tiles_n;
+      k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, 0, nslabs, cnt, h->mom_acc);
       CKL();
       continue;
     }

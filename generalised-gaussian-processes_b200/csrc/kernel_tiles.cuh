@@ -4,6 +4,7 @@
 // (rows 4*ty+i, columns tx+16*j: shared reads are conflict-free and global stores are 128-byte coalesced).
 #pragma once
 #include "common.cuh"
+#include "gemm_i8.cuh"
 
 namespace ggp {
 
@@ -106,6 +107,118 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc(const double* __restric
       const int m = m0 + tx + 16 * j;
       if (m >= ldk) continue;
       out[(int64_t)n * ldk + m] = (nv && m < M) ? (deriv ? kgrad(kind, sf2, d2[i][j]) : kval(kind, sf2, d2[i][j])) : 0.0;
+    }
+  }
+}
+
+// Tile build of the sliced-integer path (gemm_i8.cuh must be included first): one pass produces
+//   * the FP64 tile Kc[n][m] (multiplier of the backward epilogue),
+//   * its int8 digit planes Kq[i][n][m] with the fixed exponent e = ilogb(sf2) + 2 (k <= sf2 < 2^(e-1)), and
+//   * the partial sums kty_part[blockIdx.y][m] = sum over the block's 64 rows of k(x_n, z_m) y_n, from which b = A y = L^{-1} (Kzx y)
+//     follows in the m x m section (no row dots in the triangular multiply's epilogue).
+// Thread (tx, ty) owns rows 4 ty + i and the 4 CONSECUTIVE columns 4 tx + j: 32-byte FP64 stores and 4-byte digit stores, a half-warp
+// covers 512 / 64 contiguous bytes of one row.  zs is laid out [d][4][16] so that the shared reads stay conflict-free.
+// grid: (ldk / 64, ceil(n_valid / 64)); batch = 1.
+__global__ void __launch_bounds__(KT_THREADS) k_build_kc_i8(const double* __restrict__ X, const double* __restrict__ y, int n_valid,
+                                                           int d, const double* __restrict__ Z, int M, const double* __restrict__ theta,
+                                                           int kind, double* __restrict__ Kc, int64_t ldk, int8_t* __restrict__ Kq,
+                                                           int64_t ldq, int64_t plane, double* __restrict__ kty_part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* xs = reinterpret_cast<double*>(smem_raw);   // [KT_N][d]
+  double* zs = xs + KT_N * d;                          // [d][4][16]   (z / ell)
+  double* il = zs + KT_M * d;                          // [d]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ double ys[KT_N];
+  __shared__ double red[16][KT_M + 1];
+
+  const double sf2 = theta[d];
+  const int n0 = blockIdx.y * KT_N, m0 = blockIdx.x * KT_M;
+  const int tid = threadIdx.x;
+  const int rows = min(KT_N, n_valid - n0);
+
+  const bool bulk = (rows == KT_N) && ((((uintptr_t)(X + (int64_t)n0 * d)) & 15) == 0) && (((KT_N * d * 8) & 15) == 0);
+  if (bulk) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar, KT_N * d * 8);
+      tma_bulk_g2s(xs, X + (int64_t)n0 * d, KT_N * d * 8, &bar);
+    }
+  } else {
+    for (int i = tid; i < KT_N * d; i += KT_THREADS) {
+      const int r = i / d;
+      xs[i] = (r < rows) ? X[(int64_t)n0 * d + i] : 0.0;
+    }
+  }
+  if (tid < KT_N) ys[tid] = (y && tid < rows) ? y[n0 + tid] : 0.0;
+  for (int i = tid; i < d; i += KT_THREADS) il[i] = 1.0 / theta[i];
+  for (int i = tid; i < KT_M * d; i += KT_THREADS) {
+    const int r = i / d, c = i % d;
+    zs[c * KT_M + (r & 3) * 16 + (r >> 2)] = (m0 + r < M) ? Z[(int64_t)(m0 + r) * d + c] / theta[c] : 0.0;
+  }
+  if (bulk) mbar_wait(&bar, 0);
+  __syncthreads();
+
+  const int tx = tid & 15, ty = tid >> 4;  // tx -> columns 4 tx + j, ty -> rows 4 ty + i
+  double d2[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d2[i][j] = 0.0;
+  for (int c = 0; c < d; ++c) {
+    const double ic = il[c];
+    double xv[4], zv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xv[i] = xs[(ty * 4 + i) * d + c] * ic;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) zv[j] = zs[c * KT_M + j * 16 + tx];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double t = xv[i] - zv[j];
+        d2[i][j] = fma(t, t, d2[i][j]);
+      }
+  }
+  const double si = exp2((double)-(ilogb(sf2) + 2));
+  double ky[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    const bool nv = n < n_valid;
+    double kv[4];
+    uint32_t pk[I8_NS];
+#pragma unroll
+    for (int q = 0; q < I8_NS; ++q) pk[q] = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      kv[j] = (nv && m0 + 4 * tx + j < M) ? kval(kind, sf2, d2[i][j]) : 0.0;
+      ky[j] = fma(kv[j], ys[ty * 4 + i], ky[j]);
+      int8_t dg[I8_NS];
+      i8_digits(kv[j] * si, dg);
+#pragma unroll
+      for (int q = 0; q < I8_NS; ++q) pk[q] |= ((uint32_t)(uint8_t)dg[q]) << (8 * j);
+    }
+    if (nv) {
+      double* o = Kc + (int64_t)n * ldk + m0 + 4 * tx;
+      *reinterpret_cast<double2*>(o) = make_double2(kv[0], kv[1]);
+      *reinterpret_cast<double2*>(o + 2) = make_double2(kv[2], kv[3]);
+#pragma unroll
+      for (int q = 0; q < I8_NS; ++q) *reinterpret_cast<uint32_t*>(Kq + (int64_t)q * plane + (int64_t)n * ldq + m0 + 4 * tx) = pk[q];
+    }
+  }
+  if (kty_part) {   // fixed-order sum over the 16 row groups
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[ty][4 * tx + j] = ky[j];
+    __syncthreads();
+    if (tid < KT_M) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s += red[k][tid];
+      kty_part[(int64_t)blockIdx.y * ldk + m0 + tid] = s;
     }
   }
 }
