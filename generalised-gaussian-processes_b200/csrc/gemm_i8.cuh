@@ -61,7 +61,8 @@ struct I8P {
   double* C; int64_t ldc, sSplit;
   // I8_EPI_SLICE: digits of alpha * acc with the fixed exponent eo -> Oq[plane][row][col]; optional fused row dots against yv
   int8_t* Oq; int64_t o_ld, o_plane; int eo;
-  const double* yv; double* rowdot;      // rowdot[tn][M]
+  const double* yv; double* rowdot;      // rowdot[2 tn + half][M] (+= when rowdot_acc: one buffer over the chunks of a pass)
+  int rowdot_acc;
   // I8_EPI_MOMENTS: W = (alpha * acc + u[row] * yv[col]) * Kmul[col][row];  mom[tn][row][:] = sum_col W * [1, x_col, x_col^2]
   const double* u; const double* Kmul; int64_t ldk; const double* Xc; int d; double* mom; int64_t sMomTile;
   int mom_accum;                         // I8_EPI_MOMENTS, 2 d + 1 <= 24: grid = tiles_m x ng, CTA b owns row tile b % tiles_m and the column tiles
@@ -470,7 +471,10 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
       } else if (EPI == I8_EPI_SLICE) {
-        if (p.rowdot) {   // (not used by the streamed pass any more: b = L^{-1} (Kzx y) comes from the tile build)
+        if (p.rowdot) {
+          // fused b-partials A y from the QUANTISED A (the digits just built): S = A A^T is formed from those digits, and dF/dKzx =
+          // P Kzx + u y^T cancels by cond(Kzz), so b must belong to the same A (b = L^{-1} (Kzx y) computed on the side, even in
+          // double-double, moved the gradient by 8e-8 at the headline shape; consistent b: 5e-9 against the FP64 path)
           const double so = exp2((double)(p.eo - 56));
 #pragma unroll
           for (int c = 0; c < I8_EC; ++c) acc[c] = (double)fx[c] * so;
@@ -482,7 +486,11 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             s2 = fma(acc[c + 2], (col0 + c + 2 < p.N) ? __ldg(p.yv + col0 + c + 2) : 0.0, s2);
             s3 = fma(acc[c + 3], (col0 + c + 3 < p.N) ? __ldg(p.yv + col0 + c + 3) : 0.0, s3);
           }
-          if (rok) p.rowdot[(int64_t)(it.tn * 2 + half) * p.M + row] = (s0 + s1) + (s2 + s3);   // one slab per 32 columns
+          if (rok) {   // one slab per 32 columns
+            double* rd = p.rowdot + (int64_t)(it.tn * 2 + half) * p.M + row;
+            const double sv = (s0 + s1) + (s2 + s3);
+            *rd = p.rowdot_acc ? *rd + sv : sv;
+          }
         }
         // digit planes of the tile row: this thread's 32 columns are 32 consecutive bytes per plane = one full sector, written with one
         // 256-bit store (two 16-byte stores made every sector a pair of partial writes; the kernel runs at the L2 throughput cap).

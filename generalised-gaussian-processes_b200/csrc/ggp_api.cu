@@ -67,7 +67,6 @@ struct ggp_handle {
   size_t arena_i8_bytes = 0;
   int8_t *Lq = 0, *Pq = 0, *Atq = 0, *Kq = 0;
   int *eL = 0, *eP = 0;
-  double* kzy = nullptr;   // Kzx y accumulated over the chunks (b = L^{-1} Kzx y)
   int8_t* kq_all = nullptr;
   size_t kq_all_bytes = 0;
   long long* i8_dbg = nullptr;   // developer timeline buffer (GGP_I8_TIMELINE=2)
@@ -540,7 +539,7 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   if (cfg && cfg->precision == GGP_PREC_FP64_I8 && batch == 1 && p.Mp >= I8_BM) {
     const size_t MMq = align_up((size_t)I8_NS * p.Mp * p.Mp, 256), CHq = align_up((size_t)I8_NS * p.Mp * p.nc, 256),
                  EX = align_up((size_t)p.Mp * 4, 256);
-    const size_t need = 2 * MMq + 2 * CHq + 2 * EX + align_up((size_t)p.Mp * 8, 256);
+    const size_t need = 2 * MMq + 2 * CHq + 2 * EX;
     if (need > h->arena_i8_bytes) {
       if (h->arena_i8) CK(cudaFree(h->arena_i8));
       h->arena_i8 = nullptr;
@@ -554,8 +553,7 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
     h->Atq = (int8_t*)q; q += CHq;
     h->Kq = (int8_t*)q; q += CHq;
     h->eL = (int*)q; q += EX;
-    h->eP = (int*)q; q += EX;
-    h->kzy = (double*)q;
+    h->eP = (int*)q;
     if (h->kc_all) {
       const size_t needq = (size_t)h->kc_rows * p.Mp * I8_NS;
       const size_t budget = (size_t)cfg->tile_cache_mib * 1024 * 1024;
@@ -611,13 +609,13 @@ static int build_chunk(ggp_handle* h, cudaStream_t st, const double* Xc, int nv,
   return 0;
 }
 
-// sliced-integer path: FP64 tile + digit planes + (optionally) the Kzx y partials of the chunk in one kernel
-static int build_chunk_i8(ggp_handle* h, cudaStream_t st, const double* Xc, const double* yc, int nv, int d, const double* Z, int m,
-                          const double* theta, int kind, double* Kc, int8_t* Kq, int64_t plane, double* kty_part) {
+// sliced-integer path: FP64 tile + digit planes in one kernel
+static int build_chunk_i8(ggp_handle* h, cudaStream_t st, const double* Xc, int nv, int d, const double* Z, int m,
+                          const double* theta, int kind, double* Kc, int8_t* Kq, int64_t plane) {
   const int Mp = h->Mp;
   dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N);
   const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
-  k_build_kc_i8<<<grid, KT_THREADS, smem, st>>>(Xc, yc, nv, d, Z, m, theta, kind, Kc, Mp, Kq, Mp, plane, kty_part);
+  k_build_kc_i8<<<grid, KT_THREADS, smem, st>>>(Xc, nv, d, Z, m, theta, kind, Kc, Mp, Kq, Mp, plane);
   CKL();
   return 0;
 }
@@ -650,7 +648,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     ProfScope ps(h, st, CAT_BUILD);
     k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->Linv, Mp, Mp, Mp, h->Lq, Mp, (int64_t)Mp * Mp, Mp, h->eL);
     CKL();
-    CK(cudaMemsetAsync(h->kzy, 0, (size_t)Mp * 8, st));
+    CK(cudaMemsetAsync(h->mom_part, 0, (size_t)2 * ((nc + I8_BN - 1) / I8_BN) * m * 8, st));   // b partials, accumulated over the chunks
   }
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
@@ -659,19 +657,16 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     if (i8) {
       int8_t* Kq_c = h->kq_all ? h->kq_all + c0 * Mp : h->Kq;
       const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
-      const int ntb = (nv + KT_N - 1) / KT_N;
-      {   // k(X,Z) tile, its digit planes and the Kzx y partials of the chunk (one slab per 64 rows)
+      {   // k(X,Z) tile and its digit planes
         ProfScope ps(h, st, CAT_BUILD);
-        RUN(build_chunk_i8(h, st, X + c0 * d, y + c0, nv, d, Z, m, theta, kind, Kc_c, Kq_c, plK, h->mom_part));
-        k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), 1), 256, 0, st>>>(h->mom_part, Mp, 0, ntb, m, h->kzy);
-        CKL();
+        RUN(build_chunk_i8(h, st, X + c0 * d, nv, d, Z, m, theta, kind, Kc_c, Kq_c, plK));
       }
-      {   // A^T digits [m x nv] = L^{-1} (lower) x Kc^T; all-integer epilogue
+      {   // A^T digits [m x nv] = L^{-1} (lower) x Kc^T, fused b-partials = A y (accumulated into one slab set over the chunks)
         I8P t;
         memset(&t, 0, sizeof(t));
         t.M = m; t.N = nv; t.K = Mp; t.lower_a = 1; t.splits = 1; t.snake = 1;
         { const char* e = getenv("GGP_I8_TRMM_ORDER"); t.n_major = (e && e[0] == '0') ? 0 : 1; }
-        if (getenv("GGP_I8_ROWDOT")) { t.yv = y + c0; t.rowdot = h->mom_part; }
+        t.yv = y + c0; t.rowdot = h->mom_part; t.rowdot_acc = 1;
         if (getenv("GGP_I8_TRMM_SERIAL")) t.serial_epi = 1;
         t.ea = h->eL; t.eb0 = eK; t.alpha = 1.0;
         t.Oq = h->Atq; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo = eA;
@@ -691,11 +686,6 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
         const I8Operand A{h->Atq, m, nc, (int64_t)Mp * nc};
         ProfScope ps(h, st, CAT_SYRK);
         RUN(launch_i8(h, st, I8_EPI_F64, sy, A, A));
-      }
-      if (getenv("GGP_I8_ROWDOT")) {
-        ProfScope ps_o(h, st, CAT_OTHER);
-        k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), batch), 256, 0, st>>>(h->mom_part, m, 0, 2 * ((nv + I8_BN - 1) / I8_BN), m, h->bvec);
-        CKL();
       }
       continue;
     }
@@ -717,9 +707,10 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
                                                                               (nv + BN - 1) / BN, m, h->bvec);
     CKL();
   }
-  if (i8 && n_local > 0 && !getenv("GGP_I8_ROWDOT")) {   // b = A y = L^{-1} (Kzx y)
+  if (i8 && n_local > 0) {   // b = sum of the row-dot slabs (fixed order)
     ProfScope ps(h, st, CAT_OTHER);
-    k_gemv<<<dim3((m + 7) / 8, 1), 256, 0, st>>>(h->Linv, Mp, (int64_t)Mp * Mp, h->kzy, 0, h->bvec, m, m, m, 1.0, theta, d, 0);
+    const int nslab = 2 * (int)((std::min<int64_t>(nc, n_local) + I8_BN - 1) / I8_BN);
+    k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), 1), 256, 0, st>>>(h->mom_part, m, 0, nslab, m, h->bvec);
     CKL();
   }
   if (h->kc_all) {
@@ -822,7 +813,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
       if (!cached) {
         ProfScope ps(h, st, CAT_BUILD);
-        RUN(build_chunk_i8(h, st, X + c0 * d, nullptr, nv, d, Z, m, theta, kind, Kc_c, Kq_c, plK, nullptr));
+        RUN(build_chunk_i8(h, st, X + c0 * d, nv, d, Z, m, theta, kind, Kc_c, Kq_c, plK));
       }
       const double* Kmul = Kc_c;
       if (kind != GGP_KERNEL_RBF) {
