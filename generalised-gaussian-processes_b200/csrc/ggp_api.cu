@@ -61,6 +61,10 @@ struct ggp_handle {
   const void *kc_X = nullptr, *kc_Z = nullptr, *kc_theta = nullptr;
   int64_t kc_n = 0;
   int kc_batch = 0, kc_kind = 0;
+  bool pf_valid = false;        // ggp_sgpr_prefetch_tiles filled the cache for the key below; the next pass 1 with that key skips its builds
+  const void *pf_X = nullptr, *pf_Z = nullptr, *pf_theta = nullptr;
+  int64_t pf_n = 0;
+  int pf_batch = 0, pf_kind = 0;
   double *sv[5] = {0, 0, 0, 0, 0}, *rowout = 0;
   // int8 digit planes of the sliced-integer path (GGP_PREC_FP64_I8; gemm_i8.cuh)
   char* arena_i8 = nullptr;
@@ -512,6 +516,7 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   h->n_local = n_local; h->m = m; h->d = d; h->batch = batch;
   h->Mp = p.Mp; h->nc = p.nc; h->splits = p.splits;
   h->kc_valid = false;
+  h->pf_valid = false;
   {
     const int64_t rows = (n_local + 127) / 128 * 128;
     const size_t need = (size_t)batch * rows * p.Mp * 8;
@@ -620,6 +625,27 @@ static int build_chunk_i8(ggp_handle* h, cudaStream_t st, const double* Xc, int 
   return 0;
 }
 
+int ggp_sgpr_prefetch_tiles(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, int64_t n_local, const double* Z,
+                            const double* theta, int m, int d, int batch) {
+  if (!h || !Z || !theta || (n_local > 0 && !X)) return fail(-1, "ggp_sgpr_prefetch_tiles: NULL argument");
+  if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_prefetch_tiles: handle not reserved for this shape");
+  const int kind = cfg ? cfg->kernel : 0;
+  h->pf_valid = false;
+  if (!h->kc_all || n_local <= 0) return 0;   // no tile cache: pass 1 builds chunk by chunk as before
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool i8 = use_i8(h, cfg, d, batch) && h->kq_all;
+  const int Mp = h->Mp, nc = h->nc;
+  ProfScope ps(h, st, CAT_BUILD);
+  for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
+    const int nv = (int)std::min<int64_t>(nc, n_local - c0);
+    if (i8) RUN(build_chunk_i8(h, st, X + c0 * d, nv, d, Z, m, theta, kind, h->kc_all + c0 * Mp, h->kq_all + c0 * Mp, h->kc_rows * Mp));
+    else RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, h->kc_all + c0 * Mp, h->kc_rows * Mp));
+  }
+  h->pf_valid = true;
+  h->pf_X = X; h->pf_Z = Z; h->pf_theta = theta; h->pf_n = n_local; h->pf_batch = batch; h->pf_kind = kind;
+  return 0;
+}
+
 int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, const double* y, int64_t n_local,
                    const double* Z, const double* theta, int m, int d, int batch, double* partial) {
   if (!h || !Z || !theta || !partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass1: NULL argument");
@@ -636,6 +662,10 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   k_sumsq<<<1, 1024, 0, st>>>(y, n_local, h->yty);
   CKL();
   const bool i8 = use_i8(h, cfg, d, batch);
+  // tiles already in the cache (ggp_sgpr_prefetch_tiles with the same operands, typically overlapped with the factorisation)
+  const bool prefetched = h->kc_all && h->pf_valid && h->pf_X == X && h->pf_Z == Z && h->pf_theta == theta && h->pf_n == n_local &&
+                          h->pf_batch == batch && h->pf_kind == kind && (!i8 || h->kq_all);
+  h->pf_valid = false;
   int eK = 0, eA = 0;
   if (i8) {
     // fixed exponents of the bounded operands: k(x,z) <= sf2 and |A[m,n]| <= sqrt(k_nn) = sqrt(sf2) (theta is read on the host: one
@@ -657,7 +687,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     if (i8) {
       int8_t* Kq_c = h->kq_all ? h->kq_all + c0 * Mp : h->Kq;
       const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
-      {   // k(X,Z) tile and its digit planes
+      if (!prefetched) {   // k(X,Z) tile and its digit planes
         ProfScope ps(h, st, CAT_BUILD);
         RUN(build_chunk_i8(h, st, X + c0 * d, nv, d, Z, m, theta, kind, Kc_c, Kq_c, plK));
       }
@@ -689,7 +719,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       }
       continue;
     }
-    { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
+    if (!prefetched) { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
     // At[m x nv] = Linv[m x m] * Kc[nv x m]^T   (k clipped to the lower triangle)
     GemmP t = gemm_basic(h->Linv, Mp, sM, Kc_c, Mp, sK, h->At, nc, (int64_t)nc * Mp, m, nv, m, 1.0, 0.0,
                          KM_A_LOWER);

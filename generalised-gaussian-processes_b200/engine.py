@@ -73,6 +73,8 @@ class Engine:
         self.h = h
         self._shape = None
         self.launch_count = 0
+        self._side = None            # side stream: tile prefetch overlapped with the factorisation
+        self.prefetch_min_rows = 65536
 
     def __del__(self):
         try:
@@ -144,8 +146,21 @@ class Engine:
         assert theta.shape[1] == d + 2 and Z.shape[1] == d and y.shape[0] == n_local
         self.reserve(n_local, m, d, batch)
         with torch.cuda.device(dev):
-            jit, info1 = self.factor(Z, theta, jitter_policy, raise_on_fail)
             cfgp = ctypes.byref(self.cfg)
+            # the k(X,Z) tiles do not depend on the Cholesky of Kzz: build them into the tile cache on a side stream while the
+            # factorisation (latency-bound m x m kernels) runs on the caller's stream; pass 1 then finds them in place
+            ev = None
+            if (self.cfg.tile_cache_mib > 0 and n_local >= self.prefetch_min_rows and not torch.cuda.is_current_stream_capturing()):
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=dev)
+                main = torch.cuda.current_stream(dev)
+                self._side.wait_stream(main)
+                check(self.lib.ggp_sgpr_prefetch_tiles(self.h, cfgp, ctypes.c_void_p(self._side.cuda_stream), _ptr(X), n_local,
+                                                       _ptr(Z), _ptr(theta), m, d, batch), "ggp_sgpr_prefetch_tiles")
+                ev = self._side.record_event()
+            jit, info1 = self.factor(Z, theta, jitter_policy, raise_on_fail)
+            if ev is not None:
+                torch.cuda.current_stream(dev).wait_event(ev)
             partial = torch.empty(batch, m * m + m + 3, dtype=torch.float64, device=dev)
             check(self.lib.ggp_sgpr_pass1(self.h, cfgp, _stream(), _ptr(X), _ptr(y), n_local, _ptr(Z), _ptr(theta), m, d, batch,
                                           _ptr(partial)), "ggp_sgpr_pass1")

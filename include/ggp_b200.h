@@ -67,6 +67,14 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
                     const double* Z /*[m,d]*/, const double* theta /*[batch,d+2]*/,
                     const double* jitter /*[batch]*/, int m, int d, int batch, int32_t* info /*[batch]*/);
 
+/* Optional: build the k(X_local, Z) tiles of ALL local rows into the handle's tile cache (cfg.tile_cache_mib) on `stream` -- which
+ * may be a different stream from the one ggp_sgpr_factor runs on: the tiles do not depend on the factorisation, so the two overlap
+ * (the host joins the streams before ggp_sgpr_pass1).  The next ggp_sgpr_pass1 with the same X, Z, theta pointers, n_local and batch
+ * skips its tile builds; the operands must not change in between.  A no-op (returns 0) when the handle has no tile cache.
+ * (the Kxz block of InducingPointKernel.forward, models/sgpr.py:41, evaluated ahead of the Cholesky of Kzz) */
+int ggp_sgpr_prefetch_tiles(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X /*[n_local,d]*/, int64_t n_local,
+                            const double* Z, const double* theta, int m, int d, int batch);
+
 /* stream the local rows: partial[b] = [ A A^T (m*m, row-major, symmetric) | A y (m) | y^T y, sum_n k_nn, n_local ]
  * with A = L^{-1} k(Z, X_local).  Never materialises more than chunk_rows x m of k(X,Z). */
 int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
