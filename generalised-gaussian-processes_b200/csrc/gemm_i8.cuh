@@ -339,7 +339,8 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;  // column half of the tile handled by this warp
     const int et = threadIdx.x - 64;   // 0..255
-    double cmA[4][3][2];               // I8_EPI_MOMENTS with mom_accum: moments of this warp's rows over all tiles of the CTA
+    double rsA = 0.0;                  // I8_EPI_MOMENTS with mom_accum: row sum of W (the constant moment) of this thread's row
+    double cmA[4][3][2];               // ... and the x / x^2 moments of this warp's rows, over all tiles of the CTA
 #pragma unroll
     for (int G4 = 0; G4 < 4; ++G4)
 #pragma unroll
@@ -543,7 +544,9 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // lane = 4g + q:  a = W[8G + g][4kq + q],  b = Phi[4kq + q][8B + g],  (c0, c1) = mom[8G + g][8B + 2q, + 1]
         const int g = lane >> 2, q4 = lane & 3;
         double* wsm = wstage + (warp - 2) * 32 * I8_WSTAGE_LD;   // private patch of this warp
-        auto sweep = [&](int b0, double (&cm)[4][3][2]) {   // cm += W (this warp's 32 x 32 patch) x Phi[:, 8 b0 .. 8 b0 + 24)
+        // off = 1 (mom_accum): the constant moment (row sums of W) is summed on the vector pipe instead, the DMMA blocks start at x_0
+        // and a block with no moment left is skipped (d = 8: 2 blocks of 8 instead of 3, a third fewer DMMAs on the serial path)
+        auto sweep = [&](int b0, double (&cm)[4][3][2], int off) {   // cm += W (this warp's 32 x 32 patch) x Phi[:, off + 8 b0 .. + 24)
 #pragma unroll
           for (int pc = 0; pc < I8_EC / 8; ++pc) {
             __syncwarp();
@@ -559,7 +562,8 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               const double* xr = xs + (half * I8_EC + pc * 8 + 4 * kq + q4) * d;
 #pragma unroll
               for (int B = 0; B < 3; ++B) {
-                const int m = (b0 + B) * 8 + g;
+                if ((b0 + B) * 8 + off > 2 * d) continue;   // warp-uniform
+                const int m = (b0 + B) * 8 + g + off;
                 double b = 0.0;
                 if (m == 0) b = 1.0;
                 else if (m <= d) b = xr[m - 1];
@@ -571,7 +575,11 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         };
         if (p.mom_accum) {
-          sweep(0, cmA);   // one sweep covers all 2 d + 1 <= 24 moments; written after the CTA's last tile
+          sweep(0, cmA, 1);   // one sweep covers the 2 d <= 23 non-constant moments; written after the CTA's last tile
+          double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+#pragma unroll
+          for (int c = 0; c < I8_EC; c += 4) { r0 += acc[c]; r1 += acc[c + 1]; r2 += acc[c + 2]; r3 += acc[c + 3]; }
+          rsA += (r0 + r1) + (r2 + r3);
         } else {
           for (int b0 = 0; b0 * 8 < nq; b0 += 3) {   // three blocks of 8 moments per sweep (one sweep for d <= 11)
             double cm[4][3][2];
@@ -579,7 +587,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int G = 0; G < 4; ++G)
 #pragma unroll
               for (int B = 0; B < 3; ++B) cm[G][B][0] = cm[G][B][1] = 0.0;
-            sweep(b0, cm);
+            sweep(b0, cm, 0);
 #pragma unroll
             for (int G = 0; G < 4; ++G) {
               const int rr = it.tm * I8_BM + quarter * 32 + 8 * G + g;
@@ -611,11 +619,13 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         double* mo = p.mom + (int64_t)slab * p.sMomTile + (int64_t)rr * nq;
 #pragma unroll
         for (int B = 0; B < 3; ++B) {
-          const int m = B * 8 + 2 * q4;
+          const int m = B * 8 + 2 * q4 + 1;
           if (m < nq) mo[m] = cmA[G4][B][0];
           if (m + 1 < nq) mo[m + 1] = cmA[G4][B][1];
         }
       }
+      const int rown = tm * I8_BM + quarter * 32 + lane;
+      if (rown < p.M) p.mom[(int64_t)slab * p.sMomTile + (int64_t)rown * nq] = rsA;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
