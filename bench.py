@@ -310,22 +310,22 @@ def main():
         except Exception:
             pass
         if args.precision == "fp64_i8":
-            # sliced-integer path: 36 int8 digit-pair products per FP64 product; int8 dense tensor peak = 2 x the bf16 dense peak (nominal
+            # sliced-integer path: 28 int8 digit-pair products per FP64 product (7 radix-256 digits, pairs i + j <= 6); int8 dense tensor peak = 2 x the bf16 dense peak (nominal
             # ratio); the bf16 figure is the cuBLAS burst number the driver measured on this pool (MEASURED_PEAKS.json), else the
             # profiling recipe's fallback 1590 TFLOP/s
             bf16 = float(peaks.get("bf16_tflops", 1590.0))
             src = "measured (MEASURED_PEAKS.json bf16_tflops x 2)" if "bf16_tflops" in peaks else "fallback (1590 bf16 TFLOP/s x 2)"
-            tops = 36.0 * flops_local / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+            tops = 28.0 * flops_local / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
             roof = {"bound": "tensor", "kernel": "k_gemm_i8 (TMA-fed tcgen05.mma kind::i8, int32 TMEM accumulators: triangular multiply + SYRK + backward GEMM)",
                     "achieved": tops, "peak": 2.0 * bf16, "unit": "TOP/s (int8)", "frac": tops / (2.0 * bf16) if tops else None,
                     "peak_source": src, "fp64_equivalent_tflops": achieved,
                     "fp64_equivalent_vs_dmma_peak": (achieved / peak["best"]) if achieved else None, "dmma_peak_tflops": peak["best"],
-                    "digit_products_per_fp64_product": 36, "launches_per_step": gemm_launches,
+                    "digit_products_per_fp64_product": 28, "launches_per_step": gemm_launches,
                     "avg_launch_ms": gemm_ms / gemm_launches if gemm_launches else None,
                     "algorithmic_flops_per_step_per_rank": flops_local, "traffic": traffic_i8,
                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full, avg of the 3 GEMM roles on a 16384-row chunk)",
                     "whole_step_fp64_equivalent_tflops": flops_local / (ms_step * 1e-3) / 1e12}
-            dtype = "f64 via 8x7-bit int8 digits (exact int32 accumulation on tcgen05, f64 recombination); parity 1e-8 as the DMMA path"
+            dtype = "f64 via 7 radix-256 int8 digits (exact int32 accumulation on tcgen05, 64-bit integer / f64 recombination); parity 1e-8 as the DMMA path"
         else:
             roof = {"bound": "tensor", "kernel": "k_gemm_tma (TMA-fed DMMA.8x8x4 mainloop: triangular multiply + SYRK + backward GEMM)",
                     "achieved": achieved, "peak": peak["best"], "unit": "TFLOP/s", "frac": (achieved / peak["best"]) if achieved else None,

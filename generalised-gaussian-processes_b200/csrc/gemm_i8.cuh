@@ -2,21 +2,22 @@
 //     C[i,j] = sum_k A[i,k] * B[j,k]
 // tcgen05.mma has no f64 kind, and the DMMA path (gemm_tma.cuh) already keeps the FP64 tensor pipe 88-94 % busy; this is the route
 // past that roofline that still meets the 1e-8 parity budget.
-//   * operands: I8_NS balanced 7-bit digits (|d_i| <= 64) of a row-scaled fixed-point value,
-//     x = 2^e * sum_i d_i 2^(-7 (i+1)), stored as
-//     digit PLANES [I8_NS][rows][K] of int8, K contiguous (k_slice_rows / k_build_kc_i8 / the EPI_SLICE epilogue below);
+//   * operands: I8_NS = 7 balanced radix-256 digits (d_i in [-128, 127]) of a row-scaled fixed-point value,
+//     x = 2^e * sum_i d_i 2^(-8 (i+1)), |x| / 2^e < 0.498 (i8_exp_for), stored as
+//     digit PLANES [I8_NS][rows][K] of int8, K contiguous (k_slice_rows / k_build_kc_i8 / the EPI_SLICE epilogue below).  The digit
+//     bytes are the bytes of the 56-bit integer rn(x 2^(56 - e)) + C with the top bit of the six low bytes flipped (i8_digits_fixed);
 //   * tcgen05.mma kind::i8 (SASS UTCIMMA): 128 x N x 32 products, int32 accumulators in TMEM.  All digit pairs (i, j) of one
-//     significance level l = i + j are accumulated EXACTLY in one accumulator (|d|^2 (l+1) K <= 4096 * 8 * K < 2^31 for K < 2^16),
-//     so a 128 x 64 output tile owns I8_NS accumulators = 512 TMEM columns;
-//   * digit i of A is multiplied against digits 0..NS-1-i of B in ONE wide MMA: the B digit tiles are consecutive K-major tiles in
-//     shared memory (= one tall tile) and their products belong to consecutive levels (= consecutive accumulator columns), which
-//     keeps the shared-memory operand reads below the 128 B/clk limit (12 MMAs per 32-byte k-step instead of 36);
-//   * TMA (cp.async.bulk.tensor, 64-byte swizzle) stages 8 + 8 digit tiles per 64-byte k-block into a 2-stage mbarrier ring;
+//     significance level l = i + j <= 6 are accumulated EXACTLY in one accumulator (|d_i d_j| (l+1) K <= 2^14 * 7 * K < 2^31 for
+//     K <= 16384), so a 128 x 64 output tile owns I8_NS accumulators = 448 TMEM columns; 28 digit products per FP64 product
+//     (8 x 7-bit digits needed 36 for the same 56 bits);
+//   * digit i of A is multiplied against digits 0..NS-1-i of B in ONE or TWO wide MMAs: the B digit tiles are consecutive K-major
+//     tiles in shared memory (= one tall tile) and their products belong to consecutive levels (= consecutive accumulator columns):
+//     10 MMAs per 32-byte k-step instead of 28, which keeps the shared-memory operand reads below the 128 B/clk limit;
+//   * TMA (cp.async.bulk.tensor, 64-byte swizzle) stages 7 + 7 digit tiles per 64-byte k-block into a 2-stage mbarrier ring;
 //   * persistent CTAs, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and TMEM owner, warps 2..9 =
-//     epilogue (TMEM lane quarter w % 4, column half (w - 2) / 4).  The epilogue first drains the accumulators to FP64 registers (levels combined from
-//     the least significant up), releases TMEM so the next tile's MMAs start, then runs its role-specific part.
-// Measured by scripts/probes/ozaki_probe.cu on a B200: |err| / sum|a||b| = 1.7e-16 (an FP64 FMA chain: ~3e-15), 64 TF/s
-// FP64-equivalent at K = 1024 and 88 TF/s at K = 16384 (the DMMA peak is 37.2).
+//     epilogue (TMEM lane quarter w % 4, column half (w - 2) / 4).  The epilogue first drains the accumulators to registers (levels
+//     combined in exact 64-bit integers), releases TMEM so the next tile's MMAs start, then runs its role-specific part.
+// Measured by scripts/probes/ozaki_probe.cu on a B200 (8 x 7-bit variant): |err| / sum|a||b| = 1.7e-16 (an FP64 FMA chain: ~3e-15).
 #pragma once
 #include <cuda.h>
 #include <type_traits>
@@ -24,8 +25,8 @@
 
 namespace ggp {
 
-constexpr int I8_NS = 8;                       // digits per operand (56 bits)
-constexpr int I8_BM = 128, I8_BN = 64;         // output tile; I8_NS * I8_BN = 512 TMEM columns
+constexpr int I8_NS = 7;                       // radix-256 digits per operand (56 bits)
+constexpr int I8_BM = 128, I8_BN = 64;         // output tile; I8_NS * I8_BN = 448 TMEM columns
 constexpr int I8_BKB = 64;                     // bytes of k per stage row (one 64-byte swizzle row)
 constexpr int I8_STAGES = 2;
 constexpr int I8_A_BYTES = I8_BM * I8_BKB, I8_B_BYTES = I8_BN * I8_BKB;
@@ -40,7 +41,8 @@ constexpr int I8_WSTAGE_BYTES = I8_EPI_WARPS * 32 * I8_WSTAGE_LD * 8;
 constexpr int I8_SMEM = I8_STAGES * I8_STAGE_BYTES + 1024 + 256 + I8_EPI_SMEM + I8_WSTAGE_BYTES;
 static_assert(I8_SMEM <= 232448, "shared memory budget (227 KB)");
 constexpr int I8_TMEM_COLS = 512;
-constexpr int I8_MAX_K = 32768;                // exact int32 accumulation bound (see i8_digits)
+constexpr int I8_MAX_K = 16384;                // exact int32 accumulation bound: 7 pairs x 2^14 x K < 2^31 (see i8_digits)
+constexpr int I8_K_GROUP4 = 4096;              // k extent up to which four level sums combine exactly in one 64-bit integer < 2^53
 static_assert(I8_NS * I8_BN <= 512, "level accumulators must fit TMEM");
 
 enum { I8_EPI_F64 = 0, I8_EPI_SLICE = 1, I8_EPI_MOMENTS = 2 };
@@ -70,6 +72,7 @@ struct I8P {
                                          // mom[(b / tiles_m) * 2 + half][row][:]  (2 ng slabs instead of one per 32 columns)
   int serial_epi;                        // 1: hand TMEM back only after the whole epilogue (FP64 epilogue math and the running
                                          // UTCIMMA stream throttle each other on the tensor / FP64 pipe: measured 10x slower when overlapped)
+  int exp_skip_b;                        // developer experiment: do not load the B operand (wrong results; measures the L2 -> SM bound)
   long long* dbg;                        // developer timeline (CTA 0): [role][item][4] clock64 stamps, or NULL
 };
 constexpr int I8_DBG_ITEMS = 16;
@@ -163,67 +166,71 @@ __device__ __forceinline__ int i8_rounds(const I8P& p, int G) {
   return (p.total + G - 1) / G;
 }
 
-// Balanced 7-bit digits of v (|v| < 1/2), most significant first: t = rn(v 2^56) = sum_i d_i 2^(7 (7-i)) with d_1..d_7 in
-// [-64, 63] and |d_0| <= 64.  Adding C = sum_{i>=1} 64 * 2^(7 (7-i)) first turns the balanced recoding (carries) into plain bit
-// fields: d_i = field_i(t + C) - 64, d_0 = (t + C) >> 49.  One conversion, one 64-bit add, three integer ops per digit.
+// Exponent of a row (or of a bounded operand) with largest magnitude mx: the smallest e with mx / 2^e < 0.498, so that the top digit
+// d_0 = floor(x 2^(8 - e) + 0.502) stays in [-128, 127] (a plain |x| / 2^e < 1/2 would let the top 0.4 % of the range reach 128; a
+// whole extra bit of headroom costs 4x in the product's relative accuracy).  Host and device must agree: one function.
+__host__ __device__ inline int i8_exp_for(double mx) {
+  if (!(mx > 0.0)) return 0;
+  int e = ilogb(mx) + 2;
+  if (ldexp(mx, -e) >= 0.498) ++e;
+  return e;
+}
+
+// Balanced radix-256 digits of v (-1/2 < v < 0.498), most significant first: T = rn(v 2^56) = sum_i d_i 256^(6-i) with all d_i in
+// [-128, 127].  Adding C = sum_{i>=1} 128 * 256^(6-i) turns the balanced recoding (carries) into plain byte fields:
+// d_i = byte_{6-i}(T + C) - 128 = byte_{6-i}(T + C) ^ 0x80 as int8, d_0 = (T + C) >> 48: one 64-bit add, one 64-bit xor, and the
+// digit bytes are the seven low bytes of the result.
 // Balanced digits matter: the digit pairs with i + j >= NS are dropped, and with zero-mean digits what is dropped is zero-mean
 // (with unsigned fields it is a one-sided bias that grows linearly in K: measured 50x worse).
-// Exactness of the level sums: |d_i d_j| <= 4096, at most 8 pairs per level -> K < 2^31 / 2^15 = 65536 (I8_MAX_K = 32768).
+// Exactness of the level sums: |d_i d_j| <= 2^14, at most 7 pairs per level -> K < 2^31 / (7 * 2^14) = 18724 (I8_MAX_K = 16384).
+__device__ __forceinline__ unsigned long long i8_digit_bytes(long long T) {   // byte 6 - i = digit i
+  static_assert(I8_NS == 7, "56-bit fixed point in 7 bytes");
+  return (unsigned long long)(T + 0x0000808080808080ll) ^ 0x0000808080808080ull;
+}
 // T = rn(v 2^56) already in hand (the all-integer epilogue of the triangular multiply)
 __device__ __forceinline__ void i8_digits_fixed(long long T, int8_t (&dg)[I8_NS]) {
-  static_assert(I8_NS == 8, "56-bit fixed point");
-  const long long t = T + 283691315109952ll;   // + C, C = 64 (2^49 - 1) / 127
-  const unsigned lo = (unsigned)((unsigned long long)t & 0x0FFFFFFFull);   // bits 0..27  -> digits 7..4
-  const int hi = (int)(t >> 28);                                            // bits 28..55 -> digits 3..0
-  dg[7] = (int8_t)((int)(lo & 127u) - 64);
-  dg[6] = (int8_t)((int)((lo >> 7) & 127u) - 64);
-  dg[5] = (int8_t)((int)((lo >> 14) & 127u) - 64);
-  dg[4] = (int8_t)((int)((lo >> 21) & 127u) - 64);
-  dg[3] = (int8_t)((hi & 127) - 64);
-  dg[2] = (int8_t)(((hi >> 7) & 127) - 64);
-  dg[1] = (int8_t)(((hi >> 14) & 127) - 64);
-  dg[0] = (int8_t)(hi >> 21);
+  const unsigned long long V = i8_digit_bytes(T);
+#pragma unroll
+  for (int i = 0; i < I8_NS; ++i) dg[i] = (int8_t)(uint8_t)(V >> (8 * (I8_NS - 1 - i)));
 }
 __device__ __forceinline__ void i8_digits(double v, int8_t (&dg)[I8_NS]) { i8_digits_fixed(__double2ll_rn(v * 72057594037927936.0), dg); }
 
-// I8_EPI_SLICE builds its output digits without touching the FP64 pipe (FP64 instructions issued while the UTCIMMA stream runs are
-// throttled and slow the MMAs down in turn: the mainloop ran at 2830 clk per k-block next to the FP64 epilogue, 2470 alone).
-// The product value is (t_hi 2^28 + t_lo) 2^(-63 + e_row + e_col) with t_hi / t_lo the combined level sums 0..3 / 4..7, the output
-// fixed point is rn(value 2^(56 - eo)) = rn((t_hi 2^28 + t_lo) / 2^sh), sh = 7 + eo - e_row - e_col: two shifts and an add.
+// I8_EPI_SLICE builds its output digits in integer arithmetic (no FP64 instructions next to the UTCIMMA stream).  With k <=
+// I8_K_GROUP4 the product value is (t_hi 2^24 + t_lo) 2^(-64 + e_row + e_col), t_hi / t_lo the combined level sums 0..3 / 4..6; the
+// output fixed point is rn(value 2^(56 - eo)) = rn((t_hi 2^24 + t_lo) / 2^sh), sh = 8 + eo - e_row - e_col.
 __device__ __forceinline__ long long i8_fx_lo(long long t, int sh) {
   if (sh <= 0) return (long long)((unsigned long long)t << min(-sh, 63));
-  if (sh <= 28) return (t + (1ll << (sh - 1))) >> sh;
-  return (t + (1ll << 27)) >> 28;   // in units of 2^28: joins t_hi before the final shift
+  if (sh <= 24) return (t + (1ll << (sh - 1))) >> sh;
+  return (t + (1ll << 23)) >> 24;   // in units of 2^24: joins t_hi before the final shift
 }
 __device__ __forceinline__ long long i8_fx_hi(long long t, long long lo, int sh) {
-  if (sh <= 28) return (long long)((unsigned long long)t << min(28 - sh, 63)) + lo;
-  const int s = min(sh - 28, 62);
+  if (sh <= 24) return (long long)((unsigned long long)t << min(24 - sh, 63)) + lo;
+  const int s = min(sh - 24, 62);
   return (t + lo + (1ll << (s - 1))) >> s;
 }
-// the common case 1 <= sh <= 28 (whole warp) with 32-bit funnel shifts: (t + 2^(sh-1)) >> sh and (t << (28 - sh)) + lo
-__device__ __forceinline__ long long i8_fx_lo_fast(long long t, int sh, long long rnd) {
-  const long long r = t + rnd;
-  const uint32_t rl = (uint32_t)r, rh = (uint32_t)((unsigned long long)r >> 32);
-  const uint32_t ol = __funnelshift_r(rl, rh, sh);
-  const int oh = (int)rh >> sh;
-  return (long long)(((unsigned long long)(uint32_t)oh << 32) | ol);
+// the common case -32 < sh <= 24 (whole warp), branch-free: ((t_lo << l1) + rnd) >> r1 and (t_hi << (24 - sh)) + lo
+__device__ __forceinline__ long long i8_fx_lo_fast(long long t, int l1, int r1, long long rnd) {
+  return ((long long)((unsigned long long)t << l1) + rnd) >> r1;
 }
 __device__ __forceinline__ long long i8_fx_hi_fast(long long t, long long lo, int s2) {
-  const uint32_t tl = (uint32_t)t, th = (uint32_t)((unsigned long long)t >> 32);
-  const uint32_t oh = __funnelshift_l(tl, th, s2), ol = tl << s2;
-  return (long long)(((unsigned long long)oh << 32) | ol) + lo;
+  return (long long)((unsigned long long)t << s2) + lo;
 }
-// four level sums -> one exact 64-bit integer, t = a0 2^21 + a1 2^14 + a2 2^7 + a3 (three IMAD.WIDE)
+// level sums -> one exact 64-bit integer (IMAD.WIDE chains)
 __device__ __forceinline__ long long i8_mad_wide(int a, int b, long long c) {
   long long d;
   asm("mad.wide.s32 %0, %1, %2, %3;\n" : "=l"(d) : "r"(a), "r"(b), "l"(c));
   return d;
 }
-__device__ __forceinline__ long long i8_comb4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
+__device__ __forceinline__ long long i8_comb4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {   // a0 2^24 + a1 2^16 + a2 2^8 + a3
   long long t = (long long)(int)a3;
-  t = i8_mad_wide((int)a2, 128, t);
-  t = i8_mad_wide((int)a1, 16384, t);
-  return i8_mad_wide((int)a0, 2097152, t);
+  t = i8_mad_wide((int)a2, 256, t);
+  t = i8_mad_wide((int)a1, 65536, t);
+  return i8_mad_wide((int)a0, 16777216, t);
+}
+__device__ __forceinline__ long long i8_comb3(uint32_t a0, uint32_t a1, uint32_t a2) {   // a0 2^16 + a1 2^8 + a2
+  long long t = (long long)(int)a2;
+  t = i8_mad_wide((int)a1, 256, t);
+  return i8_mad_wide((int)a0, 65536, t);
 }
 
 template <int EPI>
@@ -280,13 +287,15 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int kb = it.kb_lo; kb < it.kb_hi; ++kb, ++n) {
           const int s = n % I8_STAGES;
           if (n >= I8_STAGES) i8_mbar_wait(&empty[s], ((n / I8_STAGES) - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], I8_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[s], p.exp_skip_b ? I8_NS * I8_A_BYTES : I8_STAGE_BYTES);
           unsigned char* st = base + s * I8_STAGE_BYTES;
 #pragma unroll
           for (int i = 0; i < I8_NS; ++i) i8_tma_load_3d(st + i * I8_A_BYTES, &tmA, kb * I8_BKB, it.tm * I8_BM, i, &full[s]);
+          if (!p.exp_skip_b) {
 #pragma unroll
-          for (int j = 0; j < I8_NS; ++j)
-            i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * I8_B_BYTES, &tmB, kb * I8_BKB, it.tn * I8_BN, j, &full[s]);
+            for (int j = 0; j < I8_NS; ++j)
+              i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * I8_B_BYTES, &tmB, kb * I8_BKB, it.tn * I8_BN, j, &full[s]);
+          }
         }
       }
     }
@@ -314,13 +323,17 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int i = 0; i < I8_NS; ++i) {
               const uint64_t ad = i8_desc_sw64(sa + i * I8_A_BYTES + kk * 32);
+              // digit i of A x digits 0 .. NS-1-i of B: one tall B tile of ncols rows -> accumulator columns [i * BN, i * BN + ncols);
+              // more than 256 columns are issued as two equal halves (multiples of 16 columns and of the 8-row swizzle group)
               const int ncols = I8_BN * (I8_NS - i);
+              const int nsplit = ncols > 256 ? 2 : 1, nn = ncols / nsplit;
+              static_assert(I8_BN % 32 == 0, "half of any ncols is a multiple of 16");
 #pragma unroll
-              for (int off = 0; off < ncols; off += 256) {
-                const int nn = (ncols - off) < 256 ? (ncols - off) : 256;
+              for (int hs = 0; hs < nsplit; ++hs) {
+                const int off = hs * nn;
                 // D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
                 const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
-                const uint64_t bd = i8_desc_sw64(sb + (off / I8_BN) * I8_B_BYTES + kk * 32);
+                const uint64_t bd = i8_desc_sw64(sb + off * I8_BKB + kk * 32);   // row `off` of the tall tile: 8-row groups of 512 bytes
                 i8_umma(tmem_base + (uint32_t)(i * I8_BN + off), ad, bd, idesc, (kb > it.kb_lo || kk > 0 || i > 0) ? 1u : 0u);
               }
             }
@@ -384,9 +397,10 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
       }
       const int e_r = p.ea ? p.ea[min(row, p.M - 1)] : p.ea0;
-      const int sh = 7 + p.eo - e_r - p.eb0;   // I8_EPI_SLICE (scalar column exponent, alpha = 1: checked on the host)
-      const bool fx_fast = (EPI == I8_EPI_SLICE) && __all_sync(0xffffffffu, sh >= 1 && sh <= 28);
-      const long long fx_rnd = 1ll << ((sh - 1) & 63);
+      const int sh = 8 + p.eo - e_r - p.eb0;   // I8_EPI_SLICE (scalar column exponent, alpha = 1, k <= I8_K_GROUP4: checked on the host)
+      const bool fx_fast = (EPI == I8_EPI_SLICE) && __all_sync(0xffffffffu, sh > -32 && sh <= 24);
+      const int fx_l1 = sh < 0 ? -sh : 0, fx_r1 = sh > 0 ? sh : 0, fx_s2 = (24 - sh) & 63;
+      const long long fx_rnd = sh > 0 ? 1ll << ((sh - 1) & 63) : 0ll;
       if (et == 0) I8_STAMP(1, item, 0);
       i8_mbar_wait(tmem_full, item & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
@@ -395,38 +409,85 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       long long fx[I8_EC];   // I8_EPI_SLICE: rn(value 2^(56 - eo)), integer arithmetic only
 #pragma unroll
       for (int c = 0; c < I8_EC; ++c) { acc[c] = 0.0; fx[c] = 0; }
-      // four levels per TMEM round trip, combined exactly in int64 (|sum| < 2^53) before ONE int->double conversion (or, in the
-      // all-integer epilogue, two shifts): levels l0..l0+3 -> t = ((a0 * 128 + a1) * 128 + a2) * 128 + a3, value = t * 2^(-7 (l0 + 5))
-      static_assert(I8_NS == 8, "two groups of four levels");
-      auto drain = [&](auto fast_tag) {
-        constexpr bool FAST = decltype(fast_tag)::value;
+      // The seven level sums of a column are combined exactly in 64-bit integers before ONE int->double conversion per group (or, in
+      // the all-integer epilogue, two shifts).  value = U 2^(-64 + e_row + e_col), U = sum_l a_l 2^(8 (6 - l)).
+      //   k <= I8_K_GROUP4 (MODE 0 / 1 = integer epilogue, fast / general shifts): U = t_hi 2^24 + t_lo, t_hi = levels 0..3, t_lo = levels 4..6
+      //   longer k          (MODE 2):  U = g0 2^32 + g1 2^8 + g2, g0 = levels 0..2, g1 = levels 3..5, g2 = level 6   (each < 2^53)
+      static_assert(I8_NS == 7, "level grouping");
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * I8_EC);
+      auto drain = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
         for (int c0 = 0; c0 < I8_EC; c0 += 16) {
+          if (MODE != 2) {
+            {   // levels 4..6
+              uint32_t v0[16], v1[16], v2[16];
+              const uint32_t ta = tbase + (uint32_t)(4 * I8_BN + c0);
+              i8_tmem_ld16(ta, v0);
+              i8_tmem_ld16(ta + I8_BN, v1);
+              i8_tmem_ld16(ta + 2 * I8_BN, v2);
+              asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-          for (int l0 = 4; l0 >= 0; l0 -= 4) {
-            uint32_t v0[16], v1[16], v2[16], v3[16];
-            const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(l0 * I8_BN + half * I8_EC + c0);
-            i8_tmem_ld16(ta, v0);
-            i8_tmem_ld16(ta + I8_BN, v1);
-            i8_tmem_ld16(ta + 2 * I8_BN, v2);
-            i8_tmem_ld16(ta + 3 * I8_BN, v3);
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-            const double wl = (l0 == 4) ? 1.0842021724855044e-19 /* 2^-63 */ : 2.9103830456733704e-11 /* 2^-35 */;
+              for (int c = 0; c < 16; ++c) {
+                const long long t = i8_comb3(v0[c], v1[c], v2[c]);
+                if (EPI == I8_EPI_SLICE) fx[c0 + c] = (MODE == 0) ? i8_fx_lo_fast(t, fx_l1, fx_r1, fx_rnd) : i8_fx_lo(t, sh);
+                else acc[c0 + c] = (double)t * 5.421010862427522e-20 /* 2^-64 */;
+              }
+            }
+            {   // levels 0..3
+              uint32_t v0[16], v1[16], v2[16], v3[16];
+              const uint32_t ta = tbase + (uint32_t)c0;
+              i8_tmem_ld16(ta, v0);
+              i8_tmem_ld16(ta + I8_BN, v1);
+              i8_tmem_ld16(ta + 2 * I8_BN, v2);
+              i8_tmem_ld16(ta + 3 * I8_BN, v3);
+              asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const long long t = i8_comb4(v0[c], v1[c], v2[c], v3[c]);
-              if (EPI == I8_EPI_SLICE) {
-                if (FAST) fx[c0 + c] = (l0 == 4) ? i8_fx_lo_fast(t, sh, fx_rnd) : i8_fx_hi_fast(t, fx[c0 + c], 28 - sh);
-                else fx[c0 + c] = (l0 == 4) ? i8_fx_lo(t, sh) : i8_fx_hi(t, fx[c0 + c], sh);
-              } else {
-                acc[c0 + c] = fma((double)t, wl, acc[c0 + c]);
+              for (int c = 0; c < 16; ++c) {
+                const long long t = i8_comb4(v0[c], v1[c], v2[c], v3[c]);
+                if (EPI == I8_EPI_SLICE) fx[c0 + c] = (MODE == 0) ? i8_fx_hi_fast(t, fx[c0 + c], fx_s2) : i8_fx_hi(t, fx[c0 + c], sh);
+                else acc[c0 + c] = fma((double)t, 9.094947017729282e-13 /* 2^-40 */, acc[c0 + c]);
+              }
+            }
+          } else {
+            {   // levels 3..5 and 6
+              uint32_t v0[16], v1[16], v2[16], v3[16];
+              const uint32_t ta = tbase + (uint32_t)(3 * I8_BN + c0);
+              i8_tmem_ld16(ta, v0);
+              i8_tmem_ld16(ta + I8_BN, v1);
+              i8_tmem_ld16(ta + 2 * I8_BN, v2);
+              i8_tmem_ld16(ta + 3 * I8_BN, v3);
+              asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const long long t = i8_comb3(v0[c], v1[c], v2[c]);
+                acc[c0 + c] = fma((double)t, 1.3877787807814457e-17 /* 2^-56 */, (double)(int)v3[c] * 5.421010862427522e-20 /* 2^-64 */);
+              }
+            }
+            {   // levels 0..2
+              uint32_t v0[16], v1[16], v2[16];
+              const uint32_t ta = tbase + (uint32_t)c0;
+              i8_tmem_ld16(ta, v0);
+              i8_tmem_ld16(ta + I8_BN, v1);
+              i8_tmem_ld16(ta + 2 * I8_BN, v2);
+              asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const long long t = i8_comb3(v0[c], v1[c], v2[c]);
+                acc[c0 + c] = fma((double)t, 2.3283064365386963e-10 /* 2^-32 */, acc[c0 + c]);
               }
             }
           }
         }
       };
-      if (fx_fast) drain(std::true_type{});
-      else drain(std::false_type{});
+      if (EPI == I8_EPI_SLICE) {
+        if (fx_fast) drain(std::integral_constant<int, 0>{});
+        else drain(std::integral_constant<int, 1>{});
+      } else if (p.K <= I8_K_GROUP4) {
+        drain(std::integral_constant<int, 0>{});
+      } else {
+        drain(std::integral_constant<int, 2>{});
+      }
       // accumulators are in registers: hand TMEM back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
       __syncwarp();
@@ -639,7 +700,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 // row-scaled signed-digit slicing of X[R x K] (leading dimension ld): planes Xq[i][row][k] (leading dimension ldq, plane stride
-// plane), per-row exponent ex[row] with |x| / 2^e < 1/2.  One warp per row.  Columns [K, Kpad) are written as zero.
+// plane), per-row exponent ex[row] = i8_exp_for(row maximum).  One warp per row.  Columns [K, Kpad) are written as zero.
 __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X, int R, int K, int64_t ld, int8_t* __restrict__ Xq,
                                                     int64_t ldq, int64_t plane, int Kpad, int* __restrict__ ex) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -648,7 +709,7 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
   for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(X[(int64_t)row * ld + k]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const int e = mx > 0.0 ? ilogb(mx) + 2 : 0;
+  const int e = i8_exp_for(mx);
   if (lane == 0) ex[row] = e;
   for (int k = lane; k < Kpad; k += 32) {
     int8_t dg[I8_NS];
@@ -658,7 +719,7 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
   }
 }
 
-// digit planes of an existing k(X,Z) tile Kc[n][m] (FP64, leading dimension ldk) with the fixed exponent e (k <= sf2 < 2^(e-1)):
+// digit planes of an existing k(X,Z) tile Kc[n][m] (FP64, leading dimension ldk) with the fixed exponent e = i8_exp_for(sf2) (k <= sf2):
 // Kq[i][n][m].  Each thread converts 4 consecutive m of one row: the warp reads 1 KB contiguous and writes 128 B per plane.
 __global__ void __launch_bounds__(256) k_slice_fixed(const double* __restrict__ Kc, int64_t rows, int cols, int64_t ldk,
                                                      int8_t* __restrict__ Kq, int64_t ldq, int64_t plane, const double* __restrict__ theta,
@@ -668,7 +729,7 @@ __global__ void __launch_bounds__(256) k_slice_fixed(const double* __restrict__ 
   const int64_t row = t / cpr;
   const int c0 = (int)(t - row * cpr) * 4;
   if (row >= rows) return;
-  const int e = ilogb(theta[d]) + 2;
+  const int e = i8_exp_for(theta[d]);
   const double si = exp2((double)-e);
   const double2 a = *reinterpret_cast<const double2*>(Kc + row * ldk + c0);
   const double2 b = *reinterpret_cast<const double2*>(Kc + row * ldk + c0 + 2);

@@ -146,6 +146,7 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   const double budget = 4.0 * 1024 * 1024 * 1024;
   while (nc > 128 && 2.0 * batch * (double)nc * p.Mp * 8.0 > budget) nc /= 2;
   nc = std::max<int64_t>(128, nc / 128 * 128);
+  if (cfg && cfg->precision == GGP_PREC_FP64_I8) nc = std::min<int64_t>(nc, I8_MAX_K);   // the SYRK's k extent is one chunk
   p.nc = (int)std::min<int64_t>(nc, nmax);
   const int tiles = sym_upper_tiles((m + BM - 1) / BM, (m + BN - 1) / BN);
   const int ctas = sm_count * CTAS_PER_SM;
@@ -387,9 +388,9 @@ struct I8Operand { const int8_t* q; int64_t rows, ld, plane; };
 
 static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Operand& A, const I8Operand& B) {
   if (p.K < 1 || p.M < 1 || p.N < 1) return 0;
-  if (p.K > I8_MAX_K) return fail(-4, "launch_i8: k extent exceeds the exact int32 accumulation bound (32768)");
-  if (epi == I8_EPI_SLICE && (p.eb || p.alpha != 1.0))
-    return fail(-4, "launch_i8: the digit-plane epilogue takes a scalar column exponent and alpha = 1");
+  if (p.K > I8_MAX_K) return fail(-4, "launch_i8: k extent exceeds the exact int32 accumulation bound (16384)");
+  if (epi == I8_EPI_SLICE && (p.eb || p.alpha != 1.0 || p.K > I8_K_GROUP4))
+    return fail(-4, "launch_i8: the digit-plane epilogue takes a scalar column exponent, alpha = 1 and k <= 4096");
   p.tiles_m = (p.M + I8_BM - 1) / I8_BM;
   p.tiles_n = (p.N + I8_BN - 1) / I8_BN;
   int tiles = p.tiles_m * p.tiles_n;
@@ -399,6 +400,7 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
   }
   if (p.splits < 1) p.splits = 1;
   p.total = tiles * p.splits;
+  if (getenv("GGP_I8_EXP_SKIPB")) p.exp_skip_b = 1;
   CUtensorMap tmA, tmB;
   if (!make_i8_map(&tmA, A.q, A.rows, p.K, A.ld, A.plane, I8_BM) || !make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN))
     return fail(-4, "launch_i8: operand planes cannot be described by a tensor map (alignment)");
@@ -447,7 +449,8 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
 }
 
 static bool use_i8(const ggp_handle* h, const ggp_cfg* cfg, int d, int batch) {
-  return cfg && cfg->precision == GGP_PREC_FP64_I8 && batch == 1 && h->Mp >= I8_BM && d <= I8_MAX_D && h->arena_i8 != nullptr;
+  return cfg && cfg->precision == GGP_PREC_FP64_I8 && batch == 1 && h->Mp >= I8_BM && h->Mp <= I8_K_GROUP4 && d <= I8_MAX_D &&
+         h->arena_i8 != nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -673,8 +676,8 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     double sf2 = 1.0;
     CK(cudaMemcpyAsync(&sf2, theta + d, sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    eK = ilogb(sf2) + 2;
-    eA = ilogb(sqrt(sf2)) + 3;
+    eK = i8_exp_for(sf2);
+    eA = i8_exp_for(sqrt(sf2)) + 1;   // one bit of margin: the computed |A| may exceed sqrt(sf2) by rounding
     ProfScope ps(h, st, CAT_BUILD);
     k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->Linv, Mp, Mp, Mp, h->Lq, Mp, (int64_t)Mp * Mp, Mp, h->eL);
     CKL();
@@ -824,7 +827,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     double sf2 = 1.0;
     CK(cudaMemcpyAsync(&sf2, theta + d, sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    eK = ilogb(sf2) + 2;
+    eK = i8_exp_for(sf2);
     ProfScope ps(h, st, CAT_BUILD);
     k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->P, Mp, Mp, Mp, h->Pq, Mp, (int64_t)Mp * Mp, Mp, h->eP);
     CKL();
@@ -1113,7 +1116,7 @@ int ggp_gemm_nt_ex(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
 int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                    int64_t ldc, int mm, int nn, int kk) {
   if (!h || !A || !B || !C) return fail(-1, "ggp_gemm_nt_i8: NULL argument");
-  if (mm < 1 || nn < 1 || kk < 1 || kk > I8_MAX_K) return fail(-2, "ggp_gemm_nt_i8: bad shape (1 <= kk <= 32768)");
+  if (mm < 1 || nn < 1 || kk < 1 || kk > I8_MAX_K) return fail(-2, "ggp_gemm_nt_i8: bad shape (1 <= kk <= 16384)");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t kp = (kk + 63) / 64 * 64;
   int8_t *qa = nullptr, *qb = nullptr;

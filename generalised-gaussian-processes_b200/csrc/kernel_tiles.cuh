@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc(const double* __restric
 
 // Tile build of the sliced-integer path (gemm_i8.cuh must be included first): one pass produces
 //   * the FP64 tile Kc[n][m] (multiplier of the backward epilogue),
-//   * its int8 digit planes Kq[i][n][m] with the fixed exponent e = ilogb(sf2) + 2 (k <= sf2 < 2^(e-1)).
+//   * its int8 digit planes Kq[i][n][m] with the fixed exponent e = i8_exp_for(sf2) (k <= sf2).
 // Thread (tx, ty) owns rows 4 ty + i and the 4 CONSECUTIVE columns 4 tx + j: 32-byte FP64 stores and 4-byte digit stores, a half-warp
 // covers 512 / 64 contiguous bytes of one row.  zs is laid out [d][4][16] so that the shared reads stay conflict-free.
 // grid: (ldk / 64, ceil(n_valid / 64)); batch = 1.
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc_i8(const double* __rest
         d2[i][j] = fma(t, t, d2[i][j]);
       }
   }
-  const double si = exp2((double)-(ilogb(sf2) + 2));
+  const double si = exp2((double)-i8_exp_for(sf2));
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int n = n0 + ty * 4 + i;
