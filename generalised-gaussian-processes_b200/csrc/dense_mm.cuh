@@ -10,15 +10,16 @@ constexpr int NB = 64;  // diagonal block size of the blocked Cholesky / recursi
 constexpr int POTF2_SMEM = 0;
 
 // Factor diagonal block kb in place (lower) and write its inverse T = L_kk^{-1}.  One CTA (16 x 16 threads) per batch element.
-// Register-resident right-looking sweeps: thread (tx,ty) owns the 4 x 4 elements (ty+16i, tx+16k).  Per column j the owners
-// publish the (unscaled) column through a double-buffered shared vector, ONE barrier, then every thread applies the rank-1
-// update to its registers.  The inverse is the same sweep on T (start from I): T[r,:] -= L[r,j] * T[j,:] / L[j,j].
+// Register-resident right-looking sweep: thread (tx,ty) owns the 4 x 4 elements (ty+16i, tx+16k) of A and of T (start: I).  Per
+// column j the owners publish the (unscaled) column of A and the (unscaled) row j of T through double-buffered shared vectors, ONE
+// barrier, then every thread applies the rank-1 update to both register tiles:
+//   A[r,c] -= x_r x_c / d_j ;  T[j,:] /= L[j,j] ;  T[r,:] -= L[r,j] T[j,:] = x_r xT_c / d_j   (r > j)
+// (column j of L is final at step j, so the inverse sweep rides in the same loop: 64 barriers instead of 128).
 // info[b] = global index (1-based) of the first non-positive pivot, LAPACK potrf style; first failure wins.
 __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int64_t ld, int64_t sA, int kb,
                                                      double* __restrict__ T, int64_t sT, int32_t* info) {
-  __shared__ double xch[2][NB];
+  __shared__ double xch[2][NB], xtr[2][NB];
   __shared__ double Ls[NB][NB + 1];
-  __shared__ double dinvs[NB];   // 1 / L[j][j], kept for the inverse sweep (no division on its critical path)
   __shared__ int bad;
   const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double* Ab = A + b * sA + (int64_t)kb * NB * (ld + 1);
@@ -32,15 +33,19 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
       t[i][k] = (r == c) ? 1.0 : 0.0;
     }
   if (tid == 0) bad = 0;
-  // ---- Cholesky sweep ----
 #pragma unroll
   for (int kj = 0; kj < 4; ++kj) {
     for (int tj = 0; tj < 16; ++tj) {
       const int j = kj * 16 + tj;
       double* x = xch[j & 1];
+      double* xt = xtr[j & 1];
       if (tx == tj) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[ty + 16 * i] = a[i][kj];
+      }
+      if (ty == tj) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xt[tx + 16 * k] = t[kj][k];
       }
       __syncthreads();
       const double dj = x[j];
@@ -49,7 +54,6 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
       // (each ~100+ clk of dependent FP64 latency, 64 columns deep): inv = rsqrt(dj) (<= 1 ulp), piv = dj * inv
       const double inv = rsqrt(dj);
       const double piv = dj * inv, dinv = inv * inv;
-      if (tid == 0) dinvs[j] = inv;
       if (tx == tj) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -57,48 +61,28 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
           Ls[r][j] = (r > j) ? a[i][kj] * inv : ((r == j) ? piv : 0.0);
         }
       }
-      double xr[4], xc[4];
+      if (ty == tj) {   // row j of T is final
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[kj][k] *= inv;
+      }
+      double xr[4], xc[4], xtc[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) xr[i] = x[ty + 16 * i];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) xc[k] = x[tx + 16 * k] * dinv;
+      for (int k = 0; k < 4; ++k) {
+        xc[k] = x[tx + 16 * k] * dinv;
+        xtc[k] = xt[tx + 16 * k] * dinv;
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (k < kj) continue;
-        if (tx + 16 * k > j) {
+        if (k >= kj && tx + 16 * k > j) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) a[i][k] = fma(-xr[i], xc[k], a[i][k]);
         }
-      }
-    }
-  }
-  __syncthreads();
-  // ---- inverse sweep:  for j: T[j,:] /= L[j,j];  T[r,:] -= L[r,j] T[j,:] for r > j ----
+        if (k <= kj && tx + 16 * k <= j) {   // T[j, c] is zero beyond c = j
 #pragma unroll
-  for (int kj = 0; kj < 4; ++kj) {
-    for (int tj = 0; tj < 16; ++tj) {
-      const int j = kj * 16 + tj;
-      double* x = xch[j & 1];
-      if (ty == tj) {
-        const double dinv = dinvs[j];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          t[kj][k] *= dinv;
-          x[tx + 16 * k] = t[kj][k];
-        }
-      }
-      __syncthreads();
-      double xc[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) xc[k] = x[tx + 16 * k];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i < kj) continue;
-        const int r = ty + 16 * i;
-        if (r > j) {
-          const double lrj = Ls[r][j];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) t[i][k] = fma(-lrj, xc[k], t[i][k]);
+          for (int i = 0; i < 4; ++i)
+            if (i >= kj && ty + 16 * i > j) t[i][k] = fma(-xr[i], xtc[k], t[i][k]);
         }
       }
     }
@@ -191,13 +175,20 @@ __global__ void __launch_bounds__(256) k_gemv_acc(const double* __restrict__ A, 
   if (lane == 0) y[b * sy + row] += s;
 }
 
-// out[0] = sum_i y_i^2 over n (single CTA, deterministic)
+// out[0] = sum_i y_i^2 over n, deterministic: SUMSQ_BLOCKS block partials (out[1 + block], contiguous slices) then a fixed-order sum
+constexpr int SUMSQ_BLOCKS = 16;
 __global__ void __launch_bounds__(1024) k_sumsq(const double* __restrict__ y, int64_t n, double* __restrict__ out) {
   __shared__ double red[32];
+  const int64_t per = (n + SUMSQ_BLOCKS - 1) / SUMSQ_BLOCKS, lo = blockIdx.x * per, hi = lo + per < n ? lo + per : n;
   double s = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += 1024) s = fma(y[i], y[i], s);
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 1024) s = fma(y[i], y[i], s);
   s = block_sum<1024>(s, red);
-  if (threadIdx.x == 0) out[0] = s;
+  if (threadIdx.x == 0) out[1 + blockIdx.x] = s;
+}
+__global__ void k_sumsq_final(double* __restrict__ out) {
+  double s = 0.0;
+  for (int i = 0; i < SUMSQ_BLOCKS; ++i) s += out[1 + i];
+  out[0] = s;
 }
 
 // partial[b] = [ S (upper tiles summed over splits, mirrored) | bvec | yty, n*sf2, n ]

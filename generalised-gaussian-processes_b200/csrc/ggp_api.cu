@@ -662,7 +662,9 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   const int64_t sM = (int64_t)Mp * Mp;
   CK(cudaMemsetAsync(h->Spart, 0, (size_t)batch * splits * sM * 8, st));
   CK(cudaMemsetAsync(h->bvec, 0, (size_t)batch * m * 8, st));
-  k_sumsq<<<1, 1024, 0, st>>>(y, n_local, h->yty);
+  k_sumsq<<<SUMSQ_BLOCKS, 1024, 0, st>>>(y, n_local, h->yty);   // yty: 256 bytes = total + SUMSQ_BLOCKS partials
+  CKL();
+  k_sumsq_final<<<1, 1, 0, st>>>(h->yty);
   CKL();
   const bool i8 = use_i8(h, cfg, d, batch);
   // tiles already in the cache (ggp_sgpr_prefetch_tiles with the same operands, typically overlapped with the factorisation)
@@ -773,7 +775,9 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   k_make_B<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Bm, sM);
   CKL();
   RUN(chol_and_inverse(h, st, h->Bm, h->LBinv, h->LBinvT, batch, info));
-  // Binv = LBinv^T LBinv
+  // Binv = LBinv^T LBinv.  (The m x m products stay on the FP64 DMMA kernel: routed through the sliced-integer GEMM they were 0.36 ms
+  // faster at M = 1024, but its row-scaled fixed point resolves an element only relative to its ROW maximum, and the operands
+  // here -- L^{-T}, P_A -- span many orders of magnitude within a row: 8e-8 on the ell-gradient at N = 1777, M = 100, D = 1.)
   RUN(launch_gemm(h, st, EPI_STORE,
                   gemm_basic(h->LBinvT, Mp, sM, h->LBinvT, Mp, sM, h->Binv, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER | KM_B_UPPER),
                   batch));
