@@ -193,6 +193,27 @@ __device__ __forceinline__ void i8_digits_fixed(long long T, int8_t (&dg)[I8_NS]
 #pragma unroll
   for (int i = 0; i < I8_NS; ++i) dg[i] = (int8_t)(uint8_t)(V >> (8 * (I8_NS - 1 - i)));
 }
+// digit-plane words of four consecutive columns: pk[i] = digit i of columns 0..3 in bytes 0..3.  Two 4 x 4 byte transposes with
+// PRMT (16 instructions for 28 digit bytes) instead of a shift / mask / or per byte.
+__device__ __forceinline__ void i8_pack4(unsigned long long V0, unsigned long long V1, unsigned long long V2, unsigned long long V3,
+                                         uint32_t (&pk)[I8_NS]) {
+  const uint32_t l0 = (uint32_t)V0, l1 = (uint32_t)V1, l2 = (uint32_t)V2, l3 = (uint32_t)V3;
+  const uint32_t h0 = (uint32_t)(V0 >> 32), h1 = (uint32_t)(V1 >> 32), h2 = (uint32_t)(V2 >> 32), h3 = (uint32_t)(V3 >> 32);
+  const uint32_t a01 = __byte_perm(l0, l1, 0x5140), a23 = __byte_perm(l2, l3, 0x5140);   // bytes 0, 1 of each
+  const uint32_t b01 = __byte_perm(l0, l1, 0x7362), b23 = __byte_perm(l2, l3, 0x7362);   // bytes 2, 3 of each
+  pk[6] = __byte_perm(a01, a23, 0x5410);   // byte 0 = digit 6
+  pk[5] = __byte_perm(a01, a23, 0x7632);   // byte 1 = digit 5
+  pk[4] = __byte_perm(b01, b23, 0x5410);
+  pk[3] = __byte_perm(b01, b23, 0x7632);
+  const uint32_t c01 = __byte_perm(h0, h1, 0x5140), c23 = __byte_perm(h2, h3, 0x5140);   // bytes 4, 5
+  const uint32_t d01 = __byte_perm(h0, h1, 0x7362), d23 = __byte_perm(h2, h3, 0x7362);   // bytes 6, (7)
+  pk[2] = __byte_perm(c01, c23, 0x5410);   // byte 4 = digit 2
+  pk[1] = __byte_perm(c01, c23, 0x7632);
+  pk[0] = __byte_perm(d01, d23, 0x5410);   // byte 6 = digit 0
+}
+__device__ __forceinline__ unsigned long long i8_digit_bytes_of(double v) {
+  return i8_digit_bytes(__double2ll_rn(v * 72057594037927936.0));
+}
 __device__ __forceinline__ void i8_digits(double v, int8_t (&dg)[I8_NS]) { i8_digits_fixed(__double2ll_rn(v * 72057594037927936.0), dg); }
 
 // I8_EPI_SLICE builds its output digits in integer arithmetic (no FP64 instructions next to the UTCIMMA stream).  With k <=
@@ -560,15 +581,11 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         {
           uint32_t pk[I8_NS][I8_EC / 4];
 #pragma unroll
-          for (int i = 0; i < I8_NS; ++i)
+          for (int c = 0; c < I8_EC; c += 4) {
+            uint32_t w[I8_NS];
+            i8_pack4(i8_digit_bytes(fx[c]), i8_digit_bytes(fx[c + 1]), i8_digit_bytes(fx[c + 2]), i8_digit_bytes(fx[c + 3]), w);
 #pragma unroll
-            for (int j = 0; j < I8_EC / 4; ++j) pk[i][j] = 0u;
-#pragma unroll
-          for (int c = 0; c < I8_EC; ++c) {
-            int8_t dg[I8_NS];
-            i8_digits_fixed(fx[c], dg);
-#pragma unroll
-            for (int i = 0; i < I8_NS; ++i) pk[i][c >> 2] |= ((uint32_t)(uint8_t)dg[i]) << (8 * (c & 3));
+            for (int i = 0; i < I8_NS; ++i) pk[i][c >> 2] = w[i];
           }
           static_assert(I8_EC == 32, "one 32-byte sector per thread and plane");
           if (rok) {
@@ -735,15 +752,7 @@ __global__ void __launch_bounds__(256) k_slice_fixed(const double* __restrict__ 
   const double2 b = *reinterpret_cast<const double2*>(Kc + row * ldk + c0 + 2);
   const double x[4] = {a.x, a.y, b.x, b.y};
   uint32_t pk[I8_NS];
-#pragma unroll
-  for (int i = 0; i < I8_NS; ++i) pk[i] = 0u;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    int8_t dg[I8_NS];
-    i8_digits(x[c] * si, dg);
-#pragma unroll
-    for (int i = 0; i < I8_NS; ++i) pk[i] |= ((uint32_t)(uint8_t)dg[i]) << (8 * c);
-  }
+  i8_pack4(i8_digit_bytes_of(x[0] * si), i8_digit_bytes_of(x[1] * si), i8_digit_bytes_of(x[2] * si), i8_digit_bytes_of(x[3] * si), pk);
 #pragma unroll
   for (int i = 0; i < I8_NS; ++i) *reinterpret_cast<uint32_t*>(Kq + (int64_t)i * plane + row * ldq + c0) = pk[i];
 }

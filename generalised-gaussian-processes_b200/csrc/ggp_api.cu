@@ -618,11 +618,12 @@ static int build_chunk(ggp_handle* h, cudaStream_t st, const double* Xc, int nv,
 }
 
 // sliced-integer path: FP64 tile + digit planes in one kernel
-static int build_chunk_i8(ggp_handle* h, cudaStream_t st, const double* Xc, int nv, int d, const double* Z, int m,
+static int build_chunk_i8(ggp_handle* h, cudaStream_t st, const double* Xc, int64_t nv, int d, const double* Z, int m,
                           const double* theta, int kind, double* Kc, int8_t* Kq, int64_t plane) {
   const int Mp = h->Mp;
-  dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N);
-  const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
+  const int64_t rows_per_cta = (int64_t)KT_N * KT_RT;
+  dim3 grid(Mp / KT_M, (unsigned)((nv + rows_per_cta - 1) / rows_per_cta));
+  const size_t smem = (size_t)(2 * KT_N * d + KT_M * d + d) * 8;
   k_build_kc_i8<<<grid, KT_THREADS, smem, st>>>(Xc, nv, d, Z, m, theta, kind, Kc, Mp, Kq, Mp, plane);
   CKL();
   return 0;
@@ -639,10 +640,13 @@ int ggp_sgpr_prefetch_tiles(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, c
   const bool i8 = use_i8(h, cfg, d, batch) && h->kq_all;
   const int Mp = h->Mp, nc = h->nc;
   ProfScope ps(h, st, CAT_BUILD);
-  for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
-    const int nv = (int)std::min<int64_t>(nc, n_local - c0);
-    if (i8) RUN(build_chunk_i8(h, st, X + c0 * d, nv, d, Z, m, theta, kind, h->kc_all + c0 * Mp, h->kq_all + c0 * Mp, h->kc_rows * Mp));
-    else RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, h->kc_all + c0 * Mp, h->kc_rows * Mp));
+  if (i8) {   // the cache is one row-major [rows][Mp] array (+ digit planes): one launch covers all local rows
+    RUN(build_chunk_i8(h, st, X, n_local, d, Z, m, theta, kind, h->kc_all, h->kq_all, h->kc_rows * Mp));
+  } else {
+    for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
+      const int nv = (int)std::min<int64_t>(nc, n_local - c0);
+      RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, h->kc_all + c0 * Mp, h->kc_rows * Mp));
+    }
   }
   h->pf_valid = true;
   h->pf_X = X; h->pf_Z = Z; h->pf_theta = theta; h->pf_n = n_local; h->pf_batch = batch; h->pf_kind = kind;

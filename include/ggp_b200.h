@@ -28,8 +28,8 @@ typedef struct ggp_handle ggp_handle_t;
 
 enum { GGP_KERNEL_RBF = 0, GGP_KERNEL_MATERN32 = 1, GGP_KERNEL_MATERN52 = 2 };
 /* GGP_PREC_FP64: FP64 tensor-core DMMA.  GGP_PREC_FP64_I8: the same contractions evaluated to FP64-class accuracy by exact integer
- * slicing (8 signed 7-bit digits per operand, tcgen05.mma kind::i8, int32 TMEM accumulators; csrc/gemm_i8.cuh); used for the
- * streamed passes when batch == 1, the padded inducing count is >= 128 and d <= 16, the DMMA path otherwise.
+ * slicing (7 balanced radix-256 digits per operand, tcgen05.mma kind::i8, int32 TMEM accumulators; csrc/gemm_i8.cuh); used for the
+ * streamed passes when batch == 1, the padded inducing count is in [128, 4096] and d <= 16, the DMMA path otherwise.
  * GGP_PREC_TF32X3 is rejected (-3): split-precision cannot meet the gradient tolerance. */
 enum { GGP_PREC_FP64 = 0, GGP_PREC_TF32X3 = 1, GGP_PREC_FP64_I8 = 2 };
 enum { GGP_LIK_GAUSSIAN = 0, GGP_LIK_BERNOULLI_PROBIT = 1 };
@@ -144,8 +144,8 @@ int ggp_gemm_nt(ggp_handle_t* h, void* stream, const double* A, int64_t lda, con
 int ggp_gemm_nt_ex(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb,
                    double* C, int64_t ldc, int mm, int nn, int kk, double alpha, double beta, int kmode, int sym,
                    int splits, int64_t split_stride);
-/* C[mm,nn] = A[mm,kk] * B[nn,kk]^T evaluated by the sliced-integer tcgen05 path (row-scaled 8 x 7-bit digits, exact int32
- * accumulation, kk <= 32768).  Allocates and frees its digit planes (synchronous): a test / probe entry, not a hot-path one. */
+/* C[mm,nn] = A[mm,kk] * B[nn,kk]^T evaluated by the sliced-integer tcgen05 path (row-scaled 7 x 8-bit digits, exact int32
+ * accumulation, kk <= 16384).  Allocates and frees its digit planes (synchronous): a test / probe entry, not a hot-path one. */
 int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, const double* B, int64_t ldb,
                    double* C, int64_t ldc, int mm, int nn, int kk);
 /* k(X1, X2)[n1, n2] dense tile (tests) */

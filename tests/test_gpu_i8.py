@@ -10,7 +10,7 @@ TOL = 1e-8
 
 @pytest.mark.parametrize("mm,nn,kk", [(128, 64, 64), (200, 100, 70), (1024, 2048, 1024), (384, 384, 4096), (256, 128, 16384), (130, 65, 1000)])
 def test_gemm_i8_matches_float64_matmul(mm, nn, kk):
-    """Row-scaled 8 x 7-bit digits, exact int32 accumulation per significance level: error relative to sum |a||b| at the FP64 level,
+    """Row-scaled 7 balanced radix-256 digits, exact int32 accumulation per significance level: error relative to sum |a||b| at the FP64 level,
     also for rows of very different magnitude (L^{-1} / P like) and ragged shapes (TMA zero fill)."""
     import ggp_b200
     eng = ggp_b200.Engine.get(torch.device("cuda:0"))
