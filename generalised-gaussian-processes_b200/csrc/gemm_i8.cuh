@@ -275,7 +275,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (p.dbg && threadIdx.x == 0) {   // developer timeline: wall-clock span of every CTA
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-    p.dbg[2 * I8_DBG_ITEMS * 4 + 2 * blockIdx.x] = (long long)gt;
+    p.dbg[3 * I8_DBG_ITEMS * 4 + 2 * blockIdx.x] = (long long)gt;
   }
 
   if (threadIdx.x == 0) {
@@ -400,6 +400,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (EPI == I8_EPI_MOMENTS) {
         // stage the tile's x rows and y into shared memory (previous tile's readers are past their last read: barrier below)
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (et == 0) I8_STAMP(2, item, 0);
         const int d = p.d;
         {   // the tile's x rows are one contiguous block of 64 d doubles: coalesced copy, 4 independent loads in flight per thread
           const double* src = p.Xc + (int64_t)colt * d;
@@ -413,9 +414,16 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           if (et < I8_BN) ys[et] = (colt + et < p.N) ? __ldg(p.yv + colt + et) : 0.0;
         }
-        load_kv(kv0, 0);   // both groups of this warp's 32 columns are in flight while the MMAs of this tile run
+        if (et == 0) I8_STAMP(2, item, 1);
+        // both groups of this warp's 32 columns are in flight while the MMAs of this tile run.  (With the register file full these 32
+        // loads issue one memory latency at a time -- 16 k clk of this 25 k clk phase -- which is hidden behind the 37 k clk mainloop in
+        // the serial-epilogue mode.  An overlapped variant with an L2 prefetch here and the loads after the drain cut the phase to
+        // 6.5 k clk, but the FP64 work next to the UTCIMMA stream then took 39 k clk: no gain, removed.)
+        load_kv(kv0, 0);
         load_kv(kv1, 1);
+        if (et == 0) I8_STAMP(2, item, 2);
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (et == 0) I8_STAMP(2, item, 3);
       }
       const int e_r = p.ea ? p.ea[min(row, p.M - 1)] : p.ea0;
       const int sh = 8 + p.eo - e_r - p.eb0;   // I8_EPI_SLICE (scalar column exponent, alpha = 1, k <= I8_K_GROUP4: checked on the host)
@@ -711,7 +719,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (p.dbg && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-    p.dbg[2 * I8_DBG_ITEMS * 4 + 2 * blockIdx.x + 1] = (long long)gt;
+    p.dbg[3 * I8_DBG_ITEMS * 4 + 2 * blockIdx.x + 1] = (long long)gt;
   }
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(I8_TMEM_COLS));
 }

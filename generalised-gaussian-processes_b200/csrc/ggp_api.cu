@@ -413,8 +413,8 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
   const char* tl = getenv("GGP_I8_TIMELINE");
   const bool dbg = tl && tl[0] == '2' && h->i8_dbg_prints < 9 && !p.dbg;
   if (dbg) {
-    if (!h->i8_dbg) CK(cudaMalloc((void**)&h->i8_dbg, (2 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long)));
-    CK(cudaMemsetAsync(h->i8_dbg, 0, (2 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long), st));
+    if (!h->i8_dbg) CK(cudaMalloc((void**)&h->i8_dbg, (3 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long)));
+    CK(cudaMemsetAsync(h->i8_dbg, 0, (3 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long), st));
     p.dbg = h->i8_dbg;
   }
   if (epi == I8_EPI_F64) k_gemm_i8<I8_EPI_F64><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
@@ -423,10 +423,10 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
   CKL();
   if (dbg) {
     CK(cudaStreamSynchronize(st));
-    long long hb[2 * I8_DBG_ITEMS * 4 + 2 * 256];
+    long long hb[3 * I8_DBG_ITEMS * 4 + 2 * 256];
     CK(cudaMemcpy(hb, h->i8_dbg, sizeof(hb), cudaMemcpyDeviceToHost));
     {
-      const long long* g = hb + 2 * I8_DBG_ITEMS * 4;
+      const long long* g = hb + 3 * I8_DBG_ITEMS * 4;
       long long s0 = g[0], s1 = g[0], e0 = g[1], e1 = g[1];
       for (int b = 0; b < grid && b < 256; ++b) {
         s0 = std::min(s0, g[2 * b]); s1 = std::max(s1, g[2 * b]);
@@ -442,6 +442,8 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
       const long long* ep = hb + (I8_DBG_ITEMS + it) * 4;
       fprintf(stderr, "tile %2d  mma: start %8lld tmem_free %8lld first_kb %8lld all_issued %8lld | epi: wait %8lld full %8lld drained %8lld done %8lld\n",
               it, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, ep[0] - t0, ep[1] - t0, ep[2] - t0, ep[3] - t0);
+      const long long* pw = hb + (2 * I8_DBG_ITEMS + it) * 4;
+      if (pw[0]) fprintf(stderr, "         pre-wait: bar1 %8lld x-staged %8lld kv-issued %8lld bar2 %8lld\n", pw[0] - t0, pw[1] - t0, pw[2] - t0, pw[3] - t0);
     }
     h->i8_dbg_prints++;
   }
@@ -1160,6 +1162,8 @@ int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
       const long long* ep = hb + (I8_DBG_ITEMS + it) * 4;
       fprintf(stderr, "tile %2d  mma: start %8lld  tmem_free %8lld  first_kb_issued %8lld  all_issued %8lld | epi: wait %8lld  full %8lld  drained %8lld  done %8lld\n",
               it, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, ep[0] - t0, ep[1] - t0, ep[2] - t0, ep[3] - t0);
+      const long long* pw = hb + (2 * I8_DBG_ITEMS + it) * 4;
+      if (pw[0]) fprintf(stderr, "         pre-wait: bar1 %8lld x-staged %8lld kv-issued %8lld bar2 %8lld\n", pw[0] - t0, pw[1] - t0, pw[2] - t0, pw[3] - t0);
     }
     cudaFree(dbg);
   }
