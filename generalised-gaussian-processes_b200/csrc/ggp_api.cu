@@ -1147,8 +1147,8 @@ int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
   long long* dbg = nullptr;
   const char* tl = getenv("GGP_I8_TIMELINE");   // developer switch: print CTA 0's clock64 timeline of the first tiles to stderr
   if (tl && tl[0] == '1') {
-    CK(cudaMalloc((void**)&dbg, 2 * I8_DBG_ITEMS * 4 * sizeof(long long)));
-    CK(cudaMemsetAsync(dbg, 0, 2 * I8_DBG_ITEMS * 4 * sizeof(long long), st));
+    CK(cudaMalloc((void**)&dbg, (3 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long)));   // 3 stamp rows + per-CTA wall-clock spans
+    CK(cudaMemsetAsync(dbg, 0, (3 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long), st));
     p.dbg = dbg;
   }
   int rc = launch_i8(h, st, I8_EPI_F64, p, {qa, mm, kp, (int64_t)mm * kp}, {qb, nn, kp, (int64_t)nn * kp});
@@ -1162,8 +1162,6 @@ int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
       const long long* ep = hb + (I8_DBG_ITEMS + it) * 4;
       fprintf(stderr, "tile %2d  mma: start %8lld  tmem_free %8lld  first_kb_issued %8lld  all_issued %8lld | epi: wait %8lld  full %8lld  drained %8lld  done %8lld\n",
               it, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, ep[0] - t0, ep[1] - t0, ep[2] - t0, ep[3] - t0);
-      const long long* pw = hb + (2 * I8_DBG_ITEMS + it) * 4;
-      if (pw[0]) fprintf(stderr, "         pre-wait: bar1 %8lld x-staged %8lld kv-issued %8lld bar2 %8lld\n", pw[0] - t0, pw[1] - t0, pw[2] - t0, pw[3] - t0);
     }
     cudaFree(dbg);
   }
