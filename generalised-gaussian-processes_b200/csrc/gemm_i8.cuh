@@ -63,8 +63,12 @@ struct I8P {
   double* C; int64_t ldc, sSplit;
   // I8_EPI_SLICE: digits of alpha * acc with the fixed exponent eo -> Oq[plane][row][col]; optional fused row dots against yv
   int8_t* Oq; int64_t o_ld, o_plane; int eo;
+  int o_chunk; int64_t o_chunk_stride;   // o_chunk > 0: column block c = col / o_chunk lives at Oq + c * o_chunk_stride, columns relative to it
+                                         // (one [plane][row][o_chunk] array per chunk: the SYRK reads a chunk with a 16 KB row pitch, not n_local)
   const double* yv; double* rowdot;      // rowdot[2 tn + half][M] (+= when rowdot_acc: one buffer over the chunks of a pass)
   int rowdot_acc;
+  int rowdot_reg;                        // row dots stay in registers over all tiles of the CTA (n-major snake order with 2 G % tiles_m == 0: a
+                                         // CTA only ever sees two row tiles, one per round parity) and are written once: rowdot[2 b + half][M]
   // I8_EPI_MOMENTS: W = (alpha * acc + u[row] * yv[col]) * Kmul[col][row];  mom[tn][row][:] = sum_col W * [1, x_col, x_col^2]
   const double* u; const double* Kmul; int64_t ldk; const double* Xc; int d; double* mom; int64_t sMomTile;
   int mom_accum;                         // I8_EPI_MOMENTS, 2 d + 1 <= 24: grid = tiles_m x ng, CTA b owns row tile b % tiles_m and the column tiles
@@ -373,6 +377,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;  // column half of the tile handled by this warp
     const int et = threadIdx.x - 64;   // 0..255
+    double rdA[2] = {0.0, 0.0};        // I8_EPI_SLICE with rowdot_reg: b-partials of this thread's row in the CTA's two row tiles
     double rsA = 0.0;                  // I8_EPI_MOMENTS with mom_accum: row sum of W (the constant moment) of this thread's row
     double cmA[4][3][2];               // ... and the x / x^2 moments of this warp's rows, over all tiles of the CTA
 #pragma unroll
@@ -577,9 +582,11 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             s2 = fma(acc[c + 2], (col0 + c + 2 < p.N) ? __ldg(p.yv + col0 + c + 2) : 0.0, s2);
             s3 = fma(acc[c + 3], (col0 + c + 3 < p.N) ? __ldg(p.yv + col0 + c + 3) : 0.0, s3);
           }
-          if (rok) {   // one slab per 32 columns
+          const double sv = (s0 + s1) + (s2 + s3);
+          if (p.rowdot_reg) {
+            rdA[rnd & 1] += sv;
+          } else if (rok) {   // one slab per 32 columns
             double* rd = p.rowdot + (int64_t)(it.tn * 2 + half) * p.M + row;
-            const double sv = (s0 + s1) + (s2 + s3);
             *rd = p.rowdot_acc ? *rd + sv : sv;
           }
         }
@@ -598,6 +605,10 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           static_assert(I8_EC == 32, "one 32-byte sector per thread and plane");
           if (rok) {
             int8_t* dst = p.Oq + (int64_t)row * p.o_ld + col0;
+            if (p.o_chunk > 0) {
+              const int cb = col0 / p.o_chunk;
+              dst = p.Oq + (int64_t)cb * p.o_chunk_stride + (int64_t)row * p.o_ld + (col0 - cb * p.o_chunk);
+            }
             if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0 && (p.o_plane & 31) == 0) {
 #pragma unroll
               for (int i = 0; i < I8_NS; ++i)
@@ -694,6 +705,21 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) i8_mbar_arrive(tmem_empty);
       }
       if (et == 0) I8_STAMP(1, item_done, 3);
+    }
+    if (EPI == I8_EPI_SLICE && p.rowdot && p.rowdot_reg) {   // slab 2 b + half (zeroed by the host): rows of the CTA's two row tiles
+      int tmv[2] = {-1, -1};
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const int w = i8_item(p, par, blockIdx.x, G);
+        if (par < i8_rounds(p, G) && w < p.total) { I8Item it; i8_decode(p, w, it); tmv[par] = it.tm; }
+      }
+      double* slab = p.rowdot + (int64_t)(blockIdx.x * 2 + half) * p.M;
+      if (tmv[0] >= 0 && tmv[0] == tmv[1]) { rdA[0] += rdA[1]; tmv[1] = -1; }
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const int rown = tmv[par] * I8_BM + quarter * 32 + lane;
+        if (tmv[par] >= 0 && rown < p.M) slab[rown] = rdA[par];
+      }
     }
     if (EPI == I8_EPI_MOMENTS && p.mom_accum) {
       const int nq = 2 * p.d + 1, g = lane >> 2, q4 = lane & 3;

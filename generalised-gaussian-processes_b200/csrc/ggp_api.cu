@@ -73,6 +73,8 @@ struct ggp_handle {
   int *eL = 0, *eP = 0;
   int8_t* kq_all = nullptr;
   size_t kq_all_bytes = 0;
+  int8_t* atq_all = nullptr;   // digit planes of A^T for ALL local rows: the triangular multiply of pass 1 becomes one launch
+  size_t atq_all_bytes = 0;
   long long* i8_dbg = nullptr;   // developer timeline buffer (GGP_I8_TIMELINE=2)
   int i8_dbg_prints = 0;
   int nsv = 0;
@@ -489,6 +491,7 @@ int ggp_destroy(ggp_handle_t* h) {
   if (h->arena) cudaFree(h->arena);
   if (h->kc_all) cudaFree(h->kc_all);
   if (h->kq_all) cudaFree(h->kq_all);
+  if (h->atq_all) cudaFree(h->atq_all);
   if (h->arena_i8) cudaFree(h->arena_i8);
   delete h;
   return 0;
@@ -575,11 +578,26 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
         if (cudaMalloc((void**)&h->kq_all, needq) == cudaSuccess) h->kq_all_bytes = needq;
         else { (void)cudaGetLastError(); ok = false; }
       }
+      if (ok && 8 * (size_t)h->kc_rows * p.Mp + 2 * needq <= budget && !getenv("GGP_I8_NO_ATQ_ALL")) {   // optional third array
+        const size_t needa = (size_t)((n_local + p.nc - 1) / p.nc) * I8_NS * p.Mp * p.nc;   // one [plane][m][nc] array per chunk
+        if (needa > h->atq_all_bytes) {
+          if (h->atq_all) CK(cudaFree(h->atq_all));
+          h->atq_all = nullptr;
+          h->atq_all_bytes = 0;
+          if (cudaMalloc((void**)&h->atq_all, needa) == cudaSuccess) h->atq_all_bytes = needa;
+          else (void)cudaGetLastError();
+        }
+      } else if (h->atq_all) {
+        CK(cudaFree(h->atq_all));
+        h->atq_all = nullptr;
+        h->atq_all_bytes = 0;
+      }
       if (!ok) {   // the cache must hold both the FP64 tiles and their digit planes, or neither
         CK(cudaFree(h->kc_all));
         h->kc_all = nullptr;
         h->kc_all_bytes = 0;
         if (h->kq_all) { CK(cudaFree(h->kq_all)); h->kq_all = nullptr; h->kq_all_bytes = 0; }
+        if (h->atq_all) { CK(cudaFree(h->atq_all)); h->atq_all = nullptr; h->atq_all_bytes = 0; }
       }
     }
   }
@@ -691,6 +709,29 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     CKL();
     CK(cudaMemsetAsync(h->mom_part, 0, (size_t)2 * ((nc + I8_BN - 1) / I8_BN) * m * 8, st));   // b partials, accumulated over the chunks
   }
+  // With the tile cache and room for the digits of A^T over all local rows, the triangular multiply is ONE launch (no per-chunk
+  // tails: 2048 tiles over 148 CTAs leave the last round 16 % full; no per-launch start-up) and the b-partials stay in registers:
+  // in the n-major snake order a CTA only ever works on two row tiles when 2 G is a multiple of the row-tile count.
+  const int i8_tiles_m = (m + I8_BM - 1) / I8_BM;
+  const int64_t i8_tiles = (int64_t)i8_tiles_m * ((n_local + I8_BN - 1) / I8_BN);
+  const bool trmm_once = i8 && h->kq_all && h->atq_all && h->kc_all && i8_tiles >= h->sm_count && (2 * h->sm_count) % i8_tiles_m == 0 &&
+                         i8_tiles < ((int64_t)1 << 30) && n_local > 0 && (int64_t)(nc / 32) * (2 * d + 1) >= 2 * h->sm_count /* slab room */;
+  if (trmm_once) {
+    if (!prefetched) {
+      ProfScope ps(h, st, CAT_BUILD);
+      RUN(build_chunk_i8(h, st, X, n_local, d, Z, m, theta, kind, h->kc_all, h->kq_all, h->kc_rows * Mp));
+    }
+    CK(cudaMemsetAsync(h->mom_part, 0, (size_t)2 * h->sm_count * m * 8, st));
+    I8P t;
+    memset(&t, 0, sizeof(t));
+    t.M = m; t.N = (int)n_local; t.K = Mp; t.lower_a = 1; t.splits = 1; t.snake = 1; t.n_major = 1;
+    t.ea = h->eL; t.eb0 = eK; t.alpha = 1.0;
+    t.Oq = h->atq_all; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo = eA;
+    t.o_chunk = nc; t.o_chunk_stride = (int64_t)I8_NS * Mp * nc;
+    t.yv = y; t.rowdot = h->mom_part; t.rowdot_reg = 1;
+    ProfScope ps(h, st, CAT_TRMM);
+    RUN(launch_i8(h, st, I8_EPI_SLICE, t, {h->Lq, Mp, Mp, (int64_t)Mp * Mp}, {h->kq_all, n_local, Mp, h->kc_rows * Mp}));
+  }
   for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
     double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
@@ -698,19 +739,19 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     if (i8) {
       int8_t* Kq_c = h->kq_all ? h->kq_all + c0 * Mp : h->Kq;
       const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
-      if (!prefetched) {   // k(X,Z) tile and its digit planes
+      if (!prefetched && !trmm_once) {   // k(X,Z) tile and its digit planes
         ProfScope ps(h, st, CAT_BUILD);
         RUN(build_chunk_i8(h, st, X + c0 * d, nv, d, Z, m, theta, kind, Kc_c, Kq_c, plK));
       }
-      {   // A^T digits [m x nv] = L^{-1} (lower) x Kc^T, fused b-partials = A y (accumulated into one slab set over the chunks)
+      if (!trmm_once) {   // A^T digits [m x nv] = L^{-1} (lower) x Kc^T, fused b-partials = A y (accumulated into one slab set over the chunks)
         I8P t;
         memset(&t, 0, sizeof(t));
         t.M = m; t.N = nv; t.K = Mp; t.lower_a = 1; t.splits = 1; t.snake = 1;
         { const char* e = getenv("GGP_I8_TRMM_ORDER"); t.n_major = (e && e[0] == '0') ? 0 : 1; }
-        t.yv = y + c0; t.rowdot = h->mom_part; t.rowdot_acc = 1;
-        if (getenv("GGP_I8_TRMM_SERIAL")) t.serial_epi = 1;
         t.ea = h->eL; t.eb0 = eK; t.alpha = 1.0;
         t.Oq = h->Atq; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo = eA;
+        t.yv = y + c0; t.rowdot = h->mom_part; t.rowdot_acc = 1;
+        if (getenv("GGP_I8_TRMM_SERIAL")) t.serial_epi = 1;
         ProfScope ps(h, st, CAT_TRMM);
         RUN(launch_i8(h, st, I8_EPI_SLICE, t, {h->Lq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK}));
       }
@@ -724,7 +765,8 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
         sy.splits = std::max(1, std::min(std::min(splits, h->sm_count / std::max(1, tiles)), (nv + 4 * I8_BKB - 1) / (4 * I8_BKB)));
         sy.ea0 = eA; sy.eb0 = eA; sy.alpha = 1.0; sy.beta = 1.0;
         sy.C = h->Spart; sy.ldc = Mp; sy.sSplit = sM;
-        const I8Operand A{h->Atq, m, nc, (int64_t)Mp * nc};
+        const I8Operand A = trmm_once ? I8Operand{h->atq_all + (c0 / nc) * (int64_t)I8_NS * Mp * nc, m, nc, (int64_t)Mp * nc}
+                                      : I8Operand{h->Atq, m, nc, (int64_t)Mp * nc};
         ProfScope ps(h, st, CAT_SYRK);
         RUN(launch_i8(h, st, I8_EPI_F64, sy, A, A));
       }
@@ -750,7 +792,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   }
   if (i8 && n_local > 0) {   // b = sum of the row-dot slabs (fixed order)
     ProfScope ps(h, st, CAT_OTHER);
-    const int nslab = 2 * (int)((std::min<int64_t>(nc, n_local) + I8_BN - 1) / I8_BN);
+    const int nslab = trmm_once ? 2 * h->sm_count : 2 * (int)((std::min<int64_t>(nc, n_local) + I8_BN - 1) / I8_BN);
     k_reduce_moments<<<dim3((unsigned)((m + 31) / 32), 1), 256, 0, st>>>(h->mom_part, m, 0, nslab, m, h->bvec);
     CKL();
   }
