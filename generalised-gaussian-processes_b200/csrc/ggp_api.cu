@@ -172,7 +172,9 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   take((size_t)batch * p.nc * p.Mp * 8);                // Kc
   take((size_t)batch * p.nc * p.Mp * 8);                // At
   take((size_t)batch * p.splits * MM);                  // Spart
-  take((size_t)batch * (p.nc / 32) * m * nq * 8);       // mom_part (one slab per 32 rows of the chunk = tile x warp column)
+  // mom_part: one slab per 32 rows of the chunk (tile x warp column) on the per-chunk plans, 2 slabs per CTA on the one-launch plans
+  // of the sliced-integer path (register-resident moments / row dots), whichever is larger
+  take((size_t)batch * std::max(p.nc / 32, 2 * sm_count) * m * nq * 8);
   take((size_t)batch * m * nq * 8);                     // mom_acc
   take((size_t)batch * 8);                              // rk
   take((size_t)batch * 4 + 256);                        // info_ws

@@ -137,7 +137,7 @@ class Engine:
         """
         import torch.distributed as dist
         dev = self.device
-        X, y, Z, theta = _f64c(X, dev), _f64c(y, dev), _f64c(Z, dev), _f64c(theta, dev)
+        Z, theta = _f64c(Z, dev), _f64c(theta, dev)
         if theta.dim() == 1:
             theta = theta.unsqueeze(0)
         n_local, d = X.shape
@@ -147,14 +147,31 @@ class Engine:
         self.reserve(n_local, m, d, batch)
         with torch.cuda.device(dev):
             cfgp = ctypes.byref(self.cfg)
-            # the k(X,Z) tiles do not depend on the Cholesky of Kzz: build them into the tile cache on a side stream while the
-            # factorisation (latency-bound m x m kernels) runs on the caller's stream; pass 1 then finds them in place
-            ev = None
-            if (self.cfg.tile_cache_mib > 0 and n_local >= self.prefetch_min_rows and not torch.cuda.is_current_stream_capturing()):
+            use_side = (self.cfg.tile_cache_mib > 0 and n_local >= self.prefetch_min_rows
+                        and not torch.cuda.is_current_stream_capturing())
+            host_rows = use_side and not X.is_cuda and not y.is_cuda
+            if use_side:
                 if self._side is None:
                     self._side = torch.cuda.Stream(device=dev)
                 main = torch.cuda.current_stream(dev)
                 self._side.wait_stream(main)
+            if host_rows:
+                # HOST rows (pinned or not): upload them on the side stream too, so that the H2D copy of X (72 MB at the headline
+                # shape) overlaps the factorisation, which only needs Z and theta
+                Xh, yh = X.detach().to(dtype=torch.float64).contiguous(), y.detach().to(dtype=torch.float64).contiguous()
+                X = torch.empty(Xh.shape, dtype=torch.float64, device=dev)
+                y = torch.empty(yh.shape, dtype=torch.float64, device=dev)
+                with torch.cuda.stream(self._side):
+                    X.copy_(Xh, non_blocking=True)
+                    y.copy_(yh, non_blocking=True)
+                X.record_stream(self._side)
+                y.record_stream(self._side)
+            else:
+                X, y = _f64c(X, dev), _f64c(y, dev)
+            # the k(X,Z) tiles do not depend on the Cholesky of Kzz: build them into the tile cache on a side stream while the
+            # factorisation (latency-bound m x m kernels) runs on the caller's stream; pass 1 then finds them in place
+            ev = None
+            if use_side:
                 check(self.lib.ggp_sgpr_prefetch_tiles(self.h, cfgp, ctypes.c_void_p(self._side.cuda_stream), _ptr(X), n_local,
                                                        _ptr(Z), _ptr(theta), m, d, batch), "ggp_sgpr_prefetch_tiles")
                 ev = self._side.record_event()

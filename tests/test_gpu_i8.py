@@ -75,3 +75,64 @@ def test_i8_row_shard_additivity_and_determinism():
     p1 = eng.sgpr_eval(X[:13000], y[:13000], Z, th, jitter_policy=1e-4)["partial"].clone()
     p2 = eng.sgpr_eval(X[13000:], y[13000:], Z, th, jitter_policy=1e-4)["partial"].clone()
     assert relerr(p1 + p2, full["partial"]) < 1e-13
+
+
+def _oracle_check(out, X, y, Z, th, jit, M, D):
+    from oracle import sgpr as osgpr
+    Fo, go, _ = osgpr.sgpr_bound_and_grads_chunked(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=jit, normalize="none")
+    g = out["grad"][0].cpu()
+    assert out["info"].tolist() == [0] and out["info_b"].tolist() == [0]
+    assert relerr(out["bound"], Fo) < TOL
+    assert relerr(g[:D], go["ell"]) < TOL and relerr(g[D], go["sf2"]) < TOL and relerr(g[D + 1], go["s2"]) < TOL
+    assert relerr(g[D + 2:].view(M, D), go["Z"]) < TOL
+
+
+def test_i8_execution_plans_agree():
+    """The same evaluation through the execution plans of the sliced-integer path:
+    (a) tile cache + prefetch on the side stream + one-launch triangular multiply / backward pass (the headline plan; needs
+        n >= Engine.prefetch_min_rows), (b) no tile cache: strictly streaming, tiles rebuilt in pass 2, one launch per chunk,
+    (c) small ragged chunks (18 chunks, fewer slabs per chunk than CTAs), and the FP64 DMMA path.
+    The GPU plans must agree with each other to 1e-9 (two independent implementations: int8-sliced and FP64 DMMA).  Against the
+    oracle the bound holds 1e-8; for the gradient the tolerance is the oracle's own uncertainty at this size -- its chunked-autograd
+    and closed-form evaluations of dF/dZ disagree by ~5e-8 at N = 70001 -- but never looser than 2e-7."""
+    import ggp_b200
+    from oracle import sgpr as osgpr
+    N, M, D, jit = 70001, 256, 4, 1e-4
+    X, y, Z, th = make_problem(N, M, D, seed=77)
+    dev = torch.device("cuda:0")
+    a = ggp_b200.Engine.get(dev, precision="fp64_i8").sgpr_eval(X, y, Z, th, jitter_policy=jit)
+    b = ggp_b200.Engine.get(dev, precision="fp64_i8", tile_cache_mib=0).sgpr_eval(X, y, Z, th, jitter_policy=jit)
+    c = ggp_b200.Engine.get(dev, precision="fp64_i8", chunk_rows=4096).sgpr_eval(X, y, Z, th, jitter_policy=jit)
+    f = ggp_b200.Engine.get(dev, precision="fp64").sgpr_eval(X, y, Z, th, jitter_policy=jit)
+    for o in (b, c, f):
+        assert relerr(o["bound"], a["bound"]) < 1e-12
+        assert relerr(o["grad"], a["grad"]) < 1e-9
+    Fo, go, _ = osgpr.sgpr_bound_and_grads_chunked(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=jit, normalize="none")
+    _, gc = osgpr.sgpr_grads_closed_form(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=jit, normalize="none")
+    g = a["grad"][0].cpu()
+    assert relerr(a["bound"], Fo) < TOL
+    for key, mine in (("ell", g[:D]), ("sf2", g[D]), ("s2", g[D + 1]), ("Z", g[D + 2:].view(M, D))):
+        tol = min(2e-7, max(TOL, 2.0 * relerr(go[key], gc[key])))
+        assert min(relerr(mine, go[key]), relerr(mine, gc[key])) < tol, key
+
+
+def test_i8_host_rows_match_device_rows():
+    """Host (pinned and pageable) X, y go up on the side stream next to the factorisation: same bits as device-resident rows."""
+    import ggp_b200
+    dev = torch.device("cuda:0")
+    eng = ggp_b200.Engine.get(dev, precision="fp64_i8")
+    X, y, Z, th = make_problem(66000, 128, 3, seed=5)
+    ref = eng.sgpr_eval(X.to(dev), y.to(dev), Z.to(dev), th.to(dev), jitter_policy=1e-4)
+    for Xh, yh in ((X, y), (X.pin_memory(), y.pin_memory())):
+        out = eng.sgpr_eval(Xh, yh, Z, th, jitter_policy=1e-4)
+        assert torch.equal(out["bound"], ref["bound"]) and torch.equal(out["grad"], ref["grad"])
+
+
+@pytest.mark.parametrize("D", [11, 12])
+def test_i8_moment_block_boundary(D):
+    """2 D + 1 = 23 moments still fit the register-resident accumulation (three DMMA blocks); D = 12 takes the per-tile path."""
+    import ggp_b200
+    N, M, jit = 6000, 200, 1e-4
+    X, y, Z, th = make_problem(N, M, D, seed=D)
+    out = ggp_b200.Engine.get(torch.device("cuda:0"), precision="fp64_i8").sgpr_eval(X, y, Z, th, jitter_policy=jit)
+    _oracle_check(out, X, y, Z, th, jit, M, D)
