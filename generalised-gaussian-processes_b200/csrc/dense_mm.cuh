@@ -100,6 +100,96 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
   if (tid == 0 && bad && info[b] == 0) info[b] = kb * NB + bad;
 }
 
+// One right-looking step of the blocked Cholesky after the diagonal block kb has been factored (k_potf2_trti2: T = L_kk^{-1}):
+//   panel  L21 = A21 T^T                       (rem x NB,  rem = Mp - (kb + 1) NB)
+//   update A22 -= L21 L21^T                    (lower NB x NB blocks only)
+// fused: CTA (bj, bi), bi >= bj, recomputes the two panel blocks it needs (2 x NB^3 flops: cheaper than a kernel boundary), updates
+// its block of A22 in place, and the diagonal CTAs also emit their panel block -- into the SCRATCH matrix S at the same coordinates,
+// not into A: other CTAs of this launch still read the unscaled A21 (k_tril_merge moves the panels into A after the last step).
+// Two library GEMM launches per step (in-place panel 19 us + K = 64 update 30 us, both latency-bound) become one ~10 us kernel.
+// 256 threads, thread (tx, ty) owns the 4 x 4 outputs (ty + 16 i, tx + 16 j); operands in shared memory with a 65-double row pitch
+// (conflict-free: a warp reads 2 rows of the left operand (broadcast) and 16 rows of the right one at stride 65).
+constexpr int CT_LD = NB + 1;
+constexpr int CT_SMEM = 3 * NB * CT_LD * 8;
+__device__ __forceinline__ void ct_mm_nt(const double* __restrict__ sa, const double* __restrict__ sb, int tx, int ty, double (&c)[4][4]) {
+#pragma unroll 4
+  for (int k = 0; k < NB; ++k) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = sa[(ty + 16 * i) * CT_LD + k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = sb[(tx + 16 * j) * CT_LD + k];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[i][j] = fma(a[i], b[j], c[i][j]);
+  }
+}
+__global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int64_t ld, int64_t sA, int kb, const double* __restrict__ T,
+                                                    int64_t sT, double* __restrict__ S, int64_t sS) {
+  const int bj = blockIdx.x, bi = blockIdx.y, b = blockIdx.z;
+  if (bi < bj) return;
+  extern __shared__ __align__(16) unsigned char ct_raw[];
+  double* sAi = reinterpret_cast<double*>(ct_raw);   // A21 block bi, then P_i
+  double* sAj = sAi + NB * CT_LD;                    // A21 block bj, then P_j
+  double* sTk = sAj + NB * CT_LD;                    // T
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int k0 = kb * NB, r0 = k0 + NB;
+  double* Ab = A + b * sA;
+  const double* Tb = T + b * sT + (int64_t)kb * NB * NB;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    sAi[r * CT_LD + c] = Ab[(int64_t)(r0 + bi * NB + r) * ld + k0 + c];
+    sAj[r * CT_LD + c] = Ab[(int64_t)(r0 + bj * NB + r) * ld + k0 + c];
+    sTk[r * CT_LD + c] = (c <= r) ? Tb[r * NB + c] : 0.0;
+  }
+  __syncthreads();
+  double pi[4][4], pj[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pi[i][j] = pj[i][j] = 0.0;
+  ct_mm_nt(sAi, sTk, tx, ty, pi);              // P_i[r][c] = sum_k A21_i[r][k] T[c][k]
+  if (bi != bj) ct_mm_nt(sAj, sTk, tx, ty, pj);
+  __syncthreads();                            // everyone is done reading A21_i / A21_j
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sAi[(ty + 16 * i) * CT_LD + tx + 16 * j] = pi[i][j];
+      if (bi != bj) sAj[(ty + 16 * i) * CT_LD + tx + 16 * j] = pj[i][j];
+    }
+  if (bi == bj) {   // this CTA owns panel block bi
+    double* Sb = S + b * sS;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Sb[(int64_t)(r0 + bi * NB + ty + 16 * i) * ld + k0 + tx + 16 * j] = pi[i][j];
+  }
+  __syncthreads();
+  double c[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.0;
+  ct_mm_nt(sAi, bi != bj ? sAj : sAi, tx, ty, c);   // P_i P_j^T
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double* dst = Ab + (int64_t)(r0 + bi * NB + ty + 16 * i) * ld + r0 + bj * NB + tx + 16 * j;
+      *dst -= c[i][j];
+    }
+}
+// after the last step: A = [diagonal blocks of A (lower part)] + [panel blocks from S], strict upper triangle zero
+__global__ void k_tril_merge(double* __restrict__ A, const double* __restrict__ S, int Mp, int64_t sA, int64_t sS) {
+  const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+  if (i >= Mp || j >= Mp) return;
+  double* a = A + blockIdx.z * sA + (int64_t)i * Mp + j;
+  if (j > i) *a = 0.0;
+  else if (i / NB != j / NB) *a = S[blockIdx.z * sS + (int64_t)i * Mp + j];
+}
+
 // zero the strict upper triangle.  grid (Mp/16, Mp/16, batch), block (16,16)
 __global__ void k_tril(double* __restrict__ A, int Mp, int64_t sA) {
   const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;

@@ -90,6 +90,7 @@ struct ggp_handle {
   struct CholGraph { double *A, *Linv, *LinvT; int batch; long long nodes; cudaGraphExec_t exec; };
   std::vector<CholGraph> chol_graphs;
   bool use_graphs = true;
+  bool chol_fused = true;       // fused panel + trailing-update kernel in the blocked Cholesky (GGP_CHOL_FUSED=0: two library GEMMs)
   cudaStream_t cap_stream = nullptr;
   int32_t* info_ws = nullptr;
 };
@@ -299,6 +300,12 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
     CKL();
     if (k < nblk - 1) {
       const int rem = Mp - k0 - NB;
+      if (h->chol_fused) {
+        // panel + trailing update of this step in one kernel; the panel goes to the scratch matrix T1 (merged into A below)
+        k_chol_trail<<<dim3(rem / NB, rem / NB, batch), 256, CT_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, h->T1, sM);
+        CKL();
+        continue;
+      }
       double* pan = A + (int64_t)(k0 + NB) * Mp + k0;  // L[k0+NB:, k0:k0+NB] = A[k0+NB:, k0:k0+NB] * T_k^T  (in place, one n-tile)
       GemmP p = gemm_basic(pan, Mp, sM, h->Tblk + (int64_t)k * NB * NB, NB, sM, pan, Mp, sM, rem, NB, NB, 1.0, 0.0);
       RUN(launch_gemm(h, st, EPI_STORE, p, batch));
@@ -308,8 +315,13 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
       RUN(launch_gemm(h, st, EPI_STORE, u, batch));
     }
   }
-  k_tril<<<g16, b16, 0, st>>>(A, Mp, sM);
-  CKL();
+  if (h->chol_fused) {
+    k_tril_merge<<<g16, b16, 0, st>>>(A, h->T1, Mp, sM, sM);
+    CKL();
+  } else {
+    k_tril<<<g16, b16, 0, st>>>(A, Mp, sM);
+    CKL();
+  }
   // recursive-doubling triangular inverse
   k_init_blockdiag<<<g16, b16, 0, st>>>(Linv, Mp, sM, h->Tblk, sM);
   CKL();
@@ -478,6 +490,8 @@ int ggp_create(ggp_handle_t** out, int device) {
   CK(cudaFuncSetAttribute(k_gemm_tma<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
   CK(cudaFuncSetAttribute(k_gemm_tma<EPI_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
   CK(cudaFuncSetAttribute(k_build_kc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_chol_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+  { const char* e = getenv("GGP_CHOL_FUSED"); h->chol_fused = !(e && e[0] == '0'); }
   CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
   CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_SLICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
   CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
