@@ -71,6 +71,11 @@ struct I8P {
                                          // CTA only ever sees two row tiles, one per round parity) and are written once: rowdot[2 b + half][M]
   // I8_EPI_MOMENTS: W = (alpha * acc + u[row] * yv[col]) * Kmul[col][row];  mom[tn][row][:] = sum_col W * [1, x_col, x_col^2]
   const double* u; const double* Kmul; int64_t ldk; const double* Xc; int d; double* mom; int64_t sMomTile;
+  int nchunk_groups_max;                 // host: upper bound on the chunk groups (= partial buffers available)
+  int nchunk, ntile, k_last;             // I8_EPI_F64 over nchunk k-chunks of extent K (the last one k_last) whose digit planes are stacked along the
+                                         // plane axis (plane = chunk * NS + digit): CTA b owns tile b % ntile and the chunks b / ntile + groups r,
+                                         // drains each chunk's exact int32 sums into FP64 registers and stores the total once
+                                         // (C + (b / ntile) * sSplit): the SYRK of a whole pass is one launch, no read-modify-write
   int mom_accum;                         // I8_EPI_MOMENTS, 2 d + 1 <= 24: grid = tiles_m x ng, CTA b owns row tile b % tiles_m and the column tiles
                                          // b / tiles_m + ng k; its moments stay in registers over all its tiles and are written once:
                                          // mom[(b / tiles_m) * 2 + half][row][:]  (2 ng slabs instead of one per 32 columns)
@@ -133,9 +138,14 @@ __device__ __forceinline__ void i8_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
 }
 
 struct I8Item {
-  int tm, tn, split, kb_lo, kb_hi;
+  int tm, tn, split, kb_lo, kb_hi, chunk;
 };
 __device__ __forceinline__ void i8_decode(const I8P& p, int w, I8Item& o) {
+  o.chunk = 0;
+  if (p.nchunk) {   // w = chunk * ntile + tile
+    o.chunk = w / p.ntile;
+    w -= o.chunk * p.ntile;
+  }
   o.split = w % p.splits;
   int t = w / p.splits;
   if (p.sym) {   // row tile tm owns the column tiles tn >= 2 tm
@@ -149,7 +159,7 @@ __device__ __forceinline__ void i8_decode(const I8P& p, int w, I8Item& o) {
     o.tn = t - r * p.tiles_n;
     o.tm = p.lower_a ? (p.tiles_m - 1 - r) : r;   // heavy (long-k) row tiles first
   }
-  int k_hi = p.K;
+  int k_hi = (p.nchunk && o.chunk == p.nchunk - 1) ? p.k_last : p.K;
   if (p.lower_a) k_hi = min(k_hi, (o.tm + 1) * I8_BM);
   const int nkb = (k_hi + I8_BKB - 1) / I8_BKB;
   const int per = (nkb + p.splits - 1) / p.splits;
@@ -159,6 +169,10 @@ __device__ __forceinline__ void i8_decode(const I8P& p, int w, I8Item& o) {
 
 // work item of CTA b in round k (all three warp roles enumerate the same list)
 __device__ __forceinline__ int i8_item(const I8P& p, int k, int b, int G) {
+  if (p.nchunk) {
+    const int c = b / p.ntile + (G / p.ntile) * k;
+    return c < p.nchunk ? c * p.ntile + b % p.ntile : p.total;
+  }
   if (p.mom_accum) {   // n-major encoding of (tm = b % tiles_m, tn = b / tiles_m + ng k); beyond the last column tile -> >= total
     const int ng = G / p.tiles_m, tn = b / p.tiles_m + ng * k;
     return tn < p.tiles_n ? tn * p.tiles_m + b % p.tiles_m : p.total;
@@ -166,6 +180,7 @@ __device__ __forceinline__ int i8_item(const I8P& p, int k, int b, int G) {
   return k * G + ((p.snake && (k & 1)) ? (G - 1 - b) : b);
 }
 __device__ __forceinline__ int i8_rounds(const I8P& p, int G) {
+  if (p.nchunk) { const int ng = G / p.ntile; return (p.nchunk + ng - 1) / ng; }
   if (p.mom_accum) { const int ng = G / p.tiles_m; return (p.tiles_n + ng - 1) / ng; }
   return (p.total + G - 1) / G;
 }
@@ -315,11 +330,11 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_arrive_expect_tx(&full[s], p.exp_skip_b ? I8_NS * I8_A_BYTES : I8_STAGE_BYTES);
           unsigned char* st = base + s * I8_STAGE_BYTES;
 #pragma unroll
-          for (int i = 0; i < I8_NS; ++i) i8_tma_load_3d(st + i * I8_A_BYTES, &tmA, kb * I8_BKB, it.tm * I8_BM, i, &full[s]);
+          for (int i = 0; i < I8_NS; ++i) i8_tma_load_3d(st + i * I8_A_BYTES, &tmA, kb * I8_BKB, it.tm * I8_BM, it.chunk * I8_NS + i, &full[s]);
           if (!p.exp_skip_b) {
 #pragma unroll
             for (int j = 0; j < I8_NS; ++j)
-              i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * I8_B_BYTES, &tmB, kb * I8_BKB, it.tn * I8_BN, j, &full[s]);
+              i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * I8_B_BYTES, &tmB, kb * I8_BKB, it.tn * I8_BN, it.chunk * I8_NS + j, &full[s]);
           }
         }
       }
@@ -377,6 +392,9 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;  // column half of the tile handled by this warp
     const int et = threadIdx.x - 64;   // 0..255
+    double accT[I8_EC];                // I8_EPI_F64 with nchunk: this thread's 32 tile elements summed over the CTA's chunks
+#pragma unroll
+    for (int c = 0; c < I8_EC; ++c) accT[c] = 0.0;
     double rdA[2] = {0.0, 0.0};        // I8_EPI_SLICE with rowdot_reg: b-partials of this thread's row in the CTA's two row tiles
     double rsA = 0.0;                  // I8_EPI_MOMENTS with mom_accum: row sum of W (the constant moment) of this thread's row
     double cmA[4][3][2];               // ... and the x / x^2 moments of this warp's rows, over all tiles of the CTA
@@ -541,7 +559,10 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int c = 0; c < I8_EC; ++c) acc[c] *= sc;
       }
 
-      if (EPI == I8_EPI_F64) {
+      if (EPI == I8_EPI_F64 && p.nchunk) {
+#pragma unroll
+        for (int c = 0; c < I8_EC; ++c) accT[c] += acc[c];
+      } else if (EPI == I8_EPI_F64) {
         if (rok) {
           double* dst = p.C + (int64_t)it.split * p.sSplit + (int64_t)row * p.ldc + col0;
           if (col0 + I8_EC <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -705,6 +726,17 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) i8_mbar_arrive(tmem_empty);
       }
       if (et == 0) I8_STAMP(1, item_done, 3);
+    }
+    if (EPI == I8_EPI_F64 && p.nchunk && blockIdx.x / p.ntile < p.nchunk) {   // the tile total of this CTA's chunks, stored once
+      I8Item it;
+      i8_decode(p, blockIdx.x % p.ntile, it);
+      const int rown = it.tm * I8_BM + quarter * 32 + lane, col0 = it.tn * I8_BN + half * I8_EC;
+      if (rown < p.M) {
+        double* dst = p.C + (int64_t)(blockIdx.x / p.ntile) * p.sSplit + (int64_t)rown * p.ldc + col0;
+#pragma unroll
+        for (int c = 0; c < I8_EC; ++c)
+          if (col0 + c < p.N) dst[c] = accT[c];
+      }
     }
     if (EPI == I8_EPI_SLICE && p.rowdot && p.rowdot_reg) {   // slab 2 b + half (zeroed by the host): rows of the CTA's two row tiles
       int tmv[2] = {-1, -1};

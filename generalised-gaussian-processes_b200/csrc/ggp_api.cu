@@ -388,11 +388,12 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
 // ---- sliced-integer (tcgen05 kind::i8) GEMM: host side -----------------------------------------------------------------
 // digit planes [I8_NS][rows][ld bytes] (plane stride in bytes) as a 3-D map (k, row, plane), 64-byte swizzle, box 64 x box_rows x 1;
 // rows / k beyond the extents given here are zero-filled by the TMA unit
-static bool make_i8_map(CUtensorMap* tm, const int8_t* ptr, int64_t rows, int64_t kbytes, int64_t ld, int64_t plane, int box_rows) {
+static bool make_i8_map(CUtensorMap* tm, const int8_t* ptr, int64_t rows, int64_t kbytes, int64_t ld, int64_t plane, int box_rows,
+                        int nplanes = I8_NS) {
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc || !ptr || rows < 1 || kbytes < 1) return false;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 15) || (plane & 15)) return false;
-  const cuuint64_t dims[3] = {(cuuint64_t)kbytes, (cuuint64_t)rows, (cuuint64_t)I8_NS};
+  const cuuint64_t dims[3] = {(cuuint64_t)kbytes, (cuuint64_t)rows, (cuuint64_t)nplanes};
   const cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)plane};
   const cuuint32_t box[3] = {(cuuint32_t)I8_BKB, (cuuint32_t)box_rows, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
@@ -416,11 +417,18 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
   }
   if (p.splits < 1) p.splits = 1;
   p.total = tiles * p.splits;
+  if (p.nchunk) {   // one launch over all k-chunks (digit planes stacked along the plane axis)
+    if (epi != I8_EPI_F64 || p.splits != 1 || tiles > h->sm_count) return fail(-4, "launch_i8: chunked accumulation needs the F64 epilogue, no split-K, tiles <= SMs");
+    p.ntile = tiles;
+    p.total = tiles * p.nchunk;
+  }
   if (getenv("GGP_I8_EXP_SKIPB")) p.exp_skip_b = 1;
   CUtensorMap tmA, tmB;
-  if (!make_i8_map(&tmA, A.q, A.rows, p.K, A.ld, A.plane, I8_BM) || !make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN))
+  const int npl = p.nchunk ? I8_NS * p.nchunk : I8_NS;
+  if (!make_i8_map(&tmA, A.q, A.rows, p.K, A.ld, A.plane, I8_BM, npl) || !make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN, npl))
     return fail(-4, "launch_i8: operand planes cannot be described by a tensor map (alignment)");
   int grid = std::min(p.total, h->sm_count);
+  if (p.nchunk) grid = p.ntile * std::max(1, std::min(std::min(h->sm_count / p.ntile, p.nchunk), p.nchunk_groups_max > 0 ? p.nchunk_groups_max : p.nchunk));
   if (epi == I8_EPI_MOMENTS && p.mom_accum) {
     if (p.tiles_m > h->sm_count || 2 * p.d + 1 > 24 || p.sym || p.splits != 1)
       return fail(-4, "launch_i8: mom_accum needs tiles_m <= SM count, 2 d + 1 <= 24, no symmetry and no split-K");
@@ -748,7 +756,24 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     ProfScope ps(h, st, CAT_TRMM);
     RUN(launch_i8(h, st, I8_EPI_SLICE, t, {h->Lq, Mp, Mp, (int64_t)Mp * Mp}, {h->kq_all, n_local, Mp, h->kc_rows * Mp}));
   }
-  for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
+  // ... and the SYRK of the whole pass is one launch too: CTA = (tile, chunk group), the exact int32 sums of each 16384-row chunk are
+  // drained into FP64 registers and the tile total is stored once (no read-modify-write, no per-chunk start-up)
+  int syrk_tiles = 0;
+  for (int tm = 0; tm < i8_tiles_m; ++tm) syrk_tiles += std::max(0, (m + I8_BN - 1) / I8_BN - 2 * tm);
+  const bool syrk_once = trmm_once && syrk_tiles <= h->sm_count && !getenv("GGP_I8_NO_SYRK_ONCE");
+  if (syrk_once) {
+    const int nchunk = (int)((n_local + nc - 1) / nc);
+    I8P sy;
+    memset(&sy, 0, sizeof(sy));
+    sy.M = m; sy.N = m; sy.K = (int)std::min<int64_t>(nc, n_local); sy.sym = 1; sy.splits = 1;
+    sy.nchunk = nchunk; sy.k_last = (int)(n_local - (int64_t)(nchunk - 1) * nc); sy.nchunk_groups_max = splits;
+    sy.ea0 = eA; sy.eb0 = eA; sy.alpha = 1.0; sy.beta = 0.0;
+    sy.C = h->Spart; sy.ldc = Mp; sy.sSplit = sM;
+    const I8Operand A{h->atq_all, m, nc, (int64_t)Mp * nc};
+    ProfScope ps(h, st, CAT_SYRK);
+    RUN(launch_i8(h, st, I8_EPI_F64, sy, A, A));
+  }
+  for (int64_t c0 = 0; c0 < n_local && !(trmm_once && syrk_once); c0 += nc) {
     const int nv = (int)std::min<int64_t>(nc, n_local - c0);
     double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
     const int64_t sK = h->kc_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
@@ -771,7 +796,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
         ProfScope ps(h, st, CAT_TRMM);
         RUN(launch_i8(h, st, I8_EPI_SLICE, t, {h->Lq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK}));
       }
-      {   // S_split += A A^T (tiles touching the upper triangle)
+      if (!syrk_once) {   // S_split += A A^T (tiles touching the upper triangle)
         I8P sy;
         memset(&sy, 0, sizeof(sy));
         sy.M = m; sy.N = m; sy.K = nv; sy.sym = 1;
