@@ -65,6 +65,7 @@ struct ggp_handle {
   const void *pf_X = nullptr, *pf_Z = nullptr, *pf_theta = nullptr;
   int64_t pf_n = 0;
   int pf_batch = 0, pf_kind = 0;
+  int64_t pf_next_row = 0;      // ggp_sgpr_prefetch_tiles_part: rows [0, pf_next_row) are built
   double *sv[5] = {0, 0, 0, 0, 0}, *rowout = 0;
   // int8 digit planes of the sliced-integer path (GGP_PREC_FP64_I8; gemm_i8.cuh)
   char* arena_i8 = nullptr;
@@ -673,28 +674,40 @@ static int build_chunk_i8(ggp_handle* h, cudaStream_t st, const double* Xc, int6
   return 0;
 }
 
-int ggp_sgpr_prefetch_tiles(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, int64_t n_local, const double* Z,
-                            const double* theta, int m, int d, int batch) {
+int ggp_sgpr_prefetch_tiles_part(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, int64_t n_local, int64_t row0,
+                                 int64_t nrows, const double* Z, const double* theta, int m, int d, int batch) {
   if (!h || !Z || !theta || (n_local > 0 && !X)) return fail(-1, "ggp_sgpr_prefetch_tiles: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_prefetch_tiles: handle not reserved for this shape");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > n_local) return fail(-3, "ggp_sgpr_prefetch_tiles_part: row range outside [0, n_local)");
   const int kind = cfg ? cfg->kernel : 0;
-  h->pf_valid = false;
+  if (row0 == 0) { h->pf_valid = false; h->pf_next_row = 0; }
   if (!h->kc_all || n_local <= 0) return 0;   // no tile cache: pass 1 builds chunk by chunk as before
+  if (row0 != h->pf_next_row) { h->pf_valid = false; return fail(-3, "ggp_sgpr_prefetch_tiles_part: parts must be issued in ascending row order"); }
   cudaStream_t st = (cudaStream_t)stream;
   const bool i8 = use_i8(h, cfg, d, batch) && h->kq_all;
   const int Mp = h->Mp, nc = h->nc;
+  if (!i8 && (row0 % nc) != 0) return fail(-3, "ggp_sgpr_prefetch_tiles_part: parts of the FP64 path start on a chunk boundary");
   ProfScope ps(h, st, CAT_BUILD);
-  if (i8) {   // the cache is one row-major [rows][Mp] array (+ digit planes): one launch covers all local rows
-    RUN(build_chunk_i8(h, st, X, n_local, d, Z, m, theta, kind, h->kc_all, h->kq_all, h->kc_rows * Mp));
+  if (i8) {   // the cache is one row-major [rows][Mp] array (+ digit planes): one launch covers the whole row range
+    if (nrows > 0)
+      RUN(build_chunk_i8(h, st, X + row0 * d, nrows, d, Z, m, theta, kind, h->kc_all + row0 * Mp, h->kq_all + row0 * Mp, h->kc_rows * Mp));
   } else {
-    for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
-      const int nv = (int)std::min<int64_t>(nc, n_local - c0);
+    for (int64_t c0 = row0; c0 < row0 + nrows; c0 += nc) {
+      const int nv = (int)std::min<int64_t>(nc, row0 + nrows - c0);
       RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, h->kc_all + c0 * Mp, h->kc_rows * Mp));
     }
   }
-  h->pf_valid = true;
-  h->pf_X = X; h->pf_Z = Z; h->pf_theta = theta; h->pf_n = n_local; h->pf_batch = batch; h->pf_kind = kind;
+  h->pf_next_row = row0 + nrows;
+  if (h->pf_next_row == n_local) {
+    h->pf_valid = true;
+    h->pf_X = X; h->pf_Z = Z; h->pf_theta = theta; h->pf_n = n_local; h->pf_batch = batch; h->pf_kind = kind;
+  }
   return 0;
+}
+
+int ggp_sgpr_prefetch_tiles(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, int64_t n_local, const double* Z,
+                            const double* theta, int m, int d, int batch) {
+  return ggp_sgpr_prefetch_tiles_part(h, cfg, stream, X, n_local, 0, n_local, Z, theta, m, d, batch);
 }
 
 int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, const double* y, int64_t n_local,

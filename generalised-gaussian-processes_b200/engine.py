@@ -74,6 +74,7 @@ class Engine:
         self._shape = None
         self.launch_count = 0
         self._side = None            # side stream: tile prefetch overlapped with the factorisation
+        self._copy = None            # copy stream: host rows uploaded piece by piece ahead of their tile build
         self.prefetch_min_rows = 65536
 
     def __del__(self):
@@ -155,26 +156,43 @@ class Engine:
                     self._side = torch.cuda.Stream(device=dev)
                 main = torch.cuda.current_stream(dev)
                 self._side.wait_stream(main)
+            ev = None
             if host_rows:
-                # HOST rows (pinned or not): upload them on the side stream too, so that the H2D copy of X (72 MB at the headline
-                # shape) overlaps the factorisation, which only needs Z and theta
+                # HOST rows (pinned or not): upload them piece by piece on a copy stream, each piece followed by the tile build of
+                # its rows on the side stream, so that the H2D copy of X (72 MB at the headline shape) overlaps both the tile build
+                # of the previous piece and the factorisation (which only needs Z and theta)
+                if self._copy is None:
+                    self._copy = torch.cuda.Stream(device=dev)
+                self._copy.wait_stream(main)
                 Xh, yh = X.detach().to(dtype=torch.float64).contiguous(), y.detach().to(dtype=torch.float64).contiguous()
                 X = torch.empty(Xh.shape, dtype=torch.float64, device=dev)
                 y = torch.empty(yh.shape, dtype=torch.float64, device=dev)
-                with torch.cuda.stream(self._side):
-                    X.copy_(Xh, non_blocking=True)
+                X.record_stream(self._copy); y.record_stream(self._copy)
+                X.record_stream(self._side); y.record_stream(self._side)
+                pieces = 4 if (n_local >= 4 * self.prefetch_min_rows and self.cfg.precision == PRECISIONS["fp64_i8"]) else 1
+                step = -(-n_local // pieces)
+                step = -(-step // 16384) * 16384          # chunk-aligned pieces (any execution plan)
+                with torch.cuda.stream(self._copy):
                     y.copy_(yh, non_blocking=True)
-                X.record_stream(self._side)
-                y.record_stream(self._side)
+                r0 = 0
+                while r0 < n_local:
+                    nr = min(step, n_local - r0)
+                    with torch.cuda.stream(self._copy):
+                        X[r0:r0 + nr].copy_(Xh[r0:r0 + nr], non_blocking=True)
+                        cev = self._copy.record_event()
+                    self._side.wait_event(cev)
+                    check(self.lib.ggp_sgpr_prefetch_tiles_part(self.h, cfgp, ctypes.c_void_p(self._side.cuda_stream), _ptr(X), n_local,
+                                                                r0, nr, _ptr(Z), _ptr(theta), m, d, batch), "ggp_sgpr_prefetch_tiles_part")
+                    r0 += nr
+                ev = self._side.record_event()
             else:
                 X, y = _f64c(X, dev), _f64c(y, dev)
-            # the k(X,Z) tiles do not depend on the Cholesky of Kzz: build them into the tile cache on a side stream while the
-            # factorisation (latency-bound m x m kernels) runs on the caller's stream; pass 1 then finds them in place
-            ev = None
-            if use_side:
-                check(self.lib.ggp_sgpr_prefetch_tiles(self.h, cfgp, ctypes.c_void_p(self._side.cuda_stream), _ptr(X), n_local,
-                                                       _ptr(Z), _ptr(theta), m, d, batch), "ggp_sgpr_prefetch_tiles")
-                ev = self._side.record_event()
+                # the k(X,Z) tiles do not depend on the Cholesky of Kzz: build them into the tile cache on a side stream while the
+                # factorisation (latency-bound m x m kernels) runs on the caller's stream; pass 1 then finds them in place
+                if use_side:
+                    check(self.lib.ggp_sgpr_prefetch_tiles(self.h, cfgp, ctypes.c_void_p(self._side.cuda_stream), _ptr(X), n_local,
+                                                           _ptr(Z), _ptr(theta), m, d, batch), "ggp_sgpr_prefetch_tiles")
+                    ev = self._side.record_event()
             jit, info1 = self.factor(Z, theta, jitter_policy, raise_on_fail)
             if ev is not None:
                 torch.cuda.current_stream(dev).wait_event(ev)

@@ -75,6 +75,13 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
 int ggp_sgpr_prefetch_tiles(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X /*[n_local,d]*/, int64_t n_local,
                             const double* Z, const double* theta, int m, int d, int batch);
 
+/* The same for the row range [row0, row0 + nrows) only: parts are issued in ascending order starting at row0 = 0 and together cover
+ * [0, n_local) (on the FP64 path each part starts on a chunk boundary); the cache becomes valid with the last part.  Lets a host
+ * pipeline the H2D copy of X with the tile build piece by piece. */
+int ggp_sgpr_prefetch_tiles_part(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X /*[n_local,d] base*/,
+                                 int64_t n_local, int64_t row0, int64_t nrows, const double* Z, const double* theta, int m, int d,
+                                 int batch);
+
 /* stream the local rows: partial[b] = [ A A^T (m*m, row-major, symmetric) | A y (m) | y^T y, sum_n k_nn, n_local ]
  * with A = L^{-1} k(Z, X_local).  Never materialises more than chunk_rows x m of k(X,Z). */
 int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
