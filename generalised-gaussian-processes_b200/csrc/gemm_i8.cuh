@@ -802,25 +802,4 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
   }
 }
 
-// digit planes of an existing k(X,Z) tile Kc[n][m] (FP64, leading dimension ldk) with the fixed exponent e = i8_exp_for(sf2) (k <= sf2):
-// Kq[i][n][m].  Each thread converts 4 consecutive m of one row: the warp reads 1 KB contiguous and writes 128 B per plane.
-__global__ void __launch_bounds__(256) k_slice_fixed(const double* __restrict__ Kc, int64_t rows, int cols, int64_t ldk,
-                                                     int8_t* __restrict__ Kq, int64_t ldq, int64_t plane, const double* __restrict__ theta,
-                                                     int d) {
-  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const int cpr = cols / 4;
-  const int64_t row = t / cpr;
-  const int c0 = (int)(t - row * cpr) * 4;
-  if (row >= rows) return;
-  const int e = i8_exp_for(theta[d]);
-  const double si = exp2((double)-e);
-  const double2 a = *reinterpret_cast<const double2*>(Kc + row * ldk + c0);
-  const double2 b = *reinterpret_cast<const double2*>(Kc + row * ldk + c0 + 2);
-  const double x[4] = {a.x, a.y, b.x, b.y};
-  uint32_t pk[I8_NS];
-  i8_pack4(i8_digit_bytes_of(x[0] * si), i8_digit_bytes_of(x[1] * si), i8_digit_bytes_of(x[2] * si), i8_digit_bytes_of(x[3] * si), pk);
-#pragma unroll
-  for (int i = 0; i < I8_NS; ++i) *reinterpret_cast<uint32_t*>(Kq + (int64_t)i * plane + row * ldq + c0) = pk[i];
-}
-
 }  // namespace ggp
