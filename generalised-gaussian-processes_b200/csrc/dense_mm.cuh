@@ -107,22 +107,21 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
 // its block of A22 in place, and the diagonal CTAs also emit their panel block -- into the SCRATCH matrix S at the same coordinates,
 // not into A: other CTAs of this launch still read the unscaled A21 (k_tril_merge moves the panels into A after the last step).
 // Two library GEMM launches per step (in-place panel 19 us + K = 64 update 30 us, both latency-bound) become one ~10 us kernel.
-// 256 threads, thread (tx, ty) owns the 4 x 4 outputs (ty + 16 i, tx + 16 j); operands in shared memory with a 65-double row pitch
-// (conflict-free: a warp reads 2 rows of the left operand (broadcast) and 16 rows of the right one at stride 65).
-constexpr int CT_LD = NB + 1;
+// 256 threads = 8 warps, warp w owns 8 rows of each 64 x 64 x 64 product on the FP64 tensor pipe (a plain-FMA version with 4 x 4
+// register tiles took 24-35 us: 8 shared loads per 16 FMAs at 8 warps per SM).
+constexpr int CT_LD = NB + 4;                   // 68-double pitch: DMMA fragment loads (row g, k q -> bank (4 g + q) mod 16) are conflict-free
 constexpr int CT_SMEM = 3 * NB * CT_LD * 8;
-__device__ __forceinline__ void ct_mm_nt(const double* __restrict__ sa, const double* __restrict__ sb, int tx, int ty, double (&c)[4][4]) {
+// acc[cb][0..1] += sum_k sa[8 w + g][k] * sb[8 cb + g'][k]: warp w owns the 8 rows 8 w .. 8 w + 7 of a 64 x 64 x 64 "NT" product on the
+// FP64 tensor pipe (DMMA.8x8x4: lane = 4 g + q holds a = A[g][q], b = B[q][g], c = C[g][2 q .. 2 q + 1]); 9 shared loads per 8 DMMAs.
+__device__ __forceinline__ void ct_mm_nt(const double* __restrict__ sa, const double* __restrict__ sb, int w, int lane, double (&acc)[8][2]) {
+  const int g = lane >> 2, q = lane & 3;
+  const double* pa = sa + (8 * w + g) * CT_LD + q;
+  const double* pb = sb + g * CT_LD + q;
 #pragma unroll 4
-  for (int k = 0; k < NB; ++k) {
-    double a[4], b[4];
+  for (int kk = 0; kk < NB / 4; ++kk) {
+    const double a = pa[4 * kk];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = sa[(ty + 16 * i) * CT_LD + k];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = sb[(tx + 16 * j) * CT_LD + k];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) c[i][j] = fma(a[i], b[j], c[i][j]);
+    for (int cb = 0; cb < 8; ++cb) dmma884(acc[cb][0], acc[cb][1], a, pb[cb * 8 * CT_LD + 4 * kk]);
   }
 }
 __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int64_t ld, int64_t sA, int kb, const double* __restrict__ T,
@@ -133,7 +132,7 @@ __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int6
   double* sAi = reinterpret_cast<double*>(ct_raw);   // A21 block bi, then P_i
   double* sAj = sAi + NB * CT_LD;                    // A21 block bj, then P_j
   double* sTk = sAj + NB * CT_LD;                    // T
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int k0 = kb * NB, r0 = k0 + NB;
   double* Ab = A + b * sA;
   const double* Tb = T + b * sT + (int64_t)kb * NB * NB;
@@ -144,42 +143,35 @@ __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int6
     sTk[r * CT_LD + c] = (c <= r) ? Tb[r * NB + c] : 0.0;
   }
   __syncthreads();
-  double pi[4][4], pj[4][4];
+  double pi[8][2], pj[8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int cb = 0; cb < 8; ++cb) pi[cb][0] = pi[cb][1] = pj[cb][0] = pj[cb][1] = 0.0;
+  ct_mm_nt(sAi, sTk, w, lane, pi);              // P_i[r][c] = sum_k A21_i[r][k] T[c][k]
+  if (bi != bj) ct_mm_nt(sAj, sTk, w, lane, pj);
+  __syncthreads();                              // everyone is done reading A21_i / A21_j
 #pragma unroll
-    for (int j = 0; j < 4; ++j) pi[i][j] = pj[i][j] = 0.0;
-  ct_mm_nt(sAi, sTk, tx, ty, pi);              // P_i[r][c] = sum_k A21_i[r][k] T[c][k]
-  if (bi != bj) ct_mm_nt(sAj, sTk, tx, ty, pj);
-  __syncthreads();                            // everyone is done reading A21_i / A21_j
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sAi[(ty + 16 * i) * CT_LD + tx + 16 * j] = pi[i][j];
-      if (bi != bj) sAj[(ty + 16 * i) * CT_LD + tx + 16 * j] = pj[i][j];
-    }
+  for (int cb = 0; cb < 8; ++cb) {
+    *reinterpret_cast<double2*>(sAi + (8 * w + g) * CT_LD + 8 * cb + 2 * q) = make_double2(pi[cb][0], pi[cb][1]);
+    if (bi != bj) *reinterpret_cast<double2*>(sAj + (8 * w + g) * CT_LD + 8 * cb + 2 * q) = make_double2(pj[cb][0], pj[cb][1]);
+  }
   if (bi == bj) {   // this CTA owns panel block bi
-    double* Sb = S + b * sS;
+    double* Sb = S + b * sS + (int64_t)(r0 + bi * NB + 8 * w + g) * ld + k0 + 2 * q;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) Sb[(int64_t)(r0 + bi * NB + ty + 16 * i) * ld + k0 + tx + 16 * j] = pi[i][j];
+    for (int cb = 0; cb < 8; ++cb) *reinterpret_cast<double2*>(Sb + 8 * cb) = make_double2(pi[cb][0], pi[cb][1]);
   }
   __syncthreads();
-  double c[4][4];
+  double c[8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int cb = 0; cb < 8; ++cb) c[cb][0] = c[cb][1] = 0.0;
+  ct_mm_nt(sAi, bi != bj ? sAj : sAi, w, lane, c);   // P_i P_j^T
+  double* dst = Ab + (int64_t)(r0 + bi * NB + 8 * w + g) * ld + r0 + bj * NB + 2 * q;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c[i][j] = 0.0;
-  ct_mm_nt(sAi, bi != bj ? sAj : sAi, tx, ty, c);   // P_i P_j^T
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double* dst = Ab + (int64_t)(r0 + bi * NB + ty + 16 * i) * ld + r0 + bj * NB + tx + 16 * j;
-      *dst -= c[i][j];
-    }
+  for (int cb = 0; cb < 8; ++cb) {
+    double2 o = *reinterpret_cast<double2*>(dst + 8 * cb);
+    o.x -= c[cb][0];
+    o.y -= c[cb][1];
+    *reinterpret_cast<double2*>(dst + 8 * cb) = o;
+  }
 }
 // after the last step: A = [diagonal blocks of A (lower part)] + [panel blocks from S], strict upper triangle zero
 __global__ void k_tril_merge(double* __restrict__ A, const double* __restrict__ S, int Mp, int64_t sA, int64_t sS) {
