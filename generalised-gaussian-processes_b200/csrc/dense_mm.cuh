@@ -50,15 +50,21 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
       __syncthreads();
       const double dj = x[j];
       if (!(dj > 0.0) && tid == 0 && bad == 0) bad = j + 1;
-      // The per-column critical path is barrier -> pivot -> scale -> rank-1 update -> publish the next column, 64 columns deep, and a
-      // dependent FP64 operation costs tens of clocks: only 1 / d_j sits on it (MUFU.RCP64H seed, 2^-23, + two Newton steps = 5
-      // dependent operations); the reciprocal square root that scales column j of L and row j of T is issued next to it and consumed
-      // after the update.
-      double dinv;
-      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(dinv) : "d"(dj));
-      dinv = fma(fma(-dj, dinv, 1.0), dinv, dinv);
-      dinv = fma(fma(-dj, dinv, 1.0), dinv, dinv);
+      // one reciprocal square root on the per-column critical path instead of a square root followed by a division
+      // (each ~100+ clk of dependent FP64 latency, 64 columns deep): inv = rsqrt(dj) (<= 1 ulp), piv = dj * inv
       const double inv = rsqrt(dj);
+      const double piv = dj * inv, dinv = inv * inv;
+      if (tx == tj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = ty + 16 * i;
+          Ls[r][j] = (r > j) ? a[i][kj] * inv : ((r == j) ? piv : 0.0);
+        }
+      }
+      if (ty == tj) {   // row j of T is final
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[kj][k] *= inv;
+      }
       double xr[4], xc[4], xtc[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) xr[i] = x[ty + 16 * i];
@@ -67,9 +73,6 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
         xc[k] = x[tx + 16 * k] * dinv;
         xtc[k] = xt[tx + 16 * k] * dinv;
       }
-      double lcol[4];   // column j of L before the update touches a[.][kj] (it does not: the update is restricted to columns > j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) lcol[i] = a[i][kj];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (k >= kj && tx + 16 * k > j) {
@@ -81,18 +84,6 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
           for (int i = 0; i < 4; ++i)
             if (i >= kj && ty + 16 * i > j) t[i][k] = fma(-xr[i], xtc[k], t[i][k]);
         }
-      }
-      if (tx == tj) {
-        const double piv = dj * inv;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = ty + 16 * i;
-          Ls[r][j] = (r > j) ? lcol[i] * inv : ((r == j) ? piv : 0.0);
-        }
-      }
-      if (ty == tj) {   // row j of T is final
-#pragma unroll
-        for (int k = 0; k < 4; ++k) t[kj][k] *= inv;
       }
     }
   }
