@@ -93,6 +93,8 @@ struct ggp_handle {
   bool use_graphs = true;
   bool chol_fused = true;       // fused panel + trailing-update kernel in the blocked Cholesky (GGP_CHOL_FUSED=0: two library GEMMs)
   cudaStream_t cap_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;   // second stream for the independent product chain of the finish section (fork / join by events)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t* info_ws = nullptr;
 };
 
@@ -513,6 +515,9 @@ int ggp_destroy(ggp_handle_t* h) {
   cudaSetDevice(h->device);
   for (auto& c : h->chol_graphs) cudaGraphExecDestroy(c.exec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->arena) cudaFree(h->arena);
   if (h->kc_all) cudaFree(h->kc_all);
   if (h->kq_all) cudaFree(h->kq_all);
@@ -902,10 +907,30 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
     CKL();
   }
   // P = Linv^T PA Linv ;  Gzz = -1/2 Linv^T Gbar Linv
+  // The two chains are independent and a 1024^3 product fills only 64 of the 148 SMs (64 tiles of 128 x 128): the Gzz chain runs on
+  // the handle's auxiliary stream (scratch Wk, free outside the triangular inverse) next to the P chain, fork / join by events
+  // (legal under stream capture: the auxiliary stream joins the capture through the fork event and rejoins before it ends).
+  const bool two_chains = batch * ((m + BM - 1) / BM) * ((m + BN - 1) / BN) <= h->sm_count / 2 + 16 && !getenv("GGP_MM_ONE_STREAM");
+  cudaStream_t st2 = st;
+  if (two_chains) {
+    if (!h->aux_stream) {
+      CK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    st2 = h->aux_stream;
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(st2, h->ev_fork, 0));
+  }
+  double* T2 = two_chains ? h->Wk : h->T1;
   RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
   RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_B_UPPER), batch));
-  RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->Gbar, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
-  RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->Gzz, Mp, sM, m, m, m, -0.5, 0.0, KM_B_UPPER), batch));
+  RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->Gbar, Mp, sM, T2, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
+  RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(T2, Mp, sM, h->LinvT, Mp, sM, h->Gzz, Mp, sM, m, m, m, -0.5, 0.0, KM_B_UPPER), batch));
+  if (two_chains) {
+    CK(cudaEventRecord(h->ev_join, st2));
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+  }
   k_grad_kzz_rows<<<gv, 256, 0, st>>>(h->Gzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, grad_mm + d + 2, sG);
   CKL();
   k_grad_mm_final<<<batch, 256, 0, st>>>(h->rowacc, m, d, theta, partial, sP, h->ds2, grad_mm, sG);
