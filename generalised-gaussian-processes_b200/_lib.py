@@ -51,6 +51,7 @@ SYMBOLS = {
     "ggp_profile_enable": (_I, [_P, _I]),
     "ggp_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "ggp_probe_dmma_peak": (_I, [_P, _P, _I, ctypes.POINTER(ctypes.c_double)]),
+    "ggp_probe_i8_peak": (_I, [_P, _P, _I, ctypes.POINTER(ctypes.c_double)]),
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

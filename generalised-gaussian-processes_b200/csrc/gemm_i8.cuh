@@ -81,6 +81,13 @@ struct I8P {
                                          // mom[(b / tiles_m) * 2 + half][row][:]  (2 ng slabs instead of one per 32 columns)
   int serial_epi;                        // 1: hand TMEM back only after the whole epilogue (FP64 epilogue math and the running
                                          // UTCIMMA stream throttle each other on the tensor / FP64 pipe: measured 10x slower when overlapped)
+  int b_mn;                              // B operand is MN-major: planes [plane][k rows][n contiguous] (the digit planes of A^T as the triangular
+                                         // multiply wrote them, k = inducing index): TMA box = 64 k-rows x 64 n-bytes, UMMA descriptor MN-major SW64
+                                         // with the digit tiles 4096 bytes apart (LBO); wide MMAs are split at multiples of 64 columns
+  int b_planes;                          // b_mn, host: number of planes the B tensor map spans (NS x column blocks)
+  int b_chunk;                           // b_mn: columns per chunk array (column block c = col / b_chunk lives at planes c * NS + digit), 0 = one array
+  const int* e_dev;                      // device-side scalar exponents (no host read-back of theta): e_dev[sel - 1] replaces ea0 / eb0 / eo
+  int ea0_sel, eb0_sel, eo_sel;          // 0 = use the immediate value
   int exp_skip_b;                        // developer experiment: do not load the B operand (wrong results; measures the L2 -> SM bound)
   long long* dbg;                        // developer timeline (CTA 0): [role][item][4] clock64 stamps, or NULL
 };
@@ -115,6 +122,12 @@ __device__ __forceinline__ void i8_tma_load_3d(void* dst, const CUtensorMap* tm,
 // K-major operand tile, 64-byte swizzle: 64-byte rows, 8-row groups 512 bytes apart (SBO), descriptor version 1 (Blackwell)
 __device__ __forceinline__ uint64_t i8_desc_sw64(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+// MN-major operand tile, 64-byte swizzle: 64 k-rows of 64 contiguous MN bytes (8-row groups 512 bytes apart: SBO), further 64-byte
+// MN blocks `lbo` bytes apart (LBO) -- canonical layout ((4,n),(8,k)):((1,LBO),(4,SBO)) in 16-byte units
+__device__ __forceinline__ uint64_t i8_desc_mn_sw64(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
 }
 __device__ __forceinline__ void i8_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -331,7 +344,13 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           unsigned char* st = base + s * I8_STAGE_BYTES;
 #pragma unroll
           for (int i = 0; i < I8_NS; ++i) i8_tma_load_3d(st + i * I8_A_BYTES, &tmA, kb * I8_BKB, it.tm * I8_BM, it.chunk * I8_NS + i, &full[s]);
-          if (!p.exp_skip_b) {
+          if (p.b_mn) {   // box = 64 n-bytes x 64 k-rows of plane (column block, digit)
+            const int cb = p.b_chunk > 0 ? (it.tn * I8_BN) / p.b_chunk : 0;
+            const int cn = it.tn * I8_BN - cb * p.b_chunk;
+#pragma unroll
+            for (int j = 0; j < I8_NS; ++j)
+              i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * I8_B_BYTES, &tmB, cn, kb * I8_BKB, cb * I8_NS + j, &full[s]);
+          } else if (!p.exp_skip_b) {
 #pragma unroll
             for (int j = 0; j < I8_NS; ++j)
               i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * I8_B_BYTES, &tmB, kb * I8_BKB, it.tn * I8_BN, it.chunk * I8_NS + j, &full[s]);
@@ -368,6 +387,20 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               const int ncols = I8_BN * (I8_NS - i);
               const int nsplit = ncols > 256 ? 2 : 1, nn = ncols / nsplit;
               static_assert(I8_BN % 32 == 0, "half of any ncols is a multiple of 16");
+              if (p.b_mn) {
+                // MN-major B: the digit tiles are 64-byte MN blocks LBO = 4096 bytes apart, so a wide MMA must start on a tile
+                // boundary: 448 = 256 + 192, 384 = 192 + 192, 320 = 192 + 128 columns; the k-step advances 32 rows = 2048 bytes
+                static_assert(I8_BN == 64 && I8_BKB == 64, "MN-major B tile: 64 k-rows x 64 n-bytes");
+                const int n1 = ncols > 256 ? ((ncols / 2 + 63) / 64) * 64 : ncols;
+#pragma unroll
+                for (int hs = 0; hs < nsplit; ++hs) {
+                  const int off = hs * n1, nw = hs ? ncols - n1 : n1;
+                  const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(nw >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
+                  const uint64_t bd = i8_desc_mn_sw64(sb + (off / I8_BN) * I8_B_BYTES + kk * 32 * I8_BN, I8_B_BYTES);
+                  i8_umma(tmem_base + (uint32_t)(i * I8_BN + off), ad, bd, idesc, (kb > it.kb_lo || kk > 0 || i > 0) ? 1u : 0u);
+                }
+                continue;
+              }
 #pragma unroll
               for (int hs = 0; hs < nsplit; ++hs) {
                 const int off = hs * nn;
@@ -392,6 +425,8 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;  // column half of the tile handled by this warp
     const int et = threadIdx.x - 64;   // 0..255
+    const int p_ea0 = p.ea0_sel ? p.e_dev[p.ea0_sel - 1] : p.ea0, p_eb0 = p.eb0_sel ? p.e_dev[p.eb0_sel - 1] : p.eb0,
+              p_eo = p.eo_sel ? p.e_dev[p.eo_sel - 1] : p.eo;
     double accT[I8_EC];                // I8_EPI_F64 with nchunk: this thread's 32 tile elements summed over the CTA's chunks
 #pragma unroll
     for (int c = 0; c < I8_EC; ++c) accT[c] = 0.0;
@@ -448,8 +483,8 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         if (et == 0) I8_STAMP(2, item, 3);
       }
-      const int e_r = p.ea ? p.ea[min(row, p.M - 1)] : p.ea0;
-      const int sh = 8 + p.eo - e_r - p.eb0;   // I8_EPI_SLICE (scalar column exponent, alpha = 1, k <= I8_K_GROUP4: checked on the host)
+      const int e_r = p.ea ? p.ea[min(row, p.M - 1)] : p_ea0;
+      const int sh = 8 + p_eo - e_r - p_eb0;   // I8_EPI_SLICE (scalar column exponent, alpha = 1, k <= I8_K_GROUP4: checked on the host)
       const bool fx_fast = (EPI == I8_EPI_SLICE) && __all_sync(0xffffffffu, sh > -32 && sh <= 24);
       const int fx_l1 = sh < 0 ? -sh : 0, fx_r1 = sh > 0 ? sh : 0, fx_s2 = (24 - sh) & 63;
       const long long fx_rnd = sh > 0 ? 1ll << ((sh - 1) & 63) : 0ll;
@@ -554,7 +589,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
         for (int c = 0; c < I8_EC; ++c) acc[c] = p.alpha * ldexp(acc[c], e_r + p.eb[min(col0 + c, p.N - 1)]);
       } else {
-        const double sc = p.alpha * exp2((double)(e_r + p.eb0));
+        const double sc = p.alpha * exp2((double)(e_r + p_eb0));
 #pragma unroll
         for (int c = 0; c < I8_EC; ++c) acc[c] *= sc;
       }
@@ -592,7 +627,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           // fused b-partials A y from the QUANTISED A (the digits just built): S = A A^T is formed from those digits, and dF/dKzx =
           // P Kzx + u y^T cancels by cond(Kzz), so b must belong to the same A (b = L^{-1} (Kzx y) computed on the side, even in
           // double-double, moved the gradient by 8e-8 at the headline shape; consistent b: 5e-9 against the FP64 path)
-          const double so = exp2((double)(p.eo - 56));
+          const double so = exp2((double)(p_eo - 56));
 #pragma unroll
           for (int c = 0; c < I8_EC; ++c) acc[c] = (double)fx[c] * so;
           double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -782,6 +817,14 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(I8_TMEM_COLS));
 }
 
+// e[0] = exponent of the k(X,Z) digits (k <= sf2), e[1] = exponent of the A digits (|A[m,n]| <= sqrt(k_nn) = sqrt(sf2), one bit of margin:
+// the computed |A| may exceed the bound by rounding) -- computed on the device so that no entry point reads theta back to the host
+__global__ void k_i8_exponents(const double* __restrict__ theta, int d, int* __restrict__ e) {
+  const double sf2 = theta[d];
+  e[0] = i8_exp_for(sf2);
+  e[1] = i8_exp_for(sqrt(sf2)) + 1;
+}
+
 // row-scaled signed-digit slicing of X[R x K] (leading dimension ld): planes Xq[i][row][k] (leading dimension ldq, plane stride
 // plane), per-row exponent ex[row] = i8_exp_for(row maximum).  One warp per row.  Columns [K, Kpad) are written as zero.
 __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X, int R, int K, int64_t ld, int8_t* __restrict__ Xq,
@@ -801,5 +844,74 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
     for (int i = 0; i < I8_NS; ++i) Xq[(int64_t)i * plane + (int64_t)row * ldq + k] = dg[i];
   }
 }
+
+// Tensor-pipe peak probe (roofline denominator of the sliced-integer GEMMs): the MMA issue loop of k_gemm_i8 with the operand tiles
+// resident in shared memory -- no TMA, no epilogue, accumulators never read.  One CTA per SM, one issuing thread.
+//   MODE 0: 16 x (128 x 256 x 32) per iteration: the shape-independent tcgen05 kind::i8 rate
+//   MODE 1: the production mix, two 32-byte k-steps per iteration, 10 MMAs each (N = 224+224, 192+192, 160+160, 256, 192, 128, 64):
+//           what the mainloop could reach if its operands were always ready
+// `depth` iterations may be in flight (depth = 2 mimics the 2-stage ring: iteration it waits for the commit of iteration it - 2).
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) k_i8_probe(int iters, int depth, unsigned seed) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + I8_STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  for (int i = threadIdx.x; i < I8_STAGE_BYTES / 4; i += blockDim.x) {   // pseudo-random digit bytes (the data sets the power draw)
+    unsigned x = (unsigned)i * 2654435761u + seed + blockIdx.x * 40503u;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    reinterpret_cast<uint32_t*>(base)[i] = x;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 8; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(I8_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 32) {
+    const uint32_t sa = smem_u32(base), sb = sa + I8_NS * I8_A_BYTES;
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % depth;
+      if (it >= depth) i8_mbar_wait(&bars[s], ((it / depth) - 1) & 1);
+      if (MODE == 0) {
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          i8_umma(tmem_base + (uint32_t)((j & 1) * 256), i8_desc_sw64(sa + (j % I8_NS) * I8_A_BYTES + ((j >> 3) & 1) * 32),
+                  i8_desc_sw64(sb + ((j >> 1) & 1) * 32), idesc, (it > 0 || j > 1) ? 1u : 0u);
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < I8_BKB / 32; ++kk) {
+#pragma unroll
+          for (int i = 0; i < I8_NS; ++i) {
+            const uint64_t ad = i8_desc_sw64(sa + i * I8_A_BYTES + kk * 32);
+            const int ncols = I8_BN * (I8_NS - i);
+            const int nsplit = ncols > 256 ? 2 : 1, nn = ncols / nsplit;
+#pragma unroll
+            for (int hs = 0; hs < nsplit; ++hs) {
+              const int off = hs * nn;
+              const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
+              i8_umma(tmem_base + (uint32_t)(i * I8_BN + off), ad, i8_desc_sw64(sb + off * I8_BKB + kk * 32), idesc,
+                      (it > 0 || kk > 0 || i > 0) ? 1u : 0u);
+            }
+          }
+        }
+      }
+      i8_umma_commit(&bars[s]);
+    }
+    for (int it = max(0, iters - depth); it < iters; ++it) i8_mbar_wait(&bars[it % depth], (it / depth) & 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(I8_TMEM_COLS));
+}
+constexpr int I8_PROBE_SMEM = I8_STAGE_BYTES + 1024 + 256;
 
 }  // namespace ggp

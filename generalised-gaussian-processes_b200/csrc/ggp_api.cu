@@ -71,7 +71,8 @@ struct ggp_handle {
   char* arena_i8 = nullptr;
   size_t arena_i8_bytes = 0;
   int8_t *Lq = 0, *Pq = 0, *Atq = 0, *Kq = 0;
-  int *eL = 0, *eP = 0;
+  int *eL = 0, *eP = 0, *eKA = 0;   // row exponents of L^{-1} / Q digits; eKA[0..1] = scalar exponents of the k(X,Z) / A digits (k_i8_exponents)
+  bool atq_valid = false;           // atq_all holds the A^T digits of the pass 1 identified by the kc_* key (one-launch triangular multiply)
   int8_t* kq_all = nullptr;
   size_t kq_all_bytes = 0;
   int8_t* atq_all = nullptr;   // digit planes of A^T for ALL local rows: the triangular multiply of pass 1 becomes one launch
@@ -428,7 +429,17 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
   if (getenv("GGP_I8_EXP_SKIPB")) p.exp_skip_b = 1;
   CUtensorMap tmA, tmB;
   const int npl = p.nchunk ? I8_NS * p.nchunk : I8_NS;
-  if (!make_i8_map(&tmA, A.q, A.rows, p.K, A.ld, A.plane, I8_BM, npl) || !make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN, npl))
+  bool okB;
+  if (p.b_mn) {
+    // MN-major B: planes [plane][k rows = B.rows][columns, contiguous]; the map's inner extent is one column block (chunk array), the
+    // box 64 column bytes x 64 k-rows; rows / columns beyond the extents are zero-filled
+    if (p.sym || p.nchunk || p.splits != 1 || p.lower_a) return fail(-4, "launch_i8: the MN-major B operand serves the plain product only");
+    const int64_t cols = p.b_chunk > 0 ? p.b_chunk : (int64_t)(p.N + I8_BN - 1) / I8_BN * I8_BN;
+    okB = make_i8_map(&tmB, B.q, B.rows, cols, B.ld, B.plane, I8_BKB, p.b_planes > 0 ? p.b_planes : I8_NS);
+  } else {
+    okB = make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN, npl);
+  }
+  if (!make_i8_map(&tmA, A.q, A.rows, p.K, A.ld, A.plane, I8_BM, npl) || !okB)
     return fail(-4, "launch_i8: operand planes cannot be described by a tensor map (alignment)");
   int grid = std::min(p.total, h->sm_count);
   if (p.nchunk) grid = p.ntile * std::max(1, std::min(std::min(h->sm_count / p.ntile, p.nchunk), p.nchunk_groups_max > 0 ? p.nchunk_groups_max : p.nchunk));
@@ -555,6 +566,7 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   h->Mp = p.Mp; h->nc = p.nc; h->splits = p.splits;
   h->kc_valid = false;
   h->pf_valid = false;
+  h->atq_valid = false;
   {
     const int64_t rows = (n_local + 127) / 128 * 128;
     const size_t need = (size_t)batch * rows * p.Mp * 8;
@@ -582,7 +594,7 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   if (cfg && cfg->precision == GGP_PREC_FP64_I8 && batch == 1 && p.Mp >= I8_BM) {
     const size_t MMq = align_up((size_t)I8_NS * p.Mp * p.Mp, 256), CHq = align_up((size_t)I8_NS * p.Mp * p.nc, 256),
                  EX = align_up((size_t)p.Mp * 4, 256);
-    const size_t need = 2 * MMq + 2 * CHq + 2 * EX;
+    const size_t need = 2 * MMq + 2 * CHq + 3 * EX;
     if (need > h->arena_i8_bytes) {
       if (h->arena_i8) CK(cudaFree(h->arena_i8));
       h->arena_i8 = nullptr;
@@ -596,7 +608,8 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
     h->Atq = (int8_t*)q; q += CHq;
     h->Kq = (int8_t*)q; q += CHq;
     h->eL = (int*)q; q += EX;
-    h->eP = (int*)q;
+    h->eP = (int*)q; q += EX;
+    h->eKA = (int*)q;
     if (h->kc_all) {
       const size_t needq = (size_t)h->kc_rows * p.Mp * I8_NS;
       const size_t budget = (size_t)cfg->tile_cache_mib * 1024 * 1024;
@@ -651,6 +664,7 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   const int kind = cfg ? cfg->kernel : 0;
   const int Mp = h->Mp;
   h->kc_valid = false;
+  h->atq_valid = false;
   ProfScope ps(h, st, CAT_MM);
   k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp);
   CKL();
@@ -737,16 +751,13 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   const bool prefetched = h->kc_all && h->pf_valid && h->pf_X == X && h->pf_Z == Z && h->pf_theta == theta && h->pf_n == n_local &&
                           h->pf_batch == batch && h->pf_kind == kind && (!i8 || h->kq_all);
   h->pf_valid = false;
-  int eK = 0, eA = 0;
+  h->atq_valid = false;
   if (i8) {
-    // fixed exponents of the bounded operands: k(x,z) <= sf2 and |A[m,n]| <= sqrt(k_nn) = sqrt(sf2) (theta is read on the host: one
-    // scalar; the evaluation is synchronous w.r.t. theta anyway through the jitter ladder) -- see gemm_i8.cuh
-    double sf2 = 1.0;
-    CK(cudaMemcpyAsync(&sf2, theta + d, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    eK = i8_exp_for(sf2);
-    eA = i8_exp_for(sqrt(sf2)) + 1;   // one bit of margin: the computed |A| may exceed sqrt(sf2) by rounding
+    // fixed exponents of the bounded operands: k(x,z) <= sf2 and |A[m,n]| <= sqrt(k_nn) = sqrt(sf2), computed ON THE DEVICE into
+    // h->eKA (the kernels read them through I8P::e_dev): the call only enqueues, no host read-back of theta -- see gemm_i8.cuh
     ProfScope ps(h, st, CAT_BUILD);
+    k_i8_exponents<<<1, 1, 0, st>>>(theta, d, h->eKA);
+    CKL();
     k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->Linv, Mp, Mp, Mp, h->Lq, Mp, (int64_t)Mp * Mp, Mp, h->eL);
     CKL();
     CK(cudaMemsetAsync(h->mom_part, 0, (size_t)2 * ((nc + I8_BN - 1) / I8_BN) * m * 8, st));   // b partials, accumulated over the chunks
@@ -767,12 +778,13 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     I8P t;
     memset(&t, 0, sizeof(t));
     t.M = m; t.N = (int)n_local; t.K = Mp; t.lower_a = 1; t.splits = 1; t.snake = 1; t.n_major = 1;
-    t.ea = h->eL; t.eb0 = eK; t.alpha = 1.0;
-    t.Oq = h->atq_all; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo = eA;
+    t.ea = h->eL; t.e_dev = h->eKA; t.eb0_sel = 1; t.alpha = 1.0;
+    t.Oq = h->atq_all; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo_sel = 2;
     t.o_chunk = nc; t.o_chunk_stride = (int64_t)I8_NS * Mp * nc;
     t.yv = y; t.rowdot = h->mom_part; t.rowdot_reg = 1;
     ProfScope ps(h, st, CAT_TRMM);
     RUN(launch_i8(h, st, I8_EPI_SLICE, t, {h->Lq, Mp, Mp, (int64_t)Mp * Mp}, {h->kq_all, n_local, Mp, h->kc_rows * Mp}));
+    h->atq_valid = true;
   }
   // ... and the SYRK of the whole pass is one launch too: CTA = (tile, chunk group), the exact int32 sums of each 16384-row chunk are
   // drained into FP64 registers and the tile total is stored once (no read-modify-write, no per-chunk start-up)
@@ -785,7 +797,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
     memset(&sy, 0, sizeof(sy));
     sy.M = m; sy.N = m; sy.K = (int)std::min<int64_t>(nc, n_local); sy.sym = 1; sy.splits = 1;
     sy.nchunk = nchunk; sy.k_last = (int)(n_local - (int64_t)(nchunk - 1) * nc); sy.nchunk_groups_max = splits;
-    sy.ea0 = eA; sy.eb0 = eA; sy.alpha = 1.0; sy.beta = 0.0;
+    sy.e_dev = h->eKA; sy.ea0_sel = 2; sy.eb0_sel = 2; sy.alpha = 1.0; sy.beta = 0.0;
     sy.C = h->Spart; sy.ldc = Mp; sy.sSplit = sM;
     const I8Operand A{h->atq_all, m, nc, (int64_t)Mp * nc};
     ProfScope ps(h, st, CAT_SYRK);
@@ -807,8 +819,8 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
         memset(&t, 0, sizeof(t));
         t.M = m; t.N = nv; t.K = Mp; t.lower_a = 1; t.splits = 1; t.snake = 1;
         { const char* e = getenv("GGP_I8_TRMM_ORDER"); t.n_major = (e && e[0] == '0') ? 0 : 1; }
-        t.ea = h->eL; t.eb0 = eK; t.alpha = 1.0;
-        t.Oq = h->Atq; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo = eA;
+        t.ea = h->eL; t.e_dev = h->eKA; t.eb0_sel = 1; t.alpha = 1.0;
+        t.Oq = h->Atq; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo_sel = 2;
         t.yv = y + c0; t.rowdot = h->mom_part; t.rowdot_acc = 1;
         if (getenv("GGP_I8_TRMM_SERIAL")) t.serial_epi = 1;
         ProfScope ps(h, st, CAT_TRMM);
@@ -822,7 +834,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
         const int tmn = (m + I8_BM - 1) / I8_BM, tnn = (m + I8_BN - 1) / I8_BN;
         for (int tm = 0; tm < tmn; ++tm) tiles += std::max(0, tnn - 2 * tm);
         sy.splits = std::max(1, std::min(std::min(splits, h->sm_count / std::max(1, tiles)), (nv + 4 * I8_BKB - 1) / (4 * I8_BKB)));
-        sy.ea0 = eA; sy.eb0 = eA; sy.alpha = 1.0; sy.beta = 1.0;
+        sy.e_dev = h->eKA; sy.ea0_sel = 2; sy.eb0_sel = 2; sy.alpha = 1.0; sy.beta = 1.0;
         sy.C = h->Spart; sy.ldc = Mp; sy.sSplit = sM;
         const I8Operand A = trmm_once ? I8Operand{h->atq_all + (c0 / nc) * (int64_t)I8_NS * Mp * nc, m, nc, (int64_t)Mp * nc}
                                       : I8Operand{h->Atq, m, nc, (int64_t)Mp * nc};
@@ -906,7 +918,10 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
     k_rk_from_mm<<<batch, 256, 0, st>>>(partial, sP, m, Mp, theta, d, h->PA, sM, h->beta, h->rk);
     CKL();
   }
-  // P = Linv^T PA Linv ;  Gzz = -1/2 Linv^T Gbar Linv
+  // Q = Linv^T PA (kept in h->P; pass 2 forms dF/dKzx = Q A + u y^T from A = L^{-1} Kzx) ;  Gzz = -1/2 Linv^T Gbar Linv
+  // (Not P = Linv^T PA Linv applied to Kzx, SURVEY R5 as written: P has entries of size 1 / lambda_min(Kzz) and P Kzx cancels down by
+  // cond(Kzz) -- 1e-8 .. 2e-6 of the gradient at the headline Kzz in float64 against an extended-precision evaluation, whereas Q A,
+  // which is what autograd through the triangular solve computes, loses cond(L) eps: tests/test_oracle_hp.py)
   // The two chains are independent and a 1024^3 product fills only 64 of the 148 SMs (64 tiles of 128 x 128): the Gzz chain runs on
   // the handle's auxiliary stream (scratch Wk, free outside the triangular inverse) next to the P chain, fork / join by events
   // (legal under stream capture: the auxiliary stream joins the capture through the fork event and rejoins before it ends).
@@ -923,8 +938,7 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
     CK(cudaStreamWaitEvent(st2, h->ev_fork, 0));
   }
   double* T2 = two_chains ? h->Wk : h->T1;
-  RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->T1, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
-  RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_B_UPPER), batch));
+  RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
   RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->Gbar, Mp, sM, T2, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
   RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(T2, Mp, sM, h->LinvT, Mp, sM, h->Gzz, Mp, sM, m, m, m, -0.5, 0.0, KM_B_UPPER), batch));
   if (two_chains) {
@@ -946,57 +960,77 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   if (kind < GGP_KERNEL_RBF || kind > GGP_KERNEL_MATERN52) return fail(-3, "ggp_sgpr_pass2: unknown kernel");
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc, nq = 2 * d + 1;
-  const int64_t sM = (int64_t)Mp * Mp, sG = (int64_t)d + 2 + (int64_t)m * d;
+  const int64_t sM = (int64_t)Mp * Mp, sG = (int64_t)d + 2 + (int64_t)m * d, sC = (int64_t)nc * Mp;
   const int64_t cnt = (int64_t)m * nq;
   CK(cudaMemsetAsync(h->mom_acc, 0, (size_t)batch * cnt * 8, st));
   // the tiles cached by the pass 1 of this evaluation (same operands, same handle, no factor() since) are reused as they are
   const bool cached = h->kc_all && h->kc_valid && h->kc_X == X && h->kc_Z == Z && h->kc_theta == theta && h->kc_n == n_local &&
                       h->kc_batch == batch && h->kc_kind == kind;
   const bool i8 = use_i8(h, cfg, d, batch);
-  int eK = 0;
+  // dF/dKzx = Q A + u y^T with Q = L^{-T} P_A (h->P, from finish) and A = L^{-1} Kzx: the streamed operand of the backward product is
+  // A^T -- on the sliced-integer path the digit planes the triangular multiply of pass 1 left in atq_all (read MN-major, no second
+  // copy), otherwise rebuilt per chunk -- and k(X,Z) (or dk/d(d2)) only enters as the FP64 multiplier of the epilogue.
+  const bool a_cached = i8 && cached && h->atq_valid && h->atq_all;
   if (i8) {
-    double sf2 = 1.0;
-    CK(cudaMemcpyAsync(&sf2, theta + d, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    eK = i8_exp_for(sf2);
     ProfScope ps(h, st, CAT_BUILD);
+    k_i8_exponents<<<1, 1, 0, st>>>(theta, d, h->eKA);
+    CKL();
     k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->P, Mp, Mp, Mp, h->Pq, Mp, (int64_t)Mp * Mp, Mp, h->eP);
     CKL();
+    if (!a_cached) {   // the per-chunk triangular multiply below needs the digits of L^{-1} (pass 1 may have run on another plan)
+      k_slice_rows<<<(Mp + 7) / 8, 256, 0, st>>>(h->Linv, Mp, Mp, Mp, h->Lq, Mp, (int64_t)Mp * Mp, Mp, h->eL);
+      CKL();
+    }
   }
   // sliced-integer path: the moments stay in the registers of the CTA that produced them over all its tiles (2 d + 1 <= 24), and
-  // with the cached RBF tiles of pass 1 the whole local row range is ONE launch (no per-chunk tails, 2 x 18 slabs to reduce)
+  // with the cached tiles of pass 1 the whole local row range is ONE launch (no per-chunk tails, 2 x 18 slabs to reduce)
   const bool i8_accum = i8 && nq <= 24 && (Mp / I8_BM) <= h->sm_count && !getenv("GGP_I8_NO_ACCUM");
-  const int64_t step = (i8_accum && cached && kind == GGP_KERNEL_RBF && n_local < (int64_t)1 << 30) ? std::max<int64_t>(n_local, 1) : nc;
+  const int64_t step = (i8_accum && a_cached && kind == GGP_KERNEL_RBF && n_local < (int64_t)1 << 30) ? std::max<int64_t>(n_local, 1) : nc;
   for (int64_t c0 = 0; c0 < n_local; c0 += step) {
     const int nv = (int)std::min<int64_t>(step, n_local - c0);
     double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
-    const int64_t sK = h->kc_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
+    const int64_t sK = h->kc_all ? h->kc_rows * Mp : sC;
     if (!cached && !i8) { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
     if (i8) {
       int8_t* Kq_c = h->kq_all ? h->kq_all + c0 * Mp : h->Kq;
-      const int64_t plK = h->kq_all ? h->kc_rows * Mp : (int64_t)nc * Mp;
+      const int64_t plK = h->kq_all ? h->kc_rows * Mp : sC;
       if (!cached) {
         ProfScope ps(h, st, CAT_BUILD);
         RUN(build_chunk_i8(h, st, X + c0 * d, nv, d, Z, m, theta, kind, Kc_c, Kq_c, plK));
       }
+      if (!a_cached) {   // A^T digits of this chunk: [plane][m][nc] = L^{-1} (lower) x Kc^T
+        I8P t;
+        memset(&t, 0, sizeof(t));
+        t.M = m; t.N = nv; t.K = Mp; t.lower_a = 1; t.splits = 1; t.snake = 1; t.n_major = 1;
+        t.ea = h->eL; t.e_dev = h->eKA; t.eb0_sel = 1; t.alpha = 1.0;
+        t.Oq = h->Atq; t.o_ld = nc; t.o_plane = (int64_t)Mp * nc; t.eo_sel = 2;
+        ProfScope ps(h, st, CAT_TRMM);
+        RUN(launch_i8(h, st, I8_EPI_SLICE, t, {h->Lq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK}));
+      }
       const double* Kmul = Kc_c;
-      if (kind != GGP_KERNEL_RBF) {
+      if (kind != GGP_KERNEL_RBF) {   // the multiplier is dk/d(d2), built into the FP64 A^T buffer (unused on this path)
         ProfScope ps(h, st, CAT_BUILD);
         dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
         const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
-        k_build_kc<<<grid, KT_THREADS, smem, st>>>(X + c0 * d, nv, nv, d, Z, m, theta, kind, h->At, Mp, (int64_t)nc * Mp, 1);
+        k_build_kc<<<grid, KT_THREADS, smem, st>>>(X + c0 * d, nv, nv, d, Z, m, theta, kind, h->At, Mp, sC, 1);
         CKL();
         Kmul = h->At;
       }
       I8P g8;
       memset(&g8, 0, sizeof(g8));
       g8.M = m; g8.N = nv; g8.K = Mp; g8.n_major = 1; g8.splits = 1;
-      g8.ea = h->eP; g8.eb0 = eK; g8.alpha = 1.0;
+      g8.ea = h->eP; g8.e_dev = h->eKA; g8.eb0_sel = 2; g8.alpha = 1.0;
+      g8.b_mn = 1; g8.b_chunk = a_cached ? nc : 0;
       g8.u = h->u; g8.yv = y + c0; g8.Kmul = Kmul; g8.ldk = Mp; g8.Xc = X + c0 * d; g8.d = d;
       g8.mom = h->mom_part; g8.sMomTile = cnt;
       g8.mom_accum = i8_accum ? 1 : 0;
       { const char* e = getenv("GGP_I8_SERIAL_EPI"); g8.serial_epi = (e && e[0] == '0') ? 0 : 1; }
-      { ProfScope ps(h, st, CAT_BWD); RUN(launch_i8(h, st, I8_EPI_MOMENTS, g8, {h->Pq, Mp, Mp, (int64_t)Mp * Mp}, {Kq_c, nv, Mp, plK})); }
+      // B = the A^T digit planes as the triangular multiply stores them: [plane][m (k)][columns], columns contiguous (MN-major);
+      // chunk-blocked over all local rows (one [7][Mp][nc] array per chunk) or the single chunk buffer
+      const int nchunks = a_cached ? (int)((n_local + nc - 1) / nc) : 1;
+      const I8Operand Bop{a_cached ? h->atq_all + (c0 / nc) * (int64_t)I8_NS * Mp * nc : h->Atq, m, nc, (int64_t)Mp * nc};
+      g8.b_planes = I8_NS * (a_cached ? nchunks - (int)(c0 / nc) : 1);
+      { ProfScope ps(h, st, CAT_BWD); RUN(launch_i8(h, st, I8_EPI_MOMENTS, g8, {h->Pq, Mp, Mp, (int64_t)Mp * Mp}, Bop)); }
       ProfScope ps_o(h, st, CAT_OTHER);
       const int tiles_m = (m + I8_BM - 1) / I8_BM, tiles_n = (nv + I8_BN - 1) / I8_BN;
       const int nslabs = i8_accum ? 2 * std::max(1, std::min(h->sm_count / tiles_m, tiles_n)) : 2 * tiles_n;
@@ -1005,19 +1039,25 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       continue;
     }
     const int ntiles = (nv + BN - 1) / BN;
-    GemmP g = gemm_basic(h->P, Mp, sM, Kc_c, Mp, sK, nullptr, 0, 0, m, nv, m, 1.0, 0.0);
-    g.n_major = 1;   // all row tiles of one chunk-row tile back to back: each k(X,Z) tile comes from HBM once, then from L2
+    // aT[nv x m] = Kc[nv x m] * Linv^T  (rows of A^T of this chunk; k clipped to the triangle)
+    {
+      ProfScope ps(h, st, CAT_TRMM);
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(Kc_c, Mp, sK, h->Linv, Mp, sM, h->At, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    }
+    GemmP g = gemm_basic(h->P, Mp, sM, h->At, Mp, sC, nullptr, 0, 0, m, nv, m, 1.0, 0.0);
+    g.n_major = 1;   // all row tiles of one chunk-row tile back to back: each A^T tile comes from HBM once, then from L2
     g.u = h->u; g.su = Mp;
     g.yv = y + c0;
     g.Kc = Kc_c; g.ldk = Mp; g.sK = sK;
     if (kind != GGP_KERNEL_RBF) {
-      // Matern: the epilogue multiplier is dk/d(d2), not k (RBF: -k/2, folded into k_grad_from_moments); built into the At buffer
+      // Matern: the epilogue multiplier is dk/d(d2), not k (RBF: -k/2, folded into k_grad_from_moments); built into the chunk buffer
+      // (free when the k(X,Z) tiles come from the cache; otherwise it overwrites this chunk's k(X,Z), already consumed above)
       ProfScope ps(h, st, CAT_BUILD);
       dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
       const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
-      k_build_kc<<<grid, KT_THREADS, smem, st>>>(X + c0 * d, nv, nv, d, Z, m, theta, kind, h->At, Mp, (int64_t)nc * Mp, 1);
+      k_build_kc<<<grid, KT_THREADS, smem, st>>>(X + c0 * d, nv, nv, d, Z, m, theta, kind, h->Kc, Mp, sC, 1);
       CKL();
-      g.Kc = h->At; g.ldk = Mp; g.sK = (int64_t)nc * Mp;
+      g.Kc = h->Kc; g.ldk = Mp; g.sK = sC;
     }
     g.Xc = X + c0 * d; g.d = d;
     g.mom = h->mom_part; g.sMomTile = cnt; g.sMom = (int64_t)(nc / 32) * cnt;
@@ -1365,6 +1405,40 @@ int ggp_probe_dmma_peak(ggp_handle_t* h, void* stream, int iters, double* tflops
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(sink);
+  return 0;
+}
+
+int ggp_probe_i8_peak(ggp_handle_t* h, void* stream, int iters, double* tops_out) {
+  if (!h || !tops_out || iters < 1) return fail(-1, "ggp_probe_i8_peak: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaFuncSetAttribute(k_i8_probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_PROBE_SMEM));
+  CK(cudaFuncSetAttribute(k_i8_probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_PROBE_SMEM));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  // [1] uniform 128 x 256 x 32 MMAs, 4 iterations in flight; [2] production mix, 2 in flight (the 2-stage ring); [3] production mix, 4 in flight
+  const int mode[3] = {0, 1, 1}, depth[3] = {4, 2, 4};
+  const double macs_per_iter[3] = {16.0 * 128 * 256 * 32, 2.0 * 128 * 1792 * 32, 2.0 * 128 * 1792 * 32};
+  double best = 0.0;
+  for (int v = 0; v < 3; ++v) {
+    double bestv = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+      CK(cudaEventRecord(e0, st));
+      if (mode[v] == 0) k_i8_probe<0><<<h->sm_count, 128, I8_PROBE_SMEM, st>>>(iters, depth[v], 17u + rep);
+      else k_i8_probe<1><<<h->sm_count, 128, I8_PROBE_SMEM, st>>>(iters, depth[v], 17u + rep);
+      CK(cudaEventRecord(e1, st));
+      CK(cudaEventSynchronize(e1));
+      CKL();
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      bestv = std::max(bestv, 2.0 * macs_per_iter[v] * iters * h->sm_count / (ms * 1e-3) / 1e12);
+    }
+    tops_out[1 + v] = bestv;
+    best = std::max(best, bestv);
+  }
+  tops_out[0] = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return 0;
 }
 

@@ -377,3 +377,10 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.ggp_probe_dmma_peak(self.h, _stream(), int(iters), out), "ggp_probe_dmma_peak")
         return dict(best=out[0], warps8=out[1], warps16=out[2], warps32=out[3])
+
+    def probe_i8_peak(self, iters=4000):
+        """Measured tcgen05 kind::i8 tensor-pipe rate [int8 TOP/s] with shared-memory-resident operands (no loads, no epilogue)."""
+        out = (ctypes.c_double * 4)()
+        with torch.cuda.device(self.device):
+            check(self.lib.ggp_probe_i8_peak(self.h, _stream(), int(iters), out), "ggp_probe_i8_peak")
+        return dict(best=out[0], uniform_n256=out[1], mix_depth2=out[2], mix_depth4=out[3])

@@ -97,11 +97,18 @@ def sgpr_bound_and_grads_autograd(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch
     return F.detach(), dict(ell=g[0], sf2=g[1], s2=g[2], Z=g[3])
 
 
-def sgpr_grads_closed_form(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch", normalize="n"):
+def sgpr_grads_closed_form(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch", normalize="n", form="QA"):
     """Closed-form gradient of the RBF bound; the algebra the CUDA backward implements.
 
-    beta = B^{-1} b ; P_A = (I - B^{-1})/s - beta beta^T / s^3 ; P = L^{-T} P_A L^{-1} ; u = L^{-T} beta / s^2
-    dF/dKzx = P Kzx + u y^T ; dF/dKzz = -1/2 L^{-T} (B + B^{-1} - 2I + beta beta^T / s^2) L^{-1}
+    beta = B^{-1} b ; P_A = (I - B^{-1})/s - beta beta^T / s^3 ; u = L^{-T} beta / s^2
+    dF/dKzx = Q A + u y^T with Q = L^{-T} P_A and A = L^{-1} Kzx  (form="QA", the default);
+    dF/dKzz = -1/2 L^{-T} (B + B^{-1} - 2I + beta beta^T / s^2) L^{-1}
+
+    form="P" is SURVEY R5 as written, dF/dKzx = P Kzx + u y^T with P = L^{-T} P_A L^{-1}: the same number in exact arithmetic, but
+    P has entries of size 1/lambda_min(Kzz) and P Kzx cancels down by cond(Kzz): in float64 it loses cond(Kzz) * eps
+    (1e-8 .. 2e-6 on the gradient at the headline Kzz, cond 7.6e7, measured against oracle/hp in tests/test_oracle_hp.py), whereas
+    Q A -- which is what reverse-mode autograd through the triangular solve computes, i.e. what the reference's loss.backward() does
+    -- loses only cond(L) * eps (1e-11 .. 1e-9).  form="P" is kept for that demonstration only.
     """
     N, M = X.shape[0], Z.shape[0]
     I = torch.eye(M, dtype=X.dtype)
@@ -112,9 +119,12 @@ def sgpr_grads_closed_form(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch", norm
     Binv = LBinv.T @ LBinv
     beta = Binv @ b
     PA = (I - Binv) / s2 - torch.outer(beta, beta) / s2 ** 3
-    P = Linv.T @ PA @ Linv
     u = Linv.T @ beta / s2 ** 2
-    G = P @ Kzx + torch.outer(u, y)                                   # dF/dKzx   [M,N]
+    if form == "P":
+        P = Linv.T @ PA @ Linv
+        G = P @ Kzx + torch.outer(u, y)                               # dF/dKzx   [M,N]
+    else:
+        G = (Linv.T @ PA) @ st["A"] + torch.outer(u, y)
     Bm = I + S / s2
     Gbar = Bm + Binv - 2.0 * I + torch.outer(beta, beta) / s2 ** 2
     Gzz = -0.5 * Linv.T @ Gbar @ Linv                                 # dF/dKzz   [M,M] (symmetric)
@@ -133,7 +143,7 @@ def sgpr_grads_closed_form(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch", norm
 
 
 def sgpr_bound_and_grads_chunked(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch", normalize="n",
-                                 chunk=65536):
+                                 chunk=65536, form="QA"):
     """Two-pass, N-chunked evaluation of bound + closed-form gradients (RBF).  Never holds an N x M
     buffer larger than chunk x M, so BASELINE config 4 (N=1e6, M=1024) fits in host RAM.  Used as the
     CPU baseline in bench.py and cross-checked against the unchunked oracle."""
@@ -146,9 +156,13 @@ def sgpr_bound_and_grads_chunked(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch"
     S = torch.zeros(M, M, dtype=dt)
     b = torch.zeros(M, dtype=dt)
     yty = torch.zeros((), dtype=dt)
+    keep_A = form != "P" and N * M * 8 <= 16 * 2 ** 30   # A = L^{-1} Kzx of pass 1 is reused by pass 2 when it fits in host memory
+    A_chunks = []
     for i0 in range(0, N, chunk):
         Xc, yc = X[i0:i0 + chunk], y[i0:i0 + chunk]
         A = Linv @ ard_kernel(Z, Xc, ell, sf2)
+        if keep_A:
+            A_chunks.append(A)
         S += A @ A.T
         b += A @ yc
         yty += yc @ yc
@@ -161,7 +175,8 @@ def sgpr_bound_and_grads_chunked(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch"
     Binv = LBinv.T @ LBinv
     beta = Binv @ b
     PA = (I - Binv) / s2 - torch.outer(beta, beta) / s2 ** 3
-    P = Linv.T @ PA @ Linv
+    QA = Linv.T @ PA
+    QL = QA @ Linv if form == "P" else None
     u = Linv.T @ beta / s2 ** 2
     Gbar = Bm + Binv - 2.0 * I + torch.outer(beta, beta) / s2 ** 2
     Gzz = -0.5 * Linv.T @ Gbar @ Linv
@@ -172,7 +187,11 @@ def sgpr_bound_and_grads_chunked(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch"
     for i0 in range(0, N, chunk):
         Xc, yc = X[i0:i0 + chunk], y[i0:i0 + chunk]
         Kc = ard_kernel(Z, Xc, ell, sf2)
-        W = (P @ Kc + torch.outer(u, yc)) * Kc
+        if form == "P":                                             # see sgpr_grads_closed_form on the two forms
+            G = QL @ Kc
+        else:
+            G = QA @ (A_chunks[i0 // chunk] if keep_A else Linv @ Kc)
+        W = (G + torch.outer(u, yc)) * Kc
         r += W.sum(1)
         Q += W @ Xc
         T += W @ (Xc * Xc)

@@ -37,6 +37,16 @@ def sgpr_case(name, N, M, D, seed, jitter):
     print(name, F_dense.item())
 
 
+def sgpr_hp_case(name, N, M, D, seed, jitter):
+    """Bound + gradient in IEEE binary128 (oracle/hp/sgpr_hp.c, -DUSE_QUAD): independent of float64 rounding altogether."""
+    from oracle import hp
+    X, y, Z, th = make_problem(N, M, D, seed=seed)
+    F, g = hp.bound_grad(X.numpy(), y.numpy(), Z.numpy(), th.numpy(), jitter, "quad")
+    np.savez(os.path.join(OUT, name + ".npz"), X=X.numpy(), y=y.numpy(), Z=Z.numpy(), theta=th.numpy(), jitter=jitter, F=F,
+             d_ell=g["ell"], d_sf2=g["sf2"], d_s2=g["s2"], d_Z=g["Z"])
+    print(name, F)
+
+
 def svgp_case(name, N, M, D, B, seed):
     X, y, Z, th = make_problem(N, M, D, seed=seed)
     rs = np.random.RandomState(seed + 7)
@@ -81,5 +91,6 @@ if __name__ == "__main__":
     sgpr_case("sgpr_small_1d", 200, 12, 1, 11, 1e-6)
     sgpr_case("sgpr_small_3d", 300, 25, 3, 12, 1e-6)
     sgpr_case("sgpr_mid_4d", 600, 70, 4, 13, 1e-5)
+    sgpr_hp_case("sgpr_hp_small", 500, 48, 3, 14, 1e-6)
     svgp_case("svgp_small", 400, 30, 3, 64, 21)
     rng_streams()
