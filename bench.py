@@ -190,7 +190,7 @@ def main():
     X, y, Z, th = Xh.to(dev), yh.to(dev), Zh.to(dev), thh.to(dev)
     n_local = hi - lo
     eng = ggp_b200.Engine.get(dev, precision=args.precision)
-    group = None if world > 1 else False
+    group = True if world > 1 else False   # rows are sharded over the ranks: opt in to the two all-reduces per evaluation
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step_resident():

@@ -38,6 +38,7 @@ SYMBOLS = {
     "ggp_sgpr_prefetch_tiles": (_I, [_P, _CFG, _P, _P, _I64, _P, _P, _I, _I, _I]),
     "ggp_sgpr_prefetch_tiles_part": (_I, [_P, _CFG, _P, _P, _I64, _I64, _I64, _P, _P, _I, _I, _I]),
     "ggp_sgpr_pass1": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _P]),
+    "ggp_sgpr_predict_pass1": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _P]),
     "ggp_sgpr_finish": (_I, [_P, _CFG, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "ggp_sgpr_pass2": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _P]),
     "ggp_sgpr_predict": (_I, [_P, _CFG, _P, _P, _I64, _P, _P, _I, _I, _I, _I, _P, _P, _P]),

@@ -16,13 +16,16 @@ constexpr int POTF2_SMEM = 0;
 //   A[r,c] -= x_r x_c / d_j ;  T[j,:] /= L[j,j] ;  T[r,:] -= L[r,j] T[j,:] = x_r xT_c / d_j   (r > j)
 // (column j of L is final at step j, so the inverse sweep rides in the same loop: 64 barriers instead of 128).
 // info[b] = global index (1-based) of the first non-positive pivot, LAPACK potrf style; first failure wins.
+// piv_tol[b]: pivots at or below it count as "not positive definite" (0 = LAPACK semantics; see k_build_kzz).
 __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int64_t ld, int64_t sA, int kb,
-                                                     double* __restrict__ T, int64_t sT, int32_t* info) {
+                                                     double* __restrict__ T, int64_t sT, int32_t* info,
+                                                     const double* __restrict__ piv_tol) {
   __shared__ double xch[2][NB], xtr[2][NB];
   __shared__ double Ls[NB][NB + 1];
   __shared__ int bad;
   const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double* Ab = A + b * sA + (int64_t)kb * NB * (ld + 1);
+  const double tol = piv_tol ? piv_tol[b] : 0.0;
   double a[4][4], t[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
       }
       __syncthreads();
       const double dj = x[j];
-      if (!(dj > 0.0) && tid == 0 && bad == 0) bad = j + 1;
+      if (!(dj > tol) && tid == 0 && bad == 0) bad = j + 1;
       // one reciprocal square root on the per-column critical path instead of a square root followed by a division
       // (each ~100+ clk of dependent FP64 latency, 64 columns deep): inv = rsqrt(dj) (<= 1 ulp), piv = dj * inv
       const double inv = rsqrt(dj);
@@ -244,17 +247,37 @@ __global__ void __launch_bounds__(256) k_gemv(const double* __restrict__ A, int6
     y[b * sy + row] = sc * s;
   }
 }
-// y[i] += sum_j A[i,j] x[j]  (accumulating variant used for b += A_chunk y_chunk; x shared across batch)
+// y[i] += sum_j A[i,j] x[j]  (accumulating variant used for b += A_chunk y_chunk; x has batch stride sx, 0 = shared)
 __global__ void __launch_bounds__(256) k_gemv_acc(const double* __restrict__ A, int64_t ld, int64_t sA,
-                                                  const double* __restrict__ x, double* __restrict__ y, int64_t sy,
+                                                  const double* __restrict__ x, int64_t sx, double* __restrict__ y, int64_t sy,
                                                   int M, int ncols) {
   const int b = blockIdx.y, row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   const double* a = A + b * sA + (int64_t)row * ld;
+  x += b * sx;
   double s = 0.0;
   for (int j = lane; j < ncols; j += 32) s = fma(a[j], x[j], s);
   s = warp_sum(s);
   if (lane == 0) y[b * sy + row] += s;
+}
+
+// Eval-mode training covariance of the sparse predictive (models/sgpr.py:150-160: ExactGP.__call__ evaluates the InducingPointKernel
+// on the training inputs in eval mode, so the sgpr diagonal correction clamp(k_nn - q_nn, 0) is added to the TRAINING rows as well):
+// Lambda_n = s2 + max(sf2 - ||a_n||^2, 0).  Scales column n of the chunk A^T[m x nv] (row i at At + i * ld) and y_n by sqrt(s2 / Lambda_n),
+// so that the ordinary pass-1 sums become s2 * A W A^T and s2 * A W y (W = diag(1 / Lambda)) and ggp_sgpr_finish yields
+// B = I + A W A^T, c = L_B^{-1} A W y unchanged.  One thread per column; grid (ceil(nv / 256), batch).
+__global__ void __launch_bounds__(256) k_fitc_scale(double* __restrict__ At, int64_t ld, int64_t sA, int M, int nv,
+                                                    const double* __restrict__ y, const double* __restrict__ theta, int d,
+                                                    double* __restrict__ ysc, int64_t sy) {
+  const int n = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (n >= nv) return;
+  const double sf2 = theta[(int64_t)b * (d + 2) + d], s2 = theta[(int64_t)b * (d + 2) + d + 1];
+  double* a = At + b * sA + n;
+  double q = 0.0;
+  for (int i = 0; i < M; ++i) { const double v = a[(int64_t)i * ld]; q = fma(v, v, q); }
+  const double w = sqrt(s2 / (s2 + fmax(sf2 - q, 0.0)));
+  for (int i = 0; i < M; ++i) a[(int64_t)i * ld] *= w;
+  ysc[b * sy + n] = y[n] * w;
 }
 
 // out[0] = sum_i y_i^2 over n, deterministic: SUMSQ_BLOCKS block partials (out[1 + block], contiguous slices) then a fixed-order sum

@@ -97,6 +97,8 @@ struct ggp_handle {
   cudaStream_t aux_stream = nullptr;   // second stream for the independent product chain of the finish section (fork / join by events)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t* info_ws = nullptr;
+  double* ysc = nullptr;
+  double* piv_tol = nullptr;   // [batch] pivot threshold of the next Cholesky (k_build_kzz sets it; 0 = LAPACK semantics)
 };
 
 enum { CAT_BUILD = 0, CAT_TRMM = 1, CAT_SYRK = 2, CAT_BWD = 3, CAT_MM = 4, CAT_OTHER = 5, CAT_COUNT = 6 };
@@ -186,6 +188,8 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   p.nsv = std::min(p.nc, 4096);
   for (int i = 0; i < 5; ++i) take((size_t)batch * p.nsv * p.Mp * 8);   // SVGP / SGPMC row and transposed buffers
   take((size_t)batch * 4 * p.nsv * 8);                  // rowout
+  take((size_t)batch * 8 + 256);                        // piv_tol
+  take((size_t)batch * p.nc * 8);                       // ysc (noise-weighted y chunk of the predictive's pass 1)
   p.bytes = o;
   return p;
 }
@@ -300,7 +304,7 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
   // right-looking: factor the diagonal block, form the panel with the block inverse, update the trailing lower tiles
   for (int k = 0; k < nblk; ++k) {
     const int k0 = k * NB;
-    k_potf2_trti2<<<batch, 256, POTF2_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, info);
+    k_potf2_trti2<<<batch, 256, POTF2_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, info, h->piv_tol);
     CKL();
     if (k < nblk - 1) {
       const int rem = Mp - k0 - NB;
@@ -652,6 +656,8 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   h->info_ws = reinterpret_cast<int32_t*>(h->arena + p.off[nslots]);
   for (int i = 0; i < 5; ++i) h->sv[i] = reinterpret_cast<double*>(h->arena + p.off[nslots + 1 + i]);
   h->rowout = reinterpret_cast<double*>(h->arena + p.off[nslots + 6]);
+  h->piv_tol = reinterpret_cast<double*>(h->arena + p.off[nslots + 7]);
+  h->ysc = reinterpret_cast<double*>(h->arena + p.off[nslots + 8]);
   h->nsv = p.nsv;
   return 0;
 }
@@ -666,7 +672,7 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   h->kc_valid = false;
   h->atq_valid = false;
   ProfScope ps(h, st, CAT_MM);
-  k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp);
+  k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp, h->piv_tol);
   CKL();
   return chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info);
 }
@@ -878,6 +884,40 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   return 0;
 }
 
+int ggp_sgpr_predict_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, const double* y, int64_t n_local,
+                           const double* Z, const double* theta, int m, int d, int batch, double* partial) {
+  if (!h || !Z || !theta || !partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_predict_pass1: NULL argument");
+  if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_predict_pass1: handle not reserved for this shape");
+  const int kind = cfg ? cfg->kernel : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = h->Mp, nc = h->nc, splits = h->splits;
+  const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nc * Mp;
+  h->kc_valid = false;   // the chunk buffers are reused below
+  h->pf_valid = false;
+  h->atq_valid = false;
+  CK(cudaMemsetAsync(h->Spart, 0, (size_t)batch * splits * sM * 8, st));
+  CK(cudaMemsetAsync(h->bvec, 0, (size_t)batch * Mp * 8, st));
+  CK(cudaMemsetAsync(h->yty, 0, 256, st));
+  for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
+    const int nv = (int)std::min<int64_t>(nc, n_local - c0);
+    RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, h->Kc, sC));
+    GemmP t = gemm_basic(h->Linv, Mp, sM, h->Kc, Mp, sC, h->At, nc, sC, m, nv, m, 1.0, 0.0, KM_A_LOWER);
+    t.heavy_first = 1;
+    RUN(launch_gemm(h, st, EPI_STORE, t, batch));
+    k_fitc_scale<<<dim3((nv + 255) / 256, batch), 256, 0, st>>>(h->At, nc, sC, m, nv, y + c0, theta, d, h->ysc, nc);
+    CKL();
+    GemmP s = gemm_basic(h->At, nc, sC, h->At, nc, sC, h->Spart, Mp, (int64_t)splits * sM, m, m, nv, 1.0, 1.0);
+    s.sym = 1; s.splits = splits; s.sSplit = sM;
+    RUN(launch_gemm(h, st, EPI_STORE, s, batch));
+    k_gemv_acc<<<dim3((m + 7) / 8, batch), 256, 0, st>>>(h->At, nc, sC, h->ysc, nc, h->bvec, Mp, m, nv);
+    CKL();
+  }
+  k_finalize_partial<<<dim3((m + 15) / 16, (m + 15) / 16, batch), dim3(16, 16), 0, st>>>(
+      h->Spart, Mp, sM, (int64_t)splits * sM, splits, h->bvec, Mp, h->yty, n_local, theta, d, m, partial, (int64_t)m * m + m + 3);
+  CKL();
+  return 0;
+}
+
 int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* Z, const double* theta, int m, int d,
                     int batch, const double* partial, int need_grad, double* bound, double* grad_mm, int32_t* info) {
   if (!h || !Z || !theta || !partial || !bound || !info) return fail(-1, "ggp_sgpr_finish: NULL argument");
@@ -893,6 +933,7 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   ProfScope ps(h, st, CAT_MM);
   k_make_B<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Bm, sM);
   CKL();
+  CK(cudaMemsetAsync(h->piv_tol, 0, sizeof(double) * batch, st));   // B = I + A A^T / s: LAPACK semantics
   RUN(chol_and_inverse(h, st, h->Bm, h->LBinv, h->LBinvT, batch, info));
   // Binv = LBinv^T LBinv.  (The m x m products stay on the FP64 DMMA kernel: routed through the sliced-integer GEMM they were 0.36 ms
   // faster at M = 1024, but its row-scaled fixed point resolves an element only relative to its ROW maximum, and the operands
@@ -1077,25 +1118,42 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
                      const double* theta, int m, int d, int batch, int add_noise, double* mean, double* var, double* cov) {
   if (!h || !Xs || !Z || !theta || !mean || !var) return fail(-1, "ggp_sgpr_predict: NULL argument");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_predict: handle not reserved for this shape");
-  if (cov && ns > h->nc) return fail(-4, "ggp_sgpr_predict: full covariance needs ns <= chunk_rows");
   const int kind = cfg ? cfg->kernel : 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc;
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nc * Mp;
-  for (int64_t c0 = 0; c0 < ns; c0 += nc) {
-    const int nv = (int)std::min<int64_t>(nc, ns - c0);
-    RUN(build_chunk(h, st, Xs + c0 * d, nv, d, Z, m, theta, kind, batch, h->Kc, (int64_t)h->nc * h->Mp));
-    // aT[nv x m] = Ks[nv x m] * Linv^T ; tT[nv x m] = aT * LBinv^T
-    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Linv, Mp, sM, h->At, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
-    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->At, Mp, sC, h->LBinv, Mp, sM, h->Kc, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+  h->kc_valid = false;   // the chunk buffers are scratch here
+  h->atq_valid = false;
+  // t^T[rows x m] = (k(X*, Z) Linv^T) LBinv^T of the test rows [r0, r0 + nv) into At + off (a^T) and Kc + off (t^T)
+  auto rows_t = [&](int64_t r0, int nv, int64_t off) -> int {
+    RUN(build_chunk(h, st, Xs + r0 * d, nv, d, Z, m, theta, kind, batch, h->Kc + off, sC));
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->Kc + off, Mp, sC, h->Linv, Mp, sM, h->At + off, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->At + off, Mp, sC, h->LBinv, Mp, sM, h->Kc + off, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    return 0;
+  };
+  // a full covariance over more test rows than one chunk is tiled over (row chunk, column chunk) pairs of half-chunk size, so that the
+  // t^T rows of both chunks are resident in the two halves of the chunk buffers
+  const bool tiled = cov && ns > nc;
+  const int step = tiled ? std::max(64, nc / 2 / 64 * 64) : nc;
+  const int64_t half = (int64_t)step * Mp;
+  for (int64_t c0 = 0; c0 < ns; c0 += step) {
+    const int nv = (int)std::min<int64_t>(step, ns - c0);
+    RUN(rows_t(c0, nv, 0));
     k_predict_rows<<<dim3((nv + 7) / 8, batch), 256, 0, st>>>(h->At, h->Kc, Mp, sC, h->cvec, Mp, theta, d, m, nv, add_noise,
                                                               mean + c0, var + c0, ns);
     CKL();
-    if (cov) {
-      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Kc, Mp, sC, cov, ns, ns * ns, nv, nv, m, 1.0, 0.0), batch));
-      k_cov_diag<<<dim3((nv + 255) / 256, batch), 256, 0, st>>>(cov, ns, var);
-      CKL();
+    if (!cov) continue;
+    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Kc, Mp, sC, cov + c0 * ns + c0, ns, ns * ns, nv, nv, m, 1.0, 0.0), batch));
+    for (int64_t c1 = c0 + step; tiled && c1 < ns; c1 += step) {
+      const int nw = (int)std::min<int64_t>(step, ns - c1);
+      RUN(rows_t(c1, nw, half));
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->Kc, Mp, sC, h->Kc + half, Mp, sC, cov + c0 * ns + c1, ns, ns * ns, nv, nw, m, 1.0, 0.0), batch));
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->Kc + half, Mp, sC, h->Kc, Mp, sC, cov + c1 * ns + c0, ns, ns * ns, nw, nv, m, 1.0, 0.0), batch));
     }
+  }
+  if (cov) {
+    k_cov_diag<<<dim3((unsigned)((ns + 255) / 256), batch), 256, 0, st>>>(cov, ns, var);
+    CKL();
   }
   return 0;
 }
@@ -1122,7 +1180,7 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
   // note: h->Kc / h->At hold at least nsv x Mp per batch element (nc >= nsv) and are used here as transposed scratch
   {
     ProfScope ps(h, st, CAT_MM);
-    k_build_kzz<<<g16, b16, 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, sM);
+    k_build_kzz<<<g16, b16, 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, sM, h->piv_tol);
     CKL();
     RUN(chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info));
   }
@@ -1218,7 +1276,7 @@ int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
   const bool hasS = qLs != nullptr;
   double *Kc = h->sv[0], *aT = h->sv[1], *wT = h->sv[2], *LsP = h->Bm, *LsT = h->LBinv;
-  k_build_kzz<<<g16, b16, 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, sM);
+  k_build_kzz<<<g16, b16, 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, sM, h->piv_tol);
   CKL();
   RUN(chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info));
   if (hasS) {
@@ -1252,6 +1310,7 @@ int ggp_chol_batched(ggp_handle_t* h, void* stream, double* a, double* linv, int
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
   k_pad_copy<<<g16, b16, 0, st>>>(a, m, h->L, Mp, sM, 1);
   CKL();
+  CK(cudaMemsetAsync(h->piv_tol, 0, sizeof(double) * batch, st));
   RUN(chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info));
   k_pad_copy<<<g16, b16, 0, st>>>(a, m, h->L, Mp, sM, 0);
   CKL();

@@ -321,12 +321,20 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc_i8(const double* __rest
 }
 
 // Kzz[b][i][j] = k(z_i, z_j) + jitter_b * delta_ij for i,j < M ; identity on the padding up to Mp.  grid: (Mp/16, Mp/16, batch)
+// piv_tol[b] (optional) = GGP_PIVOT_RTOL * (k(z,z) + jitter_b): the Cholesky reports "not positive definite" for a pivot at or below it.
+// LAPACK's potrf (what psd_safe_cholesky calls upstream) only fails for a pivot <= 0, but with exactly duplicated inducing rows
+// (np.random.randint draws WITH replacement, experiments/regression.py:83) the true pivot is 0 and the computed one is rounding
+// noise of either sign: LAPACK's outcome is a coin flip no other implementation can reproduce, and proceeding on a noise pivot
+// means cond(Kzz) ~ 1e16.  The relative threshold makes the ladder deterministic; oracle/linalg.py applies the same rule.
+constexpr double GGP_PIVOT_RTOL = 1e-12;
 __global__ void k_build_kzz(const double* __restrict__ Z, int M, int Mp, int d, const double* __restrict__ theta,
-                            const double* __restrict__ jitter, int kind, double* __restrict__ Kzz, int64_t sK) {
+                            const double* __restrict__ jitter, int kind, double* __restrict__ Kzz, int64_t sK,
+                            double* __restrict__ piv_tol = nullptr) {
   const int b = blockIdx.z;
   const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
   if (i >= Mp || j >= Mp) return;
   const double* th = theta + (int64_t)b * (d + 2);
+  if (i == 0 && j == 0 && piv_tol) piv_tol[b] = GGP_PIVOT_RTOL * (kval(kind, th[d], 0.0) + (jitter ? jitter[b] : 0.0));
   double v;
   if (i < M && j < M) {
     double d2 = 0.0;

@@ -68,6 +68,9 @@ class Engine:
             free_b, _ = torch.cuda.mem_get_info(torch.device(device))
             tile_cache_mib = int(min(32 * 1024, free_b // (4 * 1024 * 1024)))
         self.cfg = GgpCfg(KERNELS[kernel], PRECISIONS[precision], int(chunk_rows), int(tile_cache_mib))
+        # the FP64 DMMA plan on the same handle: an fp64_i8 engine evaluates on it when the jitter ladder had to engage (see sgpr_eval)
+        self.cfg_dmma = GgpCfg(KERNELS[kernel], PRECISIONS["fp64"], int(chunk_rows), int(tile_cache_mib))
+        self.ladder_levels = []
         h = ctypes.c_void_p()
         check(self.lib.ggp_create(ctypes.byref(h), self.device.index), "ggp_create")
         self.h = h
@@ -114,6 +117,7 @@ class Engine:
         while True:
             check(self.lib.ggp_sgpr_factor(self.h, ctypes.byref(self.cfg), _stream(), _ptr(Z), _ptr(theta), _ptr(jit),
                                            m, d, batch, _ptr(info)), "ggp_sgpr_factor")
+            self.ladder_levels = level
             if len(ladder) == 1 and not raise_on_fail:
                 # fixed jitter (pymc3 stabilize / gpflow default) and the caller handles info[b] != 0 itself: nothing to retry, so
                 # no host read-back -- the evaluation stays asynchronous and can be captured in a CUDA graph (hmc.GraphedTrajectory)
@@ -130,11 +134,26 @@ class Engine:
                 level[b] += 1
             jit = torch.tensor([ladder[l] for l in level], dtype=torch.float64, device=self.device)
 
-    def sgpr_eval(self, X, y, Z, theta, jitter_policy="gpytorch", need_grad=True, group=None, raise_on_fail=True):
+    @staticmethod
+    def _resolve_group(group):
+        """Row sharding is OPT-IN: group=False / None -> X, y are the whole data set on this rank, nothing is reduced (a model
+        that passes its full train_x on every rank of a DDP / chain-sharded launch must not have its sums multiplied by the world
+        size); group=True -> the default process group; a ProcessGroup -> that group.  Returns (distributed, pg)."""
+        import torch.distributed as dist
+        if group is None or group is False:
+            return False, None
+        if group is True:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("group=True needs an initialised torch.distributed default process group")
+            return dist.get_world_size() > 1, None
+        return True, group
+
+    def sgpr_eval(self, X, y, Z, theta, jitter_policy="gpytorch", need_grad=True, group=False, raise_on_fail=True):
         """Collapsed bound F (not divided by N) and dF/d(ell, sf2, s2, Z) for each row of theta.
 
-        X [n_local, d], y [n_local] are THIS rank's rows; with `group` (torch.distributed) the partial sums are
-        all-reduced.  Returns dict(bound[batch], grad[batch, d+2+m*d] | None, jitter, info, n_total).
+        X [n_local, d], y [n_local] are THIS rank's rows.  With `group` (True = default process group, or a ProcessGroup) they are a
+        row shard and the partial sums are all-reduced; the default group=False never reduces.
+        Returns dict(bound[batch], grad[batch, d+2+m*d] | None, jitter, info, info_b, n_total, path).
         """
         import torch.distributed as dist
         dev = self.device
@@ -194,18 +213,22 @@ class Engine:
                                                            _ptr(Z), _ptr(theta), m, d, batch), "ggp_sgpr_prefetch_tiles")
                     ev = self._side.record_event()
             jit, info1 = self.factor(Z, theta, jitter_policy, raise_on_fail)
+            on_dmma = self.cfg.precision != PRECISIONS["fp64_i8"]
+            if self.cfg.precision == PRECISIONS["fp64_i8"] and any(l > 0 for l in self.ladder_levels):
+                # Kzz was numerically singular (exactly duplicated inducing rows: the with-replacement draw of
+                # experiments/regression.py:83) and only the ladder's jitter made it factorable: cond(Kzz + jI) >= 1e8 / j.  The
+                # sliced-integer products carry an error that is absolute w.r.t. the row scale (2e-16 of sum |a||b|) and cond(Kzz)
+                # amplifies it on dF/dZ (measured 2.2e-7 against long double at the headline shape, jitter 1e-8), whereas the FP64
+                # DMMA path, relative element by element, holds 2e-9 there: evaluate this call on the DMMA plan (same handle; the
+                # prefetched FP64 tiles are reused).
+                cfgp = ctypes.byref(self.cfg_dmma)
+                on_dmma = True
             if ev is not None:
                 torch.cuda.current_stream(dev).wait_event(ev)
             partial = torch.empty(batch, m * m + m + 3, dtype=torch.float64, device=dev)
             check(self.lib.ggp_sgpr_pass1(self.h, cfgp, _stream(), _ptr(X), _ptr(y), n_local, _ptr(Z), _ptr(theta), m, d, batch,
                                           _ptr(partial)), "ggp_sgpr_pass1")
-            # group=None: use the default process group when one is initialised; group=False: never reduce
-            if group is False:
-                distributed, pg = False, None
-            elif group is None:
-                distributed, pg = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1, None
-            else:
-                distributed, pg = True, group
+            distributed, pg = self._resolve_group(group)
             if distributed:
                 dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=pg)
             P = d + 2 + m * d
@@ -222,10 +245,48 @@ class Engine:
                 if distributed:
                     dist.all_reduce(gp, op=dist.ReduceOp.SUM, group=pg)
                 grad = grad_mm + gp
-        return dict(bound=bound, grad=grad, jitter=jit, info=info1, info_b=info2, n_total=partial[:, -1], partial=partial)
+            if raise_on_fail:
+                info2_h = info2.cpu()
+                if bool((info2_h != 0).any()):
+                    raise NotPSDError(f"I + A A^T / s not positive definite; potrf info={info2_h.tolist()}")
+        return dict(bound=bound, grad=grad, jitter=jit, info=info1, info_b=info2, n_total=partial[:, -1], partial=partial,
+                    path="fp64" if on_dmma else "fp64_i8")
+
+    def sgpr_predict_state(self, X, y, Z, theta, jitter_policy="gpytorch", group=False, train_diag_correction=True):
+        """Leave the handle in the state ggp_sgpr_predict reads, for the eval-mode predictive of models/sgpr.py:150-160.
+
+        train_diag_correction=True (gpytorch's eval mode: the kernel is evaluated on the training inputs with the sgpr diagonal
+        correction on): training row n carries Lambda_n = s2 + max(k_nn - q_nn, 0).  False: plain s2 on every training row (the
+        state sgpr_eval leaves).  Returns the key sgpr_predict checks."""
+        dev = self.device
+        X, y, Z, theta = (_f64c(t, dev) for t in (X, y, Z, theta))
+        if theta.dim() == 1:
+            theta = theta.unsqueeze(0)
+        n_local, d = X.shape
+        m, batch = Z.shape[0], theta.shape[0]
+        self.reserve(n_local, m, d, batch)
+        with torch.cuda.device(dev):
+            cfgp = ctypes.byref(self.cfg_dmma)
+            jit, _ = self.factor(Z, theta, jitter_policy, True)
+            partial = torch.empty(batch, m * m + m + 3, dtype=torch.float64, device=dev)
+            fn = self.lib.ggp_sgpr_predict_pass1 if train_diag_correction else self.lib.ggp_sgpr_pass1
+            check(fn(self.h, cfgp, _stream(), _ptr(X), _ptr(y), n_local, _ptr(Z), _ptr(theta), m, d, batch, _ptr(partial)),
+                  "ggp_sgpr_predict_pass1")
+            distributed, pg = self._resolve_group(group)
+            if distributed:
+                import torch.distributed as dist
+                dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=pg)
+            bound = torch.empty(batch, dtype=torch.float64, device=dev)
+            info2 = torch.zeros(batch, dtype=torch.int32, device=dev)
+            check(self.lib.ggp_sgpr_finish(self.h, cfgp, _stream(), _ptr(Z), _ptr(theta), m, d, batch, _ptr(partial), 0, _ptr(bound),
+                                           _ptr(None), _ptr(info2)), "ggp_sgpr_finish")
+            if bool((info2 != 0).any()):
+                raise NotPSDError(f"I + A W A^T not positive definite; potrf info={info2.tolist()}")
+        self._predict_epoch = getattr(self, "_predict_epoch", 0) + 1
+        return dict(jitter=jit, epoch=self._predict_epoch)
 
     def sgpr_predict(self, Xs, Z, theta, full_cov=False, add_noise=True):
-        """Predictive at the state left by the last sgpr_eval with the same (Z, theta)."""
+        """Predictive at the state left by the last sgpr_predict_state (or sgpr_eval) with the same (Z, theta)."""
         dev = self.device
         Xs, Z, theta = _f64c(Xs, dev), _f64c(Z, dev), _f64c(theta, dev)
         if theta.dim() == 1:

@@ -12,7 +12,7 @@ import torch
 
 from .engine import Engine
 
-DEFAULT_CFG = dict(normalize="n", jitter_policy="gpytorch", precision="fp64", kernel="rbf", group=None, chunk_rows=0)
+DEFAULT_CFG = dict(normalize="n", jitter_policy="gpytorch", precision="fp64", kernel="rbf", group=False, chunk_rows=0)
 
 
 def _cfg(cfg):

@@ -165,14 +165,45 @@ def _ckpt_range(n):
     return idx_max - t + 1, idx_max
 
 
+class RunningDiagMass:
+    """pymc3's QuadPotentialDiagAdapt (what init='jitter+adapt_diag' builds for pm.NUTS(), models/bayesian_sgpr_hmc.py:73-78): the
+    diagonal inverse metric is the running variance of the tuning draws, refreshed after EVERY tuning step from a foreground
+    estimator that starts at (mean = start point, variance = 1, weight 10); every `window` draws the foreground is replaced by the
+    background estimator (which only saw the last window) and a fresh background starts.  Works for any tune length (25 / 100 in
+    models/bayesian_sgpr_hmc.py:141-146).  All state is [C, P]: one estimator per lock-step chain."""
+
+    def __init__(self, x0, window=101, initial_weight=10):
+        self.window, self.n = window, 0
+        self.fg = [int(initial_weight), x0.clone(), torch.ones_like(x0) * initial_weight]   # n_samples, mean, raw_var
+        self.bg = [0, torch.zeros_like(x0), torch.zeros_like(x0)]
+
+    @staticmethod
+    def _add(st, x):
+        st[0] += 1
+        old = x - st[1]
+        st[1] = st[1] + old / st[0]
+        st[2] = st[2] + old * (x - st[1])
+
+    def update(self, x):
+        self._add(self.fg, x)
+        self._add(self.bg, x)
+        var = self.fg[2] / self.fg[0]
+        self.n += 1
+        if self.n % self.window == 0:
+            self.fg, self.bg = self.bg, [0, torch.zeros_like(x), torch.zeros_like(x)]
+        return var
+
+
 def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_treedepth=10, step_size=None, adapt_mass=True,
-                max_energy_error=1000.0, generator=None, progress=None):
+                max_energy_error=1000.0, generator=None, progress=None, mass_adaptation="pymc3"):
     """No-U-turn sampler, C chains in lock-step, with the defaults of the sampler the reference calls: `pm.sample(n, tune=tune,
     chains=1)` with `pm.NUTS()` (models/bayesian_sgpr_hmc.py:73-78, models/all_in_HMC.py:60): multinomial NUTS, uniform progressive
     sampling inside a subtree and biased progressive sampling between the old tree and the new subtree, U-turn test
     p_sum . v_edge <= 0 at both edges of every balanced subtree, divergence at |energy change| > 1000, max_treedepth 10,
     step size by dual averaging to target_accept 0.8 from 0.25 / P^(1/4), statistic = mean over tree leaves of min(1, exp(-dE)).
-    The mass matrix is diagonal, adapted in windows (pymc3 adapts it with a running estimator; the window schedule differs).
+    The mass matrix is diagonal; mass_adaptation="pymc3" (default) is pymc3's running estimator (RunningDiagMass: refreshed every
+    tuning step, foreground / background windows of 101 draws, no restart of the step-size adaptation), "windows" the Stan-like
+    three-window scheme hmc_sample uses.
 
     Batching: one tree doubling = 2^j leapfrogs = 2^j BATCHED logp/dlogp calls shared by every chain; a chain whose tree has
     stopped is masked out (its rows are still evaluated, which is what lock-step costs).  The U-turn checks inside a subtree use
@@ -194,7 +225,8 @@ def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_tree
     nleap = torch.zeros(n_samples, C, dtype=torch.int32, device=dev)
     divs = torch.zeros(n_samples, C, dtype=torch.bool, device=dev)
     acc_sum = torch.zeros(C, dtype=dt, device=dev)
-    windows = sorted({int(tune * f) for f in (0.25, 0.5, 0.75)} - {0}) if adapt_mass and tune >= 40 else []
+    running = RunningDiagMass(x) if (adapt_mass and mass_adaptation == "pymc3") else None
+    windows = sorted({int(tune * f) for f in (0.25, 0.5, 0.75)} - {0}) if adapt_mass and running is None and tune >= 40 else []
     win_start, buf = 0, []
     ninf = torch.full((C,), -float("inf"), dtype=dt, device=dev)
     K = max(max_treedepth, 1)
@@ -281,6 +313,8 @@ def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_tree
             eps = da.update(acc_prob)
             if it == tune - 1:
                 eps = da.final()
+            if running is not None:
+                inv_mass = running.update(x)
             if windows:
                 buf.append(x.clone())
                 if it + 1 in windows:
@@ -327,11 +361,13 @@ class HyperTrace:
         return torch.cat([v[:, :self.D], v[:, self.D:] ** 2], dim=1)
 
 
-def sample_hyper(X, y, Z, n_samples, tune, chains=1, n_leapfrog=10, step_size=0.02, engine=None, generator=None, seed_jitter=True,
-                 cuda_graph=False, sampler="hmc", max_treedepth=10):
-    """HMC over theta = (ls, sig_f, sig_n) on the collapsed VFE bound with pymc3's priors and transforms
+def sample_hyper(X, y, Z, n_samples, tune, chains=1, n_leapfrog=10, step_size=None, engine=None, generator=None, seed_jitter=True,
+                 cuda_graph=False, sampler="nuts", max_treedepth=10, target_accept=0.8):
+    """Sampling over theta = (ls, sig_f, sig_n) on the collapsed VFE bound with pymc3's priors and transforms
     (models/bayesian_sgpr_hmc.py:58-80).  Start = prior test value (Gamma mean 2, HalfCauchy beta 1) + U(-1,1) jitter
-    in unconstrained space (pymc3 init='jitter+adapt_diag').  Returns (list of HyperTrace per chain, raw result)."""
+    in unconstrained space (pymc3 init='jitter+adapt_diag').  sampler="nuts" (default) is pm.NUTS() as the reference calls it
+    (:73-78); sampler="hmc" is the fixed-length lock-step sampler (step_size default 0.02; the CUDA-graph benchmark uses it).
+    Returns (list of HyperTrace per chain, raw result)."""
     import time
     from .functions import sgpr_vfe_logp_dlogp
     D = X.shape[1]
@@ -343,10 +379,13 @@ def sample_hyper(X, y, Z, n_samples, tune, chains=1, n_leapfrog=10, step_size=0.
     f = lambda xx: sgpr_vfe_logp_dlogp(xx, X, y, Z, engine=engine)
     t0 = time.perf_counter()
     if sampler == "nuts":   # pm.NUTS() defaults (models/bayesian_sgpr_hmc.py:73-78)
-        res = nuts_sample(f, x0, n_samples, tune=tune, max_treedepth=max_treedepth, generator=generator)
+        res = nuts_sample(f, x0, n_samples, tune=tune, max_treedepth=max_treedepth, target_accept=target_accept, step_size=step_size,
+                          generator=generator)
+    elif sampler == "hmc":
+        res = hmc_sample(f, x0, n_samples, tune=tune, n_leapfrog=n_leapfrog, step_size=0.02 if step_size is None else step_size,
+                         target_accept=target_accept, generator=generator, cuda_graph=cuda_graph)
     else:
-        res = hmc_sample(f, x0, n_samples, tune=tune, n_leapfrog=n_leapfrog, step_size=step_size, generator=generator,
-                         cuda_graph=cuda_graph)
+        raise ValueError(f"unknown sampler {sampler!r}: 'nuts' or 'hmc'")
     dt = time.perf_counter() - t0
     res["seconds"] = dt
     traces = [HyperTrace(res["samples"][:, c], res["step_size"][c], dt) for c in range(chains)]

@@ -126,6 +126,9 @@ class PredictiveNormal:
             L, info = torch.linalg.cholesky_ex(cov + j * eye)
             if int(info) == 0:
                 break
+        else:
+            from .engine import NotPSDError
+            raise NotPSDError("predictive covariance not positive definite after the jitter ladder (0, 1e-8, 1e-7, 1e-6)")
         r = torch.linalg.solve_triangular(L, (y.to(cov.dtype) - self.loc).unsqueeze(-1), upper=False).squeeze(-1)
         return -0.5 * (r @ r) - torch.log(torch.diagonal(L)).sum() - 0.5 * n * math.log(2.0 * math.pi)
 
@@ -181,7 +184,7 @@ class SparseGPR(nn.Module):
             eng = Engine.get(self.train_x.device)
             theta = self._theta()
             Z = self.covar_module.inducing_points
-            eng.sgpr_eval(self.train_x, self.train_y, Z, theta, jitter_policy=self.jitter_policy, need_grad=False)
+            eng.sgpr_predict_state(self.train_x, self.train_y, Z, theta, jitter_policy=self.jitter_policy)
             mean, var, cov = eng.sgpr_predict(test_x, Z, theta, full_cov=full_cov)
         return PredictiveNormal(mean[0], cov[0] if cov is not None else None, var[0])
 
@@ -199,10 +202,15 @@ class BayesianSparseGPR_HMC(SparseGPR):
                 parameter.requires_grad = False
 
     def sample_optimal_variational_hyper_dist(self, n_samples, input_dim, Z_opt, tune, sampler_params=None, chains=1):
+        """pm.sample(n_samples, tune=tune, chains=1, step=pm.NUTS()) on the VFE model (models/bayesian_sgpr_hmc.py:58-80): NUTS with
+        pymc3's defaults.  sampler_params: dict(sampler='nuts'|'hmc', max_treedepth, target_accept, step_size, n_leapfrog) -- the
+        fixed-length sampler is opt-in."""
         from .hmc import sample_hyper
         Z = torch.as_tensor(Z_opt, dtype=torch.float64, device=self.train_x.device).reshape(-1, input_dim)
-        step = 0.02 if not sampler_params else sampler_params.get('step_scale', 0.02)
-        traces, res = sample_hyper(self.train_x, self.train_y, Z, n_samples, tune, chains=chains, step_size=step)
+        sp = dict(sampler_params or {})
+        traces, res = sample_hyper(self.train_x, self.train_y, Z, n_samples, tune, chains=chains, sampler=sp.get('sampler', 'nuts'),
+                                   max_treedepth=sp.get('max_treedepth', 10), target_accept=sp.get('target_accept', 0.8),
+                                   step_size=sp.get('step_size', sp.get('step_scale')), n_leapfrog=sp.get('n_leapfrog', 10))
         self.last_sampler_result = res
         return traces[0] if chains == 1 else traces
 
@@ -279,7 +287,7 @@ def mixture_posterior_predictive(model, test_x, trace_hyper, full_cov=True):
         eng = Engine.get(model.train_x.device)
         thetas = trace_hyper.thetas().to(model.train_x.device)
         Z = model.covar_module.inducing_points
-        eng.sgpr_eval(model.train_x, model.train_y, Z, thetas, jitter_policy=model.jitter_policy, need_grad=False)
+        eng.sgpr_predict_state(model.train_x, model.train_y, Z, thetas, jitter_policy=model.jitter_policy)
         mean, var, cov = eng.sgpr_predict(test_x, Z, thetas, full_cov=full_cov)
     out = []
     eye = torch.eye(test_x.shape[0], dtype=torch.float64, device=mean.device) * 1e-4 if full_cov else None
@@ -420,6 +428,26 @@ class BayesianStochasticVariationalGP(StochasticVariationalGP):
                 optimizer.step()
             epoch_losses.append(float(np.sum(batch_losses)))
         return epoch_losses, batch_losses
+
+
+    def sample_variational_log_hyper(self, num_samples):
+        return self.log_theta(num_samples)
+
+    def mixture_posterior_predictive(self, test_x, num_samples=100):
+        """models/bayesian_svgp.py:183-207, followed literally: 100 draws l_i ~ q(log theta), theta_i = softplus(l_i) handed to
+        forward() as `log_theta`, i.e. exponentiated again (:124) before update_covar_module_at_theta (:129-133).  All draws go
+        through ONE batched predictive launch sequence; returns a list of predictive distributions (marginals), one per draw."""
+        self.eval()
+        self._maybe_init_variational()
+        with torch.no_grad():
+            test_x = test_x if test_x.dim() > 1 else test_x.unsqueeze(-1)
+            draws = self.sample_variational_log_hyper(num_samples)
+            thetas = self._thetas(Fnn.softplus(draws))
+            eng = Engine.get(self.train_x.device)
+            mean, var = eng.svgp_predict(test_x, self.inducing_inputs, self.variational_mean, self.chol_variational_covar, thetas,
+                                         add_noise=self.is_gaussian)
+        self.last_mixture_thetas = thetas
+        return [PredictiveNormal(mean[i], None, var[i]) for i in range(thetas.shape[0])]
 
 
 class _BatchedElboMean(torch.autograd.Function):

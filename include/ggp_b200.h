@@ -104,9 +104,19 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
                    const double* Z, const double* theta, int m, int d, int batch,
                    double* grad_partial /*[batch, d+2+m*d]*/);
 
-/* Sparse predictive at the state left by factor+pass1+finish  (likelihood(self(test_x)) in eval mode,
- * models/sgpr.py:150-160; models/bayesian_sgpr_hmc.py:198-231).  mean,var: [batch, ns]; cov: [batch, ns, ns] or NULL.
- * var/cov include the eval-mode diagonal correction clamp(k** - ||a*||^2, 0) and, if add_noise, + s2. */
+/* Pass 1 of the eval-mode predictive (replaces ggp_sgpr_pass1 in factor -> pass1 -> [allreduce] -> finish(need_grad = 0) -> predict):
+ * ExactGP.__call__ in eval mode evaluates the InducingPointKernel on the TRAINING inputs with the sgpr diagonal correction on
+ * (models/sgpr.py:150-160 -> likelihood(self(test_x))), so training row n carries the noise Lambda_n = s2 + max(k_nn - q_nn, 0).
+ * partial[b] = [ s2 A W A^T | s2 A W y | 0, n sf2, n ] with W = diag(1 / Lambda): ggp_sgpr_finish then leaves B = I + A W A^T and
+ * c = L_B^{-1} A W y for ggp_sgpr_predict (its `bound` output is meaningless for this state).  FP64 DMMA path. */
+int ggp_sgpr_predict_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
+                           const double* X /*[n_local,d]*/, const double* y /*[n_local]*/, int64_t n_local,
+                           const double* Z, const double* theta, int m, int d, int batch,
+                           double* partial /*[batch, m*m+m+3]*/);
+
+/* Sparse predictive at the state left by factor + (predict_)pass1 + finish  (likelihood(self(test_x)) in eval mode,
+ * models/sgpr.py:150-160; models/bayesian_sgpr_hmc.py:198-231).  mean,var: [batch, ns]; cov: [batch, ns, ns] or NULL (any ns: tiled).
+ * var/cov include the eval-mode diagonal correction clamp(k** - ||a*||^2, 0) on the test rows and, if add_noise, + s2. */
 int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
                      const double* Xs /*[ns,d]*/, int64_t ns,
                      const double* Z, const double* theta, int m, int d, int batch, int add_noise,

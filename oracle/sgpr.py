@@ -210,16 +210,27 @@ def sgpr_bound_and_grads_chunked(X, y, Z, ell, sf2, s2, jitter_policy="gpytorch"
 
 
 def sgpr_predict(Xs, X, y, Z, ell, sf2, s2, jitter_policy="gpytorch", full_cov=True, kind="rbf",
-                 diag_correction=True, add_noise=True):
-    """Eval-mode predictive of models/sgpr.py:150-160:
-    a* = L^{-1} k(Z,x*), t = L_B^{-1} a*, mean = t^T (L_B^{-1} b)/s,
-    cov_f = t^T t + diag(clamp(k** - ||a*||^2, 0)), likelihood adds s I."""
-    _, st = sgpr_bound(X, y, Z, ell, sf2, s2, jitter_policy, "none", kind, return_state=True)
-    L, LB, b = st["L"], st["LB"], st["b"]
-    Kzs = ard_kernel(Z, Xs, ell, sf2, kind)
-    a = _tri_solve(L, Kzs)
+                 diag_correction=True, add_noise=True, train_diag_correction=True):
+    """Eval-mode predictive of models/sgpr.py:150-160, `likelihood(self(test_x))` after `self.eval()`.
+
+    UPSTREAM (gpytorch 1.3-1.8 ExactGP.__call__, posterior mode): the prediction strategy is built from
+    `super().__call__(*train_inputs)` evaluated IN EVAL MODE, and the joint prior from the kernel on cat([train, test]); in both
+    calls x1 == x2 and the module is not training, so InducingPointKernel._get_covariance adds the sgpr diagonal correction
+    clamp(k_ii - q_ii, 0) to the whole diagonal -- to the TRAINING rows as well as the test rows.  The training covariance the
+    strategy inverts is therefore Q_nn + diag(Lambda), Lambda_n = s + max(k_nn - q_nn, 0) (a FITC-like heteroscedastic noise), and
+        mean* = Q*n (Q_nn + Lambda)^{-1} y ,  cov* = Q** + diag(corr*) - Q*n (Q_nn + Lambda)^{-1} Qn*  (+ s I by the likelihood).
+    With A = L^{-1} Kzx, W = diag(1 / Lambda), B = I + A W A^T, t = L_B^{-1} a*:  mean* = t^T L_B^{-1} A W y, cov_f = t^T t + diag(corr*).
+    train_diag_correction=False keeps plain s on the training rows (SURVEY A.6 as first written; B = I + A A^T / s)."""
+    N, M = X.shape[0], Z.shape[0]
+    Kzz = ard_kernel(Z, Z, ell, sf2, kind)
+    L, _ = psd_safe_cholesky(Kzz, jitter_policy)
+    A = _tri_solve(L, ard_kernel(Z, X, ell, sf2, kind))
+    lam = s2 + ((sf2 - (A * A).sum(0)).clamp_min(0.0) if (train_diag_correction and diag_correction) else 0.0) * torch.ones(N, dtype=X.dtype)
+    Aw = A / lam
+    LB = torch.linalg.cholesky(torch.eye(M, dtype=X.dtype) + Aw @ A.T)
+    c = _tri_solve(LB, (Aw @ y).unsqueeze(-1)).squeeze(-1)
+    a = _tri_solve(L, ard_kernel(Z, Xs, ell, sf2, kind))
     t = _tri_solve(LB, a)
-    c = _tri_solve(LB, b.unsqueeze(-1)).squeeze(-1) / s2
     mean = t.T @ c
     corr = (sf2 - (a * a).sum(0)).clamp_min(0.0) if diag_correction else torch.zeros(Xs.shape[0], dtype=X.dtype)
     noise = s2 if add_noise else 0.0
@@ -230,14 +241,17 @@ def sgpr_predict(Xs, X, y, Z, ell, sf2, s2, jitter_policy="gpytorch", full_cov=T
     return mean, var
 
 
-def sgpr_predict_dense(Xs, X, y, Z, ell, sf2, s2, jitter=0.0):
-    """Dense definition of the same predictive: GP with kernel Q(.,.) = K.z Kzz^{-1} Kz. + diag correction."""
+def sgpr_predict_dense(Xs, X, y, Z, ell, sf2, s2, jitter=0.0, train_diag_correction=True):
+    """Dense definition of the same predictive: GP with kernel Q(.,.) = K.z Kzz^{-1} Kz. + the eval-mode diagonal correction on every
+    diagonal entry of the joint (train and test) covariance, Gaussian noise s."""
     M = Z.shape[0]
     Kzz = ard_kernel(Z, Z, ell, sf2) + jitter * torch.eye(M, dtype=X.dtype)
     Kxz = ard_kernel(X, Z, ell, sf2)
     Ksz = ard_kernel(Xs, Z, ell, sf2)
     Kinv = torch.linalg.inv(Kzz)
-    Qnn = Kxz @ Kinv @ Kxz.T + s2 * torch.eye(X.shape[0], dtype=X.dtype)
+    Qnn = Kxz @ Kinv @ Kxz.T
+    corr_n = (sf2 - torch.diagonal(Qnn)).clamp_min(0.0) if train_diag_correction else torch.zeros(X.shape[0], dtype=X.dtype)
+    Qnn = Qnn + torch.diag(corr_n + s2)
     Qsn = Ksz @ Kinv @ Kxz.T
     Qss = Ksz @ Kinv @ Ksz.T
     sol = torch.linalg.solve(Qnn, Qsn.T)

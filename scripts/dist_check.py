@@ -14,7 +14,7 @@ N, M, D = 100_003, 512, 8
 X, y, Z, th = make_problem(N, M, D, seed=5)
 eng = ggp_b200.Engine.get(dev, precision=os.environ.get("GGP_CHECK_PRECISION", "fp64_i8"))
 lo, hi = gd.shard_rows(N, rank, world)
-out = eng.sgpr_eval(X[lo:hi], y[lo:hi], Z, th, jitter_policy=1e-6)            # group=None -> default NCCL group
+out = eng.sgpr_eval(X[lo:hi], y[lo:hi], Z, th, jitter_policy=1e-6, group=True)   # row shard: default NCCL group
 full = eng.sgpr_eval(X, y, Z, th, jitter_policy=1e-6, group=False)
 eb, eg = relerr(out["bound"], full["bound"]), relerr(out["grad"], full["grad"])
 gathered = [torch.zeros_like(out["bound"]) for _ in range(world)]

@@ -30,10 +30,12 @@ def sgpr_case(name, N, M, D, seed, jitter):
     Fd = sgpr.sgpr_bound_dense(X, y, p[3], p[0], p[1], p[2], jitter=jitter)
     g = torch.autograd.grad(Fd, p)
     Xs = torch.tensor(np.random.RandomState(seed + 1).randn(37, D))
+    # eval-mode predictive: gpytorch's (diagonal correction on the training rows too) and the plain-noise variant
     mean, cov = sgpr.sgpr_predict_dense(Xs, X, y, Z, ell, sf2, s2, jitter=jitter)
+    mean_p, cov_p = sgpr.sgpr_predict_dense(Xs, X, y, Z, ell, sf2, s2, jitter=jitter, train_diag_correction=False)
     np.savez(os.path.join(OUT, name + ".npz"), X=X.numpy(), y=y.numpy(), Z=Z.numpy(), theta=th.numpy(), jitter=jitter,
              F_dense=F_dense.item(), g_ell=g[0].numpy(), g_sf2=g[1].item(), g_s2=g[2].item(), g_Z=g[3].numpy(),
-             Xs=Xs.numpy(), pred_mean=mean.numpy(), pred_cov=cov.numpy())
+             Xs=Xs.numpy(), pred_mean=mean.numpy(), pred_cov=cov.numpy(), pred_mean_plain=mean_p.numpy(), pred_cov_plain=cov_p.numpy())
     print(name, F_dense.item())
 
 

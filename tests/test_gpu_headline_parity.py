@@ -79,7 +79,7 @@ def test_full_n_against_float64_oracle(with_replacement):
     from oracle import sgpr as osgpr
     torch.set_num_threads(os.cpu_count() or 1)
     c = syn.config4_large(with_replacement=with_replacement)
-    Xt, yt, Zt, tht = (torch.tensor(c[k]) for k in ("X", "y", "Z")) + (torch.tensor(_theta("trained")),)
+    Xt, yt, Zt, tht = [torch.tensor(c[k]) for k in ("X", "y", "Z")] + [torch.tensor(_theta("trained"))]
     dev = torch.device("cuda:0")
     Xd, yd = Xt.to(dev), yt.to(dev)
     res = {}

@@ -3,7 +3,7 @@
 Tolerances (BASELINE.json north_star): 1e-8 relative in float64 on the bound, its gradients and the predictive.
 Gradient parity is asserted at moderate conditioning of Kzz; at cond(Kzz) ~ 1e8 the oracle's own two float64 gradient
 evaluations disagree above 1e-9 (tests/test_oracle.py::test_gradient_conditioning_floor_is_inherent), so the
-ill-conditioned case is asserted at 1e-6.
+ill-conditioned case is asserted -- at the same 1e-8 -- against the long-double evaluation of oracle/hp.
 """
 import os
 
@@ -114,10 +114,14 @@ def test_ill_conditioned_parity_at_the_float64_floor(eng):
     N, M, D = 3000, 260, 4
     X, y, Z, th = make_problem(N, M, D, seed=N)
     out = eng.sgpr_eval(X, y, Z, th, jitter_policy=1e-6)  # cond(Kzz) ~ 1e8
-    Fo, go = osgpr.sgpr_grads_closed_form(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=1e-6, normalize="none")
+    # reference: the long-double evaluation (oracle/hp), whose own error at this conditioning is ~1e-11; the float64 oracle is
+    # within 1e-8 of it too (tests/test_oracle_hp.py::test_conditioning_floor_of_the_two_backward_forms)
+    from oracle import hp
+    Ft, gt = hp.bound_grad(X.numpy(), y.numpy(), Z.numpy(), th.numpy(), 1e-6, "ld")
     g = out["grad"][0].cpu()
-    assert relerr(out["bound"], Fo) < TOL
-    assert relerr(g[:D], go["ell"]) < 1e-6 and relerr(g[D + 2:].view(M, D), go["Z"]) < 1e-6
+    assert relerr(out["bound"], Ft) < TOL
+    assert relerr(g[:D], gt["ell"]) < TOL and relerr(g[D], gt["sf2"]) < TOL and relerr(g[D + 1], gt["s2"]) < TOL
+    assert relerr(g[D + 2:].view(M, D), gt["Z"]) < TOL
 
 
 @pytest.mark.parametrize("name", ["sgpr_small_1d", "sgpr_small_3d", "sgpr_mid_4d"])
@@ -129,12 +133,29 @@ def test_golden_dense_definition(eng, name):
     out = eng.sgpr_eval(X, y, Z, th, jitter_policy=float(g["jitter"]))
     assert relerr(out["bound"], float(g["F_dense"])) < TOL
     gr = out["grad"][0].cpu()
-    assert relerr(gr[:D], g["g_ell"]) < 1e-6 and relerr(gr[D + 1], g["g_s2"]) < TOL
-    assert relerr(gr[D + 2:].view(M, D), g["g_Z"]) < 1e-6
+    assert relerr(gr[:D], g["g_ell"]) < TOL and relerr(gr[D + 1], g["g_s2"]) < TOL
+    assert relerr(gr[D + 2:].view(M, D), g["g_Z"]) < TOL
+    # state left by the bound evaluation: plain noise s2 on the training rows
+    mean, var, cov = eng.sgpr_predict(T(g["Xs"]), Z, th, full_cov=True)
+    assert relerr(mean[0], g["pred_mean_plain"]) < TOL
+    assert relerr(cov[0], g["pred_cov_plain"]) < TOL
+    # gpytorch's eval mode: the diagonal correction also sits on the training rows (Lambda_n = s2 + max(k_nn - q_nn, 0))
+    eng.sgpr_predict_state(X, y, Z, th, jitter_policy=float(g["jitter"]))
     mean, var, cov = eng.sgpr_predict(T(g["Xs"]), Z, th, full_cov=True)
     assert relerr(mean[0], g["pred_mean"]) < TOL
     assert relerr(cov[0], g["pred_cov"]) < TOL
     assert relerr(var[0], np.diag(g["pred_cov"])) < TOL
+
+
+def test_predictive_full_covariance_beyond_one_chunk(eng):
+    """More test rows than the handle's chunk (small training sets reserve small chunks): the covariance is tiled."""
+    from oracle import sgpr as osgpr
+    X, y, Z, th = make_problem(300, 40, 2, seed=21)
+    Xs = torch.tensor(np.random.RandomState(5).randn(1100, 2))
+    eng.sgpr_predict_state(X, y, Z, th, jitter_policy=1e-6)
+    mean, var, cov = eng.sgpr_predict(Xs, Z, th, full_cov=True)
+    mo, co = osgpr.sgpr_predict(Xs, X, y, Z, th[:2], th[2], th[3], jitter_policy=1e-6)
+    assert relerr(mean[0], mo) < TOL and relerr(cov[0], co) < TOL and relerr(var[0], torch.diagonal(co)) < TOL
 
 
 def test_jitter_ladder_with_duplicate_inducing_rows(eng):
@@ -149,7 +170,7 @@ def test_jitter_ladder_with_duplicate_inducing_rows(eng):
     _, jit = psd_safe_cholesky(ard_kernel(Z, Z, th[:3], th[3]), "gpytorch")
     assert jit > 0 and abs(float(out["jitter"][0]) - jit) < 1e-20
     Fo = osgpr.sgpr_bound(X, y, Z, th[:3], th[3], th[4], "gpytorch", "none")
-    assert relerr(out["bound"], Fo) < 1e-7  # singular-to-jitter regime: cond ~ sf2*M/jitter
+    assert relerr(out["bound"], Fo) < TOL
     import ggp_b200
     with pytest.raises(ggp_b200.NotPSDError):
         eng.sgpr_eval(X, y, Z, th, jitter_policy=0.0)
@@ -175,7 +196,7 @@ def test_ragged_and_tiny_shapes(eng):
         out = eng.sgpr_eval(X, y, Z, th, jitter_policy=1e-4)
         Fo, go = osgpr.sgpr_grads_closed_form(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=1e-4, normalize="none")
         assert relerr(out["bound"], Fo) < TOL, (N, M, D)
-        assert relerr(out["grad"][0][D + 2:].cpu().view(M, D), go["Z"]) < 1e-7, (N, M, D)
+        assert relerr(out["grad"][0][D + 2:].cpu().view(M, D), go["Z"]) < TOL, (N, M, D)
 
 
 def test_shard_additivity_and_determinism_at_scale(eng):
@@ -262,5 +283,5 @@ def test_batched_pymc3_logp_dlogp(eng):
     lp, dlp = F.sgpr_vfe_logp_dlogp(xs.to(eng.device), X.to(eng.device), y.to(eng.device), Z.to(eng.device))
     for cidx in range(4):
         lo, go = priors.sgpr_vfe_logp_dlogp(xs[cidx], X, y, Z)
-        assert relerr(lp[cidx], lo) < 1e-7   # duplicate Z rows + 1e-6 stabilise jitter: cond(Kzz) ~ 1e8
-        assert relerr(dlp[cidx], go) < 1e-5
+        assert relerr(lp[cidx], lo) < TOL    # duplicate Z rows + pymc3's 1e-6 stabilise jitter: cond(Kzz) ~ 1e8
+        assert relerr(dlp[cidx], go) < TOL

@@ -9,6 +9,7 @@ import torch
 from helpers import make_problem, relerr
 
 pytestmark = pytest.mark.gpu
+TOL = 1e-8
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -96,8 +97,8 @@ def test_autograd_function_svgp_step(eng):
     loss.backward()
     eo, go = _oracle(X[:B], y[:B], Z, m, Ls, th, N, "gaussian", 1e-6)
     assert relerr(loss, -eo) < 1e-8
-    assert relerr(ps[1].grad, -go[4]) < 1e-7 and relerr(ps[2].grad, -torch.tril(go[5])) < 1e-7
-    assert relerr(ps[3].grad, -go[0]) < 1e-6 and relerr(ps[0].grad, -go[3]) < 1e-6
+    assert relerr(ps[1].grad, -go[4]) < TOL and relerr(ps[2].grad, -torch.tril(go[5])) < TOL
+    assert relerr(ps[3].grad, -go[0]) < TOL and relerr(ps[0].grad, -go[3]) < TOL
 
 
 @pytest.mark.parametrize("lik,N,M,D", [("gaussian", 700, 40, 3), ("bernoulli", 6000, 70, 16)])
