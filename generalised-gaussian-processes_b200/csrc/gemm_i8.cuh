@@ -27,8 +27,16 @@ namespace ggp {
 
 constexpr int I8_NS = 7;                       // radix-256 digits per operand (56 bits)
 constexpr int I8_BM = 128, I8_BN = 64;         // output tile; I8_NS * I8_BN = 448 TMEM columns
-constexpr int I8_BKB = 64;                     // bytes of k per stage row (one 64-byte swizzle row)
-constexpr int I8_STAGES = 2;
+#ifndef GGP_I8_BKB
+#define GGP_I8_BKB 64
+#endif
+#ifndef GGP_I8_STAGES
+#define GGP_I8_STAGES 2
+#endif
+constexpr int I8_BKB = GGP_I8_BKB;             // bytes of k per stage row = one swizzle row (64: SWIZZLE_64B; 32: SWIZZLE_32B, half-size
+                                               // stages and a ring twice as deep for the same shared memory)
+constexpr int I8_STAGES = GGP_I8_STAGES;
+static_assert(I8_BKB == 64 || I8_BKB == 32, "k-block = one 64- or 32-byte swizzle row");
 constexpr int I8_A_BYTES = I8_BM * I8_BKB, I8_B_BYTES = I8_BN * I8_BKB;
 constexpr int I8_STAGE_BYTES = I8_NS * (I8_A_BYTES + I8_B_BYTES);
 constexpr int I8_EPI_WARPS = 8;                // two per TMEM lane quarter, 32 of the 64 tile columns each
@@ -119,9 +127,11 @@ __device__ __forceinline__ void i8_tma_load_3d(void* dst, const CUtensorMap* tm,
                "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-// K-major operand tile, 64-byte swizzle: 64-byte rows, 8-row groups 512 bytes apart (SBO), descriptor version 1 (Blackwell)
+// K-major operand tile, rows of I8_BKB bytes = one swizzle row (64-byte: layout type 4, 32-byte: type 6), 8-row groups 8 * I8_BKB bytes
+// apart (SBO), descriptor version 1 (Blackwell)
 __device__ __forceinline__ uint64_t i8_desc_sw64(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((8 * I8_BKB) >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)(I8_BKB == 64 ? 4 : 6) << 61);
 }
 // MN-major operand tile, 64-byte swizzle: 64 k-rows of 64 contiguous MN bytes (8-row groups 512 bytes apart: SBO), further 64-byte
 // MN blocks `lbo` bytes apart (LBO) -- canonical layout ((4,n),(8,k)):((1,LBO),(4,SBO)) in 16-byte units
@@ -390,7 +400,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               if (p.b_mn) {
                 // MN-major B: the digit tiles are 64-byte MN blocks LBO = 4096 bytes apart, so a wide MMA must start on a tile
                 // boundary: 448 = 256 + 192, 384 = 192 + 192, 320 = 192 + 128 columns; the k-step advances 32 rows = 2048 bytes
-                static_assert(I8_BN == 64 && I8_BKB == 64, "MN-major B tile: 64 k-rows x 64 n-bytes");
+                static_assert(I8_BN == 64, "MN-major B tile: I8_BKB k-rows x 64 n-bytes (64-byte swizzle whatever I8_BKB is)");
                 const int n1 = ncols > 256 ? ((ncols / 2 + 63) / 64) * 64 : ncols;
 #pragma unroll
                 for (int hs = 0; hs < nsplit; ++hs) {

@@ -397,16 +397,17 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
 // digit planes [I8_NS][rows][ld bytes] (plane stride in bytes) as a 3-D map (k, row, plane), 64-byte swizzle, box 64 x box_rows x 1;
 // rows / k beyond the extents given here are zero-filled by the TMA unit
 static bool make_i8_map(CUtensorMap* tm, const int8_t* ptr, int64_t rows, int64_t kbytes, int64_t ld, int64_t plane, int box_rows,
-                        int nplanes = I8_NS) {
+                        int nplanes = I8_NS, int box_inner = I8_BKB) {
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc || !ptr || rows < 1 || kbytes < 1) return false;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 15) || (plane & 15)) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)kbytes, (cuuint64_t)rows, (cuuint64_t)nplanes};
   const cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)plane};
-  const cuuint32_t box[3] = {(cuuint32_t)I8_BKB, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct I8Operand { const int8_t* q; int64_t rows, ld, plane; };
@@ -439,7 +440,7 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
     // box 64 column bytes x 64 k-rows; rows / columns beyond the extents are zero-filled
     if (p.sym || p.nchunk || p.splits != 1 || p.lower_a) return fail(-4, "launch_i8: the MN-major B operand serves the plain product only");
     const int64_t cols = p.b_chunk > 0 ? p.b_chunk : (int64_t)(p.N + I8_BN - 1) / I8_BN * I8_BN;
-    okB = make_i8_map(&tmB, B.q, B.rows, cols, B.ld, B.plane, I8_BKB, p.b_planes > 0 ? p.b_planes : I8_NS);
+    okB = make_i8_map(&tmB, B.q, B.rows, cols, B.ld, B.plane, I8_BKB, p.b_planes > 0 ? p.b_planes : I8_NS, I8_BN);
   } else {
     okB = make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN, npl);
   }
@@ -1159,9 +1160,10 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
 }
 
 int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* xb, const double* yb, int64_t nb,
-                  const double* Z, const double* qm, const double* qLs, const double* theta, const double* jitter, int m, int d,
-                  int batch, double data_jitter, double lik_scale, double kl_scale, int likelihood, int need_grad, double* elbo,
-                  double* grad, int32_t* info) {
+                  const double* Z, const double* qm, int qm_batched, const double* qLs, const double* theta, const double* jitter,
+                  int m, int d, int batch, double data_jitter, double lik_scale, double kl_scale, int likelihood, int need_grad,
+                  double* elbo, double* grad, int32_t* info) {
+  const int64_t sqm = qm_batched ? m : 0;
   if (!h || !xb || !yb || !Z || !qm || !theta || !jitter || !elbo || !info) return fail(-1, "ggp_svgp_elbo: NULL argument");
   if (need_grad && !grad) return fail(-1, "ggp_svgp_elbo: grad is NULL");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_svgp_elbo: handle not reserved for this shape");
@@ -1212,7 +1214,7 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(Kc, Mp, sC, h->Linv, Mp, sM, aT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
     if (hasS)
       RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(aT, Mp, sC, LsT, Mp, 0, wT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_UPPER), batch));
-    k_svgp_rows<<<dim3((nv + 7) / 8, batch), 256, 0, st>>>(aT, hasS ? wT : nullptr, Mp, sC, qm, yb + c0, theta, d, m, nv, likelihood,
+    k_svgp_rows<<<dim3((nv + 7) / 8, batch), 256, 0, st>>>(aT, hasS ? wT : nullptr, Mp, sC, qm, sqm, yb + c0, theta, d, m, nv, likelihood,
                                                           data_jitter, lik_scale, h->rowout, nsv);
     CKL();
     k_svgp_reduce_rows<<<batch, 256, 0, st>>>(h->rowout, nsv, nv, scal);
@@ -1221,7 +1223,7 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
     // SL = wT * Ls^T = (S a)^T ;  GAT = gmu m^T + 2 gv (SL - aT)
     if (hasS)
       RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(wT, Mp, sC, LsP, Mp, 0, SL, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
-    k_svgp_gat<<<dim3((Mp + 255) / 256, nv, batch), 256, 0, st>>>(SL, aT, Mp, sC, qm, h->rowout, nsv, m, Mp, hasS ? 1 : 0);
+    k_svgp_gat<<<dim3((Mp + 255) / 256, nv, batch), 256, 0, st>>>(SL, aT, Mp, sC, qm, sqm, h->rowout, nsv, m, Mp, hasS ? 1 : 0);
     CKL();
     k_svgp_dm<<<dim3((m + 255) / 256, batch), 256, 0, st>>>(aT, Mp, sC, h->rowout, nsv, m, nv, dm, Mp);
     CKL();
@@ -1258,15 +1260,16 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
     k_grad_from_moments<<<batch, 256, 0, st>>>(mom, m, d, Z, theta, gk, sM, nullptr);
     CKL();
   }
-  k_svgp_final<<<batch, 256, 0, st>>>(scal, gk, sM, h->rowacc, dZzz, dm, Mp, dLsraw, sM, Mp, qm, qLs, theta, m, d, kl_scale, need_grad,
+  k_svgp_final<<<batch, 256, 0, st>>>(scal, gk, sM, h->rowacc, dZzz, dm, Mp, dLsraw, sM, Mp, qm, sqm, qLs, theta, m, d, kl_scale, need_grad,
                                       elbo, grad, sG);
   CKL();
   return 0;
 }
 
 int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* xs, int64_t ns, const double* Z,
-                     const double* qm, const double* qLs, const double* theta, const double* jitter, int m, int d, int batch,
-                     double data_jitter, int add_noise, double* mean, double* var, int32_t* info) {
+                     const double* qm, int qm_batched, const double* qLs, const double* theta, const double* jitter, int m, int d,
+                     int batch, double data_jitter, int add_noise, double* mean, double* var, int32_t* info) {
+  const int64_t sqm = qm_batched ? m : 0;
   if (!h || !xs || !Z || !qm || !theta || !jitter || !mean || !var || !info) return fail(-1, "ggp_svgp_predict: NULL argument");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_svgp_predict: handle not reserved for this shape");
   const int kind = cfg ? cfg->kernel : 0;
@@ -1294,7 +1297,7 @@ int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(Kc, Mp, sC, h->Linv, Mp, sM, aT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
     if (hasS)
       RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(aT, Mp, sC, LsT, Mp, 0, wT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_UPPER), batch));
-    k_svgp_marginals<<<dim3((nv + 7) / 8, batch), 256, 0, st>>>(aT, hasS ? wT : nullptr, Mp, sC, qm, theta, d, m, nv, data_jitter,
+    k_svgp_marginals<<<dim3((nv + 7) / 8, batch), 256, 0, st>>>(aT, hasS ? wT : nullptr, Mp, sC, qm, sqm, theta, d, m, nv, data_jitter,
                                                                add_noise, mean + c0, var + c0, ns);
     CKL();
   }

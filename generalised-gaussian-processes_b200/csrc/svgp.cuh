@@ -46,12 +46,13 @@ __global__ void k_pad_tril(const double* __restrict__ Ls, int M, double* __restr
 // rowout[b][0][n] = lik_scale * E_q[log p(y_n|f_n)], [1] = d/dmu, [2] = d/dvar, [3] = d/ds2   (row stride ldr)
 // grid (ceil(nv/8), batch), block 256.  wT may be NULL (S = 0, SGPMC).
 __global__ void __launch_bounds__(256) k_svgp_rows(const double* __restrict__ aT, const double* __restrict__ wT, int64_t ld,
-                                                   int64_t sC, const double* __restrict__ qm, const double* __restrict__ yv,
+                                                   int64_t sC, const double* __restrict__ qm, int64_t sqm, const double* __restrict__ yv,
                                                    const double* __restrict__ theta, int d, int M, int nv, int likelihood,
                                                    double data_jitter, double lik_scale, double* __restrict__ rowout,
                                                    int64_t ldr) {
   const int b = blockIdx.y, n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= nv) return;
+  qm += b * sqm;   // sqm = 0: one variational mean for every batch element; m: one whitened vector v per chain (SGPMC)
   const double* a = aT + b * sC + (int64_t)n * ld;
   double mu = 0.0, v1 = 0.0, v2 = 0.0;
   for (int j = lane; j < M; j += 32) {
@@ -101,11 +102,13 @@ __global__ void __launch_bounds__(256) k_svgp_rows(const double* __restrict__ aT
 
 // Predictive marginals only: mean[b][n] = aT[n,:].m ; var[b][n] = sf2 + data_jitter + ||wT[n]||^2 - ||aT[n]||^2 (+ s2)
 __global__ void __launch_bounds__(256) k_svgp_marginals(const double* __restrict__ aT, const double* __restrict__ wT, int64_t ld,
-                                                        int64_t sC, const double* __restrict__ qm, const double* __restrict__ theta,
+                                                        int64_t sC, const double* __restrict__ qm, int64_t sqm,
+                                                        const double* __restrict__ theta,
                                                         int d, int M, int nv, double data_jitter, int add_noise,
                                                         double* __restrict__ mean, double* __restrict__ var, int64_t sOut) {
   const int b = blockIdx.y, n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= nv) return;
+  qm += b * sqm;
   const double* a = aT + b * sC + (int64_t)n * ld;
   double mu = 0.0, v1 = 0.0, v2 = 0.0;
   for (int j = lane; j < M; j += 32) {
@@ -152,10 +155,11 @@ __global__ void __launch_bounds__(256) k_svgp_reduce_rows(const double* __restri
 // GAT[n,i] = gmu_n * m_i + 2 gv_n * (SL[n,i] - aT[n,i])     (in place in SL; SL may be NULL => S = 0)
 // grid (ceil(Mp/256), nv, batch)
 __global__ void k_svgp_gat(double* __restrict__ SL, const double* __restrict__ aT, int64_t ld, int64_t sC,
-                           const double* __restrict__ qm, const double* __restrict__ rowout, int64_t ldr, int M, int Mp,
+                           const double* __restrict__ qm, int64_t sqm, const double* __restrict__ rowout, int64_t ldr, int M, int Mp,
                            int has_S) {
   const int i = blockIdx.x * 256 + threadIdx.x, n = blockIdx.y, b = blockIdx.z;
   if (i >= Mp) return;
+  qm += b * sqm;
   const double* ro = rowout + (int64_t)b * 4 * ldr;
   const int64_t o = b * sC + (int64_t)n * ld + i;
   double v = 0.0;
@@ -233,12 +237,13 @@ __global__ void __launch_bounds__(256) k_svgp_final(const double* __restrict__ s
                                                     const double* __restrict__ rowacc, const double* __restrict__ dZzz,
                                                     const double* __restrict__ dm, int64_t sdm,
                                                     const double* __restrict__ dLsraw, int64_t sM, int Mp,
-                                                    const double* __restrict__ qm, const double* __restrict__ Ls,
+                                                    const double* __restrict__ qm, int64_t sqm, const double* __restrict__ Ls,
                                                     const double* __restrict__ theta, int M, int d, double kl_scale,
                                                     int need_grad, double* __restrict__ elbo, double* __restrict__ grad,
                                                     int64_t sG) {
   __shared__ double red[8];
   const int b = blockIdx.x, tid = threadIdx.x;
+  qm += b * sqm;
   double kl = 0.0;
   if (Ls && kl_scale != 0.0) {
     double fro = 0.0, mm = 0.0, ld = 0.0;

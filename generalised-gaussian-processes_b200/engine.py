@@ -317,6 +317,8 @@ class Engine:
         nb, d = xb.shape
         m = Z.shape[0]
         batch = theta.shape[0]
+        qm_batched = qm.dim() == 2      # one whitened vector per batch element (SGPMC chains): [batch, m]
+        assert qm.shape == ((batch, m) if qm_batched else (m,))
         if lik_scale is None:
             lik_scale = 1.0 / nb
         if kl_scale is None:
@@ -332,9 +334,13 @@ class Engine:
             while True:
                 jit = torch.tensor([ladder[l] for l in level], dtype=torch.float64, device=dev)
                 check(self.lib.ggp_svgp_elbo(self.h, ctypes.byref(self.cfg), _stream(), _ptr(xb), _ptr(yb), nb, _ptr(Z), _ptr(qm),
-                                             _ptr(qLs), _ptr(theta), _ptr(jit), m, d, batch, float(data_jitter), float(lik_scale),
+                                             1 if qm_batched else 0, _ptr(qLs), _ptr(theta), _ptr(jit), m, d, batch, float(data_jitter), float(lik_scale),
                                              float(kl_scale), LIKELIHOODS[likelihood], 1 if need_grad else 0, _ptr(value),
                                              _ptr(grad), _ptr(info)), "ggp_svgp_elbo")
+                if len(ladder) == 1 and not raise_on_fail:
+                    # fixed jitter (gpflow's default) and the caller masks failed rows itself: no host read-back, the call stays
+                    # asynchronous (HMC leapfrogs queue back to back, CUDA-graph capturable)
+                    return dict(value=value, grad=grad, jitter=jit, info=info)
                 info_h = info.cpu()
                 bad = [b for b in range(batch) if int(info_h[b]) != 0]
                 if not bad:
@@ -356,6 +362,7 @@ class Engine:
             theta = theta.unsqueeze(0)
         ns, d = xs.shape
         m, batch = Z.shape[0], theta.shape[0]
+        qm_batched = qm.dim() == 2
         self.reserve(min(ns, 4096), m, d, batch)
         mean = torch.empty(batch, ns, dtype=torch.float64, device=dev)
         var = torch.empty(batch, ns, dtype=torch.float64, device=dev)
@@ -363,7 +370,8 @@ class Engine:
         for j in jitter_ladder("gpytorch"):
             jit = torch.full((batch,), base_jitter + j, dtype=torch.float64, device=dev)
             with torch.cuda.device(dev):
-                check(self.lib.ggp_svgp_predict(self.h, ctypes.byref(self.cfg), _stream(), _ptr(xs), ns, _ptr(Z), _ptr(qm), _ptr(qLs),
+                check(self.lib.ggp_svgp_predict(self.h, ctypes.byref(self.cfg), _stream(), _ptr(xs), ns, _ptr(Z), _ptr(qm),
+                                                1 if qm_batched else 0, _ptr(qLs),
                                                 _ptr(theta), _ptr(jit), m, d, batch, float(data_jitter), 1 if add_noise else 0,
                                                 _ptr(mean), _ptr(var), _ptr(info)), "ggp_svgp_predict")
             if not bool((info != 0).any()):

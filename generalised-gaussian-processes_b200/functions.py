@@ -173,8 +173,9 @@ def sgpmc_logp_dlogp(v, raw, X, y, Z, likelihood="gaussian", jitter=1e-5, engine
     """gpflow SGPMC log_posterior_density and gradient, batched over chains (models/sgp_hmc.py:38-83).
 
     v [C, M] whitened inducing values, raw [C, D+2] softplus-unconstrained (ell[D], sf2, s2).  Returns (logp[C], d/dv[C,M],
-    d/draw[C,D+2]).  The streamed N x M work (a = L^{-1}k(Z,x), mu = a^T v, var = k - |a|^2, likelihood, backward) runs on
-    the GPU for each chain; priors Gamma(2,1) on the constrained values + softplus log-Jacobians are added here."""
+    d/draw[C,D+2]).  The streamed N x M work (a = L^{-1}k(Z,x), mu = a^T v, var = k - |a|^2, likelihood, backward) of ALL C chains
+    runs in one batched launch sequence on the GPU (every chain carries its own theta and its own v: qm_batched); priors
+    Gamma(2,1) on the constrained values + softplus log-Jacobians are added here, vectorised over the chains."""
     import torch.nn.functional as Fnn
     eng = engine or Engine.get(X.device)
     dev = eng.device
@@ -186,26 +187,24 @@ def sgpmc_logp_dlogp(v, raw, X, y, Z, likelihood="gaussian", jitter=1e-5, engine
     D = X.shape[1]
     pos = Fnn.softplus(raw)
     theta = pos.clone()
+    npos = D + 2 if likelihood == "gaussian" else D + 1
     if likelihood != "gaussian":
         theta[:, D + 1] = 1.0  # unused by the Bernoulli likelihood
-    lps, gvs, grs = [], [], []
-    for c in range(C):  # v differs per chain (it occupies the variational-mean slot), so chains are sequenced on one engine
-        out = eng.svgp_eval(X, y, Z, v[c], None, theta[c], likelihood=likelihood, jitter_policy=0.0, base_jitter=jitter,
-                            data_jitter=0.0, lik_scale=1.0, kl_scale=0.0, need_grad=True, raise_on_fail=False)
-        g = out["grad"][0]
-        lp = out["value"][0] - 0.5 * (v[c] @ v[c]) - 0.5 * M * math.log(2.0 * math.pi)
-        gv = g[D + 2 + M * D:D + 2 + M * D + M] - v[c]
-        gpos = g[:D + 2].clone()
-        npos = D + 2 if likelihood == "gaussian" else D + 1
-        if likelihood != "gaussian":
-            gpos[D + 1] = 0.0
-        sig = torch.sigmoid(raw[c])
-        graw = gpos * sig
-        if with_priors:
-            lp = lp + (torch.log(pos[c, :npos]) - pos[c, :npos]).sum() + Fnn.logsigmoid(raw[c, :npos]).sum()
-            graw[:npos] = graw[:npos] + (1.0 / pos[c, :npos] - 1.0) * sig[:npos] + (1.0 - sig[:npos])
-        if int(out["info"][0]) != 0 or not torch.isfinite(lp):
-            lp = torch.full_like(lp, -float("inf"))
-            gv, graw = torch.zeros_like(gv), torch.zeros_like(graw)
-        lps.append(lp); gvs.append(gv); grs.append(graw)
-    return torch.stack(lps), torch.stack(gvs), torch.stack(grs)
+    out = eng.svgp_eval(X, y, Z, v.contiguous(), None, theta, likelihood=likelihood, jitter_policy=0.0, base_jitter=jitter,
+                        data_jitter=0.0, lik_scale=1.0, kl_scale=0.0, need_grad=True, raise_on_fail=False)
+    g = out["grad"]
+    lp = out["value"] - 0.5 * (v * v).sum(1) - 0.5 * M * math.log(2.0 * math.pi)
+    gv = g[:, D + 2 + M * D:D + 2 + M * D + M] - v
+    gpos = g[:, :D + 2].clone()
+    if likelihood != "gaussian":
+        gpos[:, D + 1] = 0.0
+    sig = torch.sigmoid(raw)
+    graw = gpos * sig
+    if with_priors:
+        lp = lp + (torch.log(pos[:, :npos]) - pos[:, :npos]).sum(1) + Fnn.logsigmoid(raw[:, :npos]).sum(1)
+        graw[:, :npos] = graw[:, :npos] + (1.0 / pos[:, :npos] - 1.0) * sig[:, :npos] + (1.0 - sig[:, :npos])
+    bad = (out["info"].to(dev) != 0) | ~torch.isfinite(lp)
+    lp = torch.where(bad, torch.full_like(lp, -float("inf")), lp)
+    gv = torch.where(bad.unsqueeze(1), torch.zeros_like(gv), gv)
+    graw = torch.where(bad.unsqueeze(1), torch.zeros_like(graw), graw)
+    return lp, gv, graw

@@ -126,7 +126,9 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
  *   - the SVGP minibatch ELBO (models/svgp.py:104-110 ; models/bayesian_svgp.py:160-167 with batch = number of theta draws):
  *       data_jitter = 1e-4, lik_scale = 1/nb, kl_scale = 1/num_data
  *   - the SGPMC whitened-conditional log-likelihood tfp-HMC differentiates per leapfrog (models/sgp_hmc.py:63-69):
- *       qLs = NULL (S = 0), qm = v, data_jitter = 0, lik_scale = 1, kl_scale = 0, nb = N (streamed in chunks)
+ *       qLs = NULL (S = 0), qm = v, data_jitter = 0, lik_scale = 1, kl_scale = 0, nb = N (streamed in chunks);
+ *       qm_batched = 1: every batch element (HMC chain) carries its own whitened vector v[b] next to its own theta[b], so all the
+ *       chains of a rank are evaluated in ONE launch sequence (BASELINE configs[4]: 64 chains sharded over 8 GPUs)
  * out[b] = lik_scale * sum_i E_q[log p(y_i|f_i)] - kl_scale * KL(N(m, Ls Ls^T) || N(0, I)),
  *   mu_i = a_i^T m, var_i = k_ii + data_jitter + ||Ls^T a_i||^2 - ||a_i||^2, a = L^{-1} k(Z, x_i), L L^T = Kzz + jitter_b I.
  * grad[b] layout: [d_ell[d], d_sf2, d_s2, d_Z[m*d], d_m[m], d_Ls[m*m] (lower triangle, row-major, upper = 0)].
@@ -134,7 +136,8 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
  * likelihood: GGP_LIK_GAUSSIAN (noise s2 from theta) or GGP_LIK_BERNOULLI_PROBIT (20-point Gauss-Hermite). */
 int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
                   const double* xb /*[nb,d]*/, const double* yb /*[nb]*/, int64_t nb,
-                  const double* Z, const double* qm /*[m]*/, const double* qLs /*[m,m] or NULL*/,
+                  const double* Z, const double* qm /*[m], or [batch,m] when qm_batched*/, int qm_batched,
+                  const double* qLs /*[m,m] or NULL*/,
                   const double* theta /*[batch,d+2]*/, const double* jitter /*[batch]*/,
                   int m, int d, int batch, double data_jitter, double lik_scale, double kl_scale, int likelihood,
                   int need_grad, double* elbo /*[batch]*/, double* grad /*[batch, d+2+m*d+m+m*m] or NULL*/, int32_t* info);
@@ -142,8 +145,8 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
 /* SVGP predictive marginals at test inputs (posterior_predictive, models/svgp.py:132-141; diagonal only -- the exact
  * expression, see SURVEY A.7 on fast_pred_var):  mean[b][n] = a^T m ; var[b][n] = k** + data_jitter + ||Ls^T a||^2 - ||a||^2 (+ s2) */
 int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* xs /*[ns,d]*/, int64_t ns,
-                     const double* Z, const double* qm, const double* qLs /*or NULL*/, const double* theta,
-                     const double* jitter /*[batch]*/, int m, int d, int batch, double data_jitter, int add_noise,
+                     const double* Z, const double* qm /*[m] or [batch,m]*/, int qm_batched, const double* qLs /*or NULL*/,
+                     const double* theta, const double* jitter /*[batch]*/, int m, int d, int batch, double data_jitter, int add_noise,
                      double* mean /*[batch,ns]*/, double* var /*[batch,ns]*/, int32_t* info);
 
 /* building blocks, exported for the parity tests and the roofline probes ------------------------------------- */

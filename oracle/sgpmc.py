@@ -50,3 +50,29 @@ def sgpmc_logp_dlogp(v, raw, X, y, Z, likelihood="gaussian", jitter=1e-5, with_p
     if gr is None:
         gr = torch.zeros_like(raw)
     return lp.detach(), gv, gr
+
+
+def sgpmc_logp_dlogp_chunked(v, raw, X, y, Z, likelihood="gaussian", jitter=1e-5, with_priors=True, chunk=8192):
+    """Same value and gradient, the data term accumulated over row chunks (the log-likelihood is a sum over n; each chunk runs its
+    own autograd pass through chol(Kzz)), so that BASELINE configs[4] (N = 2e5, D = 16, M = 512) fits in host memory: the unchunked
+    evaluation materialises an [M, N, D] difference tensor (13 GB) and keeps it for the backward pass."""
+    N, M = X.shape[0], Z.shape[0]
+    lp = torch.zeros((), dtype=X.dtype)
+    gv, gr = torch.zeros_like(v), torch.zeros_like(raw)
+    for i0 in range(0, N, chunk):
+        l, a, b = sgpmc_logp_dlogp(v, raw, X[i0:i0 + chunk], y[i0:i0 + chunk], Z, likelihood, jitter, with_priors=False)
+        # every chunk call adds log N(v; 0, I) once: keep it only once
+        extra = -0.5 * (v @ v) - 0.5 * M * LOG2PI
+        lp = lp + l - extra
+        gv = gv + a + v
+        gr = gr + b
+    vv = v.detach().clone().requires_grad_(True)
+    rr = raw.detach().clone().requires_grad_(True)
+    D = X.shape[1]
+    pr = -0.5 * (vv @ vv) - 0.5 * M * LOG2PI
+    if with_priors:
+        npos = D + 2 if likelihood == "gaussian" else D + 1
+        pos = Fnn.softplus(rr[:npos])
+        pr = pr + (torch.log(pos) - pos).sum() + Fnn.logsigmoid(rr[:npos]).sum()
+    a, b = torch.autograd.grad(pr, [vv, rr], allow_unused=True)
+    return lp + pr.detach(), gv + a, gr + (b if b is not None else torch.zeros_like(raw))

@@ -69,29 +69,46 @@ def test_reduced_n_same_kzz_against_long_double(with_replacement, theta_name):
     _record(f"reducedN_{n}_Z_{'with' if with_replacement else 'without'}_replacement_theta_{theta_name}",
             dict(jitter=jit, reference="oracle/hp long double", errors=errs))
     for k, e in errs.items():
-        assert max(e.values()) < TOL, (k, e)
+        # with duplicated inducing rows and trained-like theta cond(Kzz + 1e-8 I) = 4.4e10: the float64 ORACLE is then ~1.3e-8 from the
+        # long-double reference itself (the GPU paths stay below 1e-8); it is recorded, and bounded at 1e-7
+        assert max(e.values()) < (1e-7 if (k == "oracle_f64" and with_replacement) else TOL), (k, e)
 
 
 @pytest.mark.parametrize("with_replacement", [False, True])
-def test_full_n_against_float64_oracle(with_replacement):
+def test_full_n_against_long_double_and_float64_oracle(with_replacement):
+    """FULL headline size.  References: (a) the committed long-double evaluation of all 1e6 rows (tests/golden/c4_headline_ld_*.npz,
+    scripts/make_headline_truth.py: ~11 minutes of host time per case, so it is a fixture), (b) the float64 oracle run here.
+    Without replacement (the benchmark's Z rule, cond(Kzz) 7.6e7) everything holds 1e-8.  With replacement the draw contains two
+    duplicated rows, the ladder settles on 1e-8 and cond(Kzz + jI) = 4.4e10: the GPU result must stay within 1e-8 of the
+    long-double reference; the float64 oracle itself is only good to ~1e-8..1e-7 there, so against IT the bar is 2e-7."""
     import ggp_b200
     import ggp_b200.synthetic as syn
     from oracle import sgpr as osgpr
     torch.set_num_threads(os.cpu_count() or 1)
     c = syn.config4_large(with_replacement=with_replacement)
     Xt, yt, Zt, tht = [torch.tensor(c[k]) for k in ("X", "y", "Z")] + [torch.tensor(_theta("trained"))]
+    tag = "with" if with_replacement else "without"
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"c4_headline_ld_{tag}_replacement.npz"))
+    assert float(z["x_checksum"]) == float(c["X"].sum()) and np.array_equal(z["z_idx_head"], c["Z_idx"][:16]), "fixture is for these inputs"
+    Ft, gt = float(z["F"]), dict(ell=z["d_ell"], sf2=float(z["d_sf2"]), s2=float(z["d_s2"]), Z=z["d_Z"])
     dev = torch.device("cuda:0")
     Xd, yd = Xt.to(dev), yt.to(dev)
     res = {}
     for prec in ("fp64_i8", "fp64"):
         out = ggp_b200.Engine.get(dev, precision=prec).sgpr_eval(Xd, yd, Zt, tht, jitter_policy="gpytorch")
-        res[prec] = (float(out["bound"][0].item()), out["grad"][0].cpu(), float(out["jitter"][0].item()))
+        res[prec] = (float(out["bound"][0].item()), out["grad"][0].cpu(), float(out["jitter"][0].item()), out["path"])
     del Xd, yd
+    assert res["fp64_i8"][2] == float(z["jitter"]) and res["fp64"][2] == float(z["jitter"])
+    # the sliced-integer engine leaves its tcgen05 plan only when the ladder had to engage
+    assert res["fp64_i8"][3] == ("fp64" if with_replacement else "fp64_i8")
     F64, g64, jit64 = osgpr.sgpr_bound_and_grads_chunked(Xt, yt, Zt, tht[:D], tht[D], tht[D + 1], "gpytorch", "none", chunk=65536)
-    errs = {k: _blocks(v[0], v[1], F64, g64) for k, v in res.items()}
-    errs["i8_vs_dmma"] = dict(bound=abs(res["fp64_i8"][0] - res["fp64"][0]) / abs(res["fp64"][0]), grad=relerr(res["fp64_i8"][1], res["fp64"][1]))
-    _record(f"fullN_1000000_Z_{'with' if with_replacement else 'without'}_replacement_theta_trained",
-            dict(jitter=jit64, reference="oracle/sgpr.py float64 (chunked)", errors=errs))
-    assert res["fp64_i8"][2] == jit64 and res["fp64"][2] == jit64
+    assert jit64 == float(z["jitter"])
+    vs_ld = {k: _blocks(v[0], v[1], Ft, gt) for k, v in res.items()}
+    vs_ld["oracle_f64"] = _blocks(F64, torch.cat([g64["ell"], g64["sf2"].reshape(1), g64["s2"].reshape(1), g64["Z"].reshape(-1)]), Ft, gt)
+    vs_64 = {k: _blocks(v[0], v[1], F64, g64) for k, v in res.items()}
+    _record(f"fullN_1000000_Z_{tag}_replacement_theta_trained",
+            dict(jitter=jit64, path_of_the_fp64_i8_engine=res["fp64_i8"][3], vs_long_double=vs_ld, vs_float64_oracle=vs_64,
+                 i8_vs_dmma=dict(bound=abs(res["fp64_i8"][0] - res["fp64"][0]) / abs(res["fp64"][0]), grad=relerr(res["fp64_i8"][1], res["fp64"][1]))))
     for k in ("fp64_i8", "fp64"):
-        assert max(errs[k].values()) < TOL, (k, errs[k])
+        assert max(vs_ld[k].values()) < TOL, (k, vs_ld[k])
+        assert max(vs_64[k].values()) < (2e-7 if with_replacement else TOL), (k, vs_64[k])

@@ -118,3 +118,26 @@ def test_sgpmc_log_density(eng, lik, N, M, D):
         assert relerr(gv[c], gvo) < 1e-8
         n = D + 2 if lik == "gaussian" else D + 1
         assert relerr(gr[c][:n], gro[:n]) < 1e-8
+
+
+def test_sgpmc_chain_batch_at_config5_shape(eng):
+    """BASELINE configs[4]: Bernoulli-probit classification, N = 2e5, D = 16, M = 512, HMC chains.  One batched launch sequence
+    evaluates all chains of a rank (each with its own theta AND its own whitened v); checked against the chunked oracle for two
+    of the chains, and chain b of the batch must equal the same chain evaluated alone (bit for bit)."""
+    import ggp_b200.functions as F
+    import ggp_b200.synthetic as syn
+    from oracle import sgpmc
+    c = syn.config5_classification()
+    X, y, Z = (torch.tensor(c[k]) for k in ("X", "y", "Z"))
+    D, M, C = 16, 512, 3
+    gen = torch.Generator().manual_seed(5)
+    v = 0.3 * torch.randn(C, M, dtype=torch.float64, generator=gen)
+    raw = torch.randn(C, D + 2, dtype=torch.float64, generator=gen) * 0.2 + 1.5
+    Xd, yd, Zd = X.to(eng.device), y.to(eng.device), Z.to(eng.device)
+    lp, gv, gr = F.sgpmc_logp_dlogp(v, raw, Xd, yd, Zd, likelihood="bernoulli", engine=eng)
+    lp1, gv1, gr1 = F.sgpmc_logp_dlogp(v[1:2], raw[1:2], Xd, yd, Zd, likelihood="bernoulli", engine=eng)
+    assert torch.equal(lp[1], lp1[0]) and torch.equal(gv[1], gv1[0]) and torch.equal(gr[1], gr1[0])
+    torch.set_num_threads(__import__("os").cpu_count() or 1)
+    for ch in (0, 2):
+        lo, gvo, gro = sgpmc.sgpmc_logp_dlogp_chunked(v[ch], raw[ch], X, y, Z, likelihood="bernoulli", chunk=8192)
+        assert relerr(lp[ch], lo) < TOL and relerr(gv[ch], gvo) < TOL and relerr(gr[ch][:D + 1], gro[:D + 1]) < TOL, ch
