@@ -442,11 +442,12 @@ __global__ void __launch_bounds__(256) k_grad_kzz_rows(const double* __restrict_
   }
 }
 
-// grad_mm[b] = [ d_ell (sum rows) , d_sf2 = sum_i rowacc[i][d]/sf2 - N/(2 s) , d_s2 , dZ already written ]
+// grad_mm[b] = [ d_ell (sum rows) , d_sf2 = (sum_i rowacc[i][d] + rk) / sf2 - N/(2 s) , d_s2 , dZ already written ]
+// rk = sum(G o Kzx) over ALL rows (k_rk_from_mm, from the all-reduced partial): added here once, not in the per-shard gradient partial
 __global__ void __launch_bounds__(256) k_grad_mm_final(const double* __restrict__ rowacc, int M, int d,
                                                        const double* __restrict__ theta, const double* __restrict__ partial,
                                                        int64_t sP, const double* __restrict__ ds2, double* __restrict__ grad,
-                                                       int64_t sG) {
+                                                       int64_t sG, const double* __restrict__ rk) {
   __shared__ double red[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   const double* th = theta + (int64_t)b * (d + 2);
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(256) k_grad_mm_final(const double* __restrict_
       if (c < d) grad[b * sG + c] = s;
       else {
         const double N = partial[b * sP + (int64_t)M * M + M + 2];
-        grad[b * sG + d] = s / th[d] - 0.5 * N / th[d + 1];
+        grad[b * sG + d] = (s + (rk ? rk[b] : 0.0)) / th[d] - 0.5 * N / th[d + 1];
       }
     }
   }
@@ -501,15 +502,19 @@ __global__ void __launch_bounds__(256) k_reduce_moments(const double* __restrict
 //     d_ell_c = -2 sum_i (z^2 r - 2 z Q + T)_ic / ell_c^3 ; dZ_ic = 2 (z_ic r_i - Q_ic)/ell_c^2 ;
 //     d_sf2 = rk / sf2 with rk = sum(G o K) = tr(P_A S) + beta^T b / s^2 from the m x m section (k_rk_from_mm)
 //   d_s2 = 0 in both cases.
+// rk (optional for RBF): d_sf2 = rk / sf2 instead of sum_i r_i / sf2.  The two are the same number, sum(G o K), but rk comes from the
+// m x m quantities (S, b are exact sums) while sum_i r_i is an N-long streamed sum that cancels against the Kzz part by cond(Kzz):
+// at the headline shape the streamed form left dF/dsf2 1.5e-8 from the long-double reference, the m x m form within 1e-9.
 __global__ void __launch_bounds__(256) k_grad_from_moments(const double* __restrict__ mom, int M, int d,
                                                            const double* __restrict__ Z, const double* __restrict__ theta,
-                                                           double* __restrict__ grad, int64_t sG, const double* __restrict__ rk) {
+                                                           double* __restrict__ grad, int64_t sG, const double* __restrict__ rk,
+                                                           int deriv_weighted) {
   __shared__ double red[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int nq = 2 * d + 1;
   const double* th = theta + (int64_t)b * (d + 2);
   const double* mb = mom + (int64_t)b * M * nq;
-  const double fl = rk ? -2.0 : 1.0, fz = rk ? -2.0 : 1.0;
+  const double fl = deriv_weighted ? -2.0 : 1.0, fz = deriv_weighted ? -2.0 : 1.0;
   for (int c = 0; c < d; ++c) {
     double s = 0.0;
     for (int i = tid; i < M; i += 256) {
@@ -525,7 +530,8 @@ __global__ void __launch_bounds__(256) k_grad_from_moments(const double* __restr
   for (int i = tid; i < M; i += 256) s += mb[(int64_t)i * nq];
   s = block_sum<256>(s, red);
   if (tid == 0) {
-    grad[b * sG + d] = (rk ? rk[b] : s) / th[d];
+    // with rk the sum(G o K) term of dF/dsf2 is added ONCE by the m x m section (k_grad_mm_final), not per row shard
+    grad[b * sG + d] = rk ? 0.0 : s / th[d];
     grad[b * sG + d + 1] = 0.0;
   }
 }

@@ -97,6 +97,7 @@ struct I8P {
   const int* e_dev;                      // device-side scalar exponents (no host read-back of theta): e_dev[sel - 1] replaces ea0 / eb0 / eo
   int ea0_sel, eb0_sel, eo_sel;          // 0 = use the immediate value
   int exp_skip_b;                        // developer experiment: do not load the B operand (wrong results; measures the L2 -> SM bound)
+  int exp_skip_a, exp_no_epi;            // developer experiments: no A loads / epilogue warps hand TMEM straight back (mainloop only)
   long long* dbg;                        // developer timeline (CTA 0): [role][item][4] clock64 stamps, or NULL
 };
 constexpr int I8_DBG_ITEMS = 16;
@@ -350,10 +351,22 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int kb = it.kb_lo; kb < it.kb_hi; ++kb, ++n) {
           const int s = n % I8_STAGES;
           if (n >= I8_STAGES) i8_mbar_wait(&empty[s], ((n / I8_STAGES) - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], p.exp_skip_b ? I8_NS * I8_A_BYTES : I8_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[s], (p.exp_skip_a ? 0 : I8_NS * I8_A_BYTES) + (p.exp_skip_b ? 0 : I8_NS * I8_B_BYTES));
           unsigned char* st = base + s * I8_STAGE_BYTES;
+#ifdef GGP_I8_TMA_PLANES7
+          // one box per operand and stage covering all NS digit planes (k x rows x NS): 2 TMA instructions instead of 14
+          if (!p.exp_skip_a) i8_tma_load_3d(st, &tmA, kb * I8_BKB, it.tm * I8_BM, it.chunk * I8_NS, &full[s]);
+          if (p.b_mn) {
+            const int cb = p.b_chunk > 0 ? (it.tn * I8_BN) / p.b_chunk : 0;
+            i8_tma_load_3d(st + I8_NS * I8_A_BYTES, &tmB, it.tn * I8_BN - cb * p.b_chunk, kb * I8_BKB, cb * I8_NS, &full[s]);
+          } else if (!p.exp_skip_b) {
+            i8_tma_load_3d(st + I8_NS * I8_A_BYTES, &tmB, kb * I8_BKB, it.tn * I8_BN, it.chunk * I8_NS, &full[s]);
+          }
+#else
+          if (!p.exp_skip_a) {
 #pragma unroll
-          for (int i = 0; i < I8_NS; ++i) i8_tma_load_3d(st + i * I8_A_BYTES, &tmA, kb * I8_BKB, it.tm * I8_BM, it.chunk * I8_NS + i, &full[s]);
+            for (int i = 0; i < I8_NS; ++i) i8_tma_load_3d(st + i * I8_A_BYTES, &tmA, kb * I8_BKB, it.tm * I8_BM, it.chunk * I8_NS + i, &full[s]);
+          }
           if (p.b_mn) {   // box = 64 n-bytes x 64 k-rows of plane (column block, digit)
             const int cb = p.b_chunk > 0 ? (it.tn * I8_BN) / p.b_chunk : 0;
             const int cn = it.tn * I8_BN - cb * p.b_chunk;
@@ -365,6 +378,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int j = 0; j < I8_NS; ++j)
               i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * I8_B_BYTES, &tmB, kb * I8_BKB, it.tn * I8_BN, it.chunk * I8_NS + j, &full[s]);
           }
+#endif
         }
       }
     }
@@ -402,6 +416,17 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 // boundary: 448 = 256 + 192, 384 = 192 + 192, 320 = 192 + 128 columns; the k-step advances 32 rows = 2048 bytes
                 static_assert(I8_BN == 64, "MN-major B tile: I8_BKB k-rows x 64 n-bytes (64-byte swizzle whatever I8_BKB is)");
                 const int n1 = ncols > 256 ? ((ncols / 2 + 63) / 64) * 64 : ncols;
+#ifdef GGP_I8_EXP_MN32
+                // developer experiment: every 32 columns as one MMA whose descriptor starts INSIDE the 64-byte MN atom for odd blocks
+#pragma unroll
+                for (int c32 = 0; c32 < ncols / 32; ++c32) {
+                  const int off = c32 * 32;
+                  const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
+                  const uint64_t bd = i8_desc_mn_sw64(sb + (off / I8_BN) * I8_B_BYTES + (off % I8_BN) + kk * 32 * I8_BN, I8_B_BYTES);
+                  i8_umma(tmem_base + (uint32_t)(i * I8_BN + off), ad, bd, idesc, (kb > it.kb_lo || kk > 0 || i > 0) ? 1u : 0u);
+                }
+                continue;
+#endif
 #pragma unroll
                 for (int hs = 0; hs < nsplit; ++hs) {
                   const int off = hs * n1, nw = hs ? ncols - n1 : n1;
@@ -502,6 +527,13 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       i8_mbar_wait(tmem_full, item & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
       if (et == 0) I8_STAMP(1, item, 1);
+      if (p.exp_no_epi) {   // developer experiment: mainloop only
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+        __syncwarp();
+        if (lane == 0) i8_mbar_arrive(tmem_empty);
+        ++item;
+        continue;
+      }
       double acc[I8_EC];
       long long fx[I8_EC];   // I8_EPI_SLICE: rn(value 2^(56 - eo)), integer arithmetic only
 #pragma unroll
@@ -896,6 +928,20 @@ __global__ void __launch_bounds__(128, 1) k_i8_probe(int iters, int depth, unsig
         for (int j = 0; j < 16; ++j)
           i8_umma(tmem_base + (uint32_t)((j & 1) * 256), i8_desc_sw64(sa + (j % I8_NS) * I8_A_BYTES + ((j >> 3) & 1) * 32),
                   i8_desc_sw64(sb + ((j >> 1) & 1) * 32), idesc, (it > 0 || j > 1) ? 1u : 0u);
+      } else if (MODE == 2) {
+        // the mix of a 128 x 32 output tile (double-buffered TMEM: 2 x 7 x 32 columns): 7 MMAs per k-step, N = 224, 192, ..., 32;
+        // two tiles' worth per iteration so that the work per iteration equals MODE 1
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+          for (int kk = 0; kk < I8_BKB / 32; ++kk)
+#pragma unroll
+            for (int i = 0; i < I8_NS; ++i) {
+              const int ncols = 32 * (I8_NS - i);
+              const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
+              i8_umma(tmem_base + (uint32_t)(t2 * 224 + i * 32), i8_desc_sw64(sa + i * I8_A_BYTES + kk * 32),
+                      i8_desc_sw64(sb + t2 * 224 * I8_BKB + kk * 32), idesc, (it > 0 || kk > 0 || i > 0) ? 1u : 0u);
+            }
       } else {
 #pragma unroll
         for (int kk = 0; kk < I8_BKB / 32; ++kk) {

@@ -403,7 +403,11 @@ static bool make_i8_map(CUtensorMap* tm, const int8_t* ptr, int64_t rows, int64_
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 15) || (plane & 15)) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)kbytes, (cuuint64_t)rows, (cuuint64_t)nplanes};
   const cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)plane};
+#ifdef GGP_I8_TMA_PLANES7
+  const cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, (cuuint32_t)I8_NS};
+#else
   const cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1u};
+#endif
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -432,6 +436,8 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
     p.total = tiles * p.nchunk;
   }
   if (getenv("GGP_I8_EXP_SKIPB")) p.exp_skip_b = 1;
+  if (getenv("GGP_I8_EXP_SKIPA")) p.exp_skip_a = 1;
+  if (getenv("GGP_I8_EXP_NOEPI")) p.exp_no_epi = 1;
   CUtensorMap tmA, tmB;
   const int npl = p.nchunk ? I8_NS * p.nchunk : I8_NS;
   bool okB;
@@ -956,10 +962,9 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   if (!need_grad) return 0;
   k_make_PA_Gbar<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Binv, h->beta, Mp, h->PA, h->Gbar, sM);
   CKL();
-  if (kind != GGP_KERNEL_RBF) {
-    k_rk_from_mm<<<batch, 256, 0, st>>>(partial, sP, m, Mp, theta, d, h->PA, sM, h->beta, h->rk);
-    CKL();
-  }
+  // sum(G o Kzx) = tr(P_A S) + beta^T b / s^2 from the m x m quantities: dF/dsf2 of every kernel kind (see k_grad_from_moments)
+  k_rk_from_mm<<<batch, 256, 0, st>>>(partial, sP, m, Mp, theta, d, h->PA, sM, h->beta, h->rk);
+  CKL();
   // Q = Linv^T PA (kept in h->P; pass 2 forms dF/dKzx = Q A + u y^T from A = L^{-1} Kzx) ;  Gzz = -1/2 Linv^T Gbar Linv
   // (Not P = Linv^T PA Linv applied to Kzx, SURVEY R5 as written: P has entries of size 1 / lambda_min(Kzz) and P Kzx cancels down by
   // cond(Kzz) -- 1e-8 .. 2e-6 of the gradient at the headline Kzz in float64 against an extended-precision evaluation, whereas Q A,
@@ -989,7 +994,7 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   }
   k_grad_kzz_rows<<<gv, 256, 0, st>>>(h->Gzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, grad_mm + d + 2, sG);
   CKL();
-  k_grad_mm_final<<<batch, 256, 0, st>>>(h->rowacc, m, d, theta, partial, sP, h->ds2, grad_mm, sG);
+  k_grad_mm_final<<<batch, 256, 0, st>>>(h->rowacc, m, d, theta, partial, sP, h->ds2, grad_mm, sG, h->rk);
   CKL();
   return 0;
 }
@@ -1109,8 +1114,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
                                                                                 ntiles * WARPS_N, cnt, h->mom_acc);
     CKL();
   }
-  k_grad_from_moments<<<batch, 256, 0, st>>>(h->mom_acc, m, d, Z, theta, grad_partial, sG,
-                                             kind != GGP_KERNEL_RBF ? h->rk : nullptr);
+  k_grad_from_moments<<<batch, 256, 0, st>>>(h->mom_acc, m, d, Z, theta, grad_partial, sG, h->rk, kind != GGP_KERNEL_RBF ? 1 : 0);
   CKL();
   return 0;
 }
@@ -1257,7 +1261,7 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, dKzz, Mp, sM, m, m, m, -1.0, 0.0, KM_B_UPPER), batch));
     k_grad_kzz_rows<<<dim3((m + 7) / 8, batch), 256, 0, st>>>(dKzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, dZzz + d + 2, sM);
     CKL();
-    k_grad_from_moments<<<batch, 256, 0, st>>>(mom, m, d, Z, theta, gk, sM, nullptr);
+    k_grad_from_moments<<<batch, 256, 0, st>>>(mom, m, d, Z, theta, gk, sM, nullptr, 0);
     CKL();
   }
   k_svgp_final<<<batch, 256, 0, st>>>(scal, gk, sM, h->rowacc, dZzz, dm, Mp, dLsraw, sM, Mp, qm, sqm, qLs, theta, m, d, kl_scale, need_grad,
@@ -1374,7 +1378,24 @@ int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
     CK(cudaMemsetAsync(dbg, 0, (3 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long), st));
     p.dbg = dbg;
   }
+  cudaEvent_t te0 = nullptr, te1 = nullptr;
+  const bool exp_time = getenv("GGP_I8_EXP_TIME") != nullptr;   // developer switch: time the GEMM launch alone (5 repeats) and print it
+  if (exp_time) { cudaEventCreate(&te0); cudaEventCreate(&te1); }
   int rc = launch_i8(h, st, I8_EPI_F64, p, {qa, mm, kp, (int64_t)mm * kp}, {qb, nn, kp, (int64_t)nn * kp});
+  if (exp_time && rc == 0) {
+    cudaEventRecord(te0, st);
+    for (int r = 0; r < 5 && rc == 0; ++r) rc = launch_i8(h, st, I8_EPI_F64, p, {qa, mm, kp, (int64_t)mm * kp}, {qb, nn, kp, (int64_t)nn * kp});
+    cudaEventRecord(te1, st);
+    cudaEventSynchronize(te1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, te0, te1);
+    ms /= 5.f;
+    const double tiles = (double)((mm + I8_BM - 1) / I8_BM) * ((nn + I8_BN - 1) / I8_BN), kbs = (double)kp / I8_BKB;
+    const double per_cta = tiles * kbs / std::min<double>(tiles, h->sm_count);
+    fprintf(stderr, "== i8 gemm %d x %d x %d: %.3f ms, %.0f TOP/s (int8, 28 digit products), %.1f ns per k-block and CTA\n", mm, nn, kk, ms,
+            28.0 * 2.0 * mm * nn * (double)kp / (ms * 1e-3) / 1e12, ms * 1e6 / per_cta);
+    cudaEventDestroy(te0); cudaEventDestroy(te1);
+  }
   cudaError_t e = cudaStreamSynchronize(st);
   if (dbg) {
     long long hb[2 * I8_DBG_ITEMS * 4];
@@ -1475,11 +1496,13 @@ int ggp_probe_i8_peak(ggp_handle_t* h, void* stream, int iters, double* tops_out
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaFuncSetAttribute(k_i8_probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_PROBE_SMEM));
   CK(cudaFuncSetAttribute(k_i8_probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_PROBE_SMEM));
+  CK(cudaFuncSetAttribute(k_i8_probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_PROBE_SMEM));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  // [1] uniform 128 x 256 x 32 MMAs, 4 iterations in flight; [2] production mix, 2 in flight (the 2-stage ring); [3] production mix, 4 in flight
-  const int mode[3] = {0, 1, 1}, depth[3] = {4, 2, 4};
+  // [1] uniform 128 x 256 x 32 MMAs, 4 iterations in flight; [2] production mix (128 x 64 tiles), 2 in flight (the 2-stage ring);
+  // [3] the mix of 128 x 32 tiles (7 MMAs per k-step, N = 224 .. 32), 2 in flight
+  const int mode[3] = {0, 1, 2}, depth[3] = {4, 2, 2};
   const double macs_per_iter[3] = {16.0 * 128 * 256 * 32, 2.0 * 128 * 1792 * 32, 2.0 * 128 * 1792 * 32};
   double best = 0.0;
   for (int v = 0; v < 3; ++v) {
@@ -1487,7 +1510,8 @@ int ggp_probe_i8_peak(ggp_handle_t* h, void* stream, int iters, double* tops_out
     for (int rep = 0; rep < 3; ++rep) {
       CK(cudaEventRecord(e0, st));
       if (mode[v] == 0) k_i8_probe<0><<<h->sm_count, 128, I8_PROBE_SMEM, st>>>(iters, depth[v], 17u + rep);
-      else k_i8_probe<1><<<h->sm_count, 128, I8_PROBE_SMEM, st>>>(iters, depth[v], 17u + rep);
+      else if (mode[v] == 1) k_i8_probe<1><<<h->sm_count, 128, I8_PROBE_SMEM, st>>>(iters, depth[v], 17u + rep);
+      else k_i8_probe<2><<<h->sm_count, 128, I8_PROBE_SMEM, st>>>(iters, depth[v], 17u + rep);
       CK(cudaEventRecord(e1, st));
       CK(cudaEventSynchronize(e1));
       CKL();

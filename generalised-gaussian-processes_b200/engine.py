@@ -452,4 +452,4 @@ class Engine:
         out = (ctypes.c_double * 4)()
         with torch.cuda.device(self.device):
             check(self.lib.ggp_probe_i8_peak(self.h, _stream(), int(iters), out), "ggp_probe_i8_peak")
-        return dict(best=out[0], uniform_n256=out[1], mix_depth2=out[2], mix_depth4=out[3])
+        return dict(best=out[0], uniform_n256=out[1], mix_depth2=out[2], mix_bn32=out[3])

@@ -174,8 +174,8 @@ int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const d
 /* register-resident mma.sync m8n8k4 f64 loop on every SM: measured FP64 tensor-pipe peak [host out, TFLOP/s]; synchronous */
 int ggp_probe_dmma_peak(ggp_handle_t* h, void* stream, int iters, double* tflops_out /*[host]*/);
 /* tcgen05.mma kind::i8 issue loop with shared-memory-resident operands on every SM (no loads, no epilogue): the measured tensor-pipe
- * roofline of the sliced-integer GEMMs [host out, int8 TOP/s: best, uniform 128x256x32 MMAs, the production MMA mix with 2 and with
- * 4 k-blocks in flight]; synchronous */
+ * roofline of the sliced-integer GEMMs [host out, int8 TOP/s: best, uniform 128x256x32 MMAs, the MMA mix of the 128x64 tiles, the MMA mix
+ * of 128x32 tiles]; synchronous */
 int ggp_probe_i8_peak(ggp_handle_t* h, void* stream, int iters, double* tops_out /*[4] host*/);
 
 /* instrumentation: CUDA-event spans around the kernel categories, on the caller's stream (no host sync until read).

@@ -79,8 +79,9 @@ def test_full_n_against_long_double_and_float64_oracle(with_replacement):
     """FULL headline size.  References: (a) the committed long-double evaluation of all 1e6 rows (tests/golden/c4_headline_ld_*.npz,
     scripts/make_headline_truth.py: ~11 minutes of host time per case, so it is a fixture), (b) the float64 oracle run here.
     Without replacement (the benchmark's Z rule, cond(Kzz) 7.6e7) everything holds 1e-8.  With replacement the draw contains two
-    duplicated rows, the ladder settles on 1e-8 and cond(Kzz + jI) = 4.4e10: the GPU result must stay within 1e-8 of the
-    long-double reference; the float64 oracle itself is only good to ~1e-8..1e-7 there, so against IT the bar is 2e-7."""
+    duplicated rows, the ladder settles on 1e-8 and cond(Kzz + jI) = 4.4e10: no float64 evaluation holds 1e-8 on dF/dZ there --
+    the float64 ORACLE is 1.4e-8 from the long-double reference, the GPU 2e-8 .. 4e-8 (bound, ell, sf2, s2 stay below 2e-9) -- so
+    that case is bounded at 1e-7 against long double and 2e-7 against the float64 oracle, and the measured values are recorded."""
     import ggp_b200
     import ggp_b200.synthetic as syn
     from oracle import sgpr as osgpr
@@ -110,5 +111,6 @@ def test_full_n_against_long_double_and_float64_oracle(with_replacement):
             dict(jitter=jit64, path_of_the_fp64_i8_engine=res["fp64_i8"][3], vs_long_double=vs_ld, vs_float64_oracle=vs_64,
                  i8_vs_dmma=dict(bound=abs(res["fp64_i8"][0] - res["fp64"][0]) / abs(res["fp64"][0]), grad=relerr(res["fp64_i8"][1], res["fp64"][1]))))
     for k in ("fp64_i8", "fp64"):
-        assert max(vs_ld[k].values()) < TOL, (k, vs_ld[k])
+        assert max(vs_ld[k].values()) < (1e-7 if with_replacement else TOL), (k, vs_ld[k])
+        assert max(v for kk, v in vs_ld[k].items() if kk != "Z") < TOL, (k, vs_ld[k])
         assert max(vs_64[k].values()) < (2e-7 if with_replacement else TOL), (k, vs_64[k])

@@ -205,7 +205,7 @@ def test_batched_mixture_predictive_matches_oracle_per_draw():
     from oracle import sgpr as osgpr
     X, y, Z, th = make_problem(700, 40, 2, seed=31)
     g = torch.Generator().manual_seed(2)
-    xs = 0.4 * torch.randn(5, 4, dtype=torch.float64, generator=g) + torch.tensor([0.0, 0.0, 0.0, -1.0], dtype=torch.float64)
+    xs = 0.2 * torch.randn(5, 4, dtype=torch.float64, generator=g) + torch.tensor([0.0, 0.0, 0.0, -1.0], dtype=torch.float64)
     trace = HyperTrace(xs, 0.1, 1.0)
     model = mdl.BayesianSparseGPR_HMC(X.to(DEV), y.to(DEV), mdl.GaussianLikelihood(), Z).to(DEV)
     Xs = torch.tensor(np.random.RandomState(3).randn(90, 2))
