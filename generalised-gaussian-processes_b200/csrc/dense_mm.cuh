@@ -536,26 +536,37 @@ __global__ void __launch_bounds__(256) k_grad_from_moments(const double* __restr
   }
 }
 
-// rk[b] = sum_{i,n} G_in K_in = tr(P_A S) + beta^T b / s^2   (G = P Kzx + u y^T, Kzx Kxz = L S L^T, Kzx y = L b)
-// -- the k-weighted total needed for dF/d sf2 when the streamed moments are weighted by dk/d(d2) instead of k.
+// rk[b] = sum_{i,n} G_in K_in = tr(P_A S) + beta^T b / s^2   (G = Q A + u y^T, Kzx = L A, Kzx y = L b)
+// -- sum(G o Kzx) from the m x m quantities: the k-weighted total of dF/dsf2 (all kernel kinds).
+// Two deterministic stages: RK_BLOCKS CTAs per batch element write block partials (contiguous row slices), one CTA adds them in order.
+constexpr int RK_BLOCKS = 64;
+__global__ void __launch_bounds__(256) k_rk_partial(const double* __restrict__ partial, int64_t sP, int M, int Mp,
+                                                    const double* __restrict__ PA, int64_t sMat, double* __restrict__ part) {
+  __shared__ double red[8];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const double* S = partial + b * sP;
+  const int rows = (M + RK_BLOCKS - 1) / RK_BLOCKS, r0 = blockIdx.x * rows, r1 = min(M, r0 + rows);
+  double acc = 0.0;
+  for (int i = r0; i < r1; ++i)
+    for (int j = tid; j < M; j += 256) acc = fma(PA[b * sMat + (int64_t)i * Mp + j], S[(int64_t)i * M + j], acc);
+  acc = block_sum<256>(acc, red);
+  if (tid == 0) part[(int64_t)b * RK_BLOCKS + blockIdx.x] = acc;
+}
 __global__ void __launch_bounds__(256) k_rk_from_mm(const double* __restrict__ partial, int64_t sP, int M, int Mp,
-                                                    const double* __restrict__ theta, int d, const double* __restrict__ PA,
-                                                    int64_t sMat, const double* __restrict__ beta, double* __restrict__ rk) {
+                                                    const double* __restrict__ theta, int d, const double* __restrict__ part,
+                                                    const double* __restrict__ beta, double* __restrict__ rk) {
   __shared__ double red[8];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const double* S = partial + b * sP;
-  const double* bv = S + (int64_t)M * M;
+  const double* bv = partial + b * sP + (int64_t)M * M;
   const double s2 = theta[(int64_t)b * (d + 2) + d + 1];
-  double acc = 0.0;
-  for (int64_t e = tid; e < (int64_t)M * M; e += 256) {
-    const int i = (int)(e / M), j = (int)(e - (int64_t)i * M);
-    acc = fma(PA[b * sMat + (int64_t)i * Mp + j], S[e], acc);
-  }
   double acc2 = 0.0;
   for (int i = tid; i < M; i += 256) acc2 = fma(beta[(int64_t)b * Mp + i], bv[i], acc2);
-  acc += acc2 / (s2 * s2);
-  acc = block_sum<256>(acc, red);
-  if (tid == 0) rk[b] = acc;
+  acc2 = block_sum<256>(acc2, red);
+  if (tid == 0) {
+    double acc = 0.0;
+    for (int k = 0; k < RK_BLOCKS; ++k) acc += part[(int64_t)b * RK_BLOCKS + k];
+    rk[b] = acc + acc2 / (s2 * s2);
+  }
 }
 
 }  // namespace ggp

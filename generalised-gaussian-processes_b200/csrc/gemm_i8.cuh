@@ -39,13 +39,34 @@ constexpr int I8_STAGES = GGP_I8_STAGES;
 static_assert(I8_BKB == 64 || I8_BKB == 32, "k-block = one 64- or 32-byte swizzle row");
 constexpr int I8_A_BYTES = I8_BM * I8_BKB, I8_B_BYTES = I8_BN * I8_BKB;
 constexpr int I8_STAGE_BYTES = I8_NS * (I8_A_BYTES + I8_B_BYTES);
-constexpr int I8_EPI_WARPS = 8;                // two per TMEM lane quarter, 32 of the 64 tile columns each
-constexpr int I8_EC = I8_BN / 2;               // columns per epilogue warp
+constexpr int I8_EPI_WARPS = 8;                // two per TMEM lane quarter
+constexpr int I8_EC = 32;                      // tile columns per epilogue warp (both tile widths)
 constexpr int I8_THREADS = 64 + 32 * I8_EPI_WARPS;
 constexpr int I8_MAX_D = 16;                   // input dimension limit of the moments epilogue (shared-memory staging of X)
 constexpr int I8_EPI_SMEM = I8_BN * (I8_MAX_D + 1) * 8;
 constexpr int I8_WSTAGE_LD = 12;               // doubles per staged W row (8 used): 24-word stride = conflict-free DMMA fragment loads
 constexpr int I8_WSTAGE_BYTES = I8_EPI_WARPS * 32 * I8_WSTAGE_LD * 8;
+
+// Two tile widths (template parameter BN of k_gemm_i8):
+//   BN = 64: one 128 x 64 tile owns all 7 x 64 = 448 TMEM columns (single-buffered); the 8 epilogue warps split its columns in two
+//            halves.  Right for long k (the SYRK: 256 k-blocks per chunk, the hand-over is amortised) -- its MMAs are wider.
+//   BN = 32: 128 x 32 tiles, TWO accumulator sets of 7 x 32 = 224 columns: the MMAs of tile t + 1 run while tile t is drained and
+//            its epilogue runs.  The 8 epilogue warps form two teams of 4 (one warp per TMEM lane quarter); team = tile parity, so
+//            each team has two tile periods for its drain + epilogue.  Right for the k = m products (triangular multiply, backward
+//            GEMM: 2 .. 16 k-blocks per tile), where the single-buffered hand-over left the tensor pipe idle 25-30 % of the time
+//            (measured: 1318 ns per k-block with the hand-over bubble alone, 1747 with the FP64 epilogue, against 1197 for the MMAs).
+template <int BN> struct I8Tile {
+  static_assert(BN == 64 || BN == 32, "tile width");
+  static constexpr int NBUF = BN == 32 ? 2 : 1;
+  static constexpr int B_BYTES = BN * I8_BKB;
+  static constexpr int STAGE_BYTES = I8_NS * (I8_A_BYTES + B_BYTES);
+  static constexpr int BUF_COLS = I8_NS * BN;          // TMEM columns of one accumulator set
+  static constexpr int TEAM_WARPS = I8_EPI_WARPS / NBUF;   // epilogue warps per tile
+};
+template <int EPI, int BN> __host__ __device__ constexpr int i8_stages() { return BN == 64 ? I8_STAGES : (EPI == 2 /* moments: staging buffers */ ? 2 : 3); }
+template <int EPI, int BN> __host__ __device__ constexpr int i8_smem() {
+  return i8_stages<EPI, BN>() * I8Tile<BN>::STAGE_BYTES + 1024 + 256 + I8_EPI_SMEM + I8_WSTAGE_BYTES * (EPI == 2 || BN == 64 ? 1 : 0);
+}
 constexpr int I8_SMEM = I8_STAGES * I8_STAGE_BYTES + 1024 + 256 + I8_EPI_SMEM + I8_WSTAGE_BYTES;
 static_assert(I8_SMEM <= 232448, "shared memory budget (227 KB)");
 constexpr int I8_TMEM_COLS = 512;
@@ -139,6 +160,12 @@ __device__ __forceinline__ uint64_t i8_desc_sw64(uint32_t saddr) {
 __device__ __forceinline__ uint64_t i8_desc_mn_sw64(uint32_t saddr, uint32_t lbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)4 << 61);
+}
+// the same for 32-byte MN blocks (BN = 32 tiles): 32-byte swizzle, k-rows 32 bytes apart, 8-row groups 256 bytes apart
+// -- canonical ((2,n),(8,k)):((1,LBO),(2,SBO))
+__device__ __forceinline__ uint64_t i8_desc_mn_sw32(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)6 << 61);
 }
 __device__ __forceinline__ void i8_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -297,21 +324,22 @@ __device__ __forceinline__ long long i8_comb3(uint32_t a0, uint32_t a1, uint32_t
   return i8_mad_wide((int)a0, 65536, t);
 }
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const I8P p) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round-trip would turn every later access into
   // a generic load that the compiler must order against the global stores of the epilogue)
+  using T = I8Tile<BN>;
+  constexpr int STAGES = i8_stages<EPI, BN>(), STAGE_BYTES = T::STAGE_BYTES, B_BYTES = T::B_BYTES, NBUF = T::NBUF;
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + I8_STAGES * I8_STAGE_BYTES);
-  uint64_t* empty = full + I8_STAGES;
-  uint64_t* tmem_full = empty + I8_STAGES;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  double* xs = reinterpret_cast<double*>(base + I8_STAGES * I8_STAGE_BYTES + 256);   // [I8_BN][d]: x rows of the tile
-  double* ys = xs + I8_BN * I8_MAX_D;                                                  // [I8_BN]
-  double* wstage = xs + I8_EPI_SMEM / 8;                                              // [4 warps][32 rows][I8_WSTAGE_LD]
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;            // [NBUF]
+  uint64_t* tmem_empty = tmem_full + 2;            // [NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  double* xs_all = reinterpret_cast<double*>(base + STAGES * STAGE_BYTES + 256);   // per team: [BN][d] x rows of the tile, then [BN] y
+  double* wstage = xs_all + I8_EPI_SMEM / 8;                                        // [8 warps][32 rows][I8_WSTAGE_LD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
@@ -322,12 +350,14 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < I8_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, I8_EPI_WARPS);
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], T::TEAM_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -349,18 +379,18 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         I8Item it;
         i8_decode(p, w, it);
         for (int kb = it.kb_lo; kb < it.kb_hi; ++kb, ++n) {
-          const int s = n % I8_STAGES;
-          if (n >= I8_STAGES) i8_mbar_wait(&empty[s], ((n / I8_STAGES) - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], (p.exp_skip_a ? 0 : I8_NS * I8_A_BYTES) + (p.exp_skip_b ? 0 : I8_NS * I8_B_BYTES));
-          unsigned char* st = base + s * I8_STAGE_BYTES;
+          const int s = n % STAGES;
+          if (n >= STAGES) i8_mbar_wait(&empty[s], ((n / STAGES) - 1) & 1);
+          mbar_arrive_expect_tx(&full[s], (p.exp_skip_a ? 0 : I8_NS * I8_A_BYTES) + (p.exp_skip_b ? 0 : I8_NS * B_BYTES));
+          unsigned char* st = base + s * STAGE_BYTES;
 #ifdef GGP_I8_TMA_PLANES7
           // one box per operand and stage covering all NS digit planes (k x rows x NS): 2 TMA instructions instead of 14
           if (!p.exp_skip_a) i8_tma_load_3d(st, &tmA, kb * I8_BKB, it.tm * I8_BM, it.chunk * I8_NS, &full[s]);
           if (p.b_mn) {
-            const int cb = p.b_chunk > 0 ? (it.tn * I8_BN) / p.b_chunk : 0;
-            i8_tma_load_3d(st + I8_NS * I8_A_BYTES, &tmB, it.tn * I8_BN - cb * p.b_chunk, kb * I8_BKB, cb * I8_NS, &full[s]);
+            const int cb = p.b_chunk > 0 ? (it.tn * BN) / p.b_chunk : 0;
+            i8_tma_load_3d(st + I8_NS * I8_A_BYTES, &tmB, it.tn * BN - cb * p.b_chunk, kb * I8_BKB, cb * I8_NS, &full[s]);
           } else if (!p.exp_skip_b) {
-            i8_tma_load_3d(st + I8_NS * I8_A_BYTES, &tmB, kb * I8_BKB, it.tn * I8_BN, it.chunk * I8_NS, &full[s]);
+            i8_tma_load_3d(st + I8_NS * I8_A_BYTES, &tmB, kb * I8_BKB, it.tn * BN, it.chunk * I8_NS, &full[s]);
           }
 #else
           if (!p.exp_skip_a) {
@@ -368,15 +398,15 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int i = 0; i < I8_NS; ++i) i8_tma_load_3d(st + i * I8_A_BYTES, &tmA, kb * I8_BKB, it.tm * I8_BM, it.chunk * I8_NS + i, &full[s]);
           }
           if (p.b_mn) {   // box = 64 n-bytes x 64 k-rows of plane (column block, digit)
-            const int cb = p.b_chunk > 0 ? (it.tn * I8_BN) / p.b_chunk : 0;
-            const int cn = it.tn * I8_BN - cb * p.b_chunk;
+            const int cb = p.b_chunk > 0 ? (it.tn * BN) / p.b_chunk : 0;
+            const int cn = it.tn * BN - cb * p.b_chunk;
 #pragma unroll
             for (int j = 0; j < I8_NS; ++j)
-              i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * I8_B_BYTES, &tmB, cn, kb * I8_BKB, cb * I8_NS + j, &full[s]);
+              i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * B_BYTES, &tmB, cn, kb * I8_BKB, cb * I8_NS + j, &full[s]);
           } else if (!p.exp_skip_b) {
 #pragma unroll
             for (int j = 0; j < I8_NS; ++j)
-              i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * I8_B_BYTES, &tmB, kb * I8_BKB, it.tn * I8_BN, it.chunk * I8_NS + j, &full[s]);
+              i8_tma_load_3d(st + I8_NS * I8_A_BYTES + j * B_BYTES, &tmB, kb * I8_BKB, it.tn * BN, it.chunk * I8_NS + j, &full[s]);
           }
 #endif
         }
@@ -392,15 +422,18 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       i8_decode(p, w, it);
       if (it.kb_hi <= it.kb_lo) continue;
       if (lane == 0) I8_STAMP(0, item, 0);
-      if (item > 0) i8_mbar_wait(tmem_empty, (item - 1) & 1);   // the epilogue has drained the previous tile's accumulators
+      const int buf = item & (NBUF - 1);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * T::BUF_COLS);
+      // the epilogue team of this accumulator set has drained the tile that used it last (NBUF tiles ago)
+      if (item >= NBUF) i8_mbar_wait(&tmem_empty[buf], ((item / NBUF) - 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
       if (lane == 0) I8_STAMP(0, item, 1);
       for (int kb = it.kb_lo; kb < it.kb_hi; ++kb, ++n) {
-        const int s = n % I8_STAGES;
-        i8_mbar_wait(&full[s], (n / I8_STAGES) & 1);
+        const int s = n % STAGES;
+        i8_mbar_wait(&full[s], (n / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
         if (lane == 0) {
-          const uint32_t sa = smem_u32(base + s * I8_STAGE_BYTES), sb = sa + I8_NS * I8_A_BYTES;
+          const uint32_t sa = smem_u32(base + s * STAGE_BYTES), sb = sa + I8_NS * I8_A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < I8_BKB / 32; ++kk) {
 #pragma unroll
@@ -408,31 +441,27 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               const uint64_t ad = i8_desc_sw64(sa + i * I8_A_BYTES + kk * 32);
               // digit i of A x digits 0 .. NS-1-i of B: one tall B tile of ncols rows -> accumulator columns [i * BN, i * BN + ncols);
               // more than 256 columns are issued as two equal halves (multiples of 16 columns and of the 8-row swizzle group)
-              const int ncols = I8_BN * (I8_NS - i);
+              const int ncols = BN * (I8_NS - i);
+              if (BN == 32) {
+                // 128 x 32 tiles: ncols <= 224, one MMA per A digit; B is the tall K-major tile (7 x 32 rows) or, MN-major, 32-byte
+                // MN blocks (one per digit) LBO = B_BYTES apart with the k-step advancing 32 rows of 32 bytes
+                const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (p.b_mn ? (1u << 16) : 0u) | ((uint32_t)(ncols >> 3) << 17) |
+                                       ((uint32_t)(I8_BM >> 4) << 24);
+                const uint64_t bd = p.b_mn ? i8_desc_mn_sw32(sb + kk * 32 * BN, B_BYTES) : i8_desc_sw64(sb + kk * 32);
+                i8_umma(tmem_acc + (uint32_t)(i * BN), ad, bd, idesc, (kb > it.kb_lo || kk > 0 || i > 0) ? 1u : 0u);
+                continue;
+              }
               const int nsplit = ncols > 256 ? 2 : 1, nn = ncols / nsplit;
-              static_assert(I8_BN % 32 == 0, "half of any ncols is a multiple of 16");
               if (p.b_mn) {
                 // MN-major B: the digit tiles are 64-byte MN blocks LBO = 4096 bytes apart, so a wide MMA must start on a tile
                 // boundary: 448 = 256 + 192, 384 = 192 + 192, 320 = 192 + 128 columns; the k-step advances 32 rows = 2048 bytes
-                static_assert(I8_BN == 64, "MN-major B tile: I8_BKB k-rows x 64 n-bytes (64-byte swizzle whatever I8_BKB is)");
                 const int n1 = ncols > 256 ? ((ncols / 2 + 63) / 64) * 64 : ncols;
-#ifdef GGP_I8_EXP_MN32
-                // developer experiment: every 32 columns as one MMA whose descriptor starts INSIDE the 64-byte MN atom for odd blocks
-#pragma unroll
-                for (int c32 = 0; c32 < ncols / 32; ++c32) {
-                  const int off = c32 * 32;
-                  const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
-                  const uint64_t bd = i8_desc_mn_sw64(sb + (off / I8_BN) * I8_B_BYTES + (off % I8_BN) + kk * 32 * I8_BN, I8_B_BYTES);
-                  i8_umma(tmem_base + (uint32_t)(i * I8_BN + off), ad, bd, idesc, (kb > it.kb_lo || kk > 0 || i > 0) ? 1u : 0u);
-                }
-                continue;
-#endif
 #pragma unroll
                 for (int hs = 0; hs < nsplit; ++hs) {
                   const int off = hs * n1, nw = hs ? ncols - n1 : n1;
                   const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(nw >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
-                  const uint64_t bd = i8_desc_mn_sw64(sb + (off / I8_BN) * I8_B_BYTES + kk * 32 * I8_BN, I8_B_BYTES);
-                  i8_umma(tmem_base + (uint32_t)(i * I8_BN + off), ad, bd, idesc, (kb > it.kb_lo || kk > 0 || i > 0) ? 1u : 0u);
+                  const uint64_t bd = i8_desc_mn_sw64(sb + (off / BN) * B_BYTES + kk * 32 * BN, B_BYTES);
+                  i8_umma(tmem_acc + (uint32_t)(i * BN + off), ad, bd, idesc, (kb > it.kb_lo || kk > 0 || i > 0) ? 1u : 0u);
                 }
                 continue;
               }
@@ -442,12 +471,12 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 // D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
                 const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
                 const uint64_t bd = i8_desc_sw64(sb + off * I8_BKB + kk * 32);   // row `off` of the tall tile: 8-row groups of 512 bytes
-                i8_umma(tmem_base + (uint32_t)(i * I8_BN + off), ad, bd, idesc, (kb > it.kb_lo || kk > 0 || i > 0) ? 1u : 0u);
+                i8_umma(tmem_acc + (uint32_t)(i * BN + off), ad, bd, idesc, (kb > it.kb_lo || kk > 0 || i > 0) ? 1u : 0u);
               }
             }
           }
           i8_umma_commit(&empty[s]);                            // frees the stage once the MMAs that read it are done
-          if (kb == it.kb_hi - 1) i8_umma_commit(tmem_full);    // accumulators of this tile complete
+          if (kb == it.kb_hi - 1) i8_umma_commit(&tmem_full[buf]);    // accumulators of this tile complete
           if (kb == it.kb_lo) I8_STAMP(0, item, 2);
         }
         __syncwarp();
@@ -456,10 +485,17 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       ++item;
     }
   } else {
-    // ================= epilogue (8 warps; warp w owns TMEM lanes [32 (w % 4), +32) and 32 of the 64 tile columns) =================
+    // ================= epilogue (8 warps; warp w owns TMEM lanes [32 (w % 4), +32) and 32 tile columns) =================
+    // BN = 64: one team of 8 warps, `half` = column half of the tile.  BN = 32: two teams of 4 warps, `half` = team = parity of the
+    // tiles (accumulator sets) the warp serves; every warp covers all 32 columns of its tiles.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;  // column half of the tile handled by this warp
+    const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;   // 0..255
+    constexpr int TT = 256 / NBUF;     // threads of a team
+    const int tt = et & (TT - 1), team_bar = 1 + (NBUF == 2 ? half : 0);
+    const int chalf = (BN == 64) ? half * I8_EC : 0;   // first tile column of this warp
+    double* xs = xs_all + (NBUF == 2 ? half * (32 * (I8_MAX_D + 1)) : 0);   // [BN][d]: x rows of the team's tile
+    double* ys = xs + BN * I8_MAX_D;                                         // [BN]
     const int p_ea0 = p.ea0_sel ? p.e_dev[p.ea0_sel - 1] : p.ea0, p_eb0 = p.eb0_sel ? p.e_dev[p.eb0_sel - 1] : p.eb0,
               p_eo = p.eo_sel ? p.e_dev[p.eo_sel - 1] : p.eo;
     double accT[I8_EC];                // I8_EPI_F64 with nchunk: this thread's 32 tile elements summed over the CTA's chunks
@@ -479,9 +515,12 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       I8Item it;
       i8_decode(p, w, it);
       if (it.kb_hi <= it.kb_lo) continue;
+      const int my_item = item++;
+      const int buf = my_item & (NBUF - 1);
+      if (NBUF == 2 && buf != half) continue;       // the other team's tile
       const int row = it.tm * I8_BM + quarter * 32 + lane;
-      const int col0 = it.tn * I8_BN + half * I8_EC;   // first column of this warp's half
-      const int colt = it.tn * I8_BN;                  // first column of the tile
+      const int col0 = it.tn * BN + chalf;          // first column of this warp's 32
+      const int colt = it.tn * BN;                  // first column of the tile
       double kv0[16], kv1[16];   // I8_EPI_MOMENTS: Kmul values of column groups, loaded ahead of their use (HBM latency)
       auto load_kv = [&](double (&kv)[16], int g) {
 #pragma unroll
@@ -492,46 +531,45 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       };
       if (EPI == I8_EPI_MOMENTS) {
         // stage the tile's x rows and y into shared memory (previous tile's readers are past their last read: barrier below)
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
-        if (et == 0) I8_STAMP(2, item, 0);
+        asm volatile("bar.sync %0, %1;\n" ::"r"(team_bar), "r"(TT) : "memory");
+        if (et == 0) I8_STAMP(2, my_item, 0);
         const int d = p.d;
         {   // the tile's x rows are one contiguous block of 64 d doubles: coalesced copy, 4 independent loads in flight per thread
           const double* src = p.Xc + (int64_t)colt * d;
-          const int cnt = I8_BN * d, lim = max(0, min(cnt, (p.N - colt) * d));
-          for (int i0 = et; i0 < cnt; i0 += 4 * 256) {
+          const int cnt = BN * d, lim = max(0, min(cnt, (p.N - colt) * d));
+          for (int i0 = tt; i0 < cnt; i0 += 4 * TT) {
             double v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const int i = i0 + j * 256; v[j] = (i < lim) ? __ldg(src + i) : 0.0; }
+            for (int j = 0; j < 4; ++j) { const int i = i0 + j * TT; v[j] = (i < lim) ? __ldg(src + i) : 0.0; }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const int i = i0 + j * 256; if (i < cnt) xs[i] = v[j]; }
+            for (int j = 0; j < 4; ++j) { const int i = i0 + j * TT; if (i < cnt) xs[i] = v[j]; }
           }
-          if (et < I8_BN) ys[et] = (colt + et < p.N) ? __ldg(p.yv + colt + et) : 0.0;
+          if (tt < BN) ys[tt] = (colt + tt < p.N) ? __ldg(p.yv + colt + tt) : 0.0;
         }
-        if (et == 0) I8_STAMP(2, item, 1);
+        if (et == 0) I8_STAMP(2, my_item, 1);
         // both groups of this warp's 32 columns are in flight while the MMAs of this tile run.  (With the register file full these 32
         // loads issue one memory latency at a time -- 16 k clk of this 25 k clk phase -- which is hidden behind the 37 k clk mainloop in
         // the serial-epilogue mode.  An overlapped variant with an L2 prefetch here and the loads after the drain cut the phase to
         // 6.5 k clk, but the FP64 work next to the UTCIMMA stream then took 39 k clk: no gain, removed.)
         load_kv(kv0, 0);
         load_kv(kv1, 1);
-        if (et == 0) I8_STAMP(2, item, 2);
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
-        if (et == 0) I8_STAMP(2, item, 3);
+        if (et == 0) I8_STAMP(2, my_item, 2);
+        asm volatile("bar.sync %0, %1;\n" ::"r"(team_bar), "r"(TT) : "memory");
+        if (et == 0) I8_STAMP(2, my_item, 3);
       }
       const int e_r = p.ea ? p.ea[min(row, p.M - 1)] : p_ea0;
       const int sh = 8 + p_eo - e_r - p_eb0;   // I8_EPI_SLICE (scalar column exponent, alpha = 1, k <= I8_K_GROUP4: checked on the host)
       const bool fx_fast = (EPI == I8_EPI_SLICE) && __all_sync(0xffffffffu, sh > -32 && sh <= 24);
       const int fx_l1 = sh < 0 ? -sh : 0, fx_r1 = sh > 0 ? sh : 0, fx_s2 = (24 - sh) & 63;
       const long long fx_rnd = sh > 0 ? 1ll << ((sh - 1) & 63) : 0ll;
-      if (et == 0) I8_STAMP(1, item, 0);
-      i8_mbar_wait(tmem_full, item & 1);
+      if (et == 0) I8_STAMP(1, my_item, 0);
+      i8_mbar_wait(&tmem_full[buf], (my_item / NBUF) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-      if (et == 0) I8_STAMP(1, item, 1);
+      if (et == 0) I8_STAMP(1, my_item, 1);
       if (p.exp_no_epi) {   // developer experiment: mainloop only
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
         __syncwarp();
-        if (lane == 0) i8_mbar_arrive(tmem_empty);
-        ++item;
+        if (lane == 0) i8_mbar_arrive(&tmem_empty[buf]);
         continue;
       }
       double acc[I8_EC];
@@ -543,7 +581,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       //   k <= I8_K_GROUP4 (MODE 0 / 1 = integer epilogue, fast / general shifts): U = t_hi 2^24 + t_lo, t_hi = levels 0..3, t_lo = levels 4..6
       //   longer k          (MODE 2):  U = g0 2^32 + g1 2^8 + g2, g0 = levels 0..2, g1 = levels 3..5, g2 = level 6   (each < 2^53)
       static_assert(I8_NS == 7, "level grouping");
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * I8_EC);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * T::BUF_COLS + chalf);
       auto drain = [&](auto mode_tag) {
         constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
@@ -551,10 +589,10 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (MODE != 2) {
             {   // levels 4..6
               uint32_t v0[16], v1[16], v2[16];
-              const uint32_t ta = tbase + (uint32_t)(4 * I8_BN + c0);
+              const uint32_t ta = tbase + (uint32_t)(4 * BN + c0);
               i8_tmem_ld16(ta, v0);
-              i8_tmem_ld16(ta + I8_BN, v1);
-              i8_tmem_ld16(ta + 2 * I8_BN, v2);
+              i8_tmem_ld16(ta + BN, v1);
+              i8_tmem_ld16(ta + 2 * BN, v2);
               asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
               for (int c = 0; c < 16; ++c) {
@@ -567,9 +605,9 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               uint32_t v0[16], v1[16], v2[16], v3[16];
               const uint32_t ta = tbase + (uint32_t)c0;
               i8_tmem_ld16(ta, v0);
-              i8_tmem_ld16(ta + I8_BN, v1);
-              i8_tmem_ld16(ta + 2 * I8_BN, v2);
-              i8_tmem_ld16(ta + 3 * I8_BN, v3);
+              i8_tmem_ld16(ta + BN, v1);
+              i8_tmem_ld16(ta + 2 * BN, v2);
+              i8_tmem_ld16(ta + 3 * BN, v3);
               asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
               for (int c = 0; c < 16; ++c) {
@@ -581,11 +619,11 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           } else {
             {   // levels 3..5 and 6
               uint32_t v0[16], v1[16], v2[16], v3[16];
-              const uint32_t ta = tbase + (uint32_t)(3 * I8_BN + c0);
+              const uint32_t ta = tbase + (uint32_t)(3 * BN + c0);
               i8_tmem_ld16(ta, v0);
-              i8_tmem_ld16(ta + I8_BN, v1);
-              i8_tmem_ld16(ta + 2 * I8_BN, v2);
-              i8_tmem_ld16(ta + 3 * I8_BN, v3);
+              i8_tmem_ld16(ta + BN, v1);
+              i8_tmem_ld16(ta + 2 * BN, v2);
+              i8_tmem_ld16(ta + 3 * BN, v3);
               asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
               for (int c = 0; c < 16; ++c) {
@@ -597,8 +635,8 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               uint32_t v0[16], v1[16], v2[16];
               const uint32_t ta = tbase + (uint32_t)c0;
               i8_tmem_ld16(ta, v0);
-              i8_tmem_ld16(ta + I8_BN, v1);
-              i8_tmem_ld16(ta + 2 * I8_BN, v2);
+              i8_tmem_ld16(ta + BN, v1);
+              i8_tmem_ld16(ta + 2 * BN, v2);
               asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
               for (int c = 0; c < 16; ++c) {
@@ -620,10 +658,9 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // accumulators are in registers: hand TMEM back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
       __syncwarp();
-      if (lane == 0 && !p.serial_epi) i8_mbar_arrive(tmem_empty);
-      if (et == 0) I8_STAMP(1, item, 2);
-      const int item_done = item;
-      ++item;
+      if (lane == 0 && !p.serial_epi) i8_mbar_arrive(&tmem_empty[buf]);
+      if (et == 0) I8_STAMP(1, my_item, 2);
+      const int item_done = my_item;
 
       const bool rok = row < p.M;
       if (EPI == I8_EPI_SLICE) {
@@ -684,7 +721,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (p.rowdot_reg) {
             rdA[rnd & 1] += sv;
           } else if (rok) {   // one slab per 32 columns
-            double* rd = p.rowdot + (int64_t)(it.tn * 2 + half) * p.M + row;
+            double* rd = p.rowdot + (int64_t)(BN == 64 ? it.tn * 2 + half : it.tn) * p.M + row;
             *rd = p.rowdot_acc ? *rd + sv : sv;
           }
         }
@@ -728,7 +765,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const double ui = rok ? p.u[row] : 0.0;
         auto apply_kv = [&](const double (&kv)[16], int g) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) acc[g * 16 + c] = fma(ui, ys[half * I8_EC + g * 16 + c], acc[g * 16 + c]) * kv[c];
+          for (int c = 0; c < 16; ++c) acc[g * 16 + c] = fma(ui, ys[chalf + g * 16 + c], acc[g * 16 + c]) * kv[c];
         };
         apply_kv(kv0, 0);
         apply_kv(kv1, 1);
@@ -754,7 +791,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               double a[4];
 #pragma unroll
               for (int G = 0; G < 4; ++G) a[G] = wsm[(8 * G + g) * I8_WSTAGE_LD + 4 * kq + q4];
-              const double* xr = xs + (half * I8_EC + pc * 8 + 4 * kq + q4) * d;
+              const double* xr = xs + (chalf + pc * 8 + 4 * kq + q4) * d;
 #pragma unroll
               for (int B = 0; B < 3; ++B) {
                 if ((b0 + B) * 8 + off > 2 * d) continue;   // warp-uniform
@@ -787,7 +824,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int G = 0; G < 4; ++G) {
               const int rr = it.tm * I8_BM + quarter * 32 + 8 * G + g;
               if (rr >= p.M) continue;
-              double* mo = p.mom + (int64_t)(it.tn * 2 + half) * p.sMomTile + (int64_t)rr * nq;   // one slab per 32 columns
+              double* mo = p.mom + (int64_t)(BN == 64 ? it.tn * 2 + half : it.tn) * p.sMomTile + (int64_t)rr * nq;   // one slab per 32 columns
 #pragma unroll
               for (int B = 0; B < 3; ++B) {
                 const int m = (b0 + B) * 8 + 2 * q4;
@@ -800,14 +837,14 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       if (p.serial_epi) {
         __syncwarp();
-        if (lane == 0) i8_mbar_arrive(tmem_empty);
+        if (lane == 0) i8_mbar_arrive(&tmem_empty[buf]);
       }
       if (et == 0) I8_STAMP(1, item_done, 3);
     }
-    if (EPI == I8_EPI_F64 && p.nchunk && blockIdx.x / p.ntile < p.nchunk) {   // the tile total of this CTA's chunks, stored once
+    if (EPI == I8_EPI_F64 && BN == 64 && p.nchunk && blockIdx.x / p.ntile < p.nchunk) {   // the tile total of this CTA's chunks, stored once
       I8Item it;
       i8_decode(p, blockIdx.x % p.ntile, it);
-      const int rown = it.tm * I8_BM + quarter * 32 + lane, col0 = it.tn * I8_BN + half * I8_EC;
+      const int rown = it.tm * I8_BM + quarter * 32 + lane, col0 = it.tn * BN + half * I8_EC;
       if (rown < p.M) {
         double* dst = p.C + (int64_t)(blockIdx.x / p.ntile) * p.sSplit + (int64_t)rown * p.ldc + col0;
 #pragma unroll

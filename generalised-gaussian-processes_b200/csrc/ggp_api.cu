@@ -98,6 +98,7 @@ struct ggp_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t* info_ws = nullptr;
   double* ysc = nullptr;
+  double* rk_part = nullptr;
   double* piv_tol = nullptr;   // [batch] pivot threshold of the next Cholesky (k_build_kzz sets it; 0 = LAPACK semantics)
 };
 
@@ -190,6 +191,7 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   take((size_t)batch * 4 * p.nsv * 8);                  // rowout
   take((size_t)batch * 8 + 256);                        // piv_tol
   take((size_t)batch * p.nc * 8);                       // ysc (noise-weighted y chunk of the predictive's pass 1)
+  take((size_t)batch * RK_BLOCKS * 8);                  // rk_part
   p.bytes = o;
   return p;
 }
@@ -416,13 +418,38 @@ static bool make_i8_map(CUtensorMap* tm, const int8_t* ptr, int64_t rows, int64_
 
 struct I8Operand { const int8_t* q; int64_t rows, ld, plane; };
 
+// Tile width of a launch.  Production: 128 x 64 single-buffered tiles for every role.  The 128 x 32 variant with two TMEM accumulator
+// sets (the hand-over and the epilogue of tile t overlap the MMAs of tile t + 1) is compiled only with -DGGP_I8_ENABLE_BN32 and selected
+// by GGP_I8_BN32=1: MEASURED SLOWER at the headline shape (backward GEMM 34.2 vs 27.8 ms, triangular multiply 15.9 vs 14.8 ms,
+// profiles/r2_summary.md) -- a 128 x 32 tile re-reads the A operand for half the work, its 7 narrower MMAs per k-step already need
+// ~124 B/clk of shared-memory operand reads (probe: 92 % of the 128 x 64 mix), and the per-thread multiplier loads of the moments
+// epilogue (a latency chain per tile, not per MAC) no longer fit in two tile periods.  Kept as a measured experiment, not a product path.
+static int i8_tile_width(int epi, const I8P& p) {
+#ifdef GGP_I8_ENABLE_BN32
+  if (getenv("GGP_I8_BN32") && !p.nchunk && !p.sym) return 32;
+#endif
+  (void)epi; (void)p;
+  return 64;
+}
+
+template <int EPI, int BN>
+static void launch_i8_kernel(int grid, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const I8P& p) {
+#ifndef GGP_I8_ENABLE_BN32
+  if (BN == 32) return;   // not compiled in
+  k_gemm_i8<EPI, 64><<<grid, I8_THREADS, i8_smem<EPI, 64>(), st>>>(tmA, tmB, p);
+#else
+  k_gemm_i8<EPI, BN><<<grid, I8_THREADS, i8_smem<EPI, BN>(), st>>>(tmA, tmB, p);
+#endif
+}
+
 static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Operand& A, const I8Operand& B) {
   if (p.K < 1 || p.M < 1 || p.N < 1) return 0;
   if (p.K > I8_MAX_K) return fail(-4, "launch_i8: k extent exceeds the exact int32 accumulation bound (16384)");
   if (epi == I8_EPI_SLICE && (p.eb || p.alpha != 1.0 || p.K > I8_K_GROUP4))
     return fail(-4, "launch_i8: the digit-plane epilogue takes a scalar column exponent, alpha = 1 and k <= 4096");
+  const int bn = i8_tile_width(epi, p);
   p.tiles_m = (p.M + I8_BM - 1) / I8_BM;
-  p.tiles_n = (p.N + I8_BN - 1) / I8_BN;
+  p.tiles_n = (p.N + bn - 1) / bn;
   int tiles = p.tiles_m * p.tiles_n;
   if (p.sym) {
     tiles = 0;
@@ -443,12 +470,12 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
   bool okB;
   if (p.b_mn) {
     // MN-major B: planes [plane][k rows = B.rows][columns, contiguous]; the map's inner extent is one column block (chunk array), the
-    // box 64 column bytes x 64 k-rows; rows / columns beyond the extents are zero-filled
+    // box bn column bytes x 64 k-rows (64-byte swizzle for 64 columns, 32-byte for 32); rows / columns beyond the extents are zero-filled
     if (p.sym || p.nchunk || p.splits != 1 || p.lower_a) return fail(-4, "launch_i8: the MN-major B operand serves the plain product only");
-    const int64_t cols = p.b_chunk > 0 ? p.b_chunk : (int64_t)(p.N + I8_BN - 1) / I8_BN * I8_BN;
-    okB = make_i8_map(&tmB, B.q, B.rows, cols, B.ld, B.plane, I8_BKB, p.b_planes > 0 ? p.b_planes : I8_NS, I8_BN);
+    const int64_t cols = p.b_chunk > 0 ? p.b_chunk : (int64_t)(p.N + 63) / 64 * 64;
+    okB = make_i8_map(&tmB, B.q, B.rows, cols, B.ld, B.plane, I8_BKB, p.b_planes > 0 ? p.b_planes : I8_NS, bn);
   } else {
-    okB = make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, I8_BN, npl);
+    okB = make_i8_map(&tmB, B.q, B.rows, p.K, B.ld, B.plane, bn, npl);
   }
   if (!make_i8_map(&tmA, A.q, A.rows, p.K, A.ld, A.plane, I8_BM, npl) || !okB)
     return fail(-4, "launch_i8: operand planes cannot be described by a tensor map (alignment)");
@@ -466,9 +493,9 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
     CK(cudaMemsetAsync(h->i8_dbg, 0, (3 * I8_DBG_ITEMS * 4 + 2 * 256) * sizeof(long long), st));
     p.dbg = h->i8_dbg;
   }
-  if (epi == I8_EPI_F64) k_gemm_i8<I8_EPI_F64><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
-  else if (epi == I8_EPI_SLICE) k_gemm_i8<I8_EPI_SLICE><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
-  else k_gemm_i8<I8_EPI_MOMENTS><<<grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);
+  if (epi == I8_EPI_F64) { if (bn == 64) launch_i8_kernel<I8_EPI_F64, 64>(grid, st, tmA, tmB, p); else launch_i8_kernel<I8_EPI_F64, 32>(grid, st, tmA, tmB, p); }
+  else if (epi == I8_EPI_SLICE) { if (bn == 64) launch_i8_kernel<I8_EPI_SLICE, 64>(grid, st, tmA, tmB, p); else launch_i8_kernel<I8_EPI_SLICE, 32>(grid, st, tmA, tmB, p); }
+  else { if (bn == 64) launch_i8_kernel<I8_EPI_MOMENTS, 64>(grid, st, tmA, tmB, p); else launch_i8_kernel<I8_EPI_MOMENTS, 32>(grid, st, tmA, tmB, p); }
   CKL();
   if (dbg) {
     CK(cudaStreamSynchronize(st));
@@ -525,9 +552,14 @@ int ggp_create(ggp_handle_t** out, int device) {
   CK(cudaFuncSetAttribute(k_build_kc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_chol_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
   { const char* e = getenv("GGP_CHOL_FUSED"); h->chol_fused = !(e && e[0] == '0'); }
-  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_SLICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_F64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_F64, 64>()));
+  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_SLICE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_SLICE, 64>()));
+  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_MOMENTS, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_MOMENTS, 64>()));
+#ifdef GGP_I8_ENABLE_BN32
+  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_F64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_F64, 32>()));
+  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_SLICE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_SLICE, 32>()));
+  CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_MOMENTS, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_MOMENTS, 32>()));
+#endif
   *out = h;
   return 0;
 }
@@ -665,6 +697,7 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   h->rowout = reinterpret_cast<double*>(h->arena + p.off[nslots + 6]);
   h->piv_tol = reinterpret_cast<double*>(h->arena + p.off[nslots + 7]);
   h->ysc = reinterpret_cast<double*>(h->arena + p.off[nslots + 8]);
+  h->rk_part = reinterpret_cast<double*>(h->arena + p.off[nslots + 9]);
   h->nsv = p.nsv;
   return 0;
 }
@@ -963,7 +996,9 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   k_make_PA_Gbar<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Binv, h->beta, Mp, h->PA, h->Gbar, sM);
   CKL();
   // sum(G o Kzx) = tr(P_A S) + beta^T b / s^2 from the m x m quantities: dF/dsf2 of every kernel kind (see k_grad_from_moments)
-  k_rk_from_mm<<<batch, 256, 0, st>>>(partial, sP, m, Mp, theta, d, h->PA, sM, h->beta, h->rk);
+  k_rk_partial<<<dim3(RK_BLOCKS, batch), 256, 0, st>>>(partial, sP, m, Mp, h->PA, sM, h->rk_part);
+  CKL();
+  k_rk_from_mm<<<batch, 256, 0, st>>>(partial, sP, m, Mp, theta, d, h->rk_part, h->beta, h->rk);
   CKL();
   // Q = Linv^T PA (kept in h->P; pass 2 forms dF/dKzx = Q A + u y^T from A = L^{-1} Kzx) ;  Gzz = -1/2 Linv^T Gbar Linv
   // (Not P = Linv^T PA Linv applied to Kzx, SURVEY R5 as written: P has entries of size 1 / lambda_min(Kzz) and P Kzx cancels down by
@@ -1079,8 +1114,10 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       g8.b_planes = I8_NS * (a_cached ? nchunks - (int)(c0 / nc) : 1);
       { ProfScope ps(h, st, CAT_BWD); RUN(launch_i8(h, st, I8_EPI_MOMENTS, g8, {h->Pq, Mp, Mp, (int64_t)Mp * Mp}, Bop)); }
       ProfScope ps_o(h, st, CAT_OTHER);
-      const int tiles_m = (m + I8_BM - 1) / I8_BM, tiles_n = (nv + I8_BN - 1) / I8_BN;
-      const int nslabs = i8_accum ? 2 * std::max(1, std::min(h->sm_count / tiles_m, tiles_n)) : 2 * tiles_n;
+      // slabs the launch wrote: 2 per CTA column group on the register-resident plan, else one per 32 columns
+      const int bn2 = i8_tile_width(I8_EPI_MOMENTS, g8);
+      const int tiles_m = (m + I8_BM - 1) / I8_BM, tiles_n = (nv + bn2 - 1) / bn2;
+      const int nslabs = i8_accum ? 2 * std::max(1, std::min(h->sm_count / tiles_m, tiles_n)) : (bn2 == 64 ? 2 * tiles_n : tiles_n);
       k_reduce_moments<<<dim3((unsigned)((cnt + 31) / 32), batch), 256, 0, st>>>(h->mom_part, cnt, 0, nslabs, cnt, h->mom_acc);
       CKL();
       continue;
