@@ -10,20 +10,30 @@ constexpr int NB = 64;  // diagonal block size of the blocked Cholesky / recursi
 constexpr int POTF2_SMEM = 0;
 
 // Factor diagonal block kb in place (lower) and write its inverse T = L_kk^{-1}.  One CTA (16 x 16 threads) per batch element.
-// Register-resident right-looking sweep: thread (tx,ty) owns the 4 x 4 elements (ty+16i, tx+16k) of A and of T (start: I).  Per
-// column j the owners publish the (unscaled) column of A and the (unscaled) row j of T through double-buffered shared vectors, ONE
-// barrier, then every thread applies the rank-1 update to both register tiles:
-//   A[r,c] -= x_r x_c / d_j ;  T[j,:] /= L[j,j] ;  T[r,:] -= L[r,j] T[j,:] = x_r xT_c / d_j   (r > j)
-// (column j of L is final at step j, so the inverse sweep rides in the same loop: 64 barriers instead of 128).
-// info[b] = global index (1-based) of the first non-positive pivot, LAPACK potrf style; first failure wins.
+// Thread (tx,ty) owns the 4 x 4 elements (ty+16i, tx+16k) of A and of T (start: I) in registers.  The 64 columns are processed in
+// 8 MICRO-BLOCKS of 8: per micro-block
+//   A  the owners publish the 8 raw panel columns of A and the 8 current rows of T to shared memory                      (barrier)
+//   B  warp 0 factors the 8 x 8 diagonal micro-block (every lane redundantly, in registers: no shuffles on the dependent chain)
+//      and lanes 0..7 form its inverse D column by column                                                                (barrier)
+//   C  all threads: panel rows L[r, g0:g0+8) = A_raw[r, g0:g0+8) D^T  and the final rows T[g0:g0+8, :] = D T_cur          (barrier)
+//   D  all threads: rank-8 updates of their register tiles  A[r,c] -= L[r,:] . L[c,:] ,  T[r,:] -= L[r,:] T[g0:g0+8, :]
+// 24 barriers and 8 dependent 8 x 8 factorisations instead of 64 barriers with a square root each on the chain (the per-column
+// version took 25.7 us for 64 columns, ~750 clk per column; this one ~7 us).  Same arithmetic otherwise: right-looking, the
+// inverse sweep rides in the same loop because the rows of T of a micro-block are final as soon as its columns of L are.
+// info[b] = global index (1-based) of the first pivot <= piv_tol[b], LAPACK potrf style; first failure wins.
 // piv_tol[b]: pivots at or below it count as "not positive definite" (0 = LAPACK semantics; see k_build_kzz).
+constexpr int PF_MB = 8;   // micro-block width
 __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int64_t ld, int64_t sA, int kb,
                                                      double* __restrict__ T, int64_t sT, int32_t* info,
-                                                     const double* __restrict__ piv_tol) {
-  __shared__ double xch[2][NB], xtr[2][NB];
-  __shared__ double Ls[NB][NB + 1];
+                                                     const double* __restrict__ piv_tol, long long* dbg = nullptr) {
+#define PF_STAMP(slot) do { if (dbg && tid == 0 && blockIdx.x == 0) dbg[slot] = clock64(); } while (0)
+  __shared__ double Praw[NB][PF_MB + 1];     // raw panel columns (rows >= g0 used)
+  __shared__ double Pnew[NB][PF_MB + 1];     // L[:, g0:g0+8) (0 above the diagonal)
+  __shared__ double Tcur[PF_MB][NB + 1];     // current rows g0..g0+7 of T
+  __shared__ double Tfin[PF_MB][NB + 1];     // final rows g0..g0+7 of T
+  __shared__ double Ldd[PF_MB][PF_MB + 1], Dd[PF_MB][PF_MB + 1];
   __shared__ int bad;
-  const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
   double* Ab = A + b * sA + (int64_t)kb * NB * (ld + 1);
   const double tol = piv_tol ? piv_tol[b] : 0.0;
   double a[4][4], t[4][4];
@@ -36,71 +46,169 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
       t[i][k] = (r == c) ? 1.0 : 0.0;
     }
   if (tid == 0) bad = 0;
+  PF_STAMP(0);
+  // owner tests are by VALUE (column / row index against g0) over the unrolled 4 x 4 register tile: no run-time register indexing, so
+  // the micro-block loop may stay rolled (measured: 32 k clk per block warm) or be unrolled (26 k clk, 4.6 x the code): unrolled
 #pragma unroll
-  for (int kj = 0; kj < 4; ++kj) {
-    for (int tj = 0; tj < 16; ++tj) {
-      const int j = kj * 16 + tj;
-      double* x = xch[j & 1];
-      double* xt = xtr[j & 1];
-      if (tx == tj) {
+  for (int jb = 0; jb < NB / PF_MB; ++jb) {
+    const int g0 = jb * PF_MB;
+    if (jb == 1) PF_STAMP(1);
+    // ---- A: publish the raw panel columns g0..g0+7 and the current T rows g0..g0+7
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[ty + 16 * i] = a[i][kj];
+    for (int k = 0; k < 4; ++k) {
+      const int c = tx + 16 * k;
+      if (c >= g0 && c < g0 + PF_MB) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Praw[ty + 16 * i][c - g0] = a[i][k];
       }
-      if (ty == tj) {
+    }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) xt[tx + 16 * k] = t[kj][k];
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 16 * i;
+      if (r >= g0 && r < g0 + PF_MB) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Tcur[r - g0][tx + 16 * k] = t[i][k];
       }
-      __syncthreads();
-      const double dj = x[j];
-      if (!(dj > tol) && tid == 0 && bad == 0) bad = j + 1;
-      // one reciprocal square root on the per-column critical path instead of a square root followed by a division
-      // (each ~100+ clk of dependent FP64 latency, 64 columns deep): inv = rsqrt(dj) (<= 1 ulp), piv = dj * inv
-      const double inv = rsqrt(dj);
-      const double piv = dj * inv, dinv = inv * inv;
-      if (tx == tj) {
+    }
+    __syncthreads();
+    if (jb == 1) PF_STAMP(2);
+    // ---- B: 8 x 8 diagonal micro-block, warp 0
+    if (tid < 32) {
+      double v[PF_MB][PF_MB], inv[PF_MB];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = ty + 16 * i;
-          Ls[r][j] = (r > j) ? a[i][kj] * inv : ((r == j) ? piv : 0.0);
+      for (int r = 0; r < PF_MB; ++r)
+#pragma unroll
+        for (int c = 0; c < PF_MB; ++c) v[r][c] = (c <= r) ? Praw[g0 + r][c] : 0.0;
+      int first_bad = 0;
+#pragma unroll
+      for (int j = 0; j < PF_MB; ++j) {
+        const double dj = v[j][j];
+        if (!(dj > tol) && first_bad == 0) first_bad = g0 + j + 1;
+        inv[j] = rsqrt(dj);            // one reciprocal square root on the chain (<= 1 ulp): L_jj = d * inv, column scaled by inv
+        v[j][j] = dj * inv[j];
+#pragma unroll
+        for (int r = j + 1; r < PF_MB; ++r) v[r][j] *= inv[j];
+#pragma unroll
+        for (int c = j + 1; c < PF_MB; ++c)
+#pragma unroll
+          for (int r = c; r < PF_MB; ++r) v[r][c] = fma(-v[r][j], v[c][j], v[r][c]);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < PF_MB; ++r)
+#pragma unroll
+          for (int c = 0; c < PF_MB; ++c) Ldd[r][c] = (c <= r) ? v[r][c] : 0.0;
+        if (first_bad && bad == 0) bad = first_bad;
+      }
+      if (lane < PF_MB) {   // column `lane` of D = L_dd^{-1} by forward substitution (1 / L_ii = inv[i])
+        double x[PF_MB];
+#pragma unroll
+        for (int i = 0; i < PF_MB; ++i) {
+          double sacc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+          for (int k = 0; k < i; ++k) sacc = fma(-v[i][k], (k >= lane) ? x[k] : 0.0, sacc);
+          x[i] = (i >= lane) ? sacc * inv[i] : 0.0;
         }
-      }
-      if (ty == tj) {   // row j of T is final
 #pragma unroll
-        for (int k = 0; k < 4; ++k) t[kj][k] *= inv;
+        for (int i = 0; i < PF_MB; ++i) Dd[i][lane] = x[i];
       }
-      double xr[4], xc[4], xtc[4];
+    }
+    if (jb == 1) PF_STAMP(3);
+    __syncthreads();
+    if (jb == 1) PF_STAMP(4);
+    // ---- C: panel rows and final T rows
+    {
+      const int r = tid >> 2, q0 = (tid & 3) * 2;   // row r, outputs q0, q0 + 1
+      double o0 = 0.0, o1 = 0.0;
+      if (r >= g0 + PF_MB) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xr[i] = x[ty + 16 * i];
+        for (int pq = 0; pq < PF_MB; ++pq) {
+          const double x = Praw[r][pq];
+          o0 = fma(x, Dd[q0][pq], o0);         // D is lower triangular: entries with pq > q are zero
+          o1 = fma(x, Dd[q0 + 1][pq], o1);
+        }
+      } else if (r >= g0) {
+        o0 = Ldd[r - g0][q0];
+        o1 = Ldd[r - g0][q0 + 1];
+      }
+      Pnew[r][q0] = o0;
+      Pnew[r][q0 + 1] = o1;
+      const int q = tid >> 5, c0 = (tid & 31) * 2;  // T row g0 + q, columns c0, c0 + 1
+      double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+      for (int pq = 0; pq < PF_MB; ++pq) {
+        const double dq = Dd[q][pq];
+        u0 = fma(dq, Tcur[pq][c0], u0);
+        u1 = fma(dq, Tcur[pq][c0 + 1], u1);
+      }
+      Tfin[q][c0] = u0;
+      Tfin[q][c0 + 1] = u1;
+    }
+    __syncthreads();
+    if (jb == 1) PF_STAMP(5);
+    // ---- D: rank-8 updates of the register tiles
+    {
+      double lr[4][PF_MB];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < PF_MB; ++q) lr[i][q] = Pnew[ty + 16 * i][q];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        xc[k] = x[tx + 16 * k] * dinv;
-        xtc[k] = xt[tx + 16 * k] * dinv;
-      }
+        const int c = tx + 16 * k;
+        if (c >= g0 + PF_MB) {                    // trailing columns of A (lower part: r >= c)
+          double lc[PF_MB];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k >= kj && tx + 16 * k > j) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a[i][k] = fma(-xr[i], xc[k], a[i][k]);
-        }
-        if (k <= kj && tx + 16 * k <= j) {   // T[j, c] is zero beyond c = j
+          for (int q = 0; q < PF_MB; ++q) lc[q] = Pnew[c][q];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (i >= kj && ty + 16 * i > j) t[i][k] = fma(-xr[i], xtc[k], t[i][k]);
+            if (i >= k) {
+#pragma unroll
+              for (int q = 0; q < PF_MB; ++q) a[i][k] = fma(-lr[i][q], lc[q], a[i][k]);
+            }
+        } else {                                  // T[r, c], c < g0 + 8, for the rows below the micro-block
+          double tc[PF_MB];
+#pragma unroll
+          for (int q = 0; q < PF_MB; ++q) tc[q] = Tfin[q][c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (ty + 16 * i >= g0 + PF_MB) {
+#pragma unroll
+              for (int q = 0; q < PF_MB; ++q) t[i][k] = fma(-lr[i][q], tc[q], t[i][k]);
+            }
+          // final values of the finished columns of L go back into the register tile of their owner
+          if (c >= g0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i][k] = Pnew[ty + 16 * i][c - g0];
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {   // ... and the final rows of T
+        const int r = ty + 16 * i;
+        if (r >= g0 && r < g0 + PF_MB) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t[i][k] = Tfin[r - g0][tx + 16 * k];
         }
       }
     }
+    // the next publish writes Praw / Tcur, which nobody reads in phase D; Pnew / Tfin are rewritten only after two more barriers
+    if (jb == 1) PF_STAMP(6);
   }
-  __syncthreads();
+  PF_STAMP(7);
   double* Tb = T + b * sT + (int64_t)kb * NB * NB;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int r = ty + 16 * i, c = tx + 16 * k;
-      Ab[(int64_t)r * ld + c] = (c <= r) ? Ls[r][c] : 0.0;
+      Ab[(int64_t)r * ld + c] = (c <= r) ? a[i][k] : 0.0;
       Tb[r * NB + c] = (c <= r) ? t[i][k] : 0.0;
     }
+  __syncthreads();
+  PF_STAMP(8);
   if (tid == 0 && bad && info[b] == 0) info[b] = kb * NB + bad;
+#undef PF_STAMP
 }
 
 // One right-looking step of the blocked Cholesky after the diagonal block kb has been factored (k_potf2_trti2: T = L_kk^{-1}):

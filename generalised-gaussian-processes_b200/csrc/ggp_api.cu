@@ -96,6 +96,7 @@ struct ggp_handle {
   cudaStream_t cap_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second stream for the independent product chain of the finish section (fork / join by events)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool aux_pending = false;            // work of the last finish() is still running on aux_stream: join before its buffers are touched
   int32_t* info_ws = nullptr;
   double* ysc = nullptr;
   double* rk_part = nullptr;
@@ -531,6 +532,18 @@ static bool use_i8(const ggp_handle* h, const ggp_cfg* cfg, int d, int batch) {
          h->arena_i8 != nullptr;
 }
 
+// The Kzz-part chain of ggp_sgpr_finish (G_zz = -1/2 L^{-T} Gbar L^{-1}, its reduction against dKzz/dtheta, the assembly of grad_mm) is
+// not on the critical path: pass 2 only needs Q and u.  It runs on the handle's auxiliary stream NEXT TO pass 2 (whose one-launch
+// plans leave a few SMs free: 8 x 18 = 144 CTAs on 148 SMs) and is joined when pass 2 has been enqueued -- or by the next entry point
+// that touches its buffers.  Legal under stream capture (fork and join both lie inside the captured evaluation).
+static int join_aux(ggp_handle* h, cudaStream_t st) {
+  if (h->aux_pending) {
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    h->aux_pending = false;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -595,6 +608,8 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   if (m <= 0 || d <= 0 || batch <= 0 || n_local < 0) return fail(-2, "ggp_reserve: bad shape");
   if ((size_t)(2 * KT_N * d + d) * 8 > 200 * 1024) return fail(-3, "ggp_reserve: input dimension d too large");
   CK(cudaSetDevice(h->device));
+  if (h->aux_stream) CK(cudaStreamSynchronize(h->aux_stream));
+  h->aux_pending = false;
   Plan p = make_plan(cfg, n_local, m, d, batch, h->sm_count);
   for (auto& c : h->chol_graphs) cudaGraphExecDestroy(c.exec);
   h->chol_graphs.clear();
@@ -711,6 +726,7 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   const int Mp = h->Mp;
   h->kc_valid = false;
   h->atq_valid = false;
+  RUN(join_aux(h, st));
   ProfScope ps(h, st, CAT_MM);
   k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp, h->piv_tol);
   CKL();
@@ -935,6 +951,7 @@ int ggp_sgpr_predict_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, co
   h->kc_valid = false;   // the chunk buffers are reused below
   h->pf_valid = false;
   h->atq_valid = false;
+  RUN(join_aux(h, st));
   CK(cudaMemsetAsync(h->Spart, 0, (size_t)batch * splits * sM * 8, st));
   CK(cudaMemsetAsync(h->bvec, 0, (size_t)batch * Mp * 8, st));
   CK(cudaMemsetAsync(h->yty, 0, 256, st));
@@ -970,6 +987,7 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   const int64_t sM = (int64_t)Mp * Mp, sP = (int64_t)m * m + m + 3, sG = (int64_t)d + 2 + (int64_t)m * d;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
   const dim3 gv((m + 7) / 8, batch);
+  RUN(join_aux(h, st));
   ProfScope ps(h, st, CAT_MM);
   k_make_B<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Bm, sM);
   CKL();
@@ -1004,12 +1022,11 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   // (Not P = Linv^T PA Linv applied to Kzx, SURVEY R5 as written: P has entries of size 1 / lambda_min(Kzz) and P Kzx cancels down by
   // cond(Kzz) -- 1e-8 .. 2e-6 of the gradient at the headline Kzz in float64 against an extended-precision evaluation, whereas Q A,
   // which is what autograd through the triangular solve computes, loses cond(L) eps: tests/test_oracle_hp.py)
-  // The two chains are independent and a 1024^3 product fills only 64 of the 148 SMs (64 tiles of 128 x 128): the Gzz chain runs on
-  // the handle's auxiliary stream (scratch Wk, free outside the triangular inverse) next to the P chain, fork / join by events
-  // (legal under stream capture: the auxiliary stream joins the capture through the fork event and rejoins before it ends).
-  const bool two_chains = batch * ((m + BM - 1) / BM) * ((m + BN - 1) / BN) <= h->sm_count / 2 + 16 && !getenv("GGP_MM_ONE_STREAM");
+  // The Gzz chain (scratch Wk, free outside the triangular inverse) and everything that hangs off it goes to the auxiliary stream:
+  // see join_aux.
+  const bool side = !getenv("GGP_MM_ONE_STREAM");
   cudaStream_t st2 = st;
-  if (two_chains) {
+  if (side) {
     if (!h->aux_stream) {
       CK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -1019,19 +1036,24 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
     CK(cudaEventRecord(h->ev_fork, st));
     CK(cudaStreamWaitEvent(st2, h->ev_fork, 0));
   }
-  double* T2 = two_chains ? h->Wk : h->T1;
+  double* T2 = side ? h->Wk : h->T1;
   RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
   RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->Gbar, Mp, sM, T2, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
   RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(T2, Mp, sM, h->LinvT, Mp, sM, h->Gzz, Mp, sM, m, m, m, -0.5, 0.0, KM_B_UPPER), batch));
-  if (two_chains) {
+  k_grad_kzz_rows<<<gv, 256, 0, st2>>>(h->Gzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, grad_mm + d + 2, sG);
+  CKL();
+  k_grad_mm_final<<<batch, 256, 0, st2>>>(h->rowacc, m, d, theta, partial, sP, h->ds2, grad_mm, sG, h->rk);
+  CKL();
+  if (side) {
     CK(cudaEventRecord(h->ev_join, st2));
-    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    h->aux_pending = true;
   }
-  k_grad_kzz_rows<<<gv, 256, 0, st>>>(h->Gzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, grad_mm + d + 2, sG);
-  CKL();
-  k_grad_mm_final<<<batch, 256, 0, st>>>(h->rowacc, m, d, theta, partial, sP, h->ds2, grad_mm, sG, h->rk);
-  CKL();
   return 0;
+}
+
+int ggp_sgpr_join(ggp_handle_t* h, void* stream) {
+  if (!h) return fail(-1, "ggp_sgpr_join: handle is NULL");
+  return join_aux(h, (cudaStream_t)stream);
 }
 
 int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, const double* y, int64_t n_local,
@@ -1153,7 +1175,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   }
   k_grad_from_moments<<<batch, 256, 0, st>>>(h->mom_acc, m, d, Z, theta, grad_partial, sG, h->rk, kind != GGP_KERNEL_RBF ? 1 : 0);
   CKL();
-  return 0;
+  return join_aux(h, st);   // grad_mm of the finish() of this evaluation is complete from here on
 }
 
 int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* Xs, int64_t ns, const double* Z,
@@ -1166,6 +1188,7 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nc * Mp;
   h->kc_valid = false;   // the chunk buffers are scratch here
   h->atq_valid = false;
+  RUN(join_aux(h, st));
   // t^T[rows x m] = (k(X*, Z) Linv^T) LBinv^T of the test rows [r0, r0 + nv) into At + off (a^T) and Kc + off (t^T)
   auto rows_t = [&](int64_t r0, int nv, int64_t off) -> int {
     RUN(build_chunk(h, st, Xs + r0 * d, nv, d, Z, m, theta, kind, batch, h->Kc + off, sC));
@@ -1217,6 +1240,7 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nsv * Mp, sG = (int64_t)d + 2 + (int64_t)m * d + m + (int64_t)m * m;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16), g16one(Mp / 16, Mp / 16, 1);
   const bool hasS = qLs != nullptr;
+  RUN(join_aux(h, st));
   double *Kc = h->sv[0], *aT = h->sv[1], *wT = h->sv[2], *SL = h->sv[3], *tA = h->sv[4], *tB = h->Kc, *tC = h->At;
   double *LsP = h->Bm, *LsT = h->LBinv, *dLsraw = h->Binv, *Gb = h->PA, *Hm = h->Gbar, *dKzz = h->Gzz, *gk = h->P,
          *dZzz = h->LBinvT, *dm = h->bvec, *scal = h->cvec, *mom = h->mom_acc;
@@ -1319,6 +1343,7 @@ int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nsv * Mp;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
   const bool hasS = qLs != nullptr;
+  RUN(join_aux(h, st));
   double *Kc = h->sv[0], *aT = h->sv[1], *wT = h->sv[2], *LsP = h->Bm, *LsT = h->LBinv;
   k_build_kzz<<<g16, b16, 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, sM, h->piv_tol);
   CKL();
@@ -1347,8 +1372,25 @@ int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
 
 int ggp_chol_batched(ggp_handle_t* h, void* stream, double* a, double* linv, int m, int batch, int32_t* info) {
   if (!h || !a || !info) return fail(-1, "ggp_chol_batched: NULL argument");
+  if (getenv("GGP_POTF2_TIMELINE") && h->arena && h->m == m) {   // developer switch: clock64 stamps of one diagonal-block factorisation
+    long long* dbg = nullptr;
+    CK(cudaMalloc((void**)&dbg, 16 * sizeof(long long)));
+    CK(cudaMemset(dbg, 0, 16 * sizeof(long long)));
+    const int Mp = h->Mp;
+    k_pad_copy<<<dim3(Mp / 16, Mp / 16, 1), dim3(16, 16), 0, (cudaStream_t)stream>>>(a, m, h->L, Mp, (int64_t)Mp * Mp, 1);
+    CK(cudaMemsetAsync(h->piv_tol, 0, sizeof(double) * batch, (cudaStream_t)stream));
+    for (int r = 0; r < 2; ++r)
+      k_potf2_trti2<<<1, 256, POTF2_SMEM, (cudaStream_t)stream>>>(h->L, Mp, (int64_t)Mp * Mp, 0, h->Tblk, (int64_t)Mp * Mp, info, h->piv_tol, dbg);
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    long long hb[16];
+    CK(cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "== potf2 timeline (clk): load %lld | micro-block 1: publish %lld, wait %lld... B(8x8 factor) %lld, barrier %lld, C %lld, D %lld | all 8 blocks %lld, store %lld\n",
+            hb[1] - hb[0] - (hb[6] - hb[1]) * 0, hb[2] - hb[1], 0ll, hb[3] - hb[2], hb[4] - hb[3], hb[5] - hb[4], hb[6] - hb[5], hb[7] - hb[0], hb[8] - hb[7]);
+    cudaFree(dbg);
+  }
   if (!(h->arena && h->m == m && batch <= h->batch)) RUN(ggp_reserve(h, nullptr, 0, m, std::max(1, h->d), batch));
   cudaStream_t st = (cudaStream_t)stream;
+  RUN(join_aux(h, st));
   const int Mp = h->Mp;
   const int64_t sM = (int64_t)Mp * Mp;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
