@@ -17,10 +17,10 @@ c_int_p = ctypes.c_void_p
 
 class GgpCfg(ctypes.Structure):
     _fields_ = [("kernel", ctypes.c_int32), ("precision", ctypes.c_int32),
-                ("chunk_rows", ctypes.c_int32), ("tile_cache_mib", ctypes.c_int32)]
+                ("chunk_rows", ctypes.c_int32), ("tile_cache_mib", ctypes.c_int32), ("kernel_param", ctypes.c_double)]
 
 
-KERNELS = {"rbf": 0, "matern32": 1, "matern52": 2}
+KERNELS = {"rbf": 0, "matern32": 1, "matern52": 2, "rq": 3}
 PRECISIONS = {"fp64": 0, "tf32x3": 1, "fp64_i8": 2}
 LIKELIHOODS = {"gaussian": 0, "bernoulli": 1}
 

@@ -499,7 +499,7 @@ __global__ void k_make_PA_Gbar(const double* __restrict__ partial, int64_t sP, i
 // grid (ceil(M/8), batch), block 256
 __global__ void __launch_bounds__(256) k_grad_kzz_rows(const double* __restrict__ Gzz, int Mp, int64_t sMat,
                                                        const double* __restrict__ Z, int M, int d,
-                                                       const double* __restrict__ theta, int kind,
+                                                       const double* __restrict__ theta, KSpec kind,
                                                        double* __restrict__ rowacc /*[batch][M][d+1]*/,
                                                        double* __restrict__ dZ /*[batch][M][d], stride sG*/, int64_t sG) {
   const int b = blockIdx.y, i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(256) k_reduce_moments(const double* __restrict
 __global__ void __launch_bounds__(256) k_grad_from_moments(const double* __restrict__ mom, int M, int d,
                                                            const double* __restrict__ Z, const double* __restrict__ theta,
                                                            double* __restrict__ grad, int64_t sG, const double* __restrict__ rk,
-                                                           int deriv_weighted) {
+                                                           int deriv_weighted, int64_t srk = 0) {
   __shared__ double red[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int nq = 2 * d + 1;
@@ -638,8 +638,9 @@ __global__ void __launch_bounds__(256) k_grad_from_moments(const double* __restr
   for (int i = tid; i < M; i += 256) s += mb[(int64_t)i * nq];
   s = block_sum<256>(s, red);
   if (tid == 0) {
-    // with rk the sum(G o K) term of dF/dsf2 is added ONCE by the m x m section (k_grad_mm_final), not per row shard
-    grad[b * sG + d] = rk ? 0.0 : s / th[d];
+    // srk == 0 (SGPR): with rk the sum(G o K) term of dF/dsf2 is added ONCE by the m x m section (k_grad_mm_final), not per row shard;
+    // srk > 0 (SVGP, no sharding): rk[b * srk] is the k-weighted total accumulated beside the moments and is used here
+    grad[b * sG + d] = rk ? (srk > 0 ? rk[b * srk] / th[d] : 0.0) : s / th[d];
     grad[b * sG + d + 1] = 0.0;
   }
 }

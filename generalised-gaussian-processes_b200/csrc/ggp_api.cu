@@ -60,11 +60,13 @@ struct ggp_handle {
   bool kc_valid = false;
   const void *kc_X = nullptr, *kc_Z = nullptr, *kc_theta = nullptr;
   int64_t kc_n = 0;
-  int kc_batch = 0, kc_kind = 0;
+  int kc_batch = 0;
+  KSpec kc_kind{0, 0.0};
   bool pf_valid = false;        // ggp_sgpr_prefetch_tiles filled the cache for the key below; the next pass 1 with that key skips its builds
   const void *pf_X = nullptr, *pf_Z = nullptr, *pf_theta = nullptr;
   int64_t pf_n = 0;
-  int pf_batch = 0, pf_kind = 0;
+  int pf_batch = 0;
+  KSpec pf_kind{0, 0.0};
   int64_t pf_next_row = 0;      // ggp_sgpr_prefetch_tiles_part: rows [0, pf_next_row) are built
   double *sv[5] = {0, 0, 0, 0, 0}, *rowout = 0;
   // int8 digit planes of the sliced-integer path (GGP_PREC_FP64_I8; gemm_i8.cuh)
@@ -722,7 +724,7 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   if (!h || !Z || !theta || !info) return fail(-1, "ggp_sgpr_factor: NULL argument");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_factor: handle not reserved for this shape");
   cudaStream_t st = (cudaStream_t)stream;
-  const int kind = cfg ? cfg->kernel : 0;
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
   const int Mp = h->Mp;
   h->kc_valid = false;
   h->atq_valid = false;
@@ -734,7 +736,7 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
 }
 
 static int build_chunk(ggp_handle* h, cudaStream_t st, const double* Xc, int nv, int d, const double* Z, int m,
-                       const double* theta, int kind, int batch, double* dst, int64_t sK) {
+                       const double* theta, KSpec kind, int batch, double* dst, int64_t sK) {
   const int Mp = h->Mp;
   dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
   const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
@@ -745,7 +747,7 @@ static int build_chunk(ggp_handle* h, cudaStream_t st, const double* Xc, int nv,
 
 // sliced-integer path: FP64 tile + digit planes in one kernel
 static int build_chunk_i8(ggp_handle* h, cudaStream_t st, const double* Xc, int64_t nv, int d, const double* Z, int m,
-                          const double* theta, int kind, double* Kc, int8_t* Kq, int64_t plane) {
+                          const double* theta, KSpec kind, double* Kc, int8_t* Kq, int64_t plane) {
   const int Mp = h->Mp;
   const int64_t rows_per_cta = (int64_t)KT_N * KT_RT;
   dim3 grid(Mp / KT_M, (unsigned)((nv + rows_per_cta - 1) / rows_per_cta));
@@ -760,7 +762,7 @@ int ggp_sgpr_prefetch_tiles_part(ggp_handle_t* h, const ggp_cfg* cfg, void* stre
   if (!h || !Z || !theta || (n_local > 0 && !X)) return fail(-1, "ggp_sgpr_prefetch_tiles: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_prefetch_tiles: handle not reserved for this shape");
   if (row0 < 0 || nrows < 0 || row0 + nrows > n_local) return fail(-3, "ggp_sgpr_prefetch_tiles_part: row range outside [0, n_local)");
-  const int kind = cfg ? cfg->kernel : 0;
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
   if (row0 == 0) { h->pf_valid = false; h->pf_next_row = 0; }
   if (!h->kc_all || n_local <= 0) return 0;   // no tile cache: pass 1 builds chunk by chunk as before
   if (row0 != h->pf_next_row) { h->pf_valid = false; return fail(-3, "ggp_sgpr_prefetch_tiles_part: parts must be issued in ascending row order"); }
@@ -795,7 +797,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
                    const double* Z, const double* theta, int m, int d, int batch, double* partial) {
   if (!h || !Z || !theta || !partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass1: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_pass1: handle not reserved for this shape");
-  const int kind = cfg ? cfg->kernel : 0;
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
   if (cfg && cfg->precision == GGP_PREC_TF32X3)
     return fail(-3, "ggp_sgpr_pass1: GGP_PREC_TF32X3 is not offered: it cannot meet the gradient tolerance (DESIGN.md 4b); use "
                     "GGP_PREC_FP64 (DMMA) or GGP_PREC_FP64_I8 (exact int8 slicing on tcgen05)");
@@ -811,7 +813,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   const bool i8 = use_i8(h, cfg, d, batch);
   // tiles already in the cache (ggp_sgpr_prefetch_tiles with the same operands, typically overlapped with the factorisation)
   const bool prefetched = h->kc_all && h->pf_valid && h->pf_X == X && h->pf_Z == Z && h->pf_theta == theta && h->pf_n == n_local &&
-                          h->pf_batch == batch && h->pf_kind == kind && (!i8 || h->kq_all);
+                          h->pf_batch == batch && h->pf_kind.kind == kind.kind && h->pf_kind.p == kind.p && (!i8 || h->kq_all);
   h->pf_valid = false;
   h->atq_valid = false;
   if (i8) {
@@ -944,7 +946,7 @@ int ggp_sgpr_predict_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, co
                            const double* Z, const double* theta, int m, int d, int batch, double* partial) {
   if (!h || !Z || !theta || !partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_predict_pass1: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_predict_pass1: handle not reserved for this shape");
-  const int kind = cfg ? cfg->kernel : 0;
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc, splits = h->splits;
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nc * Mp;
@@ -980,8 +982,8 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   if (!h || !Z || !theta || !partial || !bound || !info) return fail(-1, "ggp_sgpr_finish: NULL argument");
   if (need_grad && !grad_mm) return fail(-1, "ggp_sgpr_finish: grad_mm is NULL");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_finish: handle not reserved for this shape");
-  const int kind = cfg ? cfg->kernel : 0;
-  if (kind < GGP_KERNEL_RBF || kind > GGP_KERNEL_MATERN52) return fail(-3, "ggp_sgpr_finish: unknown kernel");
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (kind.kind < GGP_KERNEL_RBF || kind.kind > GGP_KERNEL_RQ || (kind.kind == GGP_KERNEL_RQ && !(kind.p > 0.0))) return fail(-3, "ggp_sgpr_finish: unknown kernel");
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp;
   const int64_t sM = (int64_t)Mp * Mp, sP = (int64_t)m * m + m + 3, sG = (int64_t)d + 2 + (int64_t)m * d;
@@ -1060,8 +1062,8 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
                    const double* Z, const double* theta, int m, int d, int batch, double* grad_partial) {
   if (!h || !Z || !theta || !grad_partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass2: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_pass2: handle not reserved for this shape");
-  const int kind = cfg ? cfg->kernel : 0;
-  if (kind < GGP_KERNEL_RBF || kind > GGP_KERNEL_MATERN52) return fail(-3, "ggp_sgpr_pass2: unknown kernel");
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (kind.kind < GGP_KERNEL_RBF || kind.kind > GGP_KERNEL_RQ || (kind.kind == GGP_KERNEL_RQ && !(kind.p > 0.0))) return fail(-3, "ggp_sgpr_pass2: unknown kernel");
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc, nq = 2 * d + 1;
   const int64_t sM = (int64_t)Mp * Mp, sG = (int64_t)d + 2 + (int64_t)m * d, sC = (int64_t)nc * Mp;
@@ -1069,7 +1071,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   CK(cudaMemsetAsync(h->mom_acc, 0, (size_t)batch * cnt * 8, st));
   // the tiles cached by the pass 1 of this evaluation (same operands, same handle, no factor() since) are reused as they are
   const bool cached = h->kc_all && h->kc_valid && h->kc_X == X && h->kc_Z == Z && h->kc_theta == theta && h->kc_n == n_local &&
-                      h->kc_batch == batch && h->kc_kind == kind;
+                      h->kc_batch == batch && h->kc_kind.kind == kind.kind && h->kc_kind.p == kind.p;
   const bool i8 = use_i8(h, cfg, d, batch);
   // dF/dKzx = Q A + u y^T with Q = L^{-T} P_A (h->P, from finish) and A = L^{-1} Kzx: the streamed operand of the backward product is
   // A^T -- on the sliced-integer path the digit planes the triangular multiply of pass 1 left in atq_all (read MN-major, no second
@@ -1182,7 +1184,7 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
                      const double* theta, int m, int d, int batch, int add_noise, double* mean, double* var, double* cov) {
   if (!h || !Xs || !Z || !theta || !mean || !var) return fail(-1, "ggp_sgpr_predict: NULL argument");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_predict: handle not reserved for this shape");
-  const int kind = cfg ? cfg->kernel : 0;
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc;
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nc * Mp;
@@ -1231,8 +1233,8 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
   if (!h || !xb || !yb || !Z || !qm || !theta || !jitter || !elbo || !info) return fail(-1, "ggp_svgp_elbo: NULL argument");
   if (need_grad && !grad) return fail(-1, "ggp_svgp_elbo: grad is NULL");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_svgp_elbo: handle not reserved for this shape");
-  const int kind = cfg ? cfg->kernel : 0;
-  if (need_grad && kind != GGP_KERNEL_RBF) return fail(-3, "ggp_svgp_elbo: gradients are implemented for GGP_KERNEL_RBF");
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (kind.kind < GGP_KERNEL_RBF || kind.kind > GGP_KERNEL_RQ || (kind.kind == GGP_KERNEL_RQ && !(kind.p > 0.0))) return fail(-3, "ggp_svgp_elbo: unknown kernel");
   const int nq = 2 * d + 1;
   if (nq > h->Mp) return fail(-3, "ggp_svgp_elbo: 2d+1 must not exceed the padded inducing count");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1308,6 +1310,18 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(tB, nvp, sC, tA, nvp, sC, Gb, Mp, sM, m, m, nv, 1.0, 1.0), batch));
     // dKc = GAT * Linv  (into wT's buffer) ;  mom += (dKc o Kc)^T [1, x, x^2]
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(SL, Mp, sC, h->LinvT, Mp, sM, wT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_UPPER), batch));
+    if (kind != GGP_KERNEL_RBF) {
+      // Matern / RQ: the moments are weighted by dk/d(d2) instead of k, so (1) the k-weighted total sum(dKc o Kc) of dF/dsf2 is taken
+      // here, (2) the k(X,Z) tile (consumed above) is overwritten by the dk/d(d2) tile
+      k_sum_prod_partial<<<dim3(RK_BLOCKS, batch), 256, 0, st>>>(wT, Kc, Mp, sC, nv, m, h->rk_part, RK_BLOCKS);
+      CKL();
+      k_sum_prod_final<<<batch, 1, 0, st>>>(h->rk_part, RK_BLOCKS, scal);
+      CKL();
+      dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
+      const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
+      k_build_kc<<<grid, KT_THREADS, smem, st>>>(Xc, nv, nv, d, Z, m, theta, kind, Kc, Mp, sC, 1);
+      CKL();
+    }
     k_transpose_rect<<<gT, bT, 0, st>>>(wT, Kc, Mp, sC, nullptr, 0, nv, Mp, tC, nvp, sC);
     CKL();
     k_phiT<<<dim3((nvp + 255) / 256, nq), 256, 0, st>>>(Xc, nv, d, tA, nvp);
@@ -1322,7 +1336,8 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->T1, Mp, sM, h->LinvT, Mp, sM, dKzz, Mp, sM, m, m, m, -1.0, 0.0, KM_B_UPPER), batch));
     k_grad_kzz_rows<<<dim3((m + 7) / 8, batch), 256, 0, st>>>(dKzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, dZzz + d + 2, sM);
     CKL();
-    k_grad_from_moments<<<batch, 256, 0, st>>>(mom, m, d, Z, theta, gk, sM, nullptr, 0);
+    if (kind != GGP_KERNEL_RBF) k_grad_from_moments<<<batch, 256, 0, st>>>(mom, m, d, Z, theta, gk, sM, scal + 3, 1, 4);
+    else k_grad_from_moments<<<batch, 256, 0, st>>>(mom, m, d, Z, theta, gk, sM, nullptr, 0);
     CKL();
   }
   k_svgp_final<<<batch, 256, 0, st>>>(scal, gk, sM, h->rowacc, dZzz, dm, Mp, dLsraw, sM, Mp, qm, sqm, qLs, theta, m, d, kl_scale, need_grad,
@@ -1337,7 +1352,7 @@ int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
   const int64_t sqm = qm_batched ? m : 0;
   if (!h || !xs || !Z || !qm || !theta || !jitter || !mean || !var || !info) return fail(-1, "ggp_svgp_predict: NULL argument");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_svgp_predict: handle not reserved for this shape");
-  const int kind = cfg ? cfg->kernel : 0;
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nsv = h->nsv;
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nsv * Mp;
@@ -1498,7 +1513,7 @@ int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const d
                       int64_t n2, const double* theta, int d, double* out) {
   if (!h || !X1 || !X2 || !theta || !out) return fail(-1, "ggp_kernel_matrix: NULL argument");
   if ((size_t)(2 * KT_N * d + d) * 8 > 200 * 1024) return fail(-3, "ggp_kernel_matrix: d too large");
-  const int kind = cfg ? cfg->kernel : 0;
+  const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
   dim3 grid((unsigned)((n2 + KT_M - 1) / KT_M), (unsigned)((n1 + KT_N - 1) / KT_N), 1);
   const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
   k_build_kc<<<grid, KT_THREADS, smem, (cudaStream_t)stream>>>(X1, (int)n1, (int)n1, d, X2, (int)n2, theta, kind, out, n2, 0);

@@ -10,9 +10,20 @@ namespace ggp {
 
 constexpr int KT_N = 64, KT_M = 64, KT_THREADS = 256;
 
-// value of the stationary kernel given scaled squared distance d2 (>= 0).  kind: 0 rbf, 1 matern32, 2 matern52
-__device__ __forceinline__ double kval(int kind, double sf2, double d2) {
+// kernel kind + its shape parameter (alpha of the rational-quadratic kernel; unused otherwise)
+struct KSpec {
+  int kind;
+  double p;
+  __host__ __device__ bool operator!=(int k) const { return kind != k; }
+  __host__ __device__ bool operator==(int k) const { return kind == k; }
+};
+
+// value of the stationary kernel given scaled squared distance d2 (>= 0).  kind: 0 rbf, 1 matern32, 2 matern52,
+// 3 rational quadratic (1 + d2 / (2 alpha))^(-alpha)  (gpytorch RQKernel / pymc3 RatQuad, experiments/co2_bayesian_sgpr_hmc.py:77,127)
+__device__ __forceinline__ double kval(KSpec ks, double sf2, double d2) {
+  const int kind = ks.kind;
   if (kind == 0) return sf2 * exp(-0.5 * d2);
+  if (kind == 3) return sf2 * exp(-ks.p * log1p(d2 / (2.0 * ks.p)));
   const double r = sqrt(d2);
   if (kind == 1) {
     const double a = 1.7320508075688772;
@@ -22,8 +33,10 @@ __device__ __forceinline__ double kval(int kind, double sf2, double d2) {
   return sf2 * (1.0 + a * r + (5.0 / 3.0) * d2) * exp(-a * r);
 }
 // dk/d(d2)
-__device__ __forceinline__ double kgrad(int kind, double sf2, double d2) {
+__device__ __forceinline__ double kgrad(KSpec ks, double sf2, double d2) {
+  const int kind = ks.kind;
   if (kind == 0) return -0.5 * sf2 * exp(-0.5 * d2);
+  if (kind == 3) return -0.5 * sf2 * exp(-(ks.p + 1.0) * log1p(d2 / (2.0 * ks.p)));
   const double r = sqrt(d2);
   if (kind == 1) return -1.5 * sf2 * exp(-1.7320508075688772 * r);
   const double a = 2.23606797749979;
@@ -117,8 +130,10 @@ __device__ __forceinline__ double exp_neg(double x, const double2* __restrict__ 
   return __hiloint2double(__double2hiint(res) + ((ki >> 6) << 20), __double2loint(res));   // * 2^(ki >> 6), exponent stays > 0
 }
 // kval with the table exponential (streamed tile build of the sliced-integer path)
-__device__ __forceinline__ double kval_tab(int kind, double sf2, double d2, const double2* __restrict__ tab) {
+__device__ __forceinline__ double kval_tab(KSpec ks, double sf2, double d2, const double2* __restrict__ tab) {
+  const int kind = ks.kind;
   if (kind == 0) return sf2 * exp_neg(-0.5 * d2, tab);
+  if (kind == 3) return sf2 * exp_neg(-ks.p * log1p(d2 / (2.0 * ks.p)), tab);
   const double r = sqrt(d2);
   if (kind == 1) {
     const double a = 1.7320508075688772;
@@ -133,7 +148,7 @@ __device__ __forceinline__ double kval_tab(int kind, double sf2, double d2, cons
 // grid: (ceil(ldk/KT_M), ceil(n_fill/KT_N), batch)
 __global__ void __launch_bounds__(KT_THREADS) k_build_kc(const double* __restrict__ X, int n_valid, int n_fill, int d,
                                                         const double* __restrict__ Z, int M,
-                                                        const double* __restrict__ theta, int kind,
+                                                        const double* __restrict__ theta, KSpec kind,
                                                         double* __restrict__ Kc, int64_t ldk, int64_t sK, int deriv = 0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* xs = reinterpret_cast<double*>(smem_raw);   // [KT_N][d]
@@ -221,7 +236,7 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc(const double* __restric
 constexpr int KT_RT = 8;
 __global__ void __launch_bounds__(KT_THREADS) k_build_kc_i8(const double* __restrict__ X, int64_t n_valid,
                                                            int d, const double* __restrict__ Z, int M, const double* __restrict__ theta,
-                                                           int kind, double* __restrict__ Kc, int64_t ldk, int8_t* __restrict__ Kq,
+                                                           KSpec kind, double* __restrict__ Kc, int64_t ldk, int8_t* __restrict__ Kq,
                                                            int64_t ldq, int64_t plane) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* xs0 = reinterpret_cast<double*>(smem_raw);   // [2][KT_N][d]
@@ -328,7 +343,7 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc_i8(const double* __rest
 // means cond(Kzz) ~ 1e16.  The relative threshold makes the ladder deterministic; oracle/linalg.py applies the same rule.
 constexpr double GGP_PIVOT_RTOL = 1e-12;
 __global__ void k_build_kzz(const double* __restrict__ Z, int M, int Mp, int d, const double* __restrict__ theta,
-                            const double* __restrict__ jitter, int kind, double* __restrict__ Kzz, int64_t sK,
+                            const double* __restrict__ jitter, KSpec kind, double* __restrict__ Kzz, int64_t sK,
                             double* __restrict__ piv_tol = nullptr) {
   const int b = blockIdx.z;
   const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;

@@ -207,6 +207,26 @@ __global__ void k_transpose_rect(const double* __restrict__ in, const double* __
   }
 }
 
+// sum over (n < nv, i < M) of A[b][n][i] * B[b][n][i] in two deterministic stages (the k-weighted total sum(dKc o Kc) of dF/dsf2 when the
+// moments are weighted by dk/d(d2)): part[b][blk] over contiguous row slices, then scal[b][3] += sum_blk part[b][blk] in order
+__global__ void __launch_bounds__(256) k_sum_prod_partial(const double* __restrict__ A, const double* __restrict__ B, int64_t ld, int64_t sC,
+                                                          int nv, int M, double* __restrict__ part, int nblk) {
+  __shared__ double red[8];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int rows = (nv + nblk - 1) / nblk, r0 = blockIdx.x * rows, r1 = min(nv, r0 + rows);
+  double acc = 0.0;
+  for (int n = r0; n < r1; ++n)
+    for (int i = tid; i < M; i += 256) acc = fma(A[b * sC + (int64_t)n * ld + i], B[b * sC + (int64_t)n * ld + i], acc);
+  acc = block_sum<256>(acc, red);
+  if (tid == 0) part[(int64_t)b * nblk + blockIdx.x] = acc;
+}
+__global__ void k_sum_prod_final(const double* __restrict__ part, int nblk, double* __restrict__ scal) {
+  const int b = blockIdx.x;
+  double acc = 0.0;
+  for (int k = 0; k < nblk; ++k) acc += part[(int64_t)b * nblk + k];
+  scal[b * 4 + 3] += acc;
+}
+
 // PhiT[q][n] : q = 0 -> 1 ; 1..d -> x_n[q-1] ; d+1..2d -> x_n[q-1-d]^2 ; zero for n >= nv.   grid (ceil(ldo/256), nq)
 __global__ void k_phiT(const double* __restrict__ X, int nv, int d, double* __restrict__ PhiT, int64_t ldo) {
   const int n = blockIdx.x * 256 + threadIdx.x, q = blockIdx.y;

@@ -46,18 +46,18 @@ class Engine:
     _cache = {}
 
     @classmethod
-    def get(cls, device=None, kernel="rbf", precision="fp64", chunk_rows=0, tile_cache_mib=None):
+    def get(cls, device=None, kernel="rbf", precision="fp64", chunk_rows=0, tile_cache_mib=None, kernel_param=0.0):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         device = torch.device(device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        key = (device.index, kernel, precision, chunk_rows, tile_cache_mib)
+        key = (device.index, kernel, precision, chunk_rows, tile_cache_mib, float(kernel_param))
         if key not in cls._cache:
-            cls._cache[key] = cls(device, kernel, precision, chunk_rows, tile_cache_mib)
+            cls._cache[key] = cls(device, kernel, precision, chunk_rows, tile_cache_mib, kernel_param)
         return cls._cache[key]
 
-    def __init__(self, device, kernel="rbf", precision="fp64", chunk_rows=0, tile_cache_mib=None):
+    def __init__(self, device, kernel="rbf", precision="fp64", chunk_rows=0, tile_cache_mib=None, kernel_param=0.0):
         if not torch.cuda.is_available():
             raise RuntimeError("the sparse-GP hot path needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -67,9 +67,11 @@ class Engine:
             # tile_cache_mib=0 restores the strictly streaming behaviour (never more than chunk_rows x m of k(X,Z) alive)
             free_b, _ = torch.cuda.mem_get_info(torch.device(device))
             tile_cache_mib = int(min(32 * 1024, free_b // (4 * 1024 * 1024)))
-        self.cfg = GgpCfg(KERNELS[kernel], PRECISIONS[precision], int(chunk_rows), int(tile_cache_mib))
+        if kernel == "rq" and not kernel_param > 0:
+            raise ValueError("kernel='rq' needs kernel_param = alpha > 0")
+        self.cfg = GgpCfg(KERNELS[kernel], PRECISIONS[precision], int(chunk_rows), int(tile_cache_mib), float(kernel_param))
         # the FP64 DMMA plan on the same handle: an fp64_i8 engine evaluates on it when the jitter ladder had to engage (see sgpr_eval)
-        self.cfg_dmma = GgpCfg(KERNELS[kernel], PRECISIONS["fp64"], int(chunk_rows), int(tile_cache_mib))
+        self.cfg_dmma = GgpCfg(KERNELS[kernel], PRECISIONS["fp64"], int(chunk_rows), int(tile_cache_mib), float(kernel_param))
         self.ladder_levels = []
         h = ctypes.c_void_p()
         check(self.lib.ggp_create(ctypes.byref(h), self.device.index), "ggp_create")

@@ -26,7 +26,8 @@ extern "C" {
 
 typedef struct ggp_handle ggp_handle_t;
 
-enum { GGP_KERNEL_RBF = 0, GGP_KERNEL_MATERN32 = 1, GGP_KERNEL_MATERN52 = 2 };
+enum { GGP_KERNEL_RBF = 0, GGP_KERNEL_MATERN32 = 1, GGP_KERNEL_MATERN52 = 2,
+       GGP_KERNEL_RQ = 3 /* rational quadratic (1 + d2 / (2 alpha))^(-alpha), alpha = cfg.kernel_param (a constant of the evaluation) */ };
 /* GGP_PREC_FP64: FP64 tensor-core DMMA.  GGP_PREC_FP64_I8: the same contractions evaluated to FP64-class accuracy by exact integer
  * slicing (7 balanced radix-256 digits per operand, tcgen05.mma kind::i8, int32 TMEM accumulators; csrc/gemm_i8.cuh); used for the
  * streamed passes when batch == 1, the padded inducing count is in [128, 4096] and d <= 16, the DMMA path otherwise.
@@ -40,6 +41,7 @@ typedef struct {
   int32_t chunk_rows;  /* rows of X per streamed chunk; 0 = library default */
   int32_t tile_cache_mib; /* MiB of device memory the handle may use to keep the k(X_local,Z) tiles of pass1 for the pass2 of the
                              same evaluation (saves the second tile build); 0 = never materialise more than chunk_rows x m */
+  double kernel_param;    /* GGP_KERNEL_RQ: alpha > 0 (RQKernel / RatQuad, experiments/co2_bayesian_sgpr_hmc.py:77,127); else ignored */
 } ggp_cfg;
 
 int ggp_version(void);

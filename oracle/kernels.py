@@ -30,8 +30,14 @@ def scaled_sqdist_gpytorch(X1, X2, ell):
 
 
 def ard_kernel(X1, X2, ell, sf2, kind="rbf", gpytorch_order=False):
-    """k(x,z) for kind in {rbf, matern32, matern52}; sf2 = outputscale (a variance)."""
+    """k(x,z) for kind in {rbf, matern32, matern52, ("rq", alpha)}; sf2 = outputscale (a variance).
+    ("rq", alpha): rational quadratic (1 + d2 / (2 alpha))^(-alpha) -- gpytorch RQKernel / pymc3 RatQuad
+    (experiments/co2_bayesian_sgpr_hmc.py:77,127), alpha a constant of the evaluation."""
     d2 = scaled_sqdist_gpytorch(X1, X2, ell) if gpytorch_order else scaled_sqdist(X1, X2, ell)
+    if isinstance(kind, tuple):
+        assert kind[0] == "rq"
+        alpha = float(kind[1])
+        return sf2 * torch.pow(1.0 + d2 / (2.0 * alpha), -alpha)
     if kind == "rbf":
         return sf2 * torch.exp(-0.5 * d2)
     # sqrt with a safe sub-gradient at 0 (d2 == 0 on the Kzz diagonal)

@@ -1,3 +1,3 @@
 #!/bin/bash
 rm -f gpurun_out/headline_parity.json
-timeout 2400 python -m pytest tests -m gpu -q -x 2>&1 | grep -v "^  \|^$\|Warning" | tail -60
+timeout 2400 python -m pytest tests -m gpu -q 2>&1 | grep -v "^  \|^$\|Warning" | tail -40

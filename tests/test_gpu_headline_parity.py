@@ -68,10 +68,13 @@ def test_reduced_n_same_kzz_against_long_double(with_replacement, theta_name):
     errs["oracle_f64"] = _blocks(F64, torch.cat([g64["ell"], g64["sf2"].reshape(1), g64["s2"].reshape(1), g64["Z"].reshape(-1)]), Ft, gt)
     _record(f"reducedN_{n}_Z_{'with' if with_replacement else 'without'}_replacement_theta_{theta_name}",
             dict(jitter=jit, reference="oracle/hp long double", errors=errs))
+    # with duplicated inducing rows and trained-like theta cond(Kzz + 1e-8 I) = 4.4e10: no float64 evaluation holds 1e-8 on dF/dZ there
+    # (the float64 ORACLE is 1.3e-8 from the long-double reference, the GPU 0.5e-8 .. 1.2e-8 depending on the rounding of the m x m
+    # section); that one case is bounded at 1e-7 on dF/dZ, everything else -- and every block of every other case -- at 1e-8
+    hard = with_replacement and theta_name == "trained"
     for k, e in errs.items():
-        # with duplicated inducing rows and trained-like theta cond(Kzz + 1e-8 I) = 4.4e10: the float64 ORACLE is then ~1.3e-8 from the
-        # long-double reference itself (the GPU paths stay below 1e-8); it is recorded, and bounded at 1e-7
-        assert max(e.values()) < (1e-7 if (k == "oracle_f64" and with_replacement) else TOL), (k, e)
+        assert max(v for kk, v in e.items() if kk != "Z") < TOL, (k, e)
+        assert e["Z"] < (1e-7 if hard else TOL), (k, e)
 
 
 @pytest.mark.parametrize("with_replacement", [False, True])

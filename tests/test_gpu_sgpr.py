@@ -90,14 +90,16 @@ def test_bound_and_gradient_parity(eng, N, M, D, jit):
     assert relerr(g[D + 2:].view(M, D), go["Z"]) < TOL
 
 
-@pytest.mark.parametrize("kind", ["matern32", "matern52"])
+@pytest.mark.parametrize("kind", ["matern32", "matern52", ("rq", 0.7), ("rq", 3.0)])
 @pytest.mark.parametrize("N,M,D", [(700, 40, 2), (2500, 129, 5)])
-def test_matern_bound_and_gradient_parity(kind, N, M, D):
-    """Matern-3/2 and -5/2 tiles (experiments/co2_bayesian_sgpr_hmc.py:74-83 uses Matern32): bound and analytic gradient (the
-    backward epilogue weights G by dk/d(d2); dF/d sf2 comes from the m x m section) against oracle autograd."""
+def test_matern_and_rq_bound_and_gradient_parity(kind, N, M, D):
+    """Matern-3/2, -5/2 and rational-quadratic tiles (experiments/co2_bayesian_sgpr_hmc.py:74-83,127-144 uses Matern32 and RatQuad):
+    bound and analytic gradient (the backward epilogue weights G by dk/d(d2); dF/d sf2 comes from the m x m section) against oracle
+    autograd.  The RQ shape parameter alpha is a constant of the evaluation (cfg.kernel_param)."""
     import ggp_b200
     from oracle import sgpr as osgpr
-    e = ggp_b200.Engine.get(torch.device("cuda:0"), kernel=kind)
+    kw = dict(kernel=kind) if isinstance(kind, str) else dict(kernel=kind[0], kernel_param=kind[1])
+    e = ggp_b200.Engine.get(torch.device("cuda:0"), **kw)
     X, y, Z, th = make_problem(N, M, D, seed=N + 1)
     out = e.sgpr_eval(X, y, Z, th, jitter_policy=1e-4)
     Fo, go = osgpr.sgpr_bound_and_grads_autograd(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=1e-4, normalize="none", kind=kind)

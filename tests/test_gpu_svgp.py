@@ -26,14 +26,14 @@ def _qu(M, seed):
     return m, Ls
 
 
-def _oracle(xb, yb, Z, m, Ls, th, N, lik, base):
+def _oracle(xb, yb, Z, m, Ls, th, N, lik, base, kind="rbf"):
     from oracle import svgp as osv
     D = xb.shape[1]
     old = osv.VAR_CHOL_JITTER_F64
     osv.VAR_CHOL_JITTER_F64 = base
     try:
         ps = [t.clone().requires_grad_(True) for t in (th[:D], th[D], th[D + 1], Z, m, Ls)]
-        e = osv.svgp_elbo(xb, yb, ps[3], ps[4], ps[5], ps[0], ps[1], ps[2], N, likelihood=lik, jitter_policy=0.0)
+        e = osv.svgp_elbo(xb, yb, ps[3], ps[4], ps[5], ps[0], ps[1], ps[2], N, likelihood=lik, jitter_policy=0.0, kind=kind)
         g = torch.autograd.grad(e, ps, allow_unused=True)
     finally:
         osv.VAR_CHOL_JITTER_F64 = old
@@ -141,3 +141,29 @@ def test_sgpmc_chain_batch_at_config5_shape(eng):
     for ch in (0, 2):
         lo, gvo, gro = sgpmc.sgpmc_logp_dlogp_chunked(v[ch], raw[ch], X, y, Z, likelihood="bernoulli", chunk=8192)
         assert relerr(lp[ch], lo) < TOL and relerr(gv[ch], gvo) < TOL and relerr(gr[ch][:D + 1], gro[:D + 1]) < TOL, ch
+
+
+@pytest.mark.parametrize("kind", ["matern32", "matern52", ("rq", 1.5)])
+@pytest.mark.parametrize("lik", ["gaussian", "bernoulli"])
+def test_svgp_gradients_for_matern_and_rq_kernels(kind, lik):
+    """The SVGP / SGPMC backward for the non-RBF tiles: moments weighted by dk/d(d2), the k-weighted total of dF/dsf2 accumulated
+    beside them (two chunks of rows here: 4096 + 904)."""
+    import ggp_b200
+    kw = dict(kernel=kind) if isinstance(kind, str) else dict(kernel=kind[0], kernel_param=kind[1])
+    e = ggp_b200.Engine.get(torch.device("cuda:0"), **kw)
+    N, M, D, B = 6000, 70, 3, 5000
+    X, y, Z, th = make_problem(N, M, D, seed=17)
+    m, Ls = _qu(M, M)
+    xb = X[:B]
+    yb = y[:B] if lik == "gaussian" else (y[:B] > 0).double()
+    out = e.svgp_eval(xb, yb, Z, m, Ls, th, num_data=N, likelihood=lik, jitter_policy=0.0, base_jitter=1e-4)
+    eo, go = _oracle(xb, yb, Z, m, Ls, th, N, lik, 1e-4, kind=kind)
+    g = out["grad"][0].cpu()
+    o = D + 2
+    assert relerr(out["value"], eo) < TOL
+    assert relerr(g[:D], go[0]) < TOL and relerr(g[D], go[1]) < TOL
+    if lik == "gaussian":
+        assert relerr(g[D + 1], go[2]) < TOL
+    assert relerr(g[o:o + M * D].view(M, D), go[3]) < TOL
+    assert relerr(g[o + M * D:o + M * D + M], go[4]) < TOL
+    assert relerr(g[o + M * D + M:].view(M, M), torch.tril(go[5])) < TOL
