@@ -212,7 +212,7 @@ def hmc_leg(dev, eng_cls, with_cpu, iters=40, warm=5, chains=4, n_leapfrog=10):
         if it == tune - 1:
             ev[0].record()
     xj = x0 + (torch.rand(chains, D + 2, dtype=torch.float64, device=dev, generator=g) * 2.0 - 1.0)
-    res = nuts_sample(f, xj, draws, tune=tune, generator=g, progress=nprogress)
+    res = nuts_sample(f, xj, draws, tune=tune, generator=g, progress=nprogress, cuda_graph=True)
     ev[1].record()
     torch.cuda.synchronize()
     sec = ev[0].elapsed_time(ev[1]) * 1e-3
@@ -220,7 +220,8 @@ def hmc_leg(dev, eng_cls, with_cpu, iters=40, warm=5, chains=4, n_leapfrog=10):
     out["nuts_pymc3_defaults"] = {"samples_per_s": chains * draws / sec, "tune": tune, "draws": draws, "mean_leapfrogs_per_sample": lf,
                                   "mean_tree_depth": float(res["tree_depth"].double().mean().item()),
                                   "accept_stat": float(res["accept_rate"].mean().item()),
-                                  "diverging_frac": float(res["diverging"].double().mean().item())}
+                                  "diverging_frac": float(res["diverging"].double().mean().item()),
+                                  "note": "every leapfrog evaluation of the 4 chains is one CUDA-graph replay (hmc.GraphedLogp)"}
     out["samples_per_s"] = out["nuts_pymc3_defaults"]["samples_per_s"]
     if with_cpu:
         from oracle import priors

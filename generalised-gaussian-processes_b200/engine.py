@@ -81,6 +81,7 @@ class Engine:
         self._side = None            # side stream: tile prefetch overlapped with the factorisation
         self._copy = None            # copy stream: host rows uploaded piece by piece ahead of their tile build
         self.prefetch_min_rows = 65536
+        self.i8_batch_min_elems = 1 << 26    # n_local * m above which a batch of theta rows runs draw by draw on the sliced-integer plans
 
     def __del__(self):
         try:
@@ -166,6 +167,19 @@ class Engine:
         m = Z.shape[0]
         batch = theta.shape[0]
         assert theta.shape[1] == d + 2 and Z.shape[1] == d and y.shape[0] == n_local
+        if (batch > 1 and self.cfg.precision == PRECISIONS["fp64_i8"] and n_local * m >= self.i8_batch_min_elems
+                and m >= 65 and d <= 16 and not torch.cuda.is_current_stream_capturing()):
+            # several theta rows (hyper-parameter draws of the stochastic bound, models/bayesian_sgpr_hmc.py:121-134; HMC chains) on a
+            # LARGE streamed problem: the sliced-integer plans hold one draw's tiles / digit planes at a time, so the draws are
+            # evaluated one after another at the tcgen05 rate (2-3x the batched FP64 DMMA plan); small problems stay batched
+            # (they are latency-bound: one launch sequence for all rows wins)
+            if not X.is_cuda:
+                X, y = _f64c(X, dev), _f64c(y, dev)
+            outs = [self.sgpr_eval(X, y, Z, theta[b], jitter_policy, need_grad, group, raise_on_fail) for b in range(batch)]
+            cat = lambda k: torch.cat([o[k] for o in outs]) if outs[0][k] is not None else None
+            return dict(bound=cat("bound"), grad=cat("grad"), jitter=cat("jitter"), info=torch.cat([torch.as_tensor(o["info"]).reshape(-1).cpu() for o in outs]),
+                        info_b=cat("info_b"), n_total=cat("n_total"), partial=cat("partial"),
+                        path="fp64_i8" if all(o["path"] == "fp64_i8" for o in outs) else "mixed")
         self.reserve(n_local, m, d, batch)
         with torch.cuda.device(dev):
             cfgp = ctypes.byref(self.cfg)

@@ -12,7 +12,14 @@ import torch
 
 from .engine import Engine
 
-DEFAULT_CFG = dict(normalize="n", jitter_policy="gpytorch", precision="fp64", kernel="rbf", group=False, chunk_rows=0)
+DEFAULT_CFG = dict(normalize="n", jitter_policy="gpytorch", precision="auto", kernel="rbf", group=False, chunk_rows=0)
+
+
+def pick_precision(n, m, d):
+    """precision="auto": the sliced-integer tcgen05 plans (FP64-class accuracy, 2-3x the FP64 DMMA rate) for large streamed problems
+    they support (65 <= m <= 4096 inducing points, d <= 16), the FP64 DMMA plans for everything else (small problems are
+    latency-bound; both meet the same parity tests)."""
+    return "fp64_i8" if (n * m >= (1 << 26) and 65 <= m <= 4096 and d <= 16) else "fp64"
 
 
 def _cfg(cfg):
@@ -29,7 +36,8 @@ class SGPRBound(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, y, Z, lengthscale, outputscale, noise, cfg=None):
         c = _cfg(cfg)
-        eng = Engine.get(X.device, c["kernel"], c["precision"], c["chunk_rows"])
+        prec = pick_precision(X.shape[0], Z.shape[0], X.shape[1]) if c["precision"] == "auto" else c["precision"]
+        eng = Engine.get(X.device, c["kernel"], prec, c["chunk_rows"])
         D = X.shape[1]
         theta = torch.cat([lengthscale.reshape(-1), outputscale.reshape(-1), noise.reshape(-1)]).to(torch.float64)
         need = any(ctx.needs_input_grad[2:6])
@@ -137,7 +145,7 @@ class SVGPElbo(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xb, yb, Z, q_mean, q_chol, lengthscale, outputscale, noise, num_data, cfg=None):
         c = _cfg(cfg)
-        eng = Engine.get(xb.device, c["kernel"], c["precision"], c["chunk_rows"])
+        eng = Engine.get(xb.device, c["kernel"], "fp64" if c["precision"] == "auto" else c["precision"], c["chunk_rows"])
         theta = torch.cat([lengthscale.reshape(-1), outputscale.reshape(-1), noise.reshape(-1)]).to(torch.float64)
         need = any(ctx.needs_input_grad[2:8])
         out = eng.svgp_eval(xb, yb, Z, q_mean, q_chol, theta, num_data=num_data, likelihood=c.get("likelihood", "gaussian"),

@@ -82,6 +82,31 @@ class GraphedTrajectory:
         return tuple(t.clone() for t in self.out)
 
 
+class GraphedLogp:
+    """One logp/dlogp evaluation of C lock-step chains replayed as ONE CUDA graph (static input / output buffers).  NUTS cannot
+    capture a whole trajectory (the tree depth is data dependent) but every leapfrog is the same launch sequence: replaying it removes
+    the host from the ~100 short kernels of a small-problem evaluation.  Needs a sync-free target (fixed jitter policy)."""
+
+    def __init__(self, logp_dlogp, x):
+        self.x = x.clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                logp_dlogp(self.x)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = logp_dlogp(self.x)
+
+    def __call__(self, x):
+        self.x.copy_(x)
+        self.graph.replay()
+        return self.out[0].clone(), self.out[1].clone()
+
+
 def hmc_sample(logp_dlogp, x0, n_samples, tune=500, n_leapfrog=10, step_size=0.01, target_accept=0.8, adapt_mass=True,
                adaptation="dual_averaging", num_adaptation_steps=None, generator=None, progress=None, cuda_graph=False):
     """Run C chains in lock-step.  logp_dlogp(x[C,P]) -> (logp[C], grad[C,P]) (rows with logp=-inf are rejected).
@@ -195,7 +220,7 @@ class RunningDiagMass:
 
 
 def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_treedepth=10, step_size=None, adapt_mass=True,
-                max_energy_error=1000.0, generator=None, progress=None, mass_adaptation="pymc3"):
+                max_energy_error=1000.0, generator=None, progress=None, mass_adaptation="pymc3", cuda_graph=False):
     """No-U-turn sampler, C chains in lock-step, with the defaults of the sampler the reference calls: `pm.sample(n, tune=tune,
     chains=1)` with `pm.NUTS()` (models/bayesian_sgpr_hmc.py:73-78, models/all_in_HMC.py:60): multinomial NUTS, uniform progressive
     sampling inside a subtree and biased progressive sampling between the old tree and the new subtree, U-turn test
@@ -213,6 +238,8 @@ def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_tree
     C, P = x.shape
     dev, dt = x.device, x.dtype
     U = lambda *sh: torch.rand(*sh, dtype=dt, device=dev, generator=generator)
+    if cuda_graph and x.is_cuda:
+        logp_dlogp = GraphedLogp(logp_dlogp, x)     # every leapfrog evaluation = one graph replay (bit-identical to the eager call)
     lp, g = logp_dlogp(x)
     n_evals = 1
     eps0 = float(step_size) if step_size is not None else 0.25 / P ** 0.25
@@ -380,7 +407,7 @@ def sample_hyper(X, y, Z, n_samples, tune, chains=1, n_leapfrog=10, step_size=No
     t0 = time.perf_counter()
     if sampler == "nuts":   # pm.NUTS() defaults (models/bayesian_sgpr_hmc.py:73-78)
         res = nuts_sample(f, x0, n_samples, tune=tune, max_treedepth=max_treedepth, target_accept=target_accept, step_size=step_size,
-                          generator=generator)
+                          generator=generator, cuda_graph=cuda_graph)
     elif sampler == "hmc":
         res = hmc_sample(f, x0, n_samples, tune=tune, n_leapfrog=n_leapfrog, step_size=0.02 if step_size is None else step_size,
                          target_accept=target_accept, generator=generator, cuda_graph=cuda_graph)

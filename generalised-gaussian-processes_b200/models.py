@@ -265,7 +265,7 @@ class BayesianSparseGPR_HMC(SparseGPR):
 class _BatchedBoundMean(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, y, Z, thetas, jitter_policy):
-        eng = Engine.get(X.device)
+        eng = Engine.get(X.device, precision=F.pick_precision(X.shape[0], Z.shape[0], X.shape[1]))
         out = eng.sgpr_eval(X, y, Z, thetas, jitter_policy=jitter_policy, need_grad=True)
         n, B = out["n_total"][0], thetas.shape[0]
         D, M = X.shape[1], Z.shape[0]

@@ -30,7 +30,8 @@ enum { GGP_KERNEL_RBF = 0, GGP_KERNEL_MATERN32 = 1, GGP_KERNEL_MATERN52 = 2,
        GGP_KERNEL_RQ = 3 /* rational quadratic (1 + d2 / (2 alpha))^(-alpha), alpha = cfg.kernel_param (a constant of the evaluation) */ };
 /* GGP_PREC_FP64: FP64 tensor-core DMMA.  GGP_PREC_FP64_I8: the same contractions evaluated to FP64-class accuracy by exact integer
  * slicing (7 balanced radix-256 digits per operand, tcgen05.mma kind::i8, int32 TMEM accumulators; csrc/gemm_i8.cuh); used for the
- * streamed passes when batch == 1, the padded inducing count is in [128, 4096] and d <= 16, the DMMA path otherwise.
+ * streamed passes when batch == 1, the padded inducing count is in [128, 4096] and d <= 16, the DMMA path otherwise (the host
+ * driver evaluates a batch of theta rows on a large problem row by row so that each runs on this path).
  * GGP_PREC_TF32X3 is rejected (-3): split-precision cannot meet the gradient tolerance. */
 enum { GGP_PREC_FP64 = 0, GGP_PREC_TF32X3 = 1, GGP_PREC_FP64_I8 = 2 };
 enum { GGP_LIK_GAUSSIAN = 0, GGP_LIK_BERNOULLI_PROBIT = 1 };

@@ -139,3 +139,23 @@ def test_i8_moment_block_boundary(D):
     X, y, Z, th = make_problem(N, M, D, seed=D)
     out = ggp_b200.Engine.get(torch.device("cuda:0"), precision="fp64_i8").sgpr_eval(X, y, Z, th, jitter_policy=jit)
     _oracle_check(out, X, y, Z, th, jit, M, D)
+
+
+def test_i8_batch_of_theta_rows_runs_draw_by_draw():
+    """batch > 1 on a large streamed problem (the |trace| hyper-parameter draws of models/bayesian_sgpr_hmc.py:121-134): every row
+    equals its single evaluation bit for bit, on the tcgen05 path."""
+    import ggp_b200
+    eng = ggp_b200.Engine.get(torch.device("cuda:0"), precision="fp64_i8")
+    X, y, Z, th = make_problem(140000, 512, 4, seed=9)
+    assert X.shape[0] * 512 >= eng.i8_batch_min_elems
+    g = torch.Generator().manual_seed(1)
+    thetas = th.unsqueeze(0) * (0.8 + 0.4 * torch.rand(3, 6, dtype=torch.float64, generator=g))
+    dev = eng.device
+    Xd, yd = X.to(dev), y.to(dev)
+    outb = eng.sgpr_eval(Xd, yd, Z, thetas, jitter_policy=1e-4)
+    assert outb["path"] == "fp64_i8" and outb["bound"].shape == (3,) and outb["grad"].shape == (3, 6 + 512 * 4)
+    for b in range(3):
+        o = eng.sgpr_eval(Xd, yd, Z, thetas[b], jitter_policy=1e-4)
+        assert torch.equal(o["bound"][0], outb["bound"][b]) and torch.equal(o["grad"][0], outb["grad"][b])
+    f = ggp_b200.Engine.get(dev, precision="fp64").sgpr_eval(Xd, yd, Z, thetas, jitter_policy=1e-4)
+    assert relerr(outb["bound"], f["bound"]) < 1e-12 and relerr(outb["grad"], f["grad"]) < 1e-9

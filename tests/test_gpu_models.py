@@ -259,3 +259,22 @@ def test_bayesian_svgp_mixture_posterior_predictive():
         mo, vo = osv.svgp_predict(X[:50], model.inducing_inputs.detach().cpu(), model.variational_mean.detach().cpu(),
                                   model.chol_variational_covar.detach().cpu(), thetas[i, :2], thetas[i, 2], thetas[i, 3])
         assert relerr(preds[i].loc, mo) < TOL and relerr(preds[i].variance, vo) < TOL
+
+
+def test_nuts_with_graphed_leapfrog_evaluations_is_identical_to_eager():
+    """hmc.GraphedLogp: the per-leapfrog logp/dlogp evaluation replayed as a CUDA graph gives bit-identical NUTS chains."""
+    import ggp_b200
+    from ggp_b200.functions import sgpr_vfe_logp_dlogp
+    from ggp_b200.hmc import nuts_sample
+    X, y, Z, th = make_problem(300, 24, 2, seed=11)
+    X, y, Z = X.to(DEV), y.to(DEV), Z.to(DEV)
+    eng = ggp_b200.Engine.get(torch.device(DEV))
+    f = lambda xx: sgpr_vfe_logp_dlogp(xx, X, y, Z, engine=eng, group=False)
+    x0 = torch.zeros(3, 4, dtype=torch.float64, device=DEV)
+    x0[:, 2:] = torch.tensor([0.0, -1.0], dtype=torch.float64, device=DEV)
+    runs = []
+    for use_graph in (False, True):
+        g = torch.Generator(device=DEV).manual_seed(5)
+        runs.append(nuts_sample(f, x0, 8, tune=12, max_treedepth=5, generator=g, cuda_graph=use_graph))
+    assert torch.equal(runs[0]["samples"], runs[1]["samples"]) and torch.equal(runs[0]["logp"], runs[1]["logp"])
+    assert torch.equal(runs[0]["tree_depth"], runs[1]["tree_depth"])
