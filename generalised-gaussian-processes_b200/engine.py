@@ -81,6 +81,7 @@ class Engine:
         self._side = None            # side stream: tile prefetch overlapped with the factorisation
         self._copy = None            # copy stream: host rows uploaded piece by piece ahead of their tile build
         self.prefetch_min_rows = 65536
+        self._sgpr_state = None      # (Z ptr/shape, theta values) the handle's factor + B state belongs to, or None when clobbered
         self.i8_batch_min_elems = 1 << 26    # n_local * m above which a batch of theta rows runs draw by draw on the sliced-integer plans
 
     def __del__(self):
@@ -91,6 +92,31 @@ class Engine:
             pass
 
     # ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _ident(t):
+        return (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+
+    def _mark_state(self, Z, theta, by_value=False):
+        """Remember which (Z, theta) the handle's factor + B state belongs to.  The hot path (sgpr_eval) records the IDENTITY of the
+        caller's tensors (pointer + version counter: no device read-back); sgpr_predict_state records the values."""
+        if by_value:
+            self._sgpr_state = ("values", Z.detach().cpu().clone(), theta.detach().cpu().reshape(-1).clone())
+        else:
+            self._sgpr_state = ("ident", self._ident(Z), self._ident(theta))
+
+    def _check_state(self, Z, theta):
+        st = self._sgpr_state
+        ok = False
+        if st is not None and st[0] == "ident":
+            ok = st[1] == self._ident(Z) and st[2] == self._ident(theta)
+        elif st is not None:
+            zc, tc = Z.detach().cpu(), theta.detach().cpu().reshape(-1)
+            ok = zc.shape == st[1].shape and tc.shape == st[2].shape and torch.equal(zc.to(st[1].dtype), st[1]) and torch.equal(tc.to(st[2].dtype), st[2])
+        if not ok:
+            raise RuntimeError("sgpr_predict: the handle does not hold the SGPR state of this (Z, theta) -- another evaluation "
+                               "(SVGP / SGPMC, a different theta, chol, a re-reservation) has overwritten it; call "
+                               "sgpr_predict_state(X, y, Z, theta) first")
+
     def reserve(self, n_local, m, d, batch):
         s = self._shape
         if s is not None and s[1] == m and s[2] == d and batch <= s[3] and n_local <= s[0]:
@@ -98,6 +124,7 @@ class Engine:
         if s is not None and s[1] == m and s[2] == d:
             n_local, batch = max(n_local, s[0]), max(batch, s[3])
         torch.cuda.synchronize(self.device)
+        self._sgpr_state = None
         with torch.cuda.device(self.device):
             check(self.lib.ggp_reserve(self.h, ctypes.byref(self.cfg), int(n_local), int(m), int(d), int(batch)), "ggp_reserve")
         self._shape = (int(n_local), int(m), int(d), int(batch))
@@ -160,6 +187,7 @@ class Engine:
         """
         import torch.distributed as dist
         dev = self.device
+        Z_in, theta_in = Z, theta
         Z, theta = _f64c(Z, dev), _f64c(theta, dev)
         if theta.dim() == 1:
             theta = theta.unsqueeze(0)
@@ -265,6 +293,7 @@ class Engine:
                 info2_h = info2.cpu()
                 if bool((info2_h != 0).any()):
                     raise NotPSDError(f"I + A A^T / s not positive definite; potrf info={info2_h.tolist()}")
+            self._mark_state(Z_in, theta_in)
         return dict(bound=bound, grad=grad, jitter=jit, info=info1, info_b=info2, n_total=partial[:, -1], partial=partial,
                     path="fp64" if on_dmma else "fp64_i8")
 
@@ -281,6 +310,7 @@ class Engine:
         n_local, d = X.shape
         m, batch = Z.shape[0], theta.shape[0]
         self.reserve(n_local, m, d, batch)
+        self._sgpr_state = None
         with torch.cuda.device(dev):
             cfgp = ctypes.byref(self.cfg_dmma)
             jit, _ = self.factor(Z, theta, jitter_policy, True)
@@ -298,12 +328,13 @@ class Engine:
                                            _ptr(None), _ptr(info2)), "ggp_sgpr_finish")
             if bool((info2 != 0).any()):
                 raise NotPSDError(f"I + A W A^T not positive definite; potrf info={info2.tolist()}")
-        self._predict_epoch = getattr(self, "_predict_epoch", 0) + 1
-        return dict(jitter=jit, epoch=self._predict_epoch)
+        self._mark_state(Z, theta, by_value=True)
+        return dict(jitter=jit)
 
     def sgpr_predict(self, Xs, Z, theta, full_cov=False, add_noise=True):
         """Predictive at the state left by the last sgpr_predict_state (or sgpr_eval) with the same (Z, theta)."""
         dev = self.device
+        self._check_state(Z, theta)
         Xs, Z, theta = _f64c(Xs, dev), _f64c(Z, dev), _f64c(theta, dev)
         if theta.dim() == 1:
             theta = theta.unsqueeze(0)
@@ -335,6 +366,7 @@ class Engine:
         batch = theta.shape[0]
         qm_batched = qm.dim() == 2      # one whitened vector per batch element (SGPMC chains): [batch, m]
         assert qm.shape == ((batch, m) if qm_batched else (m,))
+        self._sgpr_state = None         # the SVGP scratch aliases the SGPR m x m state
         if lik_scale is None:
             lik_scale = 1.0 / nb
         if kl_scale is None:
@@ -379,6 +411,7 @@ class Engine:
         ns, d = xs.shape
         m, batch = Z.shape[0], theta.shape[0]
         qm_batched = qm.dim() == 2
+        self._sgpr_state = None
         self.reserve(min(ns, 4096), m, d, batch)
         mean = torch.empty(batch, ns, dtype=torch.float64, device=dev)
         var = torch.empty(batch, ns, dtype=torch.float64, device=dev)
@@ -404,6 +437,7 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.ggp_chol_batched(self.h, _stream(), _ptr(a), _ptr(linv), m, batch, _ptr(info)), "ggp_chol_batched")
         self._shape = None  # chol may have re-reserved the handle for its own shape
+        self._sgpr_state = None
         return a, linv, info
 
     def gemm_nt(self, A, B, C=None, alpha=1.0, beta=0.0):

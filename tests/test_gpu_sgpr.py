@@ -287,3 +287,20 @@ def test_batched_pymc3_logp_dlogp(eng):
         lo, go = priors.sgpr_vfe_logp_dlogp(xs[cidx], X, y, Z)
         assert relerr(lp[cidx], lo) < TOL    # duplicate Z rows + pymc3's 1e-6 stabilise jitter: cond(Kzz) ~ 1e8
         assert relerr(dlp[cidx], go) < TOL
+
+
+def test_predict_refuses_a_clobbered_handle_state(eng):
+    """The SVGP / SGPMC scratch aliases the m x m state the sparse predictive reads: after such a call (or at another theta)
+    sgpr_predict must fail loudly instead of returning numbers from someone else's factorisation."""
+    X, y, Z, th = make_problem(400, 24, 2, seed=3)
+    Xs = X[:10]
+    eng.sgpr_predict_state(X, y, Z, th, jitter_policy=1e-6)
+    m0, v0, _ = eng.sgpr_predict(Xs, Z, th)
+    with pytest.raises(RuntimeError):
+        eng.sgpr_predict(Xs, Z, th * 1.1)
+    eng.svgp_eval(X[:64], y[:64], Z, torch.zeros(24, dtype=torch.float64), torch.eye(24, dtype=torch.float64), th, num_data=400)
+    with pytest.raises(RuntimeError):
+        eng.sgpr_predict(Xs, Z, th)
+    eng.sgpr_predict_state(X, y, Z, th, jitter_policy=1e-6)
+    m1, v1, _ = eng.sgpr_predict(Xs, Z, th)
+    assert torch.equal(m0, m1) and torch.equal(v0, v1)
