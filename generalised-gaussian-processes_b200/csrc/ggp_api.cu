@@ -599,9 +599,25 @@ int ggp_destroy(ggp_handle_t* h) {
 int ggp_workspace_bytes(const ggp_cfg* cfg, int64_t n_local, int m, int d, int batch, size_t* out) {
   if (!out || m <= 0 || d <= 0 || batch <= 0 || n_local < 0) return fail(-1, "ggp_workspace_bytes: bad argument");
   const Plan p = make_plan(cfg, n_local, m, d, batch, 148);
-  *out = p.bytes;
-  const size_t cache = (size_t)batch * ((n_local + 127) / 128 * 128) * p.Mp * 8;
-  if (cfg && cfg->tile_cache_mib > 0 && n_local > 0 && cache <= (size_t)cfg->tile_cache_mib * 1024 * 1024) *out += cache;
+  size_t total = p.bytes;
+  const size_t rows = (size_t)((n_local + 127) / 128 * 128);
+  const size_t cache = (size_t)batch * rows * p.Mp * 8;
+  const size_t budget = (cfg && cfg->tile_cache_mib > 0) ? (size_t)cfg->tile_cache_mib * 1024 * 1024 : 0;
+  const bool have_cache = n_local > 0 && cache <= budget;
+  if (have_cache) total += cache;
+  if (cfg && cfg->precision == GGP_PREC_FP64_I8 && batch == 1 && p.Mp >= I8_BM) {
+    // digit planes of L^{-1}, Q, one chunk of A^T and of k(X,Z), exponents (ggp_reserve: arena_i8) ...
+    total += 2 * align_up((size_t)I8_NS * p.Mp * p.Mp, 256) + 2 * align_up((size_t)I8_NS * p.Mp * p.nc, 256) + 3 * align_up((size_t)p.Mp * 4, 256);
+    // ... and, with the tile cache, the digit planes of k(X,Z) and of A^T over all local rows
+    const size_t needq = rows * p.Mp * I8_NS;
+    if (have_cache && 2 * needq <= budget) {
+      total += needq;
+      if (8 * rows * p.Mp + 2 * needq <= budget) total += (size_t)((n_local + p.nc - 1) / p.nc) * I8_NS * p.Mp * p.nc;
+    } else if (have_cache) {
+      total -= cache;   // the cache holds both the FP64 tiles and their digit planes, or neither
+    }
+  }
+  *out = total;
   return 0;
 }
 

@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc(const double* __restric
 // arithmetic (ncu: 36 % warps active, 65 % issue slots, FP64 pipe 37 %).
 // grid: (ldk / 64, ceil(n_valid / (64 * KT_RT))); batch = 1.  dynamic shared memory: (2 * 64 * d + 64 * d + d) doubles.
 constexpr int KT_RT = 8;
-__global__ void __launch_bounds__(KT_THREADS) k_build_kc_i8(const double* __restrict__ X, int64_t n_valid,
+#ifndef GGP_KT_MINB
+#define GGP_KT_MINB 1
+#endif
+__global__ void __launch_bounds__(KT_THREADS, GGP_KT_MINB) k_build_kc_i8(const double* __restrict__ X, int64_t n_valid,
                                                            int d, const double* __restrict__ Z, int M, const double* __restrict__ theta,
                                                            KSpec kind, double* __restrict__ Kc, int64_t ldk, int8_t* __restrict__ Kq,
                                                            int64_t ldq, int64_t plane) {
