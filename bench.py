@@ -203,25 +203,32 @@ def hmc_leg(dev, eng_cls, with_cpu, iters=40, warm=5, chains=4, n_leapfrog=10):
         fixed[mode] = {"samples_per_s": chains * iters / sec, "bound_grad_evals_per_s": chains * iters * n_leapfrog / sec,
                        "ms_per_batched_leapfrog": 1e3 * sec / (iters * n_leapfrog), "accept_rate": float(res["accept_rate"].mean().item())}
     out["fixed_length_hmc_L10"] = fixed
-    # pm.NUTS() with pymc3's defaults (the sampler the reference calls): 4 chains x (tune + draws), timed over the draws
-    tune, draws = 150, 250
-    g.manual_seed(173)
-    ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    # pm.NUTS() with pymc3's defaults (the sampler the reference calls), BASELINE configs[1]'s own length: 4 chains x (500 tune + 1000
+    # draws), timed over the draws.  Tree bookkeeping in csrc/nuts.cuh, one CUDA-graph replay per leapfrog (evaluation + bookkeeping).
+    def run_nuts(tune, draws, native):
+        g.manual_seed(173)
+        ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
 
-    def nprogress(it):
-        if it == tune - 1:
-            ev[0].record()
-    xj = x0 + (torch.rand(chains, D + 2, dtype=torch.float64, device=dev, generator=g) * 2.0 - 1.0)
-    res = nuts_sample(f, xj, draws, tune=tune, generator=g, progress=nprogress, cuda_graph=True)
-    ev[1].record()
-    torch.cuda.synchronize()
-    sec = ev[0].elapsed_time(ev[1]) * 1e-3
-    lf = float(res["n_leapfrog"].double().mean().item())
-    out["nuts_pymc3_defaults"] = {"samples_per_s": chains * draws / sec, "tune": tune, "draws": draws, "mean_leapfrogs_per_sample": lf,
-                                  "mean_tree_depth": float(res["tree_depth"].double().mean().item()),
-                                  "accept_stat": float(res["accept_rate"].mean().item()),
-                                  "diverging_frac": float(res["diverging"].double().mean().item()),
-                                  "note": "every leapfrog evaluation of the 4 chains is one CUDA-graph replay (hmc.GraphedLogp)"}
+        def nprogress(it):
+            if it == tune - 1:
+                ev[0].record()
+        xj = x0 + (torch.rand(chains, D + 2, dtype=torch.float64, device=dev, generator=g) * 2.0 - 1.0)
+        res = nuts_sample(f, xj, draws, tune=tune, generator=g, progress=nprogress, cuda_graph=True, native=native)
+        ev[1].record()
+        torch.cuda.synchronize()
+        sec = ev[0].elapsed_time(ev[1]) * 1e-3
+        lf = float(res["n_leapfrog"].double().mean().item())
+        return xj, lf, {"samples_per_s": chains * draws / sec, "tune": tune, "draws": draws, "mean_leapfrogs_per_sample": lf,
+                        "batched_evals_per_transition": res["n_evals_sampling"] / draws,   # lock-step: the deepest chain's tree
+                        "ms_per_batched_eval": 1e3 * sec / max(res["n_evals_sampling"], 1),
+                        "mean_tree_depth": float(res["tree_depth"].double().mean().item()),
+                        "accept_stat": float(res["accept_rate"].mean().item()),
+                        "diverging_frac": float(res["diverging"].double().mean().item())}
+    xj, lf, out["nuts_pymc3_defaults"] = run_nuts(500, 1000, True)
+    out["nuts_pymc3_defaults"]["note"] = ("tree bookkeeping on the device (csrc/nuts.cuh, ggp_nuts_*): a leapfrog of the 4 chains = ONE CUDA-graph "
+                                          "replay (evaluation + one bookkeeping launch); the host reads one flag per tree doubling")
+    _, _, out["nuts_torch_bookkeeping"] = run_nuts(60, 60, False)
+    out["nuts_torch_bookkeeping"]["note"] = "same sampler, per-leaf bookkeeping as ~60 torch calls (native=False); evaluation still a graph replay"
     out["samples_per_s"] = out["nuts_pymc3_defaults"]["samples_per_s"]
     if with_cpu:
         from oracle import priors

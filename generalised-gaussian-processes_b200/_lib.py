@@ -20,6 +20,24 @@ class GgpCfg(ctypes.Structure):
                 ("chunk_rows", ctypes.c_int32), ("tile_cache_mib", ctypes.c_int32), ("kernel_param", ctypes.c_double)]
 
 
+# ggp_nuts_state (include/ggp_b200.h): field order is the header's
+NUTS_DOUBLE_CP = ("x", "g", "inv_mass", "x_eval", "g_eval", "xl", "pl", "gl", "xr", "pr", "gr", "x_prop", "g_prop", "p_sum",
+                  "xe", "pe", "ge", "p_half", "s_p_sum", "s_x", "s_g")                              # [C,P] float64
+NUTS_DOUBLE_C = ("lp", "eps", "lp_eval", "e0", "lp_prop", "log_w", "sum_acc", "n_leaf", "e", "s_log_w", "s_lp", "acc_prob")   # [C]
+NUTS_INT_C = ("depth", "diverged", "active", "right", "s_turn", "s_div", "building", "leaf")       # [C] int32
+_NUTS_PTRS = ("x", "lp", "g", "eps", "inv_mass", "x_eval", "lp_eval", "g_eval",
+              "e0", "xl", "pl", "gl", "xr", "pr", "gr", "x_prop", "lp_prop", "g_prop", "log_w", "p_sum", "sum_acc", "n_leaf",
+              "depth", "diverged", "active",
+              "e", "xe", "pe", "ge", "p_half", "s_log_w", "s_p_sum", "s_x", "s_lp", "s_g", "p_ck", "ps_ck",
+              "right", "s_turn", "s_div", "building", "leaf", "any_active", "u",
+              "acc_prob", "samples", "lps", "depths", "nleaps", "divs")
+
+
+class GgpNutsState(ctypes.Structure):
+    _fields_ = ([("C", ctypes.c_int32), ("P", ctypes.c_int32), ("K", ctypes.c_int32), ("pad_", ctypes.c_int32),
+                 ("max_energy_error", ctypes.c_double)] + [(n, ctypes.c_void_p) for n in _NUTS_PTRS])
+
+
 KERNELS = {"rbf": 0, "matern32": 1, "matern52": 2, "rq": 3}
 PRECISIONS = {"fp64": 0, "tf32x3": 1, "fp64_i8": 2}
 LIKELIHOODS = {"gaussian": 0, "bernoulli": 1}
@@ -54,6 +72,14 @@ SYMBOLS = {
     "ggp_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "ggp_probe_dmma_peak": (_I, [_P, _P, _I, ctypes.POINTER(ctypes.c_double)]),
     "ggp_probe_i8_peak": (_I, [_P, _P, _I, ctypes.POINTER(ctypes.c_double)]),
+    "ggp_vfe_theta": (_I, [_P, _P, _I, _I, _P]),
+    "ggp_vfe_logp": (_I, [_P, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _P, _P]),
+    "ggp_nuts_state_size": (_I, []),
+    "ggp_nuts_begin": (_I, [_P, ctypes.POINTER(GgpNutsState), _P]),
+    "ggp_nuts_subtree_begin": (_I, [_P, ctypes.POINTER(GgpNutsState)]),
+    "ggp_nuts_leaf": (_I, [_P, ctypes.POINTER(GgpNutsState)]),
+    "ggp_nuts_subtree_end": (_I, [_P, ctypes.POINTER(GgpNutsState)]),
+    "ggp_nuts_end": (_I, [_P, ctypes.POINTER(GgpNutsState), _I]),
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -89,6 +115,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    if lib.ggp_nuts_state_size() != ctypes.sizeof(GgpNutsState):
+        raise RuntimeError("ggp_nuts_state: the ctypes mirror in _lib.py and include/ggp_b200.h disagree")
     _lib = lib
     return lib
 

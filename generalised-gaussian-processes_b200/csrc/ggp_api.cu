@@ -17,6 +17,7 @@
 #include "kernel_tiles.cuh"
 #include "misc.cuh"
 #include "svgp.cuh"
+#include "nuts.cuh"
 
 using namespace ggp;
 
@@ -1598,6 +1599,58 @@ int ggp_probe_dmma_peak(ggp_handle_t* h, void* stream, int iters, double* tflops
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(sink);
+  return 0;
+}
+
+// ---- NUTS tree bookkeeping (csrc/nuts.cuh) ----
+int ggp_nuts_state_size(void) { return (int)sizeof(ggp_nuts_state); }
+static int nuts_check(const ggp_nuts_state* s) {
+  if (!s || s->C < 1 || s->P < 1 || s->K < 1 || !s->x || !s->x_eval || !s->lp_eval || !s->g_eval || !s->u) return fail(-2, "ggp_nuts: bad state");
+  return 0;
+}
+int ggp_nuts_begin(void* stream, const ggp_nuts_state* s, const double* z) {
+  if (int r = nuts_check(s)) return r;
+  if (!z) return fail(-3, "ggp_nuts_begin: z is null");
+  k_nuts_begin<<<s->C, 32, 0, (cudaStream_t)stream>>>(*s, z);
+  CK(cudaGetLastError());
+  return 0;
+}
+int ggp_nuts_subtree_begin(void* stream, const ggp_nuts_state* s) {
+  if (int r = nuts_check(s)) return r;
+  k_nuts_subtree_begin<<<s->C, 32, 0, (cudaStream_t)stream>>>(*s);
+  CK(cudaGetLastError());
+  return 0;
+}
+int ggp_nuts_leaf(void* stream, const ggp_nuts_state* s) {
+  if (int r = nuts_check(s)) return r;
+  k_nuts_leaf<<<s->C, 32, 0, (cudaStream_t)stream>>>(*s);
+  CK(cudaGetLastError());
+  return 0;
+}
+int ggp_nuts_subtree_end(void* stream, const ggp_nuts_state* s) {
+  if (int r = nuts_check(s)) return r;
+  k_nuts_subtree_end<<<s->C, 32, 0, (cudaStream_t)stream>>>(*s);
+  CK(cudaGetLastError());
+  return 0;
+}
+int ggp_nuts_end(void* stream, const ggp_nuts_state* s, int k) {
+  if (int r = nuts_check(s)) return r;
+  k_nuts_end<<<s->C, 32, 0, (cudaStream_t)stream>>>(*s, k);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int ggp_vfe_theta(void* stream, const double* x, int C, int d, double* theta) {
+  if (!x || !theta || C < 1 || d < 1) return fail(-2, "ggp_vfe_theta: bad argument");
+  k_vfe_theta<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, C, d, theta);
+  CK(cudaGetLastError());
+  return 0;
+}
+int ggp_vfe_logp(void* stream, const double* x, const double* bound, const double* grad, int64_t ldg, const int* info,
+                 const int* info_b, int C, int d, int with_prior, double* lp, double* dx) {
+  if (!x || !bound || !grad || !lp || !dx || C < 1 || d < 1 || ldg < d + 2) return fail(-2, "ggp_vfe_logp: bad argument");
+  k_vfe_logp<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, bound, grad, ldg, info, info_b, C, d, with_prior, lp, dx);
+  CK(cudaGetLastError());
   return 0;
 }
 

@@ -107,9 +107,22 @@ def sgpr_vfe_logp_dlogp(x, X, y, Z, jitter_policy="pymc3", engine=None, group=Fa
     x = x.to(device=eng.device, dtype=torch.float64)
     if x.dim() == 1:
         x = x.unsqueeze(0)
-    lp, dx, _, bad = _vfe_eval(x, X, y, Z, jitter_policy, eng, group, with_prior)
-    lp = torch.where(bad, torch.full_like(lp, -float("inf")), lp)
-    dx = torch.where(bad.unsqueeze(1), torch.zeros_like(dx), dx)
+    # transforms, priors, Jacobians and the failure mask in two launches (csrc/nuts.cuh k_vfe_theta / k_vfe_logp) instead of ~55
+    # elementwise torch calls (what _vfe_eval spells out): at the reference's sizes a leapfrog is launch-latency bound
+    from ._lib import check, load
+    lib, st = load(), torch.cuda.current_stream().cuda_stream
+    x = x.contiguous()
+    C, D = x.shape[0], X.shape[1]
+    theta = torch.empty(C, D + 2, dtype=torch.float64, device=x.device)
+    check(lib.ggp_vfe_theta(st, x.data_ptr(), C, D, theta.data_ptr()), "ggp_vfe_theta")
+    out = eng.sgpr_eval(X, y, Z, theta, jitter_policy=jitter_policy, need_grad=True, group=group, raise_on_fail=False)
+    g, bound = out["grad"].contiguous(), out["bound"].contiguous()
+    info = torch.as_tensor(out["info"]).to(device=x.device, dtype=torch.int32).contiguous()
+    info_b = out["info_b"].to(device=x.device, dtype=torch.int32).contiguous()
+    lp = torch.empty(C, dtype=torch.float64, device=x.device)
+    dx = torch.empty(C, D + 2, dtype=torch.float64, device=x.device)
+    check(lib.ggp_vfe_logp(st, x.data_ptr(), bound.data_ptr(), g.data_ptr(), g.stride(0), info.data_ptr(), info_b.data_ptr(),
+                           C, D, 1 if with_prior else 0, lp.data_ptr(), dx.data_ptr()), "ggp_vfe_logp")
     return lp, dx
 
 

@@ -220,7 +220,7 @@ class RunningDiagMass:
 
 
 def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_treedepth=10, step_size=None, adapt_mass=True,
-                max_energy_error=1000.0, generator=None, progress=None, mass_adaptation="pymc3", cuda_graph=False):
+                max_energy_error=1000.0, generator=None, progress=None, mass_adaptation="pymc3", cuda_graph=False, native=None):
     """No-U-turn sampler, C chains in lock-step, with the defaults of the sampler the reference calls: `pm.sample(n, tune=tune,
     chains=1)` with `pm.NUTS()` (models/bayesian_sgpr_hmc.py:73-78, models/all_in_HMC.py:60): multinomial NUTS, uniform progressive
     sampling inside a subtree and biased progressive sampling between the old tree and the new subtree, U-turn test
@@ -233,7 +233,19 @@ def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_tree
     Batching: one tree doubling = 2^j leapfrogs = 2^j BATCHED logp/dlogp calls shared by every chain; a chain whose tree has
     stopped is masked out (its rows are still evaluated, which is what lock-step costs).  The U-turn checks inside a subtree use
     the iterative checkpoint scheme (no recursion), so the leaf index - and hence the control flow - is identical for all chains.
+    Random numbers: one normal draw [C, P] per transition and one uniform draw [2 + 2^j, C] per doubling j (row 0 direction, row 1
+    merge, rows 2.. one per leaf), so the stream does not depend on who does the bookkeeping.
+
+    native (default: x0 is on a GPU): the tree bookkeeping between two evaluations runs in the CUDA kernels of csrc/nuts.cuh
+    (NativeNutsTree below: one launch per leaf, in the same CUDA graph as the evaluation when cuda_graph=True) instead of ~60
+    elementwise torch calls per leaf; same algorithm, same random numbers, positions bit-identical per leapfrog.  native=False is
+    the torch implementation below (any device; the CPU tests and the GPU cross-check use it).
     Returns the hmc_sample dict plus tree_depth[n_samples, C], n_leapfrog[n_samples, C], diverging[n_samples, C]."""
+    if native is None:
+        native = x0.is_cuda
+    if native:
+        return _nuts_sample_native(logp_dlogp, x0, n_samples, tune, target_accept, max_treedepth, step_size, adapt_mass,
+                                   max_energy_error, generator, progress, mass_adaptation, cuda_graph)
     x = x0.clone()
     C, P = x.shape
     dev, dt = x.device, x.dtype
@@ -261,7 +273,10 @@ def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_tree
     def turning(p_left, p_right, p_sum):
         return ((p_sum * p_left * inv_mass).sum(1) <= 0) | ((p_sum * p_right * inv_mass).sum(1) <= 0)
 
+    n_evals_tune = n_evals
     for it in range(tune + n_samples):
+        if it == tune:
+            n_evals_tune = n_evals
         p0 = torch.randn(C, P, dtype=dt, device=dev, generator=generator) / torch.sqrt(inv_mass)
         e0 = -lp + 0.5 * (p0 * p0 * inv_mass).sum(1)
         xl, pl, gl = x, p0, g
@@ -277,7 +292,8 @@ def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_tree
         for j in range(max_treedepth):
             if not bool(active.any()):
                 break
-            right = U(C) < 0.5
+            u = U(2 + 2 ** j, C)
+            right = u[0] < 0.5
             sgn = torch.where(right, torch.ones_like(eps), -torch.ones_like(eps))
             e = (eps * sgn).unsqueeze(1)
             r1 = right.unsqueeze(1)
@@ -304,7 +320,7 @@ def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_tree
                 sum_acc = sum_acc + torch.where(building, torch.exp(dlt.clamp(max=0.0)), torch.zeros_like(dlt))
                 n_leaf = n_leaf + building.to(dt)
                 new_w = torch.logaddexp(s_log_w, dlt)
-                take = good & (torch.log(U(C)) < dlt - new_w)
+                take = good & (torch.log(u[2 + n]) < dlt - new_w)
                 t1 = take.unsqueeze(1)
                 s_x, s_lp, s_g = torch.where(t1, xn, s_x), torch.where(take, lpn, s_lp), torch.where(t1, gn, s_g)
                 s_log_w = torch.where(good, new_w, s_log_w)
@@ -323,7 +339,7 @@ def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_tree
                     building = building & ~tn
             diverged = diverged | (active & s_div)
             ok = active & ~s_turn & ~s_div
-            take = ok & (torch.log(U(C)) < s_log_w - log_w)
+            take = ok & (torch.log(u[1]) < s_log_w - log_w)
             t1 = take.unsqueeze(1)
             x_prop, lp_prop, g_prop = torch.where(t1, s_x, x_prop), torch.where(take, s_lp, lp_prop), torch.where(t1, s_g, g_prop)
             log_w = torch.where(ok, torch.logaddexp(log_w, s_log_w), log_w)
@@ -359,7 +375,132 @@ def nuts_sample(logp_dlogp, x0, n_samples, tune=500, target_accept=0.8, max_tree
         if progress is not None:
             progress(it)
     return dict(samples=samples, logp=lps, accept_rate=acc_sum / max(n_samples, 1), step_size=eps, n_evals=n_evals,
-                inv_mass=inv_mass, tree_depth=depths, n_leapfrog=nleap, diverging=divs)
+                n_evals_sampling=n_evals - n_evals_tune, inv_mass=inv_mass, tree_depth=depths, n_leapfrog=nleap, diverging=divs)
+
+
+class NativeNutsTree:
+    """Device-resident NUTS tree of C lock-step chains (csrc/nuts.cuh through the C ABI: ggp_nuts_*).  Owns the state buffers of
+    ggp_nuts_state; `leaf()` = one logp/dlogp evaluation at x_eval followed by ONE bookkeeping launch, replayed as a single CUDA
+    graph when cuda_graph=True (the leaf index is a device counter, so every leaf is the same launch sequence)."""
+
+    def __init__(self, logp_dlogp, x0, n_samples, max_treedepth, max_energy_error, cuda_graph):
+        import ctypes
+        from . import _lib
+        if not x0.is_cuda:
+            raise RuntimeError("NativeNutsTree needs CUDA tensors (there is no CPU build of csrc/nuts.cuh); use native=False")
+        self.lib, self._check, self._byref = _lib.load(), _lib.check, ctypes.byref
+        self.f = logp_dlogp
+        C, P = x0.shape
+        K = max(int(max_treedepth), 1)
+        dev = x0.device
+        zd = lambda *sh: torch.zeros(*sh, dtype=torch.float64, device=dev)
+        zi = lambda *sh: torch.zeros(*sh, dtype=torch.int32, device=dev)
+        t = {n: zd(C, P) for n in _lib.NUTS_DOUBLE_CP}
+        t.update({n: zd(C) for n in _lib.NUTS_DOUBLE_C})
+        t.update({n: zi(C) for n in _lib.NUTS_INT_C})
+        ns = max(int(n_samples), 1)
+        t.update(p_ck=zd(K, C, P), ps_ck=zd(K, C, P), any_active=zi(1), u=zd(2 + 2 ** K, C), samples=zd(ns, C, P), lps=zd(ns, C),
+                 depths=zi(ns, C), nleaps=zi(ns, C), divs=zi(ns, C))
+        t["inv_mass"].fill_(1.0)
+        self.t = t
+        self.st = _lib.GgpNutsState(C=C, P=P, K=K, max_energy_error=float(max_energy_error))
+        for n in _lib._NUTS_PTRS:
+            setattr(self.st, n, t[n].data_ptr())
+        self.graph, self._keep = None, None
+        lp, g = logp_dlogp(x0)
+        t["x"].copy_(x0); t["lp"].copy_(lp); t["g"].copy_(g); t["x_eval"].copy_(x0)
+        self.n_evals = 1
+        if cuda_graph:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    logp_dlogp(t["x_eval"])
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._eval_and_leaf()
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _eval_and_leaf(self):
+        lp, g = self.f(self.t["x_eval"])
+        lp, g = lp.to(torch.float64).contiguous(), g.to(torch.float64).contiguous()
+        self._keep = (lp, g)                      # graph mode: the captured outputs; eager: alive until the next evaluation
+        self.st.lp_eval, self.st.g_eval = lp.data_ptr(), g.data_ptr()
+        self._check(self.lib.ggp_nuts_leaf(self._stream(), self._byref(self.st)), "ggp_nuts_leaf")
+
+    def begin(self, z):
+        self._check(self.lib.ggp_nuts_begin(self._stream(), self._byref(self.st), z.data_ptr()), "ggp_nuts_begin")
+
+    def doubling(self, j, generator):
+        """Grow the tree by 2^j leaves in a random direction; True while some chain keeps doubling (the one host read)."""
+        t = self.t
+        torch.rand(2 + 2 ** j, t["u"].shape[1], dtype=torch.float64, device=t["u"].device, generator=generator, out=t["u"][:2 + 2 ** j])
+        self._check(self.lib.ggp_nuts_subtree_begin(self._stream(), self._byref(self.st)), "ggp_nuts_subtree_begin")
+        for _ in range(2 ** j):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._eval_and_leaf()
+        self.n_evals += 2 ** j
+        self._check(self.lib.ggp_nuts_subtree_end(self._stream(), self._byref(self.st)), "ggp_nuts_subtree_end")
+        return bool(t["any_active"].item())
+
+    def end(self, k):
+        self._check(self.lib.ggp_nuts_end(self._stream(), self._byref(self.st), int(k)), "ggp_nuts_end")
+
+
+def _nuts_sample_native(logp_dlogp, x0, n_samples, tune, target_accept, max_treedepth, step_size, adapt_mass, max_energy_error,
+                        generator, progress, mass_adaptation, cuda_graph):
+    """nuts_sample with the tree in csrc/nuts.cuh; adaptation (once per transition) stays in torch."""
+    C, P = x0.shape
+    dev, dt = x0.device, x0.dtype
+    tree = NativeNutsTree(logp_dlogp, x0.to(torch.float64), n_samples, max_treedepth, max_energy_error, cuda_graph)
+    t = tree.t
+    eps0 = float(step_size) if step_size is not None else 0.25 / P ** 0.25
+    t["eps"].fill_(eps0)
+    da = DualAveraging(t["eps"].clone(), target_accept)
+    running = RunningDiagMass(t["x"].clone()) if (adapt_mass and mass_adaptation == "pymc3") else None
+    windows = sorted({int(tune * f) for f in (0.25, 0.5, 0.75)} - {0}) if adapt_mass and running is None and tune >= 40 else []
+    win_start, buf = 0, []
+    acc_sum = torch.zeros(C, dtype=torch.float64, device=dev)
+    n_evals_tune = tree.n_evals
+    for it in range(tune + n_samples):
+        if it == tune:
+            n_evals_tune = tree.n_evals
+        tree.begin(torch.randn(C, P, dtype=torch.float64, device=dev, generator=generator))
+        for j in range(max_treedepth):
+            if not tree.doubling(j, generator):
+                break
+        tree.end(it - tune if it >= tune else -1)
+        if it < tune:
+            eps = da.update(t["acc_prob"])
+            if it == tune - 1:
+                eps = da.final()
+            t["eps"].copy_(eps)
+            if running is not None:
+                t["inv_mass"].copy_(running.update(t["x"]))
+            if windows:
+                buf.append(t["x"].clone())
+                if it + 1 in windows:
+                    S = torch.stack(buf[win_start:])
+                    if S.shape[0] >= 10:
+                        var = S.var(0, unbiased=True)
+                        nn_ = S.shape[0]
+                        t["inv_mass"].copy_((nn_ / (nn_ + 5.0)) * var + 1e-3 * (5.0 / (nn_ + 5.0)))
+                        da = DualAveraging(t["eps"].clone(), target_accept)
+                    win_start = len(buf)
+        else:
+            acc_sum += t["acc_prob"]
+        if progress is not None:
+            progress(it)
+    return dict(samples=t["samples"][:n_samples].to(dt), logp=t["lps"][:n_samples].to(dt), accept_rate=acc_sum / max(n_samples, 1),
+                step_size=t["eps"].clone(), n_evals=tree.n_evals, n_evals_sampling=tree.n_evals - n_evals_tune, inv_mass=t["inv_mass"].clone(), tree_depth=t["depths"][:n_samples],
+                n_leapfrog=t["nleaps"][:n_samples], diverging=t["divs"][:n_samples].bool(), native=True)
 
 
 class HyperTrace:

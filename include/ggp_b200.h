@@ -178,6 +178,58 @@ int ggp_gemm_nt_i8(ggp_handle_t* h, void* stream, const double* A, int64_t lda, 
 /* k(X1, X2)[n1, n2] dense tile (tests) */
 int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X1, int64_t n1,
                       const double* X2, int64_t n2, const double* theta /*[d+2]*/, int d, double* out /*[n1,n2]*/);
+/* NUTS tree bookkeeping on the device -----------------------------------------------------------------------
+ * Replaces the per-leapfrog host work of  pm.sample(n, tune, chains=1, step=pm.NUTS())  (models/bayesian_sgpr_hmc.py:73-78,
+ * models/all_in_HMC.py:60): multinomial NUTS with pymc3's defaults, C chains in lock-step, one warp per chain (csrc/nuts.cuh).
+ * The host (hmc.py nuts_sample) owns every buffer, draws the random numbers, runs the doubling loop and the step-size / mass
+ * adaptation; these calls do everything between two logp/dlogp evaluations in one launch:
+ *   ggp_nuts_begin          p0 = z / sqrt(inv_mass), initial energy, tree = {x}
+ *   ggp_nuts_subtree_begin  direction (u row 0), empty subtree, x_eval = first position to evaluate
+ *   ggp_nuts_leaf           consumes (lp_eval, g_eval) at x_eval: leaf weight (u row 2 + leaf), divergence, progressive sample,
+ *                           U-turn checks of the balanced sub-subtrees ending at this leaf, then the next x_eval; the leaf index is a
+ *                           device counter, so ONE captured launch serves every leaf (replayed in the same graph as the evaluation)
+ *   ggp_nuts_subtree_end    merge (u row 1), tree U-turn test, *any_active = some chain keeps doubling
+ *   ggp_nuts_end            state <- proposal, acc_prob, trace row k (k < 0: tuning step, nothing recorded)
+ * All pointers are device pointers; [C,P] arrays are row-major; int arrays are int32 flags / counters. */
+typedef struct ggp_nuts_state {
+  int32_t C, P, K, pad_;             /* chains, parameters per chain, checkpoint slots (>= max tree depth) */
+  double max_energy_error;           /* divergence threshold on |energy change| (pymc3: 1000) */
+  /* sampler state, persists across transitions */
+  double *x, *lp, *g;                /* [C,P], [C], [C,P] current point, its log density and gradient */
+  double *eps, *inv_mass;            /* [C], [C,P] step size, diagonal inverse metric */
+  /* exchange with the logp/dlogp evaluation */
+  double *x_eval;                    /* [C,P] point to evaluate */
+  const double *lp_eval, *g_eval;    /* [C], [C,P] its log density and gradient */
+  /* the tree of the current transition */
+  double *e0, *xl, *pl, *gl, *xr, *pr, *gr, *x_prop, *lp_prop, *g_prop, *log_w, *p_sum, *sum_acc, *n_leaf;
+  int32_t *depth, *diverged, *active;
+  /* the subtree of the current doubling */
+  double *e, *xe, *pe, *ge, *p_half, *s_log_w, *s_p_sum, *s_x, *s_lp, *s_g;
+  double *p_ck, *ps_ck;              /* [K,C,P] checkpoints of the iterative U-turn scheme */
+  int32_t *right, *s_turn, *s_div, *building, *leaf;   /* [C] */
+  int32_t *any_active;               /* [1] */
+  const double *u;                   /* [2 + 2^depth, C] uniforms of the current doubling: row 0 direction, row 1 merge, rows 2.. leaves */
+  /* outputs */
+  double *acc_prob;                  /* [C] mean over the leaves of min(1, exp(-dE)) */
+  double *samples, *lps;             /* [n,C,P], [n,C] */
+  int32_t *depths, *nleaps, *divs;   /* [n,C] */
+} ggp_nuts_state;
+int ggp_nuts_state_size(void);   /* sizeof(ggp_nuts_state), for binding checks */
+int ggp_nuts_begin(void* stream, const ggp_nuts_state* s, const double* z /*[C,P] standard normal draws*/);
+int ggp_nuts_subtree_begin(void* stream, const ggp_nuts_state* s);
+int ggp_nuts_leaf(void* stream, const ggp_nuts_state* s);
+int ggp_nuts_subtree_end(void* stream, const ggp_nuts_state* s);
+int ggp_nuts_end(void* stream, const ggp_nuts_state* s, int k);
+
+/* pymc3 log-posterior around the collapsed bound (models/bayesian_sgpr_hmc.py:60-71), batched over chains: x[C, d+2] is the
+ * unconstrained point (ls_log__[d], sig_f_log__, sig_n_log__).  ggp_vfe_theta writes the constrained theta rows the SGPR entry points
+ * take (ell = e^x, sf2 = sig_f^2, s2 = sig_n^2); ggp_vfe_logp turns the bound and its gradient rows (row stride ldg, first d+2
+ * entries used) into logp / dlogp with the Gamma(2,1) / HalfCauchy(1) priors and the log-Jacobians (with_prior = 0: the bound and the
+ * chain rule only).  info / info_b (nullable, int32[C]): a non-zero entry or a non-finite value gives logp = -inf, dlogp = 0. */
+int ggp_vfe_theta(void* stream, const double* x, int C, int d, double* theta /*[C,d+2]*/);
+int ggp_vfe_logp(void* stream, const double* x, const double* bound, const double* grad, int64_t ldg, const int* info,
+                 const int* info_b, int C, int d, int with_prior, double* lp /*[C]*/, double* dx /*[C,d+2]*/);
+
 /* register-resident mma.sync m8n8k4 f64 loop on every SM: measured FP64 tensor-pipe peak [host out, TFLOP/s]; synchronous */
 int ggp_probe_dmma_peak(ggp_handle_t* h, void* stream, int iters, double* tflops_out /*[host]*/);
 /* tcgen05.mma kind::i8 issue loop with shared-memory-resident operands on every SM (no loads, no epilogue): the measured tensor-pipe

@@ -287,6 +287,19 @@ def test_batched_pymc3_logp_dlogp(eng):
         lo, go = priors.sgpr_vfe_logp_dlogp(xs[cidx], X, y, Z)
         assert relerr(lp[cidx], lo) < TOL    # duplicate Z rows + pymc3's 1e-6 stabilise jitter: cond(Kzz) ~ 1e8
         assert relerr(dlp[cidx], go) < TOL
+    # the fused transform / prior kernels (k_vfe_theta, k_vfe_logp) against the torch spelling of the same target (_vfe_eval), with
+    # and without the priors, and the failure convention: a non-finite row gives logp = -inf and a zero gradient, others untouched
+    dev = eng.device
+    for with_prior in (True, False):
+        l1, d1 = F.sgpr_vfe_logp_dlogp(xs.to(dev), X.to(dev), y.to(dev), Z.to(dev), with_prior=with_prior)
+        l2, d2, _, bad = F._vfe_eval(xs.to(dev), X.to(dev), y.to(dev), Z.to(dev), "pymc3", eng, False, with_prior)
+        assert not bool(bad.any()) and relerr(l1, l2) < 1e-13 and relerr(d1, d2) < 1e-13
+    xb = xs.clone()
+    xb[2, 0] = float("nan")
+    lb, db = F.sgpr_vfe_logp_dlogp(xb.to(dev), X.to(dev), y.to(dev), Z.to(dev))
+    assert lb[2].item() == -float("inf") and float(db[2].abs().max()) == 0.0
+    keep = [0, 1, 3]
+    assert torch.equal(lb[keep], lp[keep]) and torch.equal(db[keep], dlp[keep])
 
 
 def test_predict_refuses_a_clobbered_handle_state(eng):
