@@ -530,13 +530,17 @@ class HyperTrace:
 
 
 def sample_hyper(X, y, Z, n_samples, tune, chains=1, n_leapfrog=10, step_size=None, engine=None, generator=None, seed_jitter=True,
-                 cuda_graph=False, sampler="nuts", max_treedepth=10, target_accept=0.8):
+                 cuda_graph=None, sampler="nuts", max_treedepth=10, target_accept=0.8):
     """Sampling over theta = (ls, sig_f, sig_n) on the collapsed VFE bound with pymc3's priors and transforms
     (models/bayesian_sgpr_hmc.py:58-80).  Start = prior test value (Gamma mean 2, HalfCauchy beta 1) + U(-1,1) jitter
     in unconstrained space (pymc3 init='jitter+adapt_diag').  sampler="nuts" (default) is pm.NUTS() as the reference calls it
     (:73-78); sampler="hmc" is the fixed-length lock-step sampler (step_size default 0.02; the CUDA-graph benchmark uses it).
+    cuda_graph=None replays the evaluation (and the NUTS bookkeeping launch) as a CUDA graph when the problem is small enough for
+    launch latency to matter (N * M <= 2^22, the reference's own data sets); larger problems run eagerly.
     Returns (list of HyperTrace per chain, raw result)."""
     import time
+    if cuda_graph is None:
+        cuda_graph = bool(X.is_cuda and X.shape[0] * Z.shape[0] <= 2 ** 22)
     from .functions import sgpr_vfe_logp_dlogp
     D = X.shape[1]
     dev = X.device
