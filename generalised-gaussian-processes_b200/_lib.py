@@ -39,6 +39,39 @@ class GgpNutsState(ctypes.Structure):
 
 
 KERNELS = {"rbf": 0, "matern32": 1, "matern52": 2, "rq": 3}
+FACTOR_KINDS = {"rbf": 0, "matern32": 1, "matern52": 2, "rq": 3, "periodic": 4}    # factors of a composite kernel (ggp_kprog.kind)
+KERNEL_COMPOSITE = 5
+KPROG_MAX_TERMS, KPROG_MAX_FACTORS, KPROG_MAX_PARAMS = 6, 3, 64
+
+
+class GgpKprog(ctypes.Structure):
+    _fields_ = [("nterms", ctypes.c_int32), ("nfactors", ctypes.c_int32 * KPROG_MAX_TERMS),
+                ("kind", (ctypes.c_int32 * KPROG_MAX_FACTORS) * KPROG_MAX_TERMS)]
+
+
+def make_kprog(prog):
+    """prog: tuple of terms, each a tuple of factor names ("rbf", "matern32", "matern52", "rq", "periodic"); the parameter row is, in
+    program order, a_t then for each factor ell[d] then (rq: alpha | periodic: period[d])  (include/ggp_b200.h)."""
+    prog = tuple(tuple(t) for t in prog)
+    if not 1 <= len(prog) <= KPROG_MAX_TERMS or any(not 1 <= len(t) <= KPROG_MAX_FACTORS for t in prog):
+        raise ValueError(f"composite kernel: 1..{KPROG_MAX_TERMS} terms of 1..{KPROG_MAX_FACTORS} factors")
+    kp = GgpKprog()
+    kp.nterms = len(prog)
+    for t, term in enumerate(prog):
+        kp.nfactors[t] = len(term)
+        for f, name in enumerate(term):
+            kp.kind[t][f] = FACTOR_KINDS[name]
+    return kp
+
+
+def kprog_layout(prog, d):
+    """(P, amplitude indices) of the parameter row of `prog` in d input dimensions."""
+    npar = {"rbf": d, "matern32": d, "matern52": d, "rq": d + 1, "periodic": 2 * d}
+    amp, p = [], 0
+    for term in prog:
+        amp.append(p)
+        p += 1 + sum(npar[f] for f in term)
+    return p, amp
 PRECISIONS = {"fp64": 0, "tf32x3": 1, "fp64_i8": 2}
 LIKELIHOODS = {"gaussian": 0, "bernoulli": 1}
 
@@ -72,6 +105,9 @@ SYMBOLS = {
     "ggp_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "ggp_probe_dmma_peak": (_I, [_P, _P, _I, ctypes.POINTER(ctypes.c_double)]),
     "ggp_probe_i8_peak": (_I, [_P, _P, _I, ctypes.POINTER(ctypes.c_double)]),
+    "ggp_kprog_nparams": (_I, [ctypes.POINTER(GgpKprog), _I]),
+    "ggp_set_kernel_program": (_I, [_P, ctypes.POINTER(GgpKprog), _I]),
+    "ggp_set_kernel_params": (_I, [_P, _P, _P, _P]),
     "ggp_vfe_theta": (_I, [_P, _P, _I, _I, _P]),
     "ggp_vfe_logp": (_I, [_P, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _P, _P]),
     "ggp_nuts_state_size": (_I, []),

@@ -18,6 +18,7 @@
 #include "misc.cuh"
 #include "svgp.cuh"
 #include "nuts.cuh"
+#include "kprog.cuh"
 
 using namespace ggp;
 
@@ -104,6 +105,13 @@ struct ggp_handle {
   double* ysc = nullptr;
   double* rk_part = nullptr;
   double* piv_tol = nullptr;   // [batch] pivot threshold of the next Cholesky (k_build_kzz sets it; 0 = LAPACK semantics)
+  // composite kernel (GGP_KERNEL_COMPOSITE; kprog.cuh)
+  KProgDev prog{};
+  bool prog_set = false;
+  const double* kth = nullptr;         // [batch, P] parameter rows
+  double *kgrad_mm = nullptr, *kgrad_partial = nullptr;
+  double* krow = nullptr;              // [batch, m, P + d] row accumulators of k_kprog_grad
+  size_t krow_bytes = 0;
 };
 
 enum { CAT_BUILD = 0, CAT_TRMM = 1, CAT_SYRK = 2, CAT_BWD = 3, CAT_MM = 4, CAT_OTHER = 5, CAT_COUNT = 6 };
@@ -531,7 +539,7 @@ static int launch_i8(ggp_handle* h, cudaStream_t st, int epi, I8P p, const I8Ope
 }
 
 static bool use_i8(const ggp_handle* h, const ggp_cfg* cfg, int d, int batch) {
-  return cfg && cfg->precision == GGP_PREC_FP64_I8 && batch == 1 && h->Mp >= I8_BM && h->Mp <= I8_K_GROUP4 && d <= I8_MAX_D &&
+  return cfg && cfg->precision == GGP_PREC_FP64_I8 && cfg->kernel != GGP_KERNEL_COMPOSITE && batch == 1 && h->Mp >= I8_BM && h->Mp <= I8_K_GROUP4 && d <= I8_MAX_D &&
          h->arena_i8 != nullptr;
 }
 
@@ -593,6 +601,7 @@ int ggp_destroy(ggp_handle_t* h) {
   if (h->kq_all) cudaFree(h->kq_all);
   if (h->atq_all) cudaFree(h->atq_all);
   if (h->arena_i8) cudaFree(h->arena_i8);
+  if (h->krow) cudaFree(h->krow);
   delete h;
   return 0;
 }
@@ -736,18 +745,68 @@ int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int
   return 0;
 }
 
+// composite kernel: the program is registered for this input dimension and the parameter rows are set
+static int prog_ready(const ggp_handle* h, int d, const char* who) {
+  if (!h->prog_set || h->prog.d != d || !h->kth) {
+    snprintf(g_err, sizeof(g_err), "%s: GGP_KERNEL_COMPOSITE needs ggp_set_kernel_program (same d) and ggp_set_kernel_params first", who);
+    return -3;
+  }
+  return 0;
+}
+static bool kernel_ok(const ggp_handle* h, KSpec kind) {
+  if (kind.kind == GGP_KERNEL_COMPOSITE) return h->prog_set;
+  return kind.kind >= GGP_KERNEL_RBF && kind.kind <= GGP_KERNEL_RQ && (kind.kind != GGP_KERNEL_RQ || kind.p > 0.0);
+}
+
+int ggp_kprog_nparams(const ggp_kprog* prog, int d) {
+  KProgDev pd;
+  if (!kprog_compile(prog, d, &pd)) return fail(-1, "ggp_kprog_nparams: malformed program (terms 1..6, factors 1..3, kinds 0..4, d 1..16, <= 64 parameters)");
+  return pd.P;
+}
+int ggp_set_kernel_program(ggp_handle_t* h, const ggp_kprog* prog, int d) {
+  if (!h || !prog) return fail(-1, "ggp_set_kernel_program: NULL argument");
+  if (h->m <= 0 || h->d != d) return fail(-2, "ggp_set_kernel_program: reserve the handle for this input dimension first");
+  KProgDev pd;
+  if (!kprog_compile(prog, d, &pd)) return fail(-3, "ggp_set_kernel_program: malformed program (terms 1..6, factors 1..3, kinds 0..4, d 1..16, <= 64 parameters)");
+  const size_t need = (size_t)std::max(1, h->batch) * h->m * (pd.P + d) * sizeof(double);
+  if (need > h->krow_bytes) {
+    CK(cudaDeviceSynchronize());
+    if (h->krow) cudaFree(h->krow);
+    h->krow = nullptr; h->krow_bytes = 0;
+    CK(cudaMalloc(&h->krow, need));
+    h->krow_bytes = need;
+  }
+  h->prog = pd;
+  h->prog_set = true;
+  h->kth = nullptr; h->kgrad_mm = nullptr; h->kgrad_partial = nullptr;
+  h->kc_valid = false; h->pf_valid = false; h->atq_valid = false;
+  return 0;
+}
+int ggp_set_kernel_params(ggp_handle_t* h, const double* kparams, double* kgrad_mm, double* kgrad_partial) {
+  if (!h || !kparams) return fail(-1, "ggp_set_kernel_params: NULL argument");
+  if (!h->prog_set) return fail(-2, "ggp_set_kernel_params: no program registered");
+  h->kth = kparams; h->kgrad_mm = kgrad_mm; h->kgrad_partial = kgrad_partial;
+  return 0;
+}
+
 int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* Z, const double* theta,
                     const double* jitter, int m, int d, int batch, int32_t* info) {
   if (!h || !Z || !theta || !info) return fail(-1, "ggp_sgpr_factor: NULL argument");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_factor: handle not reserved for this shape");
   cudaStream_t st = (cudaStream_t)stream;
   const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (!kernel_ok(h, kind)) return fail(-3, "ggp_sgpr_factor: unknown kernel");
   const int Mp = h->Mp;
   h->kc_valid = false;
   h->atq_valid = false;
   RUN(join_aux(h, st));
   ProfScope ps(h, st, CAT_MM);
-  k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp, h->piv_tol);
+  if (kind == GGP_KERNEL_COMPOSITE) {
+    if (int r = prog_ready(h, d, "ggp_sgpr_factor")) return r;
+    k_build_kzz_prog<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, h->prog, h->kth, jitter, h->L, (int64_t)Mp * Mp, h->piv_tol);
+  } else {
+    k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp, h->piv_tol);
+  }
   CKL();
   return chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info);
 }
@@ -755,6 +814,12 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
 static int build_chunk(ggp_handle* h, cudaStream_t st, const double* Xc, int nv, int d, const double* Z, int m,
                        const double* theta, KSpec kind, int batch, double* dst, int64_t sK) {
   const int Mp = h->Mp;
+  if (kind == GGP_KERNEL_COMPOSITE) {
+    if (int r = prog_ready(h, d, "build_chunk")) return r;
+    k_build_kc_prog<<<dim3(Mp / 32, (nv + 7) / 8, batch), 256, 0, st>>>(Xc, nv, Z, m, Mp, h->prog, h->kth, dst, Mp, sK);
+    CKL();
+    return 0;
+  }
   dim3 grid(Mp / KT_M, (nv + KT_N - 1) / KT_N, batch);
   const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
   k_build_kc<<<grid, KT_THREADS, smem, st>>>(Xc, nv, nv, d, Z, m, theta, kind, dst, Mp, sK);
@@ -780,6 +845,7 @@ int ggp_sgpr_prefetch_tiles_part(ggp_handle_t* h, const ggp_cfg* cfg, void* stre
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_prefetch_tiles: handle not reserved for this shape");
   if (row0 < 0 || nrows < 0 || row0 + nrows > n_local) return fail(-3, "ggp_sgpr_prefetch_tiles_part: row range outside [0, n_local)");
   const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (!kernel_ok(h, kind)) return fail(-3, "ggp_sgpr_prefetch_tiles_part: unknown kernel");
   if (row0 == 0) { h->pf_valid = false; h->pf_next_row = 0; }
   if (!h->kc_all || n_local <= 0) return 0;   // no tile cache: pass 1 builds chunk by chunk as before
   if (row0 != h->pf_next_row) { h->pf_valid = false; return fail(-3, "ggp_sgpr_prefetch_tiles_part: parts must be issued in ascending row order"); }
@@ -815,6 +881,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   if (!h || !Z || !theta || !partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass1: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_pass1: handle not reserved for this shape");
   const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (!kernel_ok(h, kind)) return fail(-3, "ggp_sgpr_pass1: unknown kernel");
   if (cfg && cfg->precision == GGP_PREC_TF32X3)
     return fail(-3, "ggp_sgpr_pass1: GGP_PREC_TF32X3 is not offered: it cannot meet the gradient tolerance (DESIGN.md 4b); use "
                     "GGP_PREC_FP64 (DMMA) or GGP_PREC_FP64_I8 (exact int8 slicing on tcgen05)");
@@ -964,6 +1031,7 @@ int ggp_sgpr_predict_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, co
   if (!h || !Z || !theta || !partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_predict_pass1: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_predict_pass1: handle not reserved for this shape");
   const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (!kernel_ok(h, kind)) return fail(-3, "ggp_sgpr_predict_pass1: unknown kernel");
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc, splits = h->splits;
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nc * Mp;
@@ -1000,7 +1068,12 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   if (need_grad && !grad_mm) return fail(-1, "ggp_sgpr_finish: grad_mm is NULL");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_finish: handle not reserved for this shape");
   const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
-  if (kind.kind < GGP_KERNEL_RBF || kind.kind > GGP_KERNEL_RQ || (kind.kind == GGP_KERNEL_RQ && !(kind.p > 0.0))) return fail(-3, "ggp_sgpr_finish: unknown kernel");
+  if (!kernel_ok(h, kind)) return fail(-3, "ggp_sgpr_finish: unknown kernel");
+  if (kind == GGP_KERNEL_COMPOSITE && need_grad) {
+    if (int r = prog_ready(h, d, "ggp_sgpr_finish")) return r;
+    if (!h->kgrad_mm) return fail(-3, "ggp_sgpr_finish: composite kernel gradient needs kgrad_mm (ggp_set_kernel_params)");
+    if ((size_t)batch * m * (h->prog.P + d) * 8 > h->krow_bytes) return fail(-2, "ggp_sgpr_finish: call ggp_set_kernel_program after ggp_reserve");
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp;
   const int64_t sM = (int64_t)Mp * Mp, sP = (int64_t)m * m + m + 3, sG = (int64_t)d + 2 + (int64_t)m * d;
@@ -1059,10 +1132,21 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
   RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
   RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->Gbar, Mp, sM, T2, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
   RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(T2, Mp, sM, h->LinvT, Mp, sM, h->Gzz, Mp, sM, m, m, m, -0.5, 0.0, KM_B_UPPER), batch));
-  k_grad_kzz_rows<<<gv, 256, 0, st2>>>(h->Gzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, grad_mm + d + 2, sG);
-  CKL();
-  k_grad_mm_final<<<batch, 256, 0, st2>>>(h->rowacc, m, d, theta, partial, sP, h->ds2, grad_mm, sG, h->rk);
-  CKL();
+  if (kind == GGP_KERNEL_COMPOSITE) {
+    // sum_ij Gzz_ij dk(z_i, z_j)/d(parameter), and dZ_i = 2 sum_j Gzz_ij dk(z_j, z_i)/d(second argument): z_i moves both as the second
+    // argument of row i and, Gzz and k being symmetric, as the first argument of column i.  The amplitudes also get the explicit
+    // -N / (2 s2) of sum_n k(x_n, x_n).  krow is shared with pass 2 (which runs on `st` after the join), so the chain stays ordered.
+    k_kprog_grad<<<gv, 256, 0, st2>>>(h->Gzz, Mp, sM, nullptr, 0, nullptr, Z, m, Z, m, h->prog, h->kth, h->krow, 0);
+    CKL();
+    k_kprog_grad_final<<<batch, 256, 0, st2>>>(h->krow, m, h->prog, 2.0, partial + (int64_t)m * m + m + 2, sP, theta, h->ds2,
+                                               h->kgrad_mm, grad_mm, sG);
+    CKL();
+  } else {
+    k_grad_kzz_rows<<<gv, 256, 0, st2>>>(h->Gzz, Mp, sM, Z, m, d, theta, kind, h->rowacc, grad_mm + d + 2, sG);
+    CKL();
+    k_grad_mm_final<<<batch, 256, 0, st2>>>(h->rowacc, m, d, theta, partial, sP, h->ds2, grad_mm, sG, h->rk);
+    CKL();
+  }
   if (side) {
     CK(cudaEventRecord(h->ev_join, st2));
     h->aux_pending = true;
@@ -1075,12 +1159,49 @@ int ggp_sgpr_join(ggp_handle_t* h, void* stream) {
   return join_aux(h, (cudaStream_t)stream);
 }
 
+// Composite kernel, pass 2: per chunk  aT = Kc Linv^T,  G = Q aT^T STORED (m x nv, into the chunk buffer the tile no longer needs),
+// then the direct contraction  sum_n (G + u y^T)_mn dk(x_n, z_m)/d(parameter, z_m)  (k_kprog_grad) instead of the moment epilogue.
+static int pass2_composite(ggp_handle* h, cudaStream_t st, const double* X, const double* y, int64_t n_local, const double* Z,
+                           const double* theta, int m, int d, int batch, double* grad_partial) {
+  if (int r = prog_ready(h, d, "ggp_sgpr_pass2")) return r;
+  if (!h->kgrad_partial) return fail(-3, "ggp_sgpr_pass2: composite kernel gradient needs kgrad_partial (ggp_set_kernel_params)");
+  if ((size_t)batch * m * (h->prog.P + d) * 8 > h->krow_bytes) return fail(-2, "ggp_sgpr_pass2: call ggp_set_kernel_program after ggp_reserve");
+  const KSpec kind{GGP_KERNEL_COMPOSITE, 0.0};
+  const int Mp = h->Mp, nc = h->nc;
+  const int64_t sM = (int64_t)Mp * Mp, sG = (int64_t)d + 2 + (int64_t)m * d, sC = (int64_t)nc * Mp;
+  const bool cached = h->kc_all && h->kc_valid && h->kc_X == X && h->kc_Z == Z && h->kc_theta == theta && h->kc_n == n_local &&
+                      h->kc_batch == batch && h->kc_kind.kind == kind.kind;
+  RUN(join_aux(h, st));   // the Kzz-part chain of finish() uses krow on the auxiliary stream
+  const dim3 gv((m + 7) / 8, batch);
+  CK(cudaMemsetAsync(h->krow, 0, (size_t)batch * m * (h->prog.P + d) * 8, st));
+  for (int64_t c0 = 0; c0 < n_local; c0 += nc) {
+    const int nv = (int)std::min<int64_t>(nc, n_local - c0);
+    double* Kc_c = h->kc_all ? h->kc_all + c0 * Mp : h->Kc;
+    const int64_t sK = h->kc_all ? h->kc_rows * Mp : sC;
+    if (!cached) { ProfScope ps(h, st, CAT_BUILD); RUN(build_chunk(h, st, X + c0 * d, nv, d, Z, m, theta, kind, batch, Kc_c, sK)); }
+    {
+      ProfScope ps(h, st, CAT_TRMM);
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(Kc_c, Mp, sK, h->Linv, Mp, sM, h->At, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
+    }
+    {
+      ProfScope ps(h, st, CAT_BWD);
+      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->P, Mp, sM, h->At, Mp, sC, h->Kc, nc, sC, m, nv, m, 1.0, 0.0), batch));
+      k_kprog_grad<<<gv, 256, 0, st>>>(h->Kc, nc, sC, h->u, Mp, y + c0, X + c0 * d, nv, Z, m, h->prog, h->kth, h->krow, 1);
+      CKL();
+    }
+  }
+  k_kprog_grad_final<<<batch, 256, 0, st>>>(h->krow, m, h->prog, 1.0, nullptr, 0, theta, nullptr, h->kgrad_partial, grad_partial, sG);
+  CKL();
+  return 0;
+}
+
 int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* X, const double* y, int64_t n_local,
                    const double* Z, const double* theta, int m, int d, int batch, double* grad_partial) {
   if (!h || !Z || !theta || !grad_partial || (n_local > 0 && (!X || !y))) return fail(-1, "ggp_sgpr_pass2: NULL argument");
   if (!reserved_for(h, n_local, m, d, batch)) return fail(-2, "ggp_sgpr_pass2: handle not reserved for this shape");
   const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
-  if (kind.kind < GGP_KERNEL_RBF || kind.kind > GGP_KERNEL_RQ || (kind.kind == GGP_KERNEL_RQ && !(kind.p > 0.0))) return fail(-3, "ggp_sgpr_pass2: unknown kernel");
+  if (!kernel_ok(h, kind)) return fail(-3, "ggp_sgpr_pass2: unknown kernel");
+  if (kind == GGP_KERNEL_COMPOSITE) return pass2_composite(h, (cudaStream_t)stream, X, y, n_local, Z, theta, m, d, batch, grad_partial);
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc, nq = 2 * d + 1;
   const int64_t sM = (int64_t)Mp * Mp, sG = (int64_t)d + 2 + (int64_t)m * d, sC = (int64_t)nc * Mp;
@@ -1202,6 +1323,7 @@ int ggp_sgpr_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
   if (!h || !Xs || !Z || !theta || !mean || !var) return fail(-1, "ggp_sgpr_predict: NULL argument");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_sgpr_predict: handle not reserved for this shape");
   const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (!kernel_ok(h, kind)) return fail(-3, "ggp_sgpr_predict: unknown kernel");
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nc = h->nc;
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nc * Mp;
@@ -1370,6 +1492,7 @@ int ggp_svgp_predict(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const do
   if (!h || !xs || !Z || !qm || !theta || !jitter || !mean || !var || !info) return fail(-1, "ggp_svgp_predict: NULL argument");
   if (!reserved_for(h, 0, m, d, batch)) return fail(-2, "ggp_svgp_predict: handle not reserved for this shape");
   const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (kind.kind < GGP_KERNEL_RBF || kind.kind > GGP_KERNEL_RQ) return fail(-3, "ggp_svgp_predict: unknown kernel (composite kernels are SGPR-only)");
   cudaStream_t st = (cudaStream_t)stream;
   const int Mp = h->Mp, nsv = h->nsv;
   const int64_t sM = (int64_t)Mp * Mp, sC = (int64_t)nsv * Mp;
@@ -1531,6 +1654,14 @@ int ggp_kernel_matrix(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const d
   if (!h || !X1 || !X2 || !theta || !out) return fail(-1, "ggp_kernel_matrix: NULL argument");
   if ((size_t)(2 * KT_N * d + d) * 8 > 200 * 1024) return fail(-3, "ggp_kernel_matrix: d too large");
   const KSpec kind{cfg ? cfg->kernel : 0, cfg ? cfg->kernel_param : 0.0};
+  if (!kernel_ok(h, kind)) return fail(-3, "ggp_kernel_matrix: unknown kernel");
+  if (kind == GGP_KERNEL_COMPOSITE) {   // theta is ignored: the registered parameter row 0
+    if (int r = prog_ready(h, d, "ggp_kernel_matrix")) return r;
+    k_build_kc_prog<<<dim3((unsigned)((n2 + 31) / 32), (unsigned)((n1 + 7) / 8), 1), 256, 0, (cudaStream_t)stream>>>(
+        X1, (int)n1, X2, (int)n2, (int)n2, h->prog, h->kth, out, n2, 0);
+    CKL();
+    return 0;
+  }
   dim3 grid((unsigned)((n2 + KT_M - 1) / KT_M), (unsigned)((n1 + KT_N - 1) / KT_N), 1);
   const size_t smem = (size_t)(KT_N * d + KT_M * d + d) * 8;
   k_build_kc<<<grid, KT_THREADS, smem, (cudaStream_t)stream>>>(X1, (int)n1, (int)n1, d, X2, (int)n2, theta, kind, out, n2, 0);

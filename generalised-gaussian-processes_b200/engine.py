@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import GgpCfg, KERNELS, LIKELIHOODS, PRECISIONS, check
+from ._lib import GgpCfg, KERNELS, KERNEL_COMPOSITE, LIKELIHOODS, PRECISIONS, check
 
 
 class NotPSDError(RuntimeError):
@@ -52,6 +52,8 @@ class Engine:
         device = torch.device(device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
+        if not isinstance(kernel, str):
+            kernel = tuple(tuple(t) for t in kernel)     # composite program: hashable
         key = (device.index, kernel, precision, chunk_rows, tile_cache_mib, float(kernel_param))
         if key not in cls._cache:
             cls._cache[key] = cls(device, kernel, precision, chunk_rows, tile_cache_mib, kernel_param)
@@ -69,9 +71,16 @@ class Engine:
             tile_cache_mib = int(min(32 * 1024, free_b // (4 * 1024 * 1024)))
         if kernel == "rq" and not kernel_param > 0:
             raise ValueError("kernel='rq' needs kernel_param = alpha > 0")
-        self.cfg = GgpCfg(KERNELS[kernel], PRECISIONS[precision], int(chunk_rows), int(tile_cache_mib), float(kernel_param))
+        # composite kernel (a tuple of terms, each a tuple of factor names: sum of scaled products, the reference's CO2 model
+        # experiments/co2_bayesian_sgpr_hmc.py:74-83): theta rows are [kernel parameters (P, _lib.make_kprog's order), s2] and the
+        # gradient rows [d/d(kernel parameters), d_s2, d_Z]; SGPR entry points only, FP64 DMMA plan
+        self.prog = None if isinstance(kernel, str) else tuple(tuple(t) for t in kernel)
+        self._kprog = _lib.make_kprog(self.prog) if self.prog is not None else None
+        self._kkeep = None
+        kcode = KERNELS[kernel] if self.prog is None else KERNEL_COMPOSITE
+        self.cfg = GgpCfg(kcode, PRECISIONS[precision], int(chunk_rows), int(tile_cache_mib), float(kernel_param))
         # the FP64 DMMA plan on the same handle: an fp64_i8 engine evaluates on it when the jitter ladder had to engage (see sgpr_eval)
-        self.cfg_dmma = GgpCfg(KERNELS[kernel], PRECISIONS["fp64"], int(chunk_rows), int(tile_cache_mib), float(kernel_param))
+        self.cfg_dmma = GgpCfg(kcode, PRECISIONS["fp64"], int(chunk_rows), int(tile_cache_mib), float(kernel_param))
         self.ladder_levels = []
         h = ctypes.c_void_p()
         check(self.lib.ggp_create(ctypes.byref(h), self.device.index), "ggp_create")
@@ -127,6 +136,8 @@ class Engine:
         self._sgpr_state = None
         with torch.cuda.device(self.device):
             check(self.lib.ggp_reserve(self.h, ctypes.byref(self.cfg), int(n_local), int(m), int(d), int(batch)), "ggp_reserve")
+            if self._kprog is not None:
+                check(self.lib.ggp_set_kernel_program(self.h, ctypes.byref(self._kprog), int(d)), "ggp_set_kernel_program")
         self._shape = (int(n_local), int(m), int(d), int(batch))
 
     def workspace_bytes(self, n_local, m, d, batch):
@@ -178,6 +189,31 @@ class Engine:
             return dist.get_world_size() > 1, None
         return True, group
 
+    # ---- composite kernels ----------------------------------------------------------------------------------
+    def kernel_nparams(self, d):
+        """Length of a theta row minus the noise entry: d + 1 (ell, sf2) for the single kernels, P of the program otherwise."""
+        return d + 1 if self.prog is None else _lib.kprog_layout(self.prog, d)[0]
+
+    def _composite_rows(self, theta, d, need_grad):
+        """theta[batch, P + 1] (program parameters, s2) -> the [batch, d + 2] rows the C ABI takes (ell slots unused, sf2 slot =
+        k(x, x) = sum of the amplitudes, s2) + the registered parameter / gradient buffers (kept alive on the engine)."""
+        P, amp = _lib.kprog_layout(self.prog, d)
+        if theta.shape[1] != P + 1:
+            raise ValueError(f"composite kernel {self.prog}: theta rows have {P} kernel parameters + the noise variance = {P + 1} entries")
+        batch = theta.shape[0]
+        kth = theta[:, :P].contiguous()
+        std = torch.ones(batch, d + 2, dtype=torch.float64, device=theta.device)
+        std[:, d] = sum(kth[:, i] for i in amp)          # no index tensor: stays capturable in a CUDA graph
+        std[:, d + 1] = theta[:, P]
+        kg = torch.zeros(2, batch, P, dtype=torch.float64, device=theta.device) if need_grad else None
+        self._kkeep = (kth, kg)
+        return std, kth, kg
+
+    def _set_kparams(self):
+        kth, kg = self._kkeep
+        check(self.lib.ggp_set_kernel_params(self.h, _ptr(kth), _ptr(kg[0]) if kg is not None else _ptr(None),
+                                             _ptr(kg[1]) if kg is not None else _ptr(None)), "ggp_set_kernel_params")
+
     def sgpr_eval(self, X, y, Z, theta, jitter_policy="gpytorch", need_grad=True, group=False, raise_on_fail=True):
         """Collapsed bound F (not divided by N) and dF/d(ell, sf2, s2, Z) for each row of theta.
 
@@ -194,8 +230,11 @@ class Engine:
         n_local, d = X.shape
         m = Z.shape[0]
         batch = theta.shape[0]
+        kg = None
+        if self.prog is not None:
+            theta, _, kg = self._composite_rows(theta, d, need_grad)
         assert theta.shape[1] == d + 2 and Z.shape[1] == d and y.shape[0] == n_local
-        if (batch > 1 and self.cfg.precision == PRECISIONS["fp64_i8"] and n_local * m >= self.i8_batch_min_elems
+        if (batch > 1 and self.prog is None and self.cfg.precision == PRECISIONS["fp64_i8"] and n_local * m >= self.i8_batch_min_elems
                 and m >= 65 and d <= 16 and not torch.cuda.is_current_stream_capturing()):
             # several theta rows (hyper-parameter draws of the stochastic bound, models/bayesian_sgpr_hmc.py:121-134; HMC chains) on a
             # LARGE streamed problem: the sliced-integer plans hold one draw's tiles / digit planes at a time, so the draws are
@@ -209,6 +248,8 @@ class Engine:
                         info_b=cat("info_b"), n_total=cat("n_total"), partial=cat("partial"),
                         path="fp64_i8" if all(o["path"] == "fp64_i8" for o in outs) else "mixed")
         self.reserve(n_local, m, d, batch)
+        if self.prog is not None:
+            self._set_kparams()
         with torch.cuda.device(dev):
             cfgp = ctypes.byref(self.cfg)
             use_side = (self.cfg.tile_cache_mib > 0 and n_local >= self.prefetch_min_rows
@@ -288,7 +329,11 @@ class Engine:
                                               batch, _ptr(gp)), "ggp_sgpr_pass2")
                 if distributed:
                     dist.all_reduce(gp, op=dist.ReduceOp.SUM, group=pg)
+                    if kg is not None:
+                        dist.all_reduce(kg[1], op=dist.ReduceOp.SUM, group=pg)
                 grad = grad_mm + gp
+                if kg is not None:   # [d/d(kernel parameters), d_s2, d_Z]
+                    grad = torch.cat([kg[0] + kg[1], grad[:, d + 1:]], dim=1)
             if raise_on_fail:
                 info2_h = info2.cpu()
                 if bool((info2_h != 0).any()):
@@ -309,7 +354,12 @@ class Engine:
             theta = theta.unsqueeze(0)
         n_local, d = X.shape
         m, batch = Z.shape[0], theta.shape[0]
+        theta_ext = theta
+        if self.prog is not None:
+            theta, _, _ = self._composite_rows(theta, d, False)
         self.reserve(n_local, m, d, batch)
+        if self.prog is not None:
+            self._set_kparams()
         self._sgpr_state = None
         with torch.cuda.device(dev):
             cfgp = ctypes.byref(self.cfg_dmma)
@@ -328,7 +378,7 @@ class Engine:
                                            _ptr(None), _ptr(info2)), "ggp_sgpr_finish")
             if bool((info2 != 0).any()):
                 raise NotPSDError(f"I + A W A^T not positive definite; potrf info={info2.tolist()}")
-        self._mark_state(Z, theta, by_value=True)
+        self._mark_state(Z, theta_ext, by_value=True)
         return dict(jitter=jit)
 
     def sgpr_predict(self, Xs, Z, theta, full_cov=False, add_noise=True):
@@ -341,6 +391,9 @@ class Engine:
         ns, d = Xs.shape
         m = Z.shape[0]
         batch = theta.shape[0]
+        if self.prog is not None:
+            theta, _, _ = self._composite_rows(theta, d, False)
+            self._set_kparams()
         mean = torch.empty(batch, ns, dtype=torch.float64, device=dev)
         var = torch.empty(batch, ns, dtype=torch.float64, device=dev)
         cov = torch.empty(batch, ns, ns, dtype=torch.float64, device=dev) if full_cov else None
@@ -472,6 +525,12 @@ class Engine:
         dev = self.device
         X1, X2, theta = _f64c(X1, dev), _f64c(X2, dev), _f64c(theta, dev)
         out = torch.empty(X1.shape[0], X2.shape[0], dtype=torch.float64, device=dev)
+        if self.prog is not None:     # the program is registered per input dimension on a reserved handle
+            d = X1.shape[1]
+            if self._shape is None or self._shape[2] != d:
+                self.reserve(64, 64, d, 1)
+            theta, _, _ = self._composite_rows(theta.reshape(1, -1), d, False)
+            self._set_kparams()
         with torch.cuda.device(dev):
             check(self.lib.ggp_kernel_matrix(self.h, ctypes.byref(self.cfg), _stream(), _ptr(X1), X1.shape[0], _ptr(X2),
                                              X2.shape[0], _ptr(theta), X1.shape[1], _ptr(out)), "ggp_kernel_matrix")

@@ -69,8 +69,109 @@ def sgpr_bound(X, y, Z, lengthscale, outputscale, noise, cfg=None):
     return SGPRBound.apply(X, y, Z, lengthscale, outputscale, noise, cfg)
 
 
+class SGPRBoundComposite(torch.autograd.Function):
+    """Collapsed bound with a composite kernel -- sums of scaled products of RBF / Matern / RQ / periodic factors, the structure of the
+    reference's CO2 model (experiments/co2_bayesian_sgpr_hmc.py:74-83: ScaleKernel(Periodic * RBF) + ScaleKernel(RBF) +
+    ScaleKernel(RQ) + ScaleKernel(RBF) inside InducingPointKernel).  cfg["kernel"] is the program (tuple of terms, each a tuple of
+    factor names); kparams[P] is its parameter row in program order (a_t, then per factor ell[d], then rq: alpha | periodic:
+    period[d]; _lib.make_kprog).  Differentiable in Z, kparams and noise (constrained values)."""
+
+    @staticmethod
+    def forward(ctx, X, y, Z, kparams, noise, cfg=None):
+        c = _cfg(cfg)
+        if isinstance(c["kernel"], str):
+            raise ValueError("SGPRBoundComposite: cfg['kernel'] must be a composite program, e.g. (('periodic', 'rbf'), ('rq',))")
+        eng = Engine.get(X.device, c["kernel"], "fp64", c["chunk_rows"])
+        theta = torch.cat([kparams.reshape(-1), noise.reshape(-1)]).to(torch.float64)
+        need = any(ctx.needs_input_grad[2:5])
+        out = eng.sgpr_eval(X, y, Z, theta, jitter_policy=c["jitter_policy"], need_grad=need, group=c["group"])
+        n_total = out["n_total"][0]
+        scale = (1.0 / n_total) if c["normalize"] == "n" else torch.ones((), dtype=torch.float64, device=X.device)
+        ctx.P = kparams.numel()
+        ctx.shapes = (Z.shape, kparams.shape, noise.shape)
+        ctx.dtypes = (Z.dtype, kparams.dtype, noise.dtype)
+        ctx.save_for_backward(out["grad"][0] * scale if need else torch.empty(0, device=X.device))
+        return (out["bound"][0] * scale).to(X.dtype)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (g,) = ctx.saved_tensors
+        P = ctx.P
+        zs, ks, ns = ctx.shapes
+        zd, kd, nd = ctx.dtypes
+        gout = gout.to(torch.float64)
+        gZ = (gout * g[P + 1:]).reshape(zs).to(zd) if ctx.needs_input_grad[2] else None
+        gk = (gout * g[:P]).reshape(ks).to(kd) if ctx.needs_input_grad[3] else None
+        gn = (gout * g[P]).reshape(ns).to(nd) if ctx.needs_input_grad[4] else None
+        return None, None, gZ, gk, gn, None
+
+
+def sgpr_bound_composite(X, y, Z, kparams, noise, cfg):
+    return SGPRBoundComposite.apply(X, y, Z, kparams, noise, cfg)
+
+
 LOG2 = math.log(2.0)
 LOGPI = math.log(math.pi)
+LOG2PI = math.log(2.0 * math.pi)
+
+# ---- the pymc3 CO2 model (experiments/co2_bayesian_sgpr_hmc.py:107-152) -------------------------------------------------------------
+# cov = n_per^2 Periodic(1, period=1, ls=l_psmooth) ExpQuad(1, l_pdecay) + n_med^2 RatQuad(1, l_med, alpha) + n_trend^2 ExpQuad(1, l_trend)
+#       + n_noise^2 Matern32(1, l_noise);  MarginalSparse(approx="VFE"), noise = sigma
+CO2_PROG = (("periodic", "rbf"), ("rq",), ("rbf",), ("matern32",))
+CO2_NAMES = ("log_n_per", "log_l_pdecay", "log_l_psmooth", "log_n_med", "log_l_med", "log_alpha", "log_n_trend", "log_l_trend",
+             "log_n_noise", "log_l_noise", "sigma_log__")
+CO2_PRIOR_SD = (3.0, 0.1, 1.0, 3.0, 3.0, 0.1, 3.0, 1.0, 3.0, 1.0)      # Normal(0, sd) on the ten logs; sigma ~ HalfNormal(1)
+
+
+_CO2_SD = {}
+
+
+def _co2_sd(device):
+    """prior scales as a device constant (created once per device: no host-to-device copy inside a captured evaluation)"""
+    key = str(device)
+    if key not in _CO2_SD:
+        _CO2_SD[key] = torch.tensor(CO2_PRIOR_SD, dtype=torch.float64, device=device)
+    return _CO2_SD[key]
+
+
+def co2_theta_from_x(x):
+    """x[C, 11] (CO2_NAMES) -> theta[C, 12] of CO2_PROG in one input dimension: [a_per, ell_per = 2 l_psmooth (pymc3's Periodic is
+    exp(-sin^2 / (2 ls^2))), period = 1, l_pdecay | a_med, l_med, alpha | a_trend, l_trend | a_noise, l_noise | sigma^2], and the
+    Jacobian factors d theta / d x of the entries that move (the period is a constant)."""
+    e = torch.exp(x)
+    one = torch.ones_like(e[:, 0])
+    theta = torch.stack([e[:, 0] ** 2, 2.0 * e[:, 2], one, e[:, 1], e[:, 3] ** 2, e[:, 4], e[:, 5], e[:, 6] ** 2, e[:, 7],
+                         e[:, 8] ** 2, e[:, 9], e[:, 10] ** 2], dim=1)
+    return theta
+
+
+def co2_logp_dlogp(x, X, y, Z, jitter_policy="pymc3", engine=None, group=False):
+    """pymc3 log-posterior of the reference's CO2 model and its gradient, batched over the rows of x[C, 11] (CO2_NAMES): the collapsed
+    VFE bound with the composite kernel + Normal priors on the ten log-parameters + HalfNormal(1) on sigma with its log-transform
+    Jacobian.  Rows whose factorisation fails get logp = -inf and a zero gradient."""
+    if X.shape[1] != 1:
+        raise ValueError("the CO2 model is one-dimensional (time)")
+    eng = engine or Engine.get(X.device, CO2_PROG)
+    x = x.to(device=eng.device, dtype=torch.float64)
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    theta = co2_theta_from_x(x)
+    out = eng.sgpr_eval(X, y, Z, theta, jitter_policy=jitter_policy, need_grad=True, group=group, raise_on_fail=False)
+    g = out["grad"]                                       # [C, 11 kernel parameters + s2 + dZ]
+    th = theta
+    # chain rule to x: amplitudes a = e^{2x}: 2 a dF/da ; lengths / alpha v = e^x: v dF/dv ; ell_per = 2 e^x: ell_per dF/d ell_per
+    dx = torch.stack([2.0 * th[:, 0] * g[:, 0], th[:, 3] * g[:, 3], th[:, 1] * g[:, 1], 2.0 * th[:, 4] * g[:, 4], th[:, 5] * g[:, 5],
+                      th[:, 6] * g[:, 6], 2.0 * th[:, 7] * g[:, 7], th[:, 8] * g[:, 8], 2.0 * th[:, 9] * g[:, 9], th[:, 10] * g[:, 10],
+                      2.0 * th[:, 11] * g[:, 11]], dim=1)
+    sd = _co2_sd(x.device)
+    lp = out["bound"] + (-0.5 * (x[:, :10] / sd) ** 2 - torch.log(sd) - 0.5 * LOG2PI).sum(1) \
+        + (0.5 * math.log(2.0 / math.pi) - 0.5 * th[:, 11] + x[:, 10])
+    dx = dx + torch.cat([-x[:, :10] / sd ** 2, (1.0 - th[:, 11]).unsqueeze(1)], dim=1)
+    info = torch.as_tensor(out["info"]).to(device=x.device)
+    bad = (info != 0) | (out["info_b"] != 0) | ~torch.isfinite(lp)
+    lp = torch.where(bad, torch.full_like(lp, -float("inf")), lp)
+    dx = torch.where(bad.unsqueeze(1), torch.zeros_like(dx), dx)
+    return lp, dx
 
 
 def _vfe_eval(x, X, y, Z, jitter_policy, eng, group, with_prior):

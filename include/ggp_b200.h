@@ -27,7 +27,25 @@ extern "C" {
 typedef struct ggp_handle ggp_handle_t;
 
 enum { GGP_KERNEL_RBF = 0, GGP_KERNEL_MATERN32 = 1, GGP_KERNEL_MATERN52 = 2,
-       GGP_KERNEL_RQ = 3 /* rational quadratic (1 + d2 / (2 alpha))^(-alpha), alpha = cfg.kernel_param (a constant of the evaluation) */ };
+       GGP_KERNEL_RQ = 3 /* rational quadratic (1 + d2 / (2 alpha))^(-alpha), alpha = cfg.kernel_param (a constant of the evaluation) */,
+       GGP_KERNEL_PERIODIC = 4 /* factor of a composite kernel only: exp(-2 sum_c sin^2(pi (x_c - z_c) / p_c) / ell_c^2) */,
+       GGP_KERNEL_COMPOSITE = 5 /* cfg.kernel: the program registered with ggp_set_kernel_program */ };
+/* Composite covariance  k(x, z) = sum_t a_t prod_f phi_tf(x, z)  -- the structure of the reference's CO2 model
+ * (experiments/co2_bayesian_sgpr_hmc.py:74-83 gpytorch, :107-149 pymc3).  Factor kinds: GGP_KERNEL_RBF / MATERN32 / MATERN52 / RQ /
+ * PERIODIC, all with ARD lengthscales.  One parameter row per theta draw, in program order:
+ *     for each term t:  a_t (variance),  then for each factor:  ell[d],  then RQ: alpha | PERIODIC: period[d].
+ * With GGP_KERNEL_COMPOSITE the `theta` rows of the SGPR entry points keep their [d+2] shape but only carry
+ * theta[d] = k(x, x) = sum_t a_t and theta[d+1] = s2 (the ell slots are ignored); the parameter rows and the gradient rows w.r.t. them
+ * are the device arrays registered with ggp_set_kernel_params.  The gradient rows of the entry points then hold [0 (d+1 slots), d_s2,
+ * d_Z].  Evaluated on the FP64 DMMA plan (GGP_PREC_FP64_I8 falls back to it); the SVGP / SGPMC entry points reject it (-3). */
+#define GGP_KPROG_MAX_TERMS 6
+#define GGP_KPROG_MAX_FACTORS 3
+#define GGP_KPROG_MAX_PARAMS 64
+typedef struct {
+  int32_t nterms;
+  int32_t nfactors[GGP_KPROG_MAX_TERMS];
+  int32_t kind[GGP_KPROG_MAX_TERMS][GGP_KPROG_MAX_FACTORS];
+} ggp_kprog;
 /* GGP_PREC_FP64: FP64 tensor-core DMMA.  GGP_PREC_FP64_I8: the same contractions evaluated to FP64-class accuracy by exact integer
  * slicing (7 balanced radix-256 digits per operand, tcgen05.mma kind::i8, int32 TMEM accumulators; csrc/gemm_i8.cuh); used for the
  * streamed passes when batch == 1, the padded inducing count is in [128, 4096] and d <= 16, the DMMA path otherwise (the host
@@ -55,6 +73,15 @@ int ggp_destroy(ggp_handle_t* h);
 int ggp_workspace_bytes(const ggp_cfg* cfg, int64_t n_local, int m, int d, int batch, size_t* out);
 /* (re)allocate the handle's workspace; synchronous (cudaMalloc); call once per shape */
 int ggp_reserve(ggp_handle_t* h, const ggp_cfg* cfg, int64_t n_local, int m, int d, int batch);
+
+/* composite kernels: number of parameters of `prog` in d input dimensions (<0: malformed / too many) */
+int ggp_kprog_nparams(const ggp_kprog* prog, int d);
+/* register the program for cfg.kernel == GGP_KERNEL_COMPOSITE on a RESERVED handle (allocates its row accumulators: synchronous) */
+int ggp_set_kernel_program(ggp_handle_t* h, const ggp_kprog* prog, int d);
+/* parameter rows kparams[batch, P] and the two gradient outputs the next finish / pass2 write: kgrad_mm[batch, P] (Kzz part + the
+ * explicit k(x,x) dependence; complete when grad_mm is) and kgrad_partial[batch, P] (this rank's rows of Kzx; all-reduced with
+ * grad_partial when rows are sharded).  Pointers only: nothing is enqueued. */
+int ggp_set_kernel_params(ggp_handle_t* h, const double* kparams, double* kgrad_mm, double* kgrad_partial);
 
 /* SGPR collapsed bound + gradient --------------------------------------------------------------------------
  * Replaces, together:  output = self.forward(train_x); loss = -mll(output, train_y); loss.backward()

@@ -163,3 +163,29 @@ def test_all_in_hmc_logp_is_vfe_logp_plus_standard_normal_on_Z():
         e = torch.zeros_like(x); e[i] = 1e-6
         fd = (priors.all_in_hmc_logp(x + e, X, y, M) - priors.all_in_hmc_logp(x - e, X, y, M)) / 2e-6
         assert abs(float(fd - g[i])) < 1e-5 * max(1.0, abs(float(g[i])))
+
+
+def test_composite_oracle_reduces_to_the_single_kernels_and_layout_matches_the_binding():
+    """oracle/composite.py is pinned to the already-pinned oracle/kernels.py + oracle/sgpr.py: a one-term program is the single
+    kernel, bound and gradients included; the parameter-row layout is the one generalised-gaussian-processes_b200/_lib.py binds."""
+    from oracle import composite as C, kernels as K, sgpr as S
+    import ggp_b200._lib as L
+    X, y, Z, th = make_problem(120, 12, 2, seed=3)
+    ell, sf2, s2 = th[:2], th[2], th[3]
+    for name, kind in (("rbf", "rbf"), ("matern32", "matern32"), ("matern52", "matern52"), ("rq", ("rq", 0.8))):
+        prog = ((name,),)
+        kth = torch.cat([sf2.reshape(1), ell] + ([torch.tensor([0.8], dtype=torch.float64)] if name == "rq" else []))
+        assert relerr(C.composite_kernel(prog, kth, X, Z), K.ard_kernel(X, Z, ell, sf2, kind)) < 1e-14
+        F1, g1 = C.sgpr_bound_and_grads_composite(X, y, Z, prog, kth, s2, jitter_policy=1e-6)
+        F0, g0 = S.sgpr_bound_and_grads_autograd(X, y, Z, ell, sf2, s2, jitter_policy=1e-6, kind=kind)
+        assert relerr(F1, F0) < 1e-13 and relerr(g1["k"][0], g0["sf2"]) < 1e-11 and relerr(g1["k"][1:3], g0["ell"]) < 1e-11
+        assert relerr(g1["Z"], g0["Z"]) < 1e-11 and relerr(g1["s2"], g0["s2"]) < 1e-11
+    # periodic factor: period p, and the pymc3 / gpytorch parameterisations it stands for
+    x1, x2 = X[:5, :1], Z[:4, :1]
+    kp = C.composite_kernel((("periodic",),), torch.tensor([1.0, 1.2, 0.7], dtype=torch.float64), x1, x2)
+    r = (x1 - x2.T).abs()
+    assert relerr(kp, torch.exp(-torch.sin(math.pi * r / 0.7) ** 2 / (2.0 * 0.6 ** 2))) < 1e-14      # pymc3 Periodic(ls=0.6): ell = 2 ls
+    assert relerr(kp, torch.exp(-2.0 * torch.sin(math.pi * r / 0.7) ** 2 / 1.44)) < 1e-14            # gpytorch: lengthscale = ell^2
+    for prog in (C.CO2_PROG, (("periodic", "rbf"), ("rq",), ("matern32", "rbf"), ("matern52",))):
+        for d in (1, 3):
+            assert (C.nparams(prog, d), C.amplitude_indices(prog, d)) == L.kprog_layout(prog, d)
