@@ -23,17 +23,18 @@ constexpr int POTF2_SMEM = 0;
 // info[b] = global index (1-based) of the first pivot <= piv_tol[b], LAPACK potrf style; first failure wins.
 // piv_tol[b]: pivots at or below it count as "not positive definite" (0 = LAPACK semantics; see k_build_kzz).
 constexpr int PF_MB = 8;   // micro-block width
-__global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int64_t ld, int64_t sA, int kb,
-                                                     double* __restrict__ T, int64_t sT, int32_t* info,
-                                                     const double* __restrict__ piv_tol, long long* dbg = nullptr) {
-#define PF_STAMP(slot) do { if (dbg && tid == 0 && blockIdx.x == 0) dbg[slot] = clock64(); } while (0)
+// Device body (256 threads of one CTA, b = batch element): shared by k_potf2_trti2 and by the look-ahead tail of k_chol_trail.
+__device__ __forceinline__ void potf2_trti2_block(double* __restrict__ A, int64_t ld, int64_t sA, int kb, double* __restrict__ T,
+                                                  int64_t sT, int32_t* info, const double* __restrict__ piv_tol, int b,
+                                                  long long* dbg) {
+#define PF_STAMP(slot) do { if (dbg && tid == 0 && b == 0) dbg[slot] = clock64(); } while (0)
   __shared__ double Praw[NB][PF_MB + 1];     // raw panel columns (rows >= g0 used)
   __shared__ double Pnew[NB][PF_MB + 1];     // L[:, g0:g0+8) (0 above the diagonal)
   __shared__ double Tcur[PF_MB][NB + 1];     // current rows g0..g0+7 of T
   __shared__ double Tfin[PF_MB][NB + 1];     // final rows g0..g0+7 of T
   __shared__ double Ldd[PF_MB][PF_MB + 1], Dd[PF_MB][PF_MB + 1];
   __shared__ int bad;
-  const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
   double* Ab = A + b * sA + (int64_t)kb * NB * (ld + 1);
   const double tol = piv_tol ? piv_tol[b] : 0.0;
   double a[4][4], t[4][4];
@@ -210,6 +211,11 @@ __global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int
   if (tid == 0 && bad && info[b] == 0) info[b] = kb * NB + bad;
 #undef PF_STAMP
 }
+__global__ void __launch_bounds__(256) k_potf2_trti2(double* __restrict__ A, int64_t ld, int64_t sA, int kb,
+                                                     double* __restrict__ T, int64_t sT, int32_t* info,
+                                                     const double* __restrict__ piv_tol, long long* dbg = nullptr) {
+  potf2_trti2_block(A, ld, sA, kb, T, sT, info, piv_tol, blockIdx.x, dbg);
+}
 
 // One right-looking step of the blocked Cholesky after the diagonal block kb has been factored (k_potf2_trti2: T = L_kk^{-1}):
 //   panel  L21 = A21 T^T                       (rem x NB,  rem = Mp - (kb + 1) NB)
@@ -235,8 +241,13 @@ __device__ __forceinline__ void ct_mm_nt(const double* __restrict__ sa, const do
     for (int cb = 0; cb < 8; ++cb) dmma884(acc[cb][0], acc[cb][1], a, pb[cb * 8 * CT_LD + 4 * kk]);
   }
 }
-__global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int64_t ld, int64_t sA, int kb, const double* __restrict__ T,
-                                                    int64_t sT, double* __restrict__ S, int64_t sS) {
+// LOOK-AHEAD (info != NULL): the CTA that owns the next diagonal block (bi = bj = 0) factors and inverts it right after its update,
+// in this launch, while the other CTAs are still updating their blocks -- the dependent chain of a step is then ONE kernel
+// (load, two products, update, 64-column factor + inverse) instead of two with a launch boundary between them, and the
+// factorisation of block k + 1 overlaps the rest of the trailing update of step k.
+__global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int64_t ld, int64_t sA, int kb, double* __restrict__ T,
+                                                    int64_t sT, double* __restrict__ S, int64_t sS, int32_t* info = nullptr,
+                                                    const double* __restrict__ piv_tol = nullptr) {
   const int bj = blockIdx.x, bi = blockIdx.y, b = blockIdx.z;
   if (bi < bj) return;
   extern __shared__ __align__(16) unsigned char ct_raw[];
@@ -282,6 +293,10 @@ __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int6
     o.x -= c[cb][0];
     o.y -= c[cb][1];
     *reinterpret_cast<double2*>(dst + 8 * cb) = o;
+  }
+  if (info && bi == 0 && bj == 0) {
+    __syncthreads();   // the updated diagonal block (global memory, written by this CTA) is visible to all its threads
+    potf2_trti2_block(A, ld, sA, kb + 1, T, sT, info, piv_tol, b, nullptr);
   }
 }
 // after the last step: A = [diagonal blocks of A (lower part)] + [panel blocks from S], strict upper triangle zero

@@ -13,6 +13,7 @@
 #include "dense_mm.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_tma.cuh"
+#include "gemm_mm64.cuh"
 #include "gemm_i8.cuh"
 #include "kernel_tiles.cuh"
 #include "misc.cuh"
@@ -97,6 +98,8 @@ struct ggp_handle {
   std::vector<CholGraph> chol_graphs;
   bool use_graphs = true;
   bool chol_fused = true;       // fused panel + trailing-update kernel in the blocked Cholesky (GGP_CHOL_FUSED=0: two library GEMMs)
+  bool chol_lookahead = true;   // the trailing-update CTA that owns the next diagonal block factors it in the same launch (GGP_CHOL_LOOKAHEAD=0: own launch)
+  int mm64_max_tiles = 96;      // EPI_STORE products with at most this many 128 x 128 work items run on k_mm64 (GGP_MM64_MAX_TILES; 0 = never)
   cudaStream_t cap_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second stream for the independent product chain of the finish section (fork / join by events)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -264,6 +267,21 @@ static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& pin
   if (p.ntm == 0 || p.ntn == 0 || nbatch == 0) return 0;
   p.tiles_per_z = p.sym == 1 ? sym_upper_tiles(p.ntm, p.ntn) : (p.sym == 2 ? sym_lower_tiles(p.ntm, p.ntn) : p.ntm * p.ntn);
   p.total = p.tiles_per_z * nbatch * p.nz2 * p.splits;
+  const bool alias = (p.C == p.A || p.C == p.B);
+  // small products (the m x m section): 64 x 64 work items, heaviest first, two CTAs per SM -- see gemm_mm64.cuh
+  auto even16 = [](const double* ptr, int64_t ld, int64_t s1, int64_t s2) {
+    return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((ld | s1 | s2) & 1) == 0;
+  };
+  if (epi == EPI_STORE && p.total <= h->mm64_max_tiles && !p.rowdot && p.splits == 1 && p.sym == 0 && !alias &&
+      even16(p.A, p.lda, p.sA, p.sA2) && even16(p.B, p.ldb, p.sB, p.sB2)) {
+    p.ntm = (p.M + S_T - 1) / S_T;
+    p.ntn = (p.N + S_T - 1) / S_T;
+    p.tiles_per_z = p.ntm * p.ntn;
+    p.total = p.tiles_per_z * nbatch * p.nz2;
+    k_mm64<<<p.total, S_THREADS, S_SMEM, st>>>(p);
+    CKL();
+    return 0;
+  }
   const int grid = std::min(p.total, h->sm_count * CTAS_PER_SM);   // persistent CTAs, static snake order over the work items
   if (g_use_tma < 0) {
     const char* e = getenv("GGP_GEMM_TMA");
@@ -272,7 +290,6 @@ static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& pin
   CUtensorMap tmA, tmB;
   // in-place products (C aliases an operand) stay on the LDGSTS kernel: its loads of a tile are complete before its epilogue,
   // whereas the TMA producer prefetches the next tiles while this tile's C is being written
-  const bool alias = (p.C == p.A || p.C == p.B);
   if (g_use_tma && !alias && make_operand_map(&tmA, p.A, p.M, p.K, p.lda, p.nz2, p.sA2, nbatch, p.sA, &p.tmA_pz, &p.tmA_bz) &&
       make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.nz2, p.sB2, nbatch, p.sB, &p.tmB_pz, &p.tmB_bz)) {
     if (epi == EPI_STORE)
@@ -316,15 +333,19 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
   const int64_t sM = (int64_t)Mp * Mp;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
   // right-looking: factor the diagonal block, form the panel with the block inverse, update the trailing lower tiles
+  const bool ahead = h->chol_fused && h->chol_lookahead;
   for (int k = 0; k < nblk; ++k) {
     const int k0 = k * NB;
-    k_potf2_trti2<<<batch, 256, POTF2_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, info, h->piv_tol);
-    CKL();
+    if (k == 0 || !ahead) {   // with look-ahead, block k > 0 was factored by the trailing update of step k - 1
+      k_potf2_trti2<<<batch, 256, POTF2_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, info, h->piv_tol);
+      CKL();
+    }
     if (k < nblk - 1) {
       const int rem = Mp - k0 - NB;
       if (h->chol_fused) {
         // panel + trailing update of this step in one kernel; the panel goes to the scratch matrix T1 (merged into A below)
-        k_chol_trail<<<dim3(rem / NB, rem / NB, batch), 256, CT_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, h->T1, sM);
+        k_chol_trail<<<dim3(rem / NB, rem / NB, batch), 256, CT_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, h->T1, sM,
+                                                                              ahead ? info : nullptr, h->piv_tol);
         CKL();
         continue;
       }
@@ -576,6 +597,9 @@ int ggp_create(ggp_handle_t** out, int device) {
   CK(cudaFuncSetAttribute(k_build_kc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_chol_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
   { const char* e = getenv("GGP_CHOL_FUSED"); h->chol_fused = !(e && e[0] == '0'); }
+  { const char* e = getenv("GGP_CHOL_LOOKAHEAD"); h->chol_lookahead = !(e && e[0] == '0'); }
+  { const char* e = getenv("GGP_MM64_MAX_TILES"); if (e) h->mm64_max_tiles = atoi(e); }
+  CK(cudaFuncSetAttribute(k_mm64, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
   CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_F64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_F64, 64>()));
   CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_SLICE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_SLICE, 64>()));
   CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_MOMENTS, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_MOMENTS, 64>()));
