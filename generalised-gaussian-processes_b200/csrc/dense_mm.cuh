@@ -245,11 +245,37 @@ __device__ __forceinline__ void ct_mm_nt(const double* __restrict__ sa, const do
 // in this launch, while the other CTAs are still updating their blocks -- the dependent chain of a step is then ONE kernel
 // (load, two products, update, 64-column factor + inverse) instead of two with a launch boundary between them, and the
 // factorisation of block k + 1 overlaps the rest of the trailing update of step k.
+// the same product when sb is LOWER triangular (sb[c][k] = 0 for k > c: the block inverse T): column block cb needs k-step kk only if
+// 4 kk <= 8 cb + 7, i.e. cb >= kk / 2 -- compile-time bounds after unrolling, so the skipped DMMAs are not issued at all (half of them)
+__device__ __forceinline__ void ct_mm_nt_lower_b(const double* __restrict__ sa, const double* __restrict__ sb, int w, int lane,
+                                                 double (&acc)[8][2]) {
+  const int g = lane >> 2, q = lane & 3;
+  const double* pa = sa + (8 * w + g) * CT_LD + q;
+  const double* pb = sb + g * CT_LD + q;
+#pragma unroll
+  for (int kk = 0; kk < NB / 4; ++kk) {
+    const double a = pa[4 * kk];
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb)
+      if (cb >= kk / 2) dmma884(acc[cb][0], acc[cb][1], a, pb[cb * 8 * CT_LD + 4 * kk]);
+  }
+}
+// 64 x 64 block (row pitch ld doubles, 16-byte aligned rows) -> shared tile with the CT_LD pitch, by 16-byte LDGSTS: 8 per thread
+__device__ __forceinline__ void ct_load_block_async(double* __restrict__ dst, const double* __restrict__ src, int64_t ld, int tid) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int e = tid + 256 * p, r = e >> 5, c2 = (e & 31) * 2;
+    cp_async16(dst + r * CT_LD + c2, src + (int64_t)r * ld + c2, 16);
+  }
+}
 __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int64_t ld, int64_t sA, int kb, double* __restrict__ T,
                                                     int64_t sT, double* __restrict__ S, int64_t sS, int32_t* info = nullptr,
-                                                    const double* __restrict__ piv_tol = nullptr) {
+                                                    const double* __restrict__ piv_tol = nullptr, long long* dbg = nullptr) {
   const int bj = blockIdx.x, bi = blockIdx.y, b = blockIdx.z;
   if (bi < bj) return;
+  // developer timeline (GGP_CHOL_TIMELINE): stamps of the CTA on the dependent chain, 8 slots per step
+#define CT_STAMP(slot, v) do { if (dbg && threadIdx.x == 0 && bi == 0 && bj == 0 && b == 0) dbg[kb * 8 + slot] = (v); } while (0)
+  if (dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); CT_STAMP(0, (long long)gt); CT_STAMP(1, clock64()); }
   extern __shared__ __align__(16) unsigned char ct_raw[];
   double* sAi = reinterpret_cast<double*>(ct_raw);   // A21 block bi, then P_i
   double* sAj = sAi + NB * CT_LD;                    // A21 block bj, then P_j
@@ -258,18 +284,19 @@ __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int6
   const int k0 = kb * NB, r0 = k0 + NB;
   double* Ab = A + b * sA;
   const double* Tb = T + b * sT + (int64_t)kb * NB * NB;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e / NB, c = e % NB;
-    sAi[r * CT_LD + c] = Ab[(int64_t)(r0 + bi * NB + r) * ld + k0 + c];
-    sAj[r * CT_LD + c] = Ab[(int64_t)(r0 + bj * NB + r) * ld + k0 + c];
-    sTk[r * CT_LD + c] = (c <= r) ? Tb[r * NB + c] : 0.0;
-  }
+  // (k_potf2_trti2 writes T with explicit zeros above the diagonal, so the block can be copied as it is)
+  ct_load_block_async(sAi, Ab + (int64_t)(r0 + bi * NB) * ld + k0, ld, tid);
+  if (bi != bj) ct_load_block_async(sAj, Ab + (int64_t)(r0 + bj * NB) * ld + k0, ld, tid);
+  ct_load_block_async(sTk, Tb, NB, tid);
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
+  CT_STAMP(2, clock64());
   double pi[8][2], pj[8][2];
 #pragma unroll
   for (int cb = 0; cb < 8; ++cb) pi[cb][0] = pi[cb][1] = pj[cb][0] = pj[cb][1] = 0.0;
-  ct_mm_nt(sAi, sTk, w, lane, pi);              // P_i[r][c] = sum_k A21_i[r][k] T[c][k]
-  if (bi != bj) ct_mm_nt(sAj, sTk, w, lane, pj);
+  ct_mm_nt_lower_b(sAi, sTk, w, lane, pi);      // P_i[r][c] = sum_{k <= c} A21_i[r][k] T[c][k]
+  if (bi != bj) ct_mm_nt_lower_b(sAj, sTk, w, lane, pj);
   __syncthreads();                              // everyone is done reading A21_i / A21_j
 #pragma unroll
   for (int cb = 0; cb < 8; ++cb) {
@@ -282,6 +309,7 @@ __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int6
     for (int cb = 0; cb < 8; ++cb) *reinterpret_cast<double2*>(Sb + 8 * cb) = make_double2(pi[cb][0], pi[cb][1]);
   }
   __syncthreads();
+  CT_STAMP(3, clock64());
   double c[8][2];
 #pragma unroll
   for (int cb = 0; cb < 8; ++cb) c[cb][0] = c[cb][1] = 0.0;
@@ -296,9 +324,115 @@ __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int6
   }
   if (info && bi == 0 && bj == 0) {
     __syncthreads();   // the updated diagonal block (global memory, written by this CTA) is visible to all its threads
+    CT_STAMP(4, clock64());
     potf2_trti2_block(A, ld, sA, kb + 1, T, sT, info, piv_tol, b, nullptr);
+    CT_STAMP(5, clock64());
+    if (dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); CT_STAMP(6, (long long)gt); }
+  }
+#undef CT_STAMP
+}
+// Whole factorisation + explicit inverse for Mp <= 128 (one or two diagonal blocks) in ONE launch, one CTA per batch element:
+//   L00, T0 = potf2(A00);  L10 = A10 T0^T;  L11, T1 = potf2(A11 - L10 L10^T);  Linv = [[T0, 0], [-T1 L10 T0, T1]];  LinvT = Linv^T
+// -- what chol_and_inverse_launches does with 8 dependent launches at this size (2 x potf2, trail, merge, blockdiag, transpose,
+// 2 products, transpose), each of them latency-bound.  This is the m x m section of the reference's own problem sizes (co2:
+// M = 100, demo: M = 20), evaluated twice per leapfrog step of every HMC chain.  Same arithmetic as the multi-launch plan
+// (DMMA 64^3 products, the same diagonal-block kernel body), so the two agree to rounding.
+__global__ void __launch_bounds__(256) k_chol_inv_small(double* __restrict__ A, int Mp, int64_t sA, double* __restrict__ T, int64_t sT,
+                                                        double* __restrict__ Linv, double* __restrict__ LinvT, int64_t sL,
+                                                        int32_t* info, const double* __restrict__ piv_tol) {
+  extern __shared__ __align__(16) unsigned char ct_raw[];
+  double* s0 = reinterpret_cast<double*>(ct_raw);
+  double* s1 = s0 + NB * CT_LD;
+  double* s2 = s1 + NB * CT_LD;
+  const int b = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  double* Ab = A + b * sA;
+  double* Li = Linv + b * sL;
+  double* LiT = LinvT + b * sL;
+  const double* Tb = T + b * sT;
+  potf2_trti2_block(A, Mp, sA, 0, T, sT, info, piv_tol, b, nullptr);
+  __syncthreads();
+  if (Mp == NB) {
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int r = e / NB, c = e % NB;
+      const double v = (c <= r) ? Tb[r * NB + c] : 0.0;
+      Li[(int64_t)r * Mp + c] = v;
+      LiT[(int64_t)c * Mp + r] = v;
+    }
+    return;
+  }
+  // ---- Mp == 2 NB
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    s0[r * CT_LD + c] = Ab[(int64_t)(NB + r) * Mp + c];          // A10
+    s2[r * CT_LD + c] = (c <= r) ? Tb[r * NB + c] : 0.0;         // T0
+  }
+  __syncthreads();
+  double acc[8][2];
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) acc[cb][0] = acc[cb][1] = 0.0;
+  ct_mm_nt_lower_b(s0, s2, w, lane, acc);                        // L10 = A10 T0^T
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) {
+    const double2 v = make_double2(acc[cb][0], acc[cb][1]);
+    *reinterpret_cast<double2*>(s1 + (8 * w + g) * CT_LD + 8 * cb + 2 * q) = v;
+    *reinterpret_cast<double2*>(Ab + (int64_t)(NB + 8 * w + g) * Mp + 8 * cb + 2 * q) = v;
+    *reinterpret_cast<double2*>(Ab + (int64_t)(8 * w + g) * Mp + NB + 8 * cb + 2 * q) = make_double2(0.0, 0.0);   // A01 = 0
+    acc[cb][0] = acc[cb][1] = 0.0;
+  }
+  __syncthreads();
+  ct_mm_nt(s1, s1, w, lane, acc);                                // A11 -= L10 L10^T
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) {
+    double2* dst = reinterpret_cast<double2*>(Ab + (int64_t)(NB + 8 * w + g) * Mp + NB + 8 * cb + 2 * q);
+    double2 o = *dst;
+    o.x -= acc[cb][0];
+    o.y -= acc[cb][1];
+    *dst = o;
+  }
+  __syncthreads();
+  potf2_trti2_block(A, Mp, sA, 1, T, sT, info, piv_tol, b, nullptr);
+  __syncthreads();
+  // W = L10 T0 (operand "B" of the NT product = T0^T), then X = T1 W (operand "B" = W^T)
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    s2[c * CT_LD + r] = (c <= r) ? Tb[r * NB + c] : 0.0;                   // s2[c][k] = T0[k][c]
+    s0[r * CT_LD + c] = (c <= r) ? Tb[NB * NB + r * NB + c] : 0.0;         // T1
+  }
+  __syncthreads();
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) acc[cb][0] = acc[cb][1] = 0.0;
+  ct_mm_nt(s1, s2, w, lane, acc);
+  __syncthreads();                                               // everyone is done reading s2 (T0^T)
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) {
+    s2[(8 * cb + 2 * q) * CT_LD + 8 * w + g] = acc[cb][0];       // s2[c][k] = W[k][c]
+    s2[(8 * cb + 2 * q + 1) * CT_LD + 8 * w + g] = acc[cb][1];
+    acc[cb][0] = acc[cb][1] = 0.0;
+  }
+  __syncthreads();
+  ct_mm_nt(s0, s2, w, lane, acc);
+  __syncthreads();
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) {                               // s1 = X = -T1 L10 T0 (staged for the coalesced output below)
+    s1[(8 * w + g) * CT_LD + 8 * cb + 2 * q] = -acc[cb][0];
+    s1[(8 * w + g) * CT_LD + 8 * cb + 2 * q + 1] = -acc[cb][1];
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    const double t0 = (c <= r) ? Tb[r * NB + c] : 0.0, t1 = s0[r * CT_LD + c];
+    Li[(int64_t)r * Mp + c] = t0;
+    Li[(int64_t)r * Mp + NB + c] = 0.0;
+    Li[(int64_t)(NB + r) * Mp + c] = s1[r * CT_LD + c];
+    Li[(int64_t)(NB + r) * Mp + NB + c] = t1;
+    // transposed copy, written row by row of LinvT: LinvT[r][c] = Linv[c][r]
+    LiT[(int64_t)r * Mp + c] = (r <= c) ? Tb[c * NB + r] : 0.0;
+    LiT[(int64_t)r * Mp + NB + c] = s1[c * CT_LD + r];
+    LiT[(int64_t)(NB + r) * Mp + c] = 0.0;
+    LiT[(int64_t)(NB + r) * Mp + NB + c] = s0[c * CT_LD + r];
   }
 }
+
 // after the last step: A = [diagonal blocks of A (lower part)] + [panel blocks from S], strict upper triangle zero
 __global__ void k_tril_merge(double* __restrict__ A, const double* __restrict__ S, int Mp, int64_t sA, int64_t sS) {
   const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
@@ -314,14 +448,20 @@ __global__ void k_tril(double* __restrict__ A, int Mp, int64_t sA) {
   if (i < Mp && j < Mp && j > i) A[blockIdx.z * sA + (int64_t)i * Mp + j] = 0.0;
 }
 
-// Linv = blockdiag(T_0, T_1, ...), zero elsewhere
-__global__ void k_init_blockdiag(double* __restrict__ Linv, int Mp, int64_t sL, const double* __restrict__ T, int64_t sT) {
+// Linv = blockdiag(T_0, T_1, ...), zero elsewhere; LinvT (optional) = its transpose
+__global__ void k_init_blockdiag(double* __restrict__ Linv, int Mp, int64_t sL, const double* __restrict__ T, int64_t sT,
+                                 double* __restrict__ LinvT = nullptr) {
   const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
   if (i >= Mp || j >= Mp) return;
   const int bi = i / NB, bj = j / NB;
-  double v = 0.0;
-  if (bi == bj) v = T[blockIdx.z * sT + (int64_t)bi * NB * NB + (i % NB) * NB + (j % NB)];
+  double v = 0.0, vt = 0.0;
+  if (bi == bj) {
+    const double* Tb = T + blockIdx.z * sT + (int64_t)bi * NB * NB;
+    v = Tb[(i % NB) * NB + (j % NB)];
+    vt = Tb[(j % NB) * NB + (i % NB)];
+  }
   Linv[blockIdx.z * sL + (int64_t)i * Mp + j] = v;
+  if (LinvT) LinvT[blockIdx.z * sL + (int64_t)i * Mp + j] = vt;
 }
 
 // out = in^T  (32x32 tiles through shared memory).  grid (Mp/32, Mp/32, batch), block (32, 8)

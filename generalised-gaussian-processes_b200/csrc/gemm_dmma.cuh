@@ -80,6 +80,9 @@ struct GemmP {
   double* mom;      int64_t sMomTile, sMom;  // [batch][tile_n*4 + warp_col][M][2d+1]
   // EPI_STORE, optional: per-tile row dots against yv (b = A y)
   double* rowdot;   int64_t sRowdot;         // [batch][tile_n][M]
+  // k_mm64 only, optional: the result is ALSO stored transposed, Ct[j * ldct + i] = C[i, j] (same batch / pair strides as C):
+  // the recursive triangular inverse keeps L^-1 and L^-T in step without a transpose kernel per level
+  double* Ct;       int64_t ldct;
 };
 
 struct WorkItem {

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_mm64(const GemmP p) {
   cp_async_wait<0>();
 
   double* __restrict__ C = p.C + bz * p.sC + pz * p.sC2;
+  double* __restrict__ Ct = p.Ct ? p.Ct + bz * p.sC + pz * p.sC2 : nullptr;
   const bool vec16 = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -125,9 +126,11 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_mm64(const GemmP p) {
           if (p.beta != 0.0) { v0 += p.beta * dst[0]; v1 += p.beta * dst[1]; }
           dst[0] = v0; dst[1] = v1;
         }
+        if (Ct) { Ct[(int64_t)gc * p.ldct + gr] = v0; Ct[(int64_t)(gc + 1) * p.ldct + gr] = v1; }
       } else if (gc < p.N) {
         if (p.beta != 0.0) v0 += p.beta * dst[0];
         dst[0] = v0;
+        if (Ct) Ct[(int64_t)gc * p.ldct + gr] = v0;
       }
     }
   }

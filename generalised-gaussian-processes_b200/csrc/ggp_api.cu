@@ -99,12 +99,14 @@ struct ggp_handle {
   bool use_graphs = true;
   bool chol_fused = true;       // fused panel + trailing-update kernel in the blocked Cholesky (GGP_CHOL_FUSED=0: two library GEMMs)
   bool chol_lookahead = true;   // the trailing-update CTA that owns the next diagonal block factors it in the same launch (GGP_CHOL_LOOKAHEAD=0: own launch)
+  bool chol_small = true;       // Mp <= 128: the whole factorisation + inverse in one launch (GGP_CHOL_SMALL=0: the multi-launch plan)
   int mm64_max_tiles = 96;      // EPI_STORE products with at most this many 128 x 128 work items run on k_mm64 (GGP_MM64_MAX_TILES; 0 = never)
   cudaStream_t cap_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second stream for the independent product chain of the finish section (fork / join by events)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool aux_pending = false;            // work of the last finish() is still running on aux_stream: join before its buffers are touched
   int32_t* info_ws = nullptr;
+  long long* ct_dbg = nullptr;         // developer timeline of the Cholesky chain (GGP_CHOL_TIMELINE)
   double* ysc = nullptr;
   double* rk_part = nullptr;
   double* piv_tol = nullptr;   // [batch] pivot threshold of the next Cholesky (k_build_kzz sets it; 0 = LAPACK semantics)
@@ -260,6 +262,16 @@ static bool make_operand_map(CUtensorMap* tm, const double* ptr, int rows, int K
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// small products (the m x m section) run on 64 x 64 work items, heaviest first, two CTAs per SM -- see gemm_mm64.cuh
+static bool mm64_eligible(const ggp_handle* h, int epi, const GemmP& p, int nbatch) {
+  auto even16 = [](const double* ptr, int64_t ld, int64_t s1, int64_t s2) {
+    return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((ld | s1 | s2) & 1) == 0;
+  };
+  const int64_t t128 = (int64_t)((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * nbatch * p.nz2;
+  return epi == EPI_STORE && t128 <= h->mm64_max_tiles && !p.rowdot && p.splits == 1 && p.sym == 0 && p.C != p.A && p.C != p.B &&
+         even16(p.A, p.lda, p.sA, p.sA2) && even16(p.B, p.ldb, p.sB, p.sB2);
+}
+
 static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& pin, int nbatch) {
   GemmP p = pin;
   p.ntm = (p.M + BM - 1) / BM;
@@ -268,12 +280,7 @@ static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& pin
   p.tiles_per_z = p.sym == 1 ? sym_upper_tiles(p.ntm, p.ntn) : (p.sym == 2 ? sym_lower_tiles(p.ntm, p.ntn) : p.ntm * p.ntn);
   p.total = p.tiles_per_z * nbatch * p.nz2 * p.splits;
   const bool alias = (p.C == p.A || p.C == p.B);
-  // small products (the m x m section): 64 x 64 work items, heaviest first, two CTAs per SM -- see gemm_mm64.cuh
-  auto even16 = [](const double* ptr, int64_t ld, int64_t s1, int64_t s2) {
-    return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((ld | s1 | s2) & 1) == 0;
-  };
-  if (epi == EPI_STORE && p.total <= h->mm64_max_tiles && !p.rowdot && p.splits == 1 && p.sym == 0 && !alias &&
-      even16(p.A, p.lda, p.sA, p.sA2) && even16(p.B, p.ldb, p.sB, p.sB2)) {
+  if (mm64_eligible(h, epi, p, nbatch)) {
     p.ntm = (p.M + S_T - 1) / S_T;
     p.ntn = (p.N + S_T - 1) / S_T;
     p.tiles_per_z = p.ntm * p.ntn;
@@ -282,6 +289,7 @@ static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& pin
     CKL();
     return 0;
   }
+  if (p.Ct) return fail(-3, "launch_gemm: the transposed second store exists on the small-tile kernel only");
   const int grid = std::min(p.total, h->sm_count * CTAS_PER_SM);   // persistent CTAs, static snake order over the work items
   if (g_use_tma < 0) {
     const char* e = getenv("GGP_GEMM_TMA");
@@ -334,6 +342,11 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
   // right-looking: factor the diagonal block, form the panel with the block inverse, update the trailing lower tiles
   const bool ahead = h->chol_fused && h->chol_lookahead;
+  if (ahead && h->chol_small && nblk <= 2) {   // one or two diagonal blocks: factor + inverse + transposed inverse in one launch
+    k_chol_inv_small<<<batch, 256, CT_SMEM, st>>>(A, Mp, sM, h->Tblk, sM, Linv, LinvT, sM, info, h->piv_tol);
+    CKL();
+    return 0;
+  }
   for (int k = 0; k < nblk; ++k) {
     const int k0 = k * NB;
     if (k == 0 || !ahead) {   // with look-ahead, block k > 0 was factored by the trailing update of step k - 1
@@ -345,7 +358,7 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
       if (h->chol_fused) {
         // panel + trailing update of this step in one kernel; the panel goes to the scratch matrix T1 (merged into A below)
         k_chol_trail<<<dim3(rem / NB, rem / NB, batch), 256, CT_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, h->T1, sM,
-                                                                              ahead ? info : nullptr, h->piv_tol);
+                                                                              ahead ? info : nullptr, h->piv_tol, h->ct_dbg);
         CKL();
         continue;
       }
@@ -365,13 +378,18 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
     k_tril<<<g16, b16, 0, st>>>(A, Mp, sM);
     CKL();
   }
-  // recursive-doubling triangular inverse
-  k_init_blockdiag<<<g16, b16, 0, st>>>(Linv, Mp, sM, h->Tblk, sM);
+  // recursive-doubling triangular inverse.  L^-T is kept in step with L^-1: the block-diagonal start writes both, and a level whose
+  // second product runs on the small-tile kernel stores its result block transposed as well (otherwise: one transpose per level)
+  k_init_blockdiag<<<g16, b16, 0, st>>>(Linv, Mp, sM, h->Tblk, sM, LinvT);
   CKL();
   const dim3 gt(Mp / 32, Mp / 32, batch), bt(32, 8);
+  bool lt_current = true;
   for (int s = NB; s < Mp; s *= 2) {
-    k_transpose<<<gt, bt, 0, st>>>(Linv, LinvT, Mp, sM);
-    CKL();
+    if (!lt_current) {
+      k_transpose<<<gt, bt, 0, st>>>(Linv, LinvT, Mp, sM);
+      CKL();
+      lt_current = true;
+    }
     const int npairs = Mp / (2 * s);
     const int64_t sPair = (int64_t)2 * s * (Mp + 1);
     // C1T = Inv11^T-rows x L21-rows :  Wk[pair upper-right block][j,i] = sum_k Inv11T[j,k] L21[i,k]
@@ -382,10 +400,18 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
     GemmP p2 = gemm_basic(Linv + (int64_t)s * (Mp + 1), Mp, sM, h->Wk + s, Mp, sM, Linv + (int64_t)s * Mp, Mp, sM, s, s, s,
                           -1.0, 0.0, KM_A_LOWER);
     p2.nz2 = npairs; p2.sA2 = sPair; p2.sB2 = sPair; p2.sC2 = sPair;
+    if (mm64_eligible(h, EPI_STORE, p2, batch)) {
+      p2.Ct = LinvT + s;          // the pair's upper-right block of L^-T (pair stride and batch stride as for C)
+      p2.ldct = Mp;
+    } else {
+      lt_current = false;
+    }
     RUN(launch_gemm(h, st, EPI_STORE, p2, batch));
   }
-  k_transpose<<<gt, bt, 0, st>>>(Linv, LinvT, Mp, sM);
-  CKL();
+  if (!lt_current) {
+    k_transpose<<<gt, bt, 0, st>>>(Linv, LinvT, Mp, sM);
+    CKL();
+  }
   return 0;
 }
 
@@ -598,6 +624,8 @@ int ggp_create(ggp_handle_t** out, int device) {
   CK(cudaFuncSetAttribute(k_chol_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
   { const char* e = getenv("GGP_CHOL_FUSED"); h->chol_fused = !(e && e[0] == '0'); }
   { const char* e = getenv("GGP_CHOL_LOOKAHEAD"); h->chol_lookahead = !(e && e[0] == '0'); }
+  { const char* e = getenv("GGP_CHOL_SMALL"); h->chol_small = !(e && e[0] == '0'); }
+  CK(cudaFuncSetAttribute(k_chol_inv_small, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
   { const char* e = getenv("GGP_MM64_MAX_TILES"); if (e) h->mm64_max_tiles = atoi(e); }
   CK(cudaFuncSetAttribute(k_mm64, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
   CK(cudaFuncSetAttribute(k_gemm_i8<I8_EPI_F64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, i8_smem<I8_EPI_F64, 64>()));
@@ -626,6 +654,7 @@ int ggp_destroy(ggp_handle_t* h) {
   if (h->atq_all) cudaFree(h->atq_all);
   if (h->arena_i8) cudaFree(h->arena_i8);
   if (h->krow) cudaFree(h->krow);
+  if (h->ct_dbg) cudaFree(h->ct_dbg);
   delete h;
   return 0;
 }
@@ -1117,29 +1146,27 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
                   batch));
   const double* bsrc = partial + (int64_t)m * m;
   // c = LBinv b / s ; beta = Binv b ; u = Linv^T beta / s^2
-  k_gemv<<<gv, 256, 0, st>>>(h->LBinv, Mp, sM, bsrc, sP, h->cvec, Mp, m, m, 1.0, theta, d, 1);
-  CKL();
+  auto bound_part = [&](cudaStream_t s1) -> int {   // c and the scalars of the bound / dF/ds2: nothing pass 2 waits for
+    k_gemv<<<gv, 256, 0, s1>>>(h->LBinv, Mp, sM, bsrc, sP, h->cvec, Mp, m, m, 1.0, theta, d, 1);
+    CKL();
+    k_bound_scalars<<<batch, 256, 0, s1>>>(partial, sP, m, Mp, theta, d, h->Bm, h->Binv, sM, h->cvec, h->beta, Mp, bound,
+                                           need_grad ? h->ds2 : nullptr);
+    CKL();
+    return 0;
+  };
   k_gemv<<<gv, 256, 0, st>>>(h->Binv, Mp, sM, bsrc, sP, h->beta, Mp, m, m, 1.0, theta, d, 0);
   CKL();
+  if (!need_grad) return bound_part(st);
   k_gemv<<<gv, 256, 0, st>>>(h->LinvT, Mp, sM, h->beta, Mp, h->u, Mp, m, m, 1.0, theta, d, 2);
   CKL();
-  k_bound_scalars<<<batch, 256, 0, st>>>(partial, sP, m, Mp, theta, d, h->Bm, h->Binv, sM, h->cvec, h->beta, Mp, bound,
-                                         need_grad ? h->ds2 : nullptr);
-  CKL();
-  if (!need_grad) return 0;
   k_make_PA_Gbar<<<g16, b16, 0, st>>>(partial, sP, m, Mp, theta, d, h->Binv, h->beta, Mp, h->PA, h->Gbar, sM);
-  CKL();
-  // sum(G o Kzx) = tr(P_A S) + beta^T b / s^2 from the m x m quantities: dF/dsf2 of every kernel kind (see k_grad_from_moments)
-  k_rk_partial<<<dim3(RK_BLOCKS, batch), 256, 0, st>>>(partial, sP, m, Mp, h->PA, sM, h->rk_part);
-  CKL();
-  k_rk_from_mm<<<batch, 256, 0, st>>>(partial, sP, m, Mp, theta, d, h->rk_part, h->beta, h->rk);
   CKL();
   // Q = Linv^T PA (kept in h->P; pass 2 forms dF/dKzx = Q A + u y^T from A = L^{-1} Kzx) ;  Gzz = -1/2 Linv^T Gbar Linv
   // (Not P = Linv^T PA Linv applied to Kzx, SURVEY R5 as written: P has entries of size 1 / lambda_min(Kzz) and P Kzx cancels down by
   // cond(Kzz) -- 1e-8 .. 2e-6 of the gradient at the headline Kzz in float64 against an extended-precision evaluation, whereas Q A,
   // which is what autograd through the triangular solve computes, loses cond(L) eps: tests/test_oracle_hp.py)
-  // The Gzz chain (scratch Wk, free outside the triangular inverse) and everything that hangs off it goes to the auxiliary stream:
-  // see join_aux.
+  // Only beta, u, P_A and Q are on the path to pass 2.  Everything else -- c and the scalars of the bound, rk, the Gzz chain (scratch Wk,
+  // free outside the triangular inverse) and what hangs off it -- goes to the auxiliary stream: see join_aux.
   const bool side = !getenv("GGP_MM_ONE_STREAM");
   cudaStream_t st2 = st;
   if (side) {
@@ -1152,8 +1179,14 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
     CK(cudaEventRecord(h->ev_fork, st));
     CK(cudaStreamWaitEvent(st2, h->ev_fork, 0));
   }
-  double* T2 = side ? h->Wk : h->T1;
   RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->PA, Mp, sM, h->P, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
+  RUN(bound_part(st2));
+  // sum(G o Kzx) = tr(P_A S) + beta^T b / s^2 from the m x m quantities: dF/dsf2 of every kernel kind (see k_grad_from_moments)
+  k_rk_partial<<<dim3(RK_BLOCKS, batch), 256, 0, st2>>>(partial, sP, m, Mp, h->PA, sM, h->rk_part);
+  CKL();
+  k_rk_from_mm<<<batch, 256, 0, st2>>>(partial, sP, m, Mp, theta, d, h->rk_part, h->beta, h->rk);
+  CKL();
+  double* T2 = side ? h->Wk : h->T1;
   RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(h->LinvT, Mp, sM, h->Gbar, Mp, sM, T2, Mp, sM, m, m, m, 1.0, 0.0, KM_A_UPPER), batch));
   RUN(launch_gemm(h, st2, EPI_STORE, gemm_basic(T2, Mp, sM, h->LinvT, Mp, sM, h->Gzz, Mp, sM, m, m, m, -0.5, 0.0, KM_B_UPPER), batch));
   if (kind == GGP_KERNEL_COMPOSITE) {
@@ -1573,10 +1606,25 @@ int ggp_chol_batched(ggp_handle_t* h, void* stream, double* a, double* linv, int
   const int Mp = h->Mp;
   const int64_t sM = (int64_t)Mp * Mp;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
+  if (getenv("GGP_CHOL_TIMELINE") && !h->ct_dbg) {   // developer switch: stamps of the CTA on the dependent chain of every step
+    CK(cudaMalloc((void**)&h->ct_dbg, 64 * 8 * sizeof(long long)));
+    CK(cudaMemset(h->ct_dbg, 0, 64 * 8 * sizeof(long long)));
+  }
   k_pad_copy<<<g16, b16, 0, st>>>(a, m, h->L, Mp, sM, 1);
   CKL();
   CK(cudaMemsetAsync(h->piv_tol, 0, sizeof(double) * batch, st));
   RUN(chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info));
+  if (h->ct_dbg && getenv("GGP_CHOL_TIMELINE")[0] == '2') {
+    CK(cudaStreamSynchronize(st));
+    long long hb[64 * 8];
+    CK(cudaMemcpy(hb, h->ct_dbg, sizeof(hb), cudaMemcpyDeviceToHost));
+    const int nblk = Mp / NB;
+    for (int k = 0; k + 1 < nblk && k < 63; ++k) {
+      const long long* s = hb + k * 8;
+      fprintf(stderr, "== chol step %2d (clk): load %lld  panel products %lld  update product + store %lld  potf2 %lld | kernel %lld ns, gap to the next step %lld ns\n",
+              k, s[2] - s[1], s[3] - s[2], s[4] - s[3], s[5] - s[4], s[6] - s[0], k + 2 < nblk ? hb[(k + 1) * 8] - s[6] : 0ll);
+    }
+  }
   k_pad_copy<<<g16, b16, 0, st>>>(a, m, h->L, Mp, sM, 0);
   CKL();
   if (linv) {

@@ -126,9 +126,10 @@ int ggp_sgpr_finish(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
                     const double* Z, const double* theta, int m, int d, int batch,
                     const double* partial /*[batch, m*m+m+3]*/, int need_grad,
                     double* bound /*[batch]*/, double* grad_mm /*[batch, d+2+m*d] or NULL*/, int32_t* info /*[batch]*/);
-/* `bound` and the state pass 2 needs are ready in stream order when ggp_sgpr_finish returns; grad_mm is written by a chain that
- * runs on the handle's auxiliary stream next to pass 2 and is complete, in `stream` order, once ggp_sgpr_pass2 of the same evaluation
- * has been enqueued -- or after ggp_sgpr_join for a caller that skips pass 2. */
+/* The state pass 2 needs is ready in stream order when ggp_sgpr_finish returns, and so is `bound` when need_grad = 0.  With
+ * need_grad = 1, `bound` and grad_mm are written by a chain that runs on the handle's auxiliary stream next to pass 2 (only beta, u,
+ * P_A and Q are on the path to pass 2) and are complete, in `stream` order, once ggp_sgpr_pass2 of the same evaluation has been
+ * enqueued -- or after ggp_sgpr_join for a caller that skips pass 2. */
 int ggp_sgpr_join(ggp_handle_t* h, void* stream);
 
 /* second streaming pass: grad_partial[b] = sum over local rows of (P Kzx + u y^T) o dKzx/d(ell,sf2,Z)
