@@ -203,7 +203,12 @@ static Plan make_plan(const ggp_cfg* cfg, int64_t n_local, int m, int d, int bat
   take((size_t)batch * m * nq * 8);                     // mom_acc
   take((size_t)batch * 8);                              // rk
   take((size_t)batch * 4 + 256);                        // info_ws
-  p.nsv = std::min(p.nc, 4096);
+  // SVGP / SGPMC row chunk: 4096 rows, more when the batch is small (about 1 GiB per buffer: 8 chains of M = 512 stream 16384 rows per
+  // launch sequence instead of 4096 -- BASELINE configs[4] on 8 GPUs)
+  {
+    const int64_t by_budget = (int64_t)((1024.0 * 1024 * 1024) / ((double)batch * p.Mp * 8.0)) / 128 * 128;
+    p.nsv = (int)std::min<int64_t>(p.nc, std::max<int64_t>(4096, by_budget));
+  }
   for (int i = 0; i < 5; ++i) take((size_t)batch * p.nsv * p.Mp * 8);   // SVGP / SGPMC row and transposed buffers
   take((size_t)batch * 4 * p.nsv * 8);                  // rowout
   take((size_t)batch * 8 + 256);                        // piv_tol
@@ -1488,7 +1493,7 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
       RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(wT, Mp, sC, LsP, Mp, 0, SL, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
     k_svgp_gat<<<dim3((Mp + 255) / 256, nv, batch), 256, 0, st>>>(SL, aT, Mp, sC, qm, sqm, h->rowout, nsv, m, Mp, hasS ? 1 : 0);
     CKL();
-    k_svgp_dm<<<dim3((m + 255) / 256, batch), 256, 0, st>>>(aT, Mp, sC, h->rowout, nsv, m, nv, dm, Mp);
+    k_svgp_dm<<<dim3((m + 31) / 32, batch), 256, 0, st>>>(aT, Mp, sC, h->rowout, nsv, m, nv, dm, Mp);
     CKL();
     const dim3 gT((nvp + 31) / 32, Mp / 32, batch), bT(32, 8);
     if (hasS) {  // dLsraw += (aT o gv)^T wT

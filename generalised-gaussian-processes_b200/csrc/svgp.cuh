@@ -170,16 +170,36 @@ __global__ void k_svgp_gat(double* __restrict__ SL, const double* __restrict__ a
   SL[o] = v;
 }
 
-// dm[b][i] += sum_n aT[n,i] * gmu_n      grid (ceil(M/256), batch)
-__global__ void k_svgp_dm(const double* __restrict__ aT, int64_t ld, int64_t sC, const double* __restrict__ rowout,
-                          int64_t ldr, int M, int nv, double* __restrict__ dm, int64_t sdm) {
-  const int i = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
-  if (i >= M) return;
+// dm[b][i] += sum_n aT[n,i] * gmu_n      grid (ceil(M/32), batch), block 256 = 32 consecutive columns x 8 row lanes
+// Row lane r sums the rows n = r, r + 8, ... of its column (coalesced 256-byte row segments, four independent partial sums in
+// flight), the 8 lanes are combined in a fixed order: deterministic.  (One thread per column walking all nv rows -- the first
+// version -- was a chain of nv dependent strided loads on 2 CTAs per chain: 1 ms per launch, 32 % of a BASELINE configs[4]
+// evaluation at 8 chains per GPU.)
+__global__ void __launch_bounds__(256) k_svgp_dm(const double* __restrict__ aT, int64_t ld, int64_t sC, const double* __restrict__ rowout,
+                                                 int64_t ldr, int M, int nv, double* __restrict__ dm, int64_t sdm) {
+  __shared__ double red[8][33];
+  const int li = threadIdx.x & 31, r = threadIdx.x >> 5, i = blockIdx.x * 32 + li, b = blockIdx.y;
   const double* ro = rowout + (int64_t)b * 4 * ldr + ldr;
   const double* a = aT + b * sC + i;
-  double s = 0.0;
-  for (int n = 0; n < nv; ++n) s = fma(a[(int64_t)n * ld], ro[n], s);
-  dm[b * sdm + i] += s;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (i < M) {
+    int n = r;
+    for (; n + 24 < nv; n += 32) {
+      s0 = fma(a[(int64_t)n * ld], ro[n], s0);
+      s1 = fma(a[(int64_t)(n + 8) * ld], ro[n + 8], s1);
+      s2 = fma(a[(int64_t)(n + 16) * ld], ro[n + 16], s2);
+      s3 = fma(a[(int64_t)(n + 24) * ld], ro[n + 24], s3);
+    }
+    for (; n < nv; n += 8) s0 = fma(a[(int64_t)n * ld], ro[n], s0);
+  }
+  red[r][li] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (r == 0 && i < M) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][li];
+    dm[b * sdm + i] += s;
+  }
 }
 
 // out[b][i][n] = in[b][n][i] * (rowscale ? rowscale[b][n] : 1) * (mul ? mul[b][n][i] : 1)   for i < rows_out(Mp), n < nv; zero for nv <= n < ldo
