@@ -273,7 +273,8 @@ static bool mm64_eligible(const ggp_handle* h, int epi, const GemmP& p, int nbat
     return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((ld | s1 | s2) & 1) == 0;
   };
   const int64_t t128 = (int64_t)((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * nbatch * p.nz2;
-  return epi == EPI_STORE && t128 <= h->mm64_max_tiles && !p.rowdot && p.splits == 1 && p.sym == 0 && p.C != p.A && p.C != p.B &&
+  // (skinny outputs -- the moment products of the SVGP path, N = 2 d + 1 -- always: a 128-wide tile is mostly padding there)
+  return epi == EPI_STORE && (t128 <= h->mm64_max_tiles || (p.N <= S_T && h->mm64_max_tiles > 0)) && !p.rowdot && p.splits == 1 && p.sym == 0 && p.C != p.A && p.C != p.B &&
          even16(p.A, p.lda, p.sA, p.sA2) && even16(p.B, p.ldb, p.sB, p.sB2);
 }
 

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_svgp_rows(const double* __restrict__ aT
   mu = warp_sum(mu);
   v1 = warp_sum(v1);
   v2 = warp_sum(v2);
-  if (lane != 0) return;
+  // (the butterfly sums leave the totals in every lane)
   const double sf2 = theta[(int64_t)b * (d + 2) + d], s2 = theta[(int64_t)b * (d + 2) + d + 1];
   const double var = sf2 + data_jitter + v1 - v2;
   const double y = yv[n];
@@ -79,20 +79,26 @@ __global__ void __launch_bounds__(256) k_svgp_rows(const double* __restrict__ aT
     gv = -0.5 / s2;
     gs = 0.5 * (r * r + var) / (s2 * s2) - 0.5 / s2;
   } else {
+    // Gauss-Hermite, 20 nodes: one node per lane (erfc / erfcx / log / exp in FP64, ~200 instructions each: with lane 0 walking all
+    // twenty, this kernel was 10 % of a BASELINE configs[4] evaluation), combined by the fixed butterfly
     const double sgn = 2.0 * y - 1.0, sd = sqrt(2.0 * var);
     double e = 0.0, gm = 0.0, gvv = 0.0;
-    for (int i = 0; i < 20; ++i) {
+    if (lane < 20) {
       double lp, ra;
-      log_ndtr_and_ratio(sgn * (mu + sd * c_gh_x[i]), lp, ra);
-      e = fma(c_gh_w[i], lp, e);
-      gm = fma(c_gh_w[i], sgn * ra, gm);
-      gvv = fma(c_gh_w[i], sgn * ra * c_gh_x[i], gvv);
+      log_ndtr_and_ratio(sgn * (mu + sd * c_gh_x[lane]), lp, ra);
+      e = c_gh_w[lane] * lp;
+      gm = c_gh_w[lane] * (sgn * ra);
+      gvv = c_gh_w[lane] * (sgn * ra * c_gh_x[lane]);
     }
+    e = warp_sum(e);
+    gm = warp_sum(gm);
+    gvv = warp_sum(gvv);
     const double ISP = 0.5641895835477563;  // 1/sqrt(pi)
     ell = e * ISP;
     gmu = gm * ISP;
     gv = gvv * ISP / sd;  // d sqrt(2 var)/d var = 1/sqrt(2 var)
   }
+  if (lane != 0) return;
   double* ro = rowout + (int64_t)b * 4 * ldr;
   ro[n] = lik_scale * ell;
   ro[ldr + n] = lik_scale * gmu;
