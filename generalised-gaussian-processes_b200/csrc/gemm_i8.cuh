@@ -503,6 +503,15 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     for (int c = 0; c < I8_EC; ++c) accT[c] = 0.0;
     double rdA[2] = {0.0, 0.0};        // I8_EPI_SLICE with rowdot_reg: b-partials of this thread's row in the CTA's two row tiles
     double rsA = 0.0;                  // I8_EPI_MOMENTS with mom_accum: row sum of W (the constant moment) of this thread's row
+#ifdef GGP_I8_MOM_VEC
+    // ... and, d <= 8, this thread's row of the x / x^2 moments on the VECTOR FP64 pipe (thread = TMEM lane = tile row: no staging of W)
+    double mvx[8], mvx2[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mvx[q] = mvx2[q] = 0.0;
+    const bool mom_vec = (EPI == I8_EPI_MOMENTS) && p.mom_accum;   // the host sets mom_accum only for d <= 8 in this build
+#else
+    constexpr bool mom_vec = false;
+#endif
     double cmA[4][3][2];               // ... and the x / x^2 moments of this warp's rows, over all tiles of the CTA
 #pragma unroll
     for (int G4 = 0; G4 < 4; ++G4)
@@ -542,7 +551,13 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int j = 0; j < 4; ++j) { const int i = i0 + j * TT; v[j] = (i < lim) ? __ldg(src + i) : 0.0; }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const int i = i0 + j * TT; if (i < cnt) xs[i] = v[j]; }
+            for (int j = 0; j < 4; ++j) {
+              const int i = i0 + j * TT;
+              if (i < cnt) {
+                xs[i] = v[j];
+                if (mom_vec) xs[cnt + i] = v[j] * v[j];   // squares behind the rows: 2 BN d <= BN I8_MAX_D for d <= 8
+              }
+            }
           }
           if (tt < BN) ys[tt] = (colt + tt < p.N) ? __ldg(p.yv + colt + tt) : 0.0;
         }
@@ -562,6 +577,10 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool fx_fast = (EPI == I8_EPI_SLICE) && __all_sync(0xffffffffu, sh > -32 && sh <= 24);
       const int fx_l1 = sh < 0 ? -sh : 0, fx_r1 = sh > 0 ? sh : 0, fx_s2 = (24 - sh) & 63;
       const long long fx_rnd = sh > 0 ? 1ll << ((sh - 1) & 63) : 0ll;
+      // everything the serial part after the drain needs and that does not depend on the accumulators is fetched / computed BEFORE the
+      // wait (the software exp2 and the dependent global load of u[row] were ~1.5 k clk on the tile's critical path)
+      const double sc_pre = (EPI != I8_EPI_SLICE && !p.eb) ? p.alpha * exp2((double)(e_r + p_eb0)) : 0.0;
+      const double ui_pre = (EPI == I8_EPI_MOMENTS && row < p.M) ? __ldg(p.u + row) : 0.0;
       if (et == 0) I8_STAMP(1, my_item, 0);
       i8_mbar_wait(&tmem_full[buf], (my_item / NBUF) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
@@ -668,7 +687,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
         for (int c = 0; c < I8_EC; ++c) acc[c] = p.alpha * ldexp(acc[c], e_r + p.eb[min(col0 + c, p.N - 1)]);
       } else {
-        const double sc = p.alpha * exp2((double)(e_r + p_eb0));
+        const double sc = sc_pre;
 #pragma unroll
         for (int c = 0; c < I8_EC; ++c) acc[c] *= sc;
       }
@@ -762,7 +781,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       } else {
         // W = (G + u y^T) o Kmul, then the moments against [1, x, x^2] of the tile's 64 columns
         const int d = p.d, nq = 2 * d + 1;
-        const double ui = rok ? p.u[row] : 0.0;
+        const double ui = ui_pre;
         auto apply_kv = [&](const double (&kv)[16], int g) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) acc[g * 16 + c] = fma(ui, ys[chalf + g * 16 + c], acc[g * 16 + c]) * kv[c];
@@ -806,13 +825,37 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
         };
+#ifdef GGP_I8_MOM_VEC
+        if (mom_vec) {
+          // mom[row][1 + q] += W[row][c] x_c[q], mom[row][1 + d + q] += W[row][c] x_c[q]^2: 2 d independent FMA chains per thread, operands
+          // broadcast from shared memory; same FP64 rate as the DMMA route (64 FMA / clk / SM) without the W patch round trip
+          const double* xr = xs + chalf * d;
+          const double* xr2 = xr + BN * d;
+#pragma unroll
+          for (int c = 0; c < I8_EC; ++c) {
+            const double w = acc[c];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < d) {
+                mvx[q] = fma(w, xr[c * d + q], mvx[q]);
+                mvx2[q] = fma(w, xr2[c * d + q], mvx2[q]);
+              }
+          }
+          double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+#pragma unroll
+          for (int c = 0; c < I8_EC; c += 4) { r0 += acc[c]; r1 += acc[c + 1]; r2 += acc[c + 2]; r3 += acc[c + 3]; }
+          rsA += (r0 + r1) + (r2 + r3);
+        } else
+#else
         if (p.mom_accum) {
           sweep(0, cmA, 1);   // one sweep covers the 2 d <= 23 non-constant moments; written after the CTA's last tile
           double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
 #pragma unroll
           for (int c = 0; c < I8_EC; c += 4) { r0 += acc[c]; r1 += acc[c + 1]; r2 += acc[c + 2]; r3 += acc[c + 3]; }
           rsA += (r0 + r1) + (r2 + r3);
-        } else {
+        } else
+#endif
+        {
           for (int b0 = 0; b0 * 8 < nq; b0 += 3) {   // three blocks of 8 moments per sweep (one sweep for d <= 11)
             double cm[4][3][2];
 #pragma unroll
@@ -870,6 +913,17 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (EPI == I8_EPI_MOMENTS && p.mom_accum) {
       const int nq = 2 * p.d + 1, g = lane >> 2, q4 = lane & 3;
       const int tm = blockIdx.x % p.tiles_m, slab = (blockIdx.x / p.tiles_m) * 2 + half;
+#ifdef GGP_I8_MOM_VEC
+      if (mom_vec) {
+        const int rr = tm * I8_BM + quarter * 32 + lane;
+        if (rr < p.M) {
+          double* mo = p.mom + (int64_t)slab * p.sMomTile + (int64_t)rr * nq;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < p.d) { mo[1 + q] = mvx[q]; mo[1 + p.d + q] = mvx2[q]; }
+        }
+      }
+#else
 #pragma unroll
       for (int G4 = 0; G4 < 4; ++G4) {
         const int rr = tm * I8_BM + quarter * 32 + 8 * G4 + g;
@@ -882,6 +936,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (m + 1 < nq) mo[m + 1] = cmA[G4][B][1];
         }
       }
+#endif
       const int rown = tm * I8_BM + quarter * 32 + lane;
       if (rown < p.M) p.mom[(int64_t)slab * p.sMomTile + (int64_t)rown * nq] = rsA;
     }

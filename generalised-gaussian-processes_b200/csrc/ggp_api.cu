@@ -1291,7 +1291,11 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   }
   // sliced-integer path: the moments stay in the registers of the CTA that produced them over all its tiles (2 d + 1 <= 24), and
   // with the cached tiles of pass 1 the whole local row range is ONE launch (no per-chunk tails, 2 x 18 slabs to reduce)
+#ifdef GGP_I8_MOM_VEC
+  const bool i8_accum = i8 && d <= 8 && (Mp / I8_BM) <= h->sm_count && !getenv("GGP_I8_NO_ACCUM");   // vector-pipe moments: 2 d register chains per thread
+#else
   const bool i8_accum = i8 && nq <= 24 && (Mp / I8_BM) <= h->sm_count && !getenv("GGP_I8_NO_ACCUM");
+#endif
   const int64_t step = (i8_accum && a_cached && kind == GGP_KERNEL_RBF && n_local < (int64_t)1 << 30) ? std::max<int64_t>(n_local, 1) : nc;
   for (int64_t c0 = 0; c0 < n_local; c0 += step) {
     const int nv = (int)std::min<int64_t>(step, n_local - c0);
