@@ -118,6 +118,7 @@ struct I8P {
   const int* e_dev;                      // device-side scalar exponents (no host read-back of theta): e_dev[sel - 1] replaces ea0 / eb0 / eo
   int ea0_sel, eb0_sel, eo_sel;          // 0 = use the immediate value
   int exp_skip_b;                        // developer experiment: do not load the B operand (wrong results; measures the L2 -> SM bound)
+  int mom_frag_off;                      // developer A/B (GGP_I8_MOM_FRAG=0): moments through the shared-memory W patch instead of the fragment-layout drain
   int exp_skip_a, exp_no_epi;            // developer experiments: no A loads / epilogue warps hand TMEM straight back (mainloop only)
   long long* dbg;                        // developer timeline (CTA 0): [role][item][4] clock64 stamps, or NULL
 };
@@ -183,6 +184,16 @@ __device__ __forceinline__ void i8_umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void i8_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+// 16 TMEM lanes x 32 columns in the mma fragment layout: thread 4 g + q gets, for column group j = 0..3 (8 columns each),
+// v[4 j + 0..1] = lane g, columns 8 j + 2 q, + 1 and v[4 j + 2..3] = lane g + 8, same columns  (PTX tcgen05.ld shape .16x256b)
+__device__ __forceinline__ void i8_tmem_ld_frag(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
@@ -503,6 +514,15 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     for (int c = 0; c < I8_EC; ++c) accT[c] = 0.0;
     double rdA[2] = {0.0, 0.0};        // I8_EPI_SLICE with rowdot_reg: b-partials of this thread's row in the CTA's two row tiles
     double rsA = 0.0;                  // I8_EPI_MOMENTS with mom_accum: row sum of W (the constant moment) of this thread's row
+#ifndef GGP_I8_NO_MOM_FRAG
+    // FRAGMENT mode of the one-launch backward plan (mom_accum, k <= I8_K_GROUP4): the accumulators are drained with the 16x256b shape,
+    // so W = (G + u y^T) o K sits in the registers in DMMA A-fragment layout and goes straight back to the FP64 tensor pipe -- no
+    // shared-memory patch, no warp barriers on the serial part of the tile (it was 7 k of the 8.5 k clk between "drained" and "done")
+    const bool mom_frag = (EPI == I8_EPI_MOMENTS) && p.mom_accum && p.K <= I8_K_GROUP4 && !p.eb && !p.mom_frag_off;
+    double rs4[4] = {0.0, 0.0, 0.0, 0.0};   // partial row sums of W (this thread's 8 columns) for the rows 8 G + g
+#else
+    constexpr bool mom_frag = false;
+#endif
 #ifdef GGP_I8_MOM_VEC
     // ... and, d <= 8, this thread's row of the x / x^2 moments on the VECTOR FP64 pipe (thread = TMEM lane = tile row: no staging of W)
     double mvx[8], mvx2[8];
@@ -555,7 +575,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               const int i = i0 + j * TT;
               if (i < cnt) {
                 xs[i] = v[j];
-                if (mom_vec) xs[cnt + i] = v[j] * v[j];   // squares behind the rows: 2 BN d <= BN I8_MAX_D for d <= 8
+                if (mom_vec || (mom_frag && 2 * d <= I8_MAX_D)) xs[cnt + i] = v[j] * v[j];   // squares behind the rows: 2 BN d <= BN I8_MAX_D
               }
             }
           }
@@ -566,12 +586,108 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // loads issue one memory latency at a time -- 16 k clk of this 25 k clk phase -- which is hidden behind the 37 k clk mainloop in
         // the serial-epilogue mode.  An overlapped variant with an L2 prefetch here and the loads after the drain cut the phase to
         // 6.5 k clk, but the FP64 work next to the UTCIMMA stream then took 39 k clk: no gain, removed.)
-        load_kv(kv0, 0);
-        load_kv(kv1, 1);
+        if (!mom_frag) {
+          load_kv(kv0, 0);
+          load_kv(kv1, 1);
+        }
         if (et == 0) I8_STAMP(2, my_item, 2);
         asm volatile("bar.sync %0, %1;\n" ::"r"(team_bar), "r"(TT) : "memory");
         if (et == 0) I8_STAMP(2, my_item, 3);
       }
+#ifndef GGP_I8_NO_MOM_FRAG
+      if (EPI == I8_EPI_MOMENTS && mom_frag) {
+        const int g = lane >> 2, q4 = lane & 3, d = p.d;
+        // this thread's four rows (8 G + g of the warp's 32) and their multipliers, fetched while the MMAs of the tile run
+        double sc4[4], ui4[4], kvf[32];
+#pragma unroll
+        for (int G4 = 0; G4 < 4; ++G4) {
+          const int rr = it.tm * I8_BM + quarter * 32 + 8 * G4 + g;
+          const int er = p.ea ? p.ea[min(rr, p.M - 1)] : p_ea0;
+          sc4[G4] = p.alpha * exp2((double)(er + p_eb0));
+          ui4[G4] = rr < p.M ? __ldg(p.u + rr) : 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int gc = col0 + 8 * j + 2 * q4 + e;
+              // element index r = 4 j + 2 (G4 & 1) + e of lane half h = G4 >> 1  ->  kvf[16 h + r]
+              kvf[16 * (G4 >> 1) + 4 * j + 2 * (G4 & 1) + e] = (rr < p.M && gc < p.N) ? __ldg(p.Kmul + (int64_t)gc * p.ldk + rr) : 0.0;
+            }
+        }
+        if (et == 0) I8_STAMP(1, my_item, 0);
+        i8_mbar_wait(&tmem_full[buf], (my_item / NBUF) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+        if (et == 0) I8_STAMP(1, my_item, 1);
+        double wf[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32 + 16 * h) << 16) + (uint32_t)(buf * T::BUF_COLS + chalf);
+          {   // levels 4..6
+            uint32_t v0[16], v1[16], v2[16];
+            i8_tmem_ld_frag(ta + 4 * BN, v0);
+            i8_tmem_ld_frag(ta + 5 * BN, v1);
+            i8_tmem_ld_frag(ta + 6 * BN, v2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < 16; ++r) wf[16 * h + r] = (double)i8_comb3(v0[r], v1[r], v2[r]) * 5.421010862427522e-20 /* 2^-64 */;
+          }
+          {   // levels 0..3
+            uint32_t v0[16], v1[16], v2[16], v3[16];
+            i8_tmem_ld_frag(ta, v0);
+            i8_tmem_ld_frag(ta + BN, v1);
+            i8_tmem_ld_frag(ta + 2 * BN, v2);
+            i8_tmem_ld_frag(ta + 3 * BN, v3);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+              wf[16 * h + r] = fma((double)i8_comb4(v0[r], v1[r], v2[r], v3[r]), 9.094947017729282e-13 /* 2^-40 */, wf[16 * h + r]);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+        __syncwarp();
+        if (lane == 0 && !p.serial_epi) i8_mbar_arrive(&tmem_empty[buf]);
+        if (et == 0) I8_STAMP(1, my_item, 2);
+        // W = (alpha acc 2^(e_row + e_col) + u[row] y[col]) * Kmul[col][row]
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int idx = 16 * h + 4 * j + 2 * r2 + e, G4 = 2 * h + r2;
+                const double w = fma(ui4[G4], ys[chalf + 8 * j + 2 * q4 + e], wf[idx] * sc4[G4]) * kvf[idx];
+                wf[idx] = w;
+                rs4[G4] += w;
+              }
+        // moments 1 .. 2 d: column 8 j + 2 q + e plays k = q of the DMMA (A and B use the same permutation of k), moment 8 B + g + 1 is n
+        const bool sq_staged = 2 * d <= I8_MAX_D;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double* xr = xs + (chalf + 8 * j + 2 * q4 + e) * d;
+#pragma unroll
+            for (int B = 0; B < 3; ++B) {
+              if (B * 8 + 1 > 2 * d) continue;   // warp-uniform
+              const int m = B * 8 + g + 1;
+              double b = 0.0;
+              if (m <= d) b = xr[m - 1];
+              else if (m <= 2 * d) { if (sq_staged) b = xr[BN * d + m - 1 - d]; else { const double x = xr[m - 1 - d]; b = x * x; } }
+#pragma unroll
+              for (int G4 = 0; G4 < 4; ++G4)
+                dmma884(cmA[G4][B][0], cmA[G4][B][1], wf[16 * (G4 >> 1) + 4 * j + 2 * (G4 & 1) + e], b);
+            }
+          }
+        if (p.serial_epi) {
+          __syncwarp();
+          if (lane == 0) i8_mbar_arrive(&tmem_empty[buf]);
+        }
+        if (et == 0) I8_STAMP(1, my_item, 3);
+        continue;
+      }
+#endif
       const int e_r = p.ea ? p.ea[min(row, p.M - 1)] : p_ea0;
       const int sh = 8 + p_eo - e_r - p_eb0;   // I8_EPI_SLICE (scalar column exponent, alpha = 1, k <= I8_K_GROUP4: checked on the host)
       const bool fx_fast = (EPI == I8_EPI_SLICE) && __all_sync(0xffffffffu, sh > -32 && sh <= 24);
@@ -937,8 +1053,21 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }
 #endif
-      const int rown = tm * I8_BM + quarter * 32 + lane;
-      if (rown < p.M) p.mom[(int64_t)slab * p.sMomTile + (int64_t)rown * nq] = rsA;
+      if (mom_frag) {   // row sums: this thread holds the partial over its 8 columns per tile; the 4 lanes of a quad cover the 32 columns
+#ifndef GGP_I8_NO_MOM_FRAG
+#pragma unroll
+        for (int G4 = 0; G4 < 4; ++G4) {
+          double sv = rs4[G4];
+          sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+          sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+          const int rr = tm * I8_BM + quarter * 32 + 8 * G4 + g;
+          if (q4 == 0 && rr < p.M) p.mom[(int64_t)slab * p.sMomTile + (int64_t)rr * nq] = sv;
+        }
+#endif
+      } else {
+        const int rown = tm * I8_BM + quarter * 32 + lane;
+        if (rown < p.M) p.mom[(int64_t)slab * p.sMomTile + (int64_t)rown * nq] = rsA;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::);

@@ -1335,6 +1335,7 @@ int ggp_sgpr_pass2(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
       g8.u = h->u; g8.yv = y + c0; g8.Kmul = Kmul; g8.ldk = Mp; g8.Xc = X + c0 * d; g8.d = d;
       g8.mom = h->mom_part; g8.sMomTile = cnt;
       g8.mom_accum = i8_accum ? 1 : 0;
+      { const char* e = getenv("GGP_I8_MOM_FRAG"); g8.mom_frag_off = (e && e[0] == '0') ? 1 : 0; }
       { const char* e = getenv("GGP_I8_SERIAL_EPI"); g8.serial_epi = (e && e[0] == '0') ? 0 : 1; }
       // B = the A^T digit planes as the triangular multiply stores them: [plane][m (k)][columns], columns contiguous (MN-major);
       // chunk-blocked over all local rows (one [7][Mp][nc] array per chunk) or the single chunk buffer
