@@ -588,7 +588,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "r1b_ncu_traffic.json")) as fh:
                 traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
-            for name in ("r2_ncu_traffic_i8.json", "r1d_ncu_traffic_i8.json"):
+            for name in ("r2d_ncu_traffic_i8.json", "r2_ncu_traffic_i8.json", "r1d_ncu_traffic_i8.json"):
                 pth = os.path.join(ROOT, "profiles", name)
                 if os.path.exists(pth):
                     with open(pth) as fh:

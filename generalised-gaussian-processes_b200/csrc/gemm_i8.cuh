@@ -629,7 +629,8 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             i8_tmem_ld_frag(ta + 6 * BN, v2);
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-            for (int r = 0; r < 16; ++r) wf[16 * h + r] = (double)i8_comb3(v0[r], v1[r], v2[r]) * 5.421010862427522e-20 /* 2^-64 */;
+            for (int r = 0; r < 16; ++r)   // the row scale rides on the conversion constants: sc 2^-64, sc 2^-40
+              wf[16 * h + r] = (double)i8_comb3(v0[r], v1[r], v2[r]) * (sc4[2 * h + ((r >> 1) & 1)] * 5.421010862427522e-20);
           }
           {   // levels 0..3
             uint32_t v0[16], v1[16], v2[16], v3[16];
@@ -640,7 +641,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
             for (int r = 0; r < 16; ++r)
-              wf[16 * h + r] = fma((double)i8_comb4(v0[r], v1[r], v2[r], v3[r]), 9.094947017729282e-13 /* 2^-40 */, wf[16 * h + r]);
+              wf[16 * h + r] = fma((double)i8_comb4(v0[r], v1[r], v2[r], v3[r]), sc4[2 * h + ((r >> 1) & 1)] * 9.094947017729282e-13, wf[16 * h + r]);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
@@ -657,7 +658,7 @@ k_gemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int idx = 16 * h + 4 * j + 2 * r2 + e, G4 = 2 * h + r2;
-                const double w = fma(ui4[G4], ys[chalf + 8 * j + 2 * q4 + e], wf[idx] * sc4[G4]) * kvf[idx];
+                const double w = fma(ui4[G4], ys[chalf + 8 * j + 2 * q4 + e], wf[idx]) * kvf[idx];
                 wf[idx] = w;
                 rs4[G4] += w;
               }
