@@ -434,12 +434,26 @@ __global__ void __launch_bounds__(256) k_chol_inv_small(double* __restrict__ A, 
 }
 
 // after the last step: A = [diagonal blocks of A (lower part)] + [panel blocks from S], strict upper triangle zero
-__global__ void k_tril_merge(double* __restrict__ A, const double* __restrict__ S, int Mp, int64_t sA, int64_t sS) {
+// Optionally (T != NULL) the same launch starts the triangular inverse: Linv = blockdiag(T_0, T_1, ...), LinvT = its transpose
+// (what k_init_blockdiag does on its own).
+__global__ void k_tril_merge(double* __restrict__ A, const double* __restrict__ S, int Mp, int64_t sA, int64_t sS,
+                             const double* __restrict__ T = nullptr, int64_t sT = 0, double* __restrict__ Linv = nullptr,
+                             double* __restrict__ LinvT = nullptr) {
   const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
   if (i >= Mp || j >= Mp) return;
   double* a = A + blockIdx.z * sA + (int64_t)i * Mp + j;
   if (j > i) *a = 0.0;
   else if (i / NB != j / NB) *a = S[blockIdx.z * sS + (int64_t)i * Mp + j];
+  if (T) {
+    double v = 0.0, vt = 0.0;
+    if (i / NB == j / NB) {
+      const double* Tb = T + blockIdx.z * sT + (int64_t)(i / NB) * NB * NB;
+      v = Tb[(i % NB) * NB + (j % NB)];
+      vt = Tb[(j % NB) * NB + (i % NB)];
+    }
+    Linv[blockIdx.z * sA + (int64_t)i * Mp + j] = v;
+    LinvT[blockIdx.z * sA + (int64_t)i * Mp + j] = vt;
+  }
 }
 
 // zero the strict upper triangle.  grid (Mp/16, Mp/16, batch), block (16,16)

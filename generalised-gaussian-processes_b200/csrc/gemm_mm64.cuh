@@ -32,8 +32,15 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_mm64(const GemmP p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
 
-  int z = blockIdx.x / p.tiles_per_z;
-  const int t = blockIdx.x - z * p.tiles_per_z;
+  // Work item of this CTA.  Items are enumerated heaviest first; the hardware places CTAs 0 .. P - 1 (P = SM count) one per SM and the
+  // rest as second CTAs of the same SMs in the same order, so the items beyond the first wave are taken in REVERSE: the lightest tile
+  // shares an SM with the heaviest one (two co-resident CTAs split the FP64 pipe; heavy + heavy took 62 us for a triangular 1024^3 product)
+  int w = blockIdx.x;
+  if (w >= p.heavy_first && p.heavy_first > 0) w = p.total - 1 - (w - p.heavy_first);
+  // slices (batch x pair) are interleaved so that "heaviest first" holds across them
+  const int nz = p.total / p.tiles_per_z;
+  int z = w % nz;
+  const int t = w / nz;
   int tm, tn;
   mm64_tile(p, t, tm, tn);
   const int pz = z % p.nz2, bz = z / p.nz2;

@@ -291,6 +291,7 @@ static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& pin
     p.ntn = (p.N + S_T - 1) / S_T;
     p.tiles_per_z = p.ntm * p.ntn;
     p.total = p.tiles_per_z * nbatch * p.nz2;
+    p.heavy_first = (p.kmode != 0 && p.total > h->sm_count && !getenv("GGP_MM64_NO_FOLD")) ? h->sm_count : 0;   // k_mm64: fold point of the grid
     k_mm64<<<p.total, S_THREADS, S_SMEM, st>>>(p);
     CKL();
     return 0;
@@ -377,17 +378,18 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
       RUN(launch_gemm(h, st, EPI_STORE, u, batch));
     }
   }
+  // recursive-doubling triangular inverse.  L^-T is kept in step with L^-1: the block-diagonal start writes both (in the launch that
+  // merges the panels into A, on the fused plan), and a level whose second product runs on the small-tile kernel stores its result
+  // block transposed as well (otherwise: one transpose per level)
   if (h->chol_fused) {
-    k_tril_merge<<<g16, b16, 0, st>>>(A, h->T1, Mp, sM, sM);
+    k_tril_merge<<<g16, b16, 0, st>>>(A, h->T1, Mp, sM, sM, h->Tblk, sM, Linv, LinvT);
     CKL();
   } else {
     k_tril<<<g16, b16, 0, st>>>(A, Mp, sM);
     CKL();
+    k_init_blockdiag<<<g16, b16, 0, st>>>(Linv, Mp, sM, h->Tblk, sM, LinvT);
+    CKL();
   }
-  // recursive-doubling triangular inverse.  L^-T is kept in step with L^-1: the block-diagonal start writes both, and a level whose
-  // second product runs on the small-tile kernel stores its result block transposed as well (otherwise: one transpose per level)
-  k_init_blockdiag<<<g16, b16, 0, st>>>(Linv, Mp, sM, h->Tblk, sM, LinvT);
-  CKL();
   const dim3 gt(Mp / 32, Mp / 32, batch), bt(32, 8);
   bool lt_current = true;
   for (int s = NB; s < Mp; s *= 2) {

@@ -38,10 +38,38 @@ def test_dmma_gemm_matches_torch(eng):
         assert relerr(C2, 1.5 * ref) < 1e-13
 
 
+def test_gemm_tile_kernels_and_triangular_k_ranges(eng):
+    """Both families of the DMMA product: the 64 x 64-tile kernel of the m x m section (k_mm64: small outputs, skinny outputs) and the
+    persistent 128 x 128 kernels (more than 96 work items, or operands that are not 16-byte aligned), with every triangular k-range
+    mode the library uses (the clipped ranges only skip exact zeros, so the result is the plain product of the triangular operands)."""
+    dev = eng.device
+    g = torch.Generator(device="cpu").manual_seed(5)
+    KM_A_LOWER, KM_A_UPPER, KM_B_LOWER, KM_B_UPPER = 1, 2, 4, 8
+    for n in (300, 1024, 1600):            # 1600: 13 x 13 = 169 work items of 128 x 128 -> the persistent kernel
+        F = torch.randn(n, n, dtype=torch.float64, generator=g).to(dev)
+        Lo, Up = torch.tril(F), torch.triu(F)
+        for a, b, km in ((Lo, F, KM_A_LOWER), (Up, F, KM_A_UPPER), (F, Lo, KM_B_LOWER), (F, Up, KM_B_UPPER), (Up, Up, KM_A_UPPER | KM_B_UPPER),
+                         (Lo, Lo, KM_A_LOWER | KM_B_LOWER), (F, F, 0)):
+            C = torch.full((n, n), 7.0, dtype=torch.float64, device=dev)
+            eng.gemm_nt_ex(a, b, C, kmode=km)
+            assert relerr(C, a @ b.T) < 1e-13, (n, km)
+    # skinny output (always on the 64-wide tiles), exact tile multiples, ragged edges; accumulate into C
+    for (mm, nn, kk) in [(200, 70, 34), (500, 17, 4096), (64, 64, 64), (65, 63, 130)]:
+        A = torch.randn(mm, kk, dtype=torch.float64, generator=g).to(dev)
+        B = torch.randn(nn, kk, dtype=torch.float64, generator=g).to(dev)
+        ref = A @ B.T
+        assert relerr(eng.gemm_nt(A, B), ref) < 1e-13, (mm, nn, kk)
+        assert relerr(eng.gemm_nt(A, B, C=ref.clone(), alpha=1.0, beta=1.0), 2.0 * ref) < 1e-13, (mm, nn, kk)
+    # rows that are not 16-byte aligned are refused loudly (the operand loads are 16-byte LDGSTS / TMA)
+    import ggp_b200
+    with pytest.raises(ggp_b200.GgpError):
+        eng.gemm_nt(torch.randn(8, 33, dtype=torch.float64, device=dev), torch.randn(8, 33, dtype=torch.float64, device=dev))
+
+
 def test_batched_cholesky_and_inverse(eng):
     dev = eng.device
     g = torch.Generator().manual_seed(1)
-    for m in [1, 20, 64, 65, 100, 500]:
+    for m in [1, 20, 64, 65, 100, 128, 129, 500, 1000]:
         R = torch.randn(3, m, m, dtype=torch.float64, generator=g).to(dev)
         S = R @ R.transpose(1, 2) + m * torch.eye(m, dtype=torch.float64, device=dev)
         L, Linv, info = eng.chol(S)
@@ -54,6 +82,12 @@ def test_batched_cholesky_and_inverse(eng):
     bad[1, 66, 66] = -1.0
     _, _, info = eng.chol(bad)
     assert info.tolist() == [0, 67]
+    # ... also when the failing block is factored by the look-ahead tail of a trailing-update launch (block 3 of 5), first failure wins
+    bad = torch.eye(300, dtype=torch.float64, device=dev).repeat(2, 1, 1)
+    bad[0, 200, 200] = -2.0
+    bad[0, 290, 290] = -1.0
+    _, _, info = eng.chol(bad)
+    assert info.tolist() == [201, 0]
 
 
 @pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52"])
