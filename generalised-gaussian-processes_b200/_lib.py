@@ -92,6 +92,7 @@ SYMBOLS = {
     "ggp_sgpr_predict_pass1": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _P]),
     "ggp_sgpr_finish": (_I, [_P, _CFG, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "ggp_sgpr_join": (_I, [_P, _P]),
+    "ggp_sgpr_expect_prefetch": (_I, [_P, _I]),
     "ggp_sgpr_pass2": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _P]),
     "ggp_sgpr_predict": (_I, [_P, _CFG, _P, _P, _I64, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ggp_svgp_elbo": (_I, [_P, _CFG, _P, _P, _P, _I64, _P, _P, _I, _P, _P, _P, _I, _I, _I, _D, _D, _D, _I, _I, _P, _P, _P]),

@@ -43,7 +43,7 @@ __device__ __forceinline__ void potf2_trti2_block(double* __restrict__ A, int64_
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int r = ty + 16 * i, c = tx + 16 * k;
-      a[i][k] = (c <= r) ? Ab[(int64_t)r * ld + c] : 0.0;
+      a[i][k] = (c <= r) ? __ldcg(Ab + (int64_t)r * ld + c) : 0.0;   // L2: the block may have been updated by another SM (k_chol_cluster)
       t[i][k] = (r == c) ? 1.0 : 0.0;
     }
   if (tid == 0) bad = 0;
@@ -331,6 +331,98 @@ __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ A, int6
   }
 #undef CT_STAMP
 }
+// ---- Cluster-resident blocked Cholesky (batch = 1): the WHOLE factorisation in one launch on CC_N SMs -----------------------------------
+// Why: the multi-launch plan is a chain of 16 dependent launches whose CTAs need an SM to themselves (250 registers x 256 threads), so next
+// to the tile build of pass 1 -- which keeps every SM filled with its own CTAs -- the chain does not run concurrently but after it: the
+// Kzz factorisation sits on the critical path of every evaluation although nothing depends on it until the triangular multiply.  One
+// thread-block cluster, launched on a high-priority stream, takes its CC_N SMs once and keeps them; the build runs on the others.
+// Schedule per step k (diagonal block k factored, T_k = L_kk^-1 known):
+//   panels   L(i,k) = A(i,k) T_k^T, i = k+1+rank, +CC_N, ...  (in place)                                  | cluster barrier
+//   updates  A(i,j) -= L(i,k) L(j,k)^T over the trailing lower blocks: rank 0 takes the next diagonal block first and factors it
+//            (look-ahead), every CTA then draws blocks from an atomic counter (each block is updated by exactly one CTA per step with
+//            the same arithmetic whoever draws it: deterministic)                                         | cluster barrier
+// All operand loads are L2 loads (LDGSTS .cg / ld.global.cg): the blocks are written by other SMs between the barriers.
+constexpr int CC_N = 8;
+__device__ __forceinline__ void cc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__global__ void __launch_bounds__(256) k_chol_cluster(double* __restrict__ A, int Mp, double* __restrict__ T, int32_t* info,
+                                                      const double* __restrict__ piv_tol, int* __restrict__ ctr) {
+  extern __shared__ __align__(16) unsigned char ct_raw[];
+  double* s0 = reinterpret_cast<double*>(ct_raw);
+  double* s1 = s0 + NB * CT_LD;
+  double* s2 = s1 + NB * CT_LD;
+  __shared__ int s_w;
+  const int rank = blockIdx.x, nrank = gridDim.x, tid = threadIdx.x, w8 = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int nblk = Mp / NB;
+  const int64_t ld = Mp;
+  if (rank == 0) potf2_trti2_block(A, ld, 0, 0, T, 0, info, piv_tol, 0, nullptr);
+  cc_cluster_sync();
+  // A(i,j) -= L(i,k) L(j,k)^T for one 64 x 64 block
+  auto update_block = [&](int i, int j, int k) {
+    ct_load_block_async(s0, A + (int64_t)i * NB * ld + k * NB, ld, tid);
+    if (i != j) ct_load_block_async(s1, A + (int64_t)j * NB * ld + k * NB, ld, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double c[8][2];
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb) c[cb][0] = c[cb][1] = 0.0;
+    ct_mm_nt(s0, i != j ? s1 : s0, w8, lane, c);
+    double* dst = A + (int64_t)(i * NB + 8 * w8 + g) * ld + j * NB + 2 * q;
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb) {
+      double2 o = __ldcg(reinterpret_cast<const double2*>(dst + 8 * cb));
+      o.x -= c[cb][0];
+      o.y -= c[cb][1];
+      *reinterpret_cast<double2*>(dst + 8 * cb) = o;
+    }
+    __syncthreads();   // s0 / s1 are free again, the block is written
+  };
+  for (int k = 0; k + 1 < nblk; ++k) {
+    // ---- panels of column k
+    if (k + 1 + rank < nblk) {
+      ct_load_block_async(s2, T + (int64_t)k * NB * NB, NB, tid);
+      for (int i = k + 1 + rank; i < nblk; i += nrank) {
+        double* blk = A + (int64_t)i * NB * ld + k * NB;
+        ct_load_block_async(s0, blk, ld, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        double pi[8][2];
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) pi[cb][0] = pi[cb][1] = 0.0;
+        ct_mm_nt_lower_b(s0, s2, w8, lane, pi);
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb)
+          *reinterpret_cast<double2*>(blk + (int64_t)(8 * w8 + g) * ld + 8 * cb + 2 * q) = make_double2(pi[cb][0], pi[cb][1]);
+        __syncthreads();
+      }
+    }
+    cc_cluster_sync();
+    // ---- trailing update; look-ahead factor of the next diagonal block by rank 0
+    const int nb = nblk - k - 1, ntrail = nb * (nb + 1) / 2;
+    if (rank == 0) {
+      update_block(k + 1, k + 1, k);
+      potf2_trti2_block(A, ld, 0, k + 1, T, 0, info, piv_tol, 0, nullptr);
+      __syncthreads();
+    }
+    for (;;) {
+      if (tid == 0) s_w = atomicAdd(ctr + k, 1) + 1;   // block 0 (the next diagonal block) belongs to rank 0
+      __syncthreads();
+      const int w = s_w;
+      __syncthreads();
+      if (w >= ntrail) break;
+      int bi = 0;
+      while ((bi + 1) * (bi + 2) / 2 <= w) ++bi;
+      const int bj = w - bi * (bi + 1) / 2;
+      update_block(k + 1 + bi, k + 1 + bj, k);
+    }
+    cc_cluster_sync();
+  }
+}
+
 // Whole factorisation + explicit inverse for Mp <= 128 (one or two diagonal blocks) in ONE launch, one CTA per batch element:
 //   L00, T0 = potf2(A00);  L10 = A10 T0^T;  L11, T1 = potf2(A11 - L10 L10^T);  Linv = [[T0, 0], [-T1 L10 T0, T1]];  LinvT = Linv^T
 // -- what chol_and_inverse_launches does with 8 dependent launches at this size (2 x potf2, trail, merge, blockdiag, transpose,

@@ -71,6 +71,7 @@ struct ggp_handle {
   int pf_batch = 0;
   KSpec pf_kind{0, 0.0};
   int64_t pf_next_row = 0;      // ggp_sgpr_prefetch_tiles_part: rows [0, pf_next_row) are built
+  bool pf_expected = false;     // ggp_sgpr_expect_prefetch: the caller will enqueue a tile prefetch right after the next ggp_sgpr_factor
   double *sv[5] = {0, 0, 0, 0, 0}, *rowout = 0;
   // int8 digit planes of the sliced-integer path (GGP_PREC_FP64_I8; gemm_i8.cuh)
   char* arena_i8 = nullptr;
@@ -94,11 +95,15 @@ struct ggp_handle {
   int cur_cat = -1;
   cudaEvent_t cur_e0 = nullptr;
   // CUDA graphs of the blocked Cholesky + inverse
-  struct CholGraph { double *A, *Linv, *LinvT; int batch; long long nodes; cudaGraphExec_t exec; };
+  struct CholGraph { double *A, *Linv, *LinvT; int batch; long long nodes; cudaGraphExec_t exec; bool factored; };
   std::vector<CholGraph> chol_graphs;
   bool use_graphs = true;
   bool chol_fused = true;       // fused panel + trailing-update kernel in the blocked Cholesky (GGP_CHOL_FUSED=0: two library GEMMs)
   bool chol_lookahead = true;   // the trailing-update CTA that owns the next diagonal block factors it in the same launch (GGP_CHOL_LOOKAHEAD=0: own launch)
+  bool chol_cluster = true;     // Kzz factorisation next to a tile build: cluster-resident plan on a high-priority stream (GGP_CHOL_CLUSTER=0: the launch chain)
+  cudaStream_t hp_stream = nullptr;
+  cudaEvent_t ev_hp0 = nullptr, ev_hp1 = nullptr;
+  int* chol_ctr = nullptr;
   bool chol_small = true;       // Mp <= 128: the whole factorisation + inverse in one launch (GGP_CHOL_SMALL=0: the multi-launch plan)
   int mm64_max_tiles = 96;      // EPI_STORE products with at most this many 128 x 128 work items run on k_mm64 (GGP_MM64_MAX_TILES; 0 = never)
   cudaStream_t cap_stream = nullptr;
@@ -343,18 +348,21 @@ static GemmP gemm_basic(const double* A, int64_t lda, int64_t sA, const double* 
 
 // In-place blocked Cholesky of A[batch][Mp][Mp] (lower), explicit inverse -> Linv, Linv^T -> LinvT.
 static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, double* Linv, double* LinvT, int batch,
-                                     int32_t* info) {
+                                     int32_t* info, bool factored = false) {
   const int Mp = h->Mp, nblk = Mp / NB;
   const int64_t sM = (int64_t)Mp * Mp;
   const dim3 g16(Mp / 16, Mp / 16, batch), b16(16, 16);
   // right-looking: factor the diagonal block, form the panel with the block inverse, update the trailing lower tiles
   const bool ahead = h->chol_fused && h->chol_lookahead;
-  if (ahead && h->chol_small && nblk <= 2) {   // one or two diagonal blocks: factor + inverse + transposed inverse in one launch
+  if (factored) {   // k_chol_cluster left L in the lower blocks of A (panels in place) and the block inverses in Tblk
+    k_tril_merge<<<g16, b16, 0, st>>>(A, A, Mp, sM, sM, h->Tblk, sM, Linv, LinvT);
+    CKL();
+  } else if (ahead && h->chol_small && nblk <= 2) {   // one or two diagonal blocks: factor + inverse + transposed inverse in one launch
     k_chol_inv_small<<<batch, 256, CT_SMEM, st>>>(A, Mp, sM, h->Tblk, sM, Linv, LinvT, sM, info, h->piv_tol);
     CKL();
     return 0;
   }
-  for (int k = 0; k < nblk; ++k) {
+  for (int k = 0; k < nblk && !factored; ++k) {
     const int k0 = k * NB;
     if (k == 0 || !ahead) {   // with look-ahead, block k > 0 was factored by the trailing update of step k - 1
       k_potf2_trti2<<<batch, 256, POTF2_SMEM, st>>>(A, Mp, sM, k, h->Tblk, sM, info, h->piv_tol);
@@ -381,7 +389,8 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
   // recursive-doubling triangular inverse.  L^-T is kept in step with L^-1: the block-diagonal start writes both (in the launch that
   // merges the panels into A, on the fused plan), and a level whose second product runs on the small-tile kernel stores its result
   // block transposed as well (otherwise: one transpose per level)
-  if (h->chol_fused) {
+  if (factored) {
+  } else if (h->chol_fused) {
     k_tril_merge<<<g16, b16, 0, st>>>(A, h->T1, Mp, sM, sM, h->Tblk, sM, Linv, LinvT);
     CKL();
   } else {
@@ -425,25 +434,58 @@ static int chol_and_inverse_launches(ggp_handle* h, cudaStream_t st, double* A, 
 
 // The blocked factorisation is ~70 short kernels: replay it as a CUDA graph (captured once per operand set) so the m x m
 // section is not launch-latency bound.  info is staged through a handle-owned buffer so the captured pointers stay valid.
-static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* Linv, double* LinvT, int batch, int32_t* info) {
+// `beside_build`: the caller knows that a tile build may be running next to this factorisation (ggp_sgpr_factor): take the
+// cluster-resident plan, which keeps its own SMs, instead of the chain of launches that would queue behind the build's CTAs.
+static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* Linv, double* LinvT, int batch, int32_t* info,
+                            bool beside_build = false) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   CK(cudaStreamIsCapturing(st, &cs));
+  const bool cluster = beside_build && h->chol_cluster && batch == 1 && h->Mp >= 4 * NB && cs == cudaStreamCaptureStatusNone && h->use_graphs;
   if (cs != cudaStreamCaptureStatusNone || !h->use_graphs) {
     CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
     return chol_and_inverse_launches(h, st, A, Linv, LinvT, batch, info);
   }
+  if (cluster) {
+    // fork to the handle's high-priority stream: [zero info + the step counters, one cluster launch], join
+    if (!h->hp_stream) {
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&h->hp_stream, cudaStreamNonBlocking, hi));
+      CK(cudaEventCreateWithFlags(&h->ev_hp0, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_hp1, cudaEventDisableTiming));
+      CK(cudaMalloc((void**)&h->chol_ctr, 64 * sizeof(int)));
+    }
+    CK(cudaEventRecord(h->ev_hp0, st));
+    CK(cudaStreamWaitEvent(h->hp_stream, h->ev_hp0, 0));
+    CK(cudaMemsetAsync(h->info_ws, 0, sizeof(int32_t), h->hp_stream));
+    CK(cudaMemsetAsync(h->chol_ctr, 0, 64 * sizeof(int), h->hp_stream));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(CC_N, 1, 1);
+    lc.blockDim = dim3(256, 1, 1);
+    lc.dynamicSmemBytes = CT_SMEM;
+    lc.stream = h->hp_stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CC_N; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&lc, k_chol_cluster, A, h->Mp, h->Tblk, h->info_ws, (const double*)h->piv_tol, h->chol_ctr));
+    h->launches++;
+    CK(cudaEventRecord(h->ev_hp1, h->hp_stream));
+    CK(cudaStreamWaitEvent(st, h->ev_hp1, 0));
+  }
   ggp_handle::CholGraph* g = nullptr;
   for (auto& c : h->chol_graphs)
-    if (c.A == A && c.Linv == Linv && c.LinvT == LinvT && c.batch == batch) g = &c;
+    if (c.A == A && c.Linv == Linv && c.LinvT == LinvT && c.batch == batch && c.factored == cluster) g = &c;
   if (!g) {
     ggp_handle::CholGraph c{};
-    c.A = A; c.Linv = Linv; c.LinvT = LinvT; c.batch = batch;
+    c.A = A; c.Linv = Linv; c.LinvT = LinvT; c.batch = batch; c.factored = cluster;
     const long long before = h->launches;
     cudaGraph_t graph = nullptr;
     // capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured
     if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = chol_and_inverse_launches(h, h->cap_stream, A, Linv, LinvT, batch, h->info_ws);
+    int rc = chol_and_inverse_launches(h, h->cap_stream, A, Linv, LinvT, batch, h->info_ws, cluster);
     cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
     if (rc != 0) return rc;
     CK(e);
@@ -454,7 +496,7 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
     h->chol_graphs.push_back(c);
     g = &h->chol_graphs.back();
   }
-  CK(cudaMemsetAsync(h->info_ws, 0, sizeof(int32_t) * batch, st));
+  if (!cluster) CK(cudaMemsetAsync(h->info_ws, 0, sizeof(int32_t) * batch, st));
   CK(cudaGraphLaunch(g->exec, st));
   h->launches += g->nodes;
   CK(cudaMemcpyAsync(info, h->info_ws, sizeof(int32_t) * batch, cudaMemcpyDeviceToDevice, st));
@@ -633,6 +675,8 @@ int ggp_create(ggp_handle_t** out, int device) {
   { const char* e = getenv("GGP_CHOL_FUSED"); h->chol_fused = !(e && e[0] == '0'); }
   { const char* e = getenv("GGP_CHOL_LOOKAHEAD"); h->chol_lookahead = !(e && e[0] == '0'); }
   { const char* e = getenv("GGP_CHOL_SMALL"); h->chol_small = !(e && e[0] == '0'); }
+  { const char* e = getenv("GGP_CHOL_CLUSTER"); h->chol_cluster = !(e && e[0] == '0'); }
+  CK(cudaFuncSetAttribute(k_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
   CK(cudaFuncSetAttribute(k_chol_inv_small, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
   { const char* e = getenv("GGP_MM64_MAX_TILES"); if (e) h->mm64_max_tiles = atoi(e); }
   CK(cudaFuncSetAttribute(k_mm64, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
@@ -663,6 +707,10 @@ int ggp_destroy(ggp_handle_t* h) {
   if (h->arena_i8) cudaFree(h->arena_i8);
   if (h->krow) cudaFree(h->krow);
   if (h->ct_dbg) cudaFree(h->ct_dbg);
+  if (h->chol_ctr) cudaFree(h->chol_ctr);
+  if (h->hp_stream) cudaStreamDestroy(h->hp_stream);
+  if (h->ev_hp0) cudaEventDestroy(h->ev_hp0);
+  if (h->ev_hp1) cudaEventDestroy(h->ev_hp1);
   delete h;
   return 0;
 }
@@ -850,6 +898,12 @@ int ggp_set_kernel_params(ggp_handle_t* h, const double* kparams, double* kgrad_
   return 0;
 }
 
+int ggp_sgpr_expect_prefetch(ggp_handle_t* h, int on) {
+  if (!h) return fail(-1, "ggp_sgpr_expect_prefetch: handle is NULL");
+  h->pf_expected = on != 0;
+  return 0;
+}
+
 int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const double* Z, const double* theta,
                     const double* jitter, int m, int d, int batch, int32_t* info) {
   if (!h || !Z || !theta || !info) return fail(-1, "ggp_sgpr_factor: NULL argument");
@@ -869,7 +923,11 @@ int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const dou
     k_build_kzz<<<dim3(Mp / 16, Mp / 16, batch), dim3(16, 16), 0, st>>>(Z, m, Mp, d, theta, jitter, kind, h->L, (int64_t)Mp * Mp, h->piv_tol);
   }
   CKL();
-  return chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info);
+  // a tile prefetch has been (ggp_sgpr_prefetch_tiles[_part] on another stream) or is about to be (ggp_sgpr_expect_prefetch) enqueued
+  // for this evaluation: its CTAs fill every SM
+  const bool beside = h->pf_valid || h->pf_next_row > 0 || h->pf_expected;
+  h->pf_expected = false;
+  return chol_and_inverse(h, st, h->L, h->Linv, h->LinvT, batch, info, beside);
 }
 
 static int build_chunk(ggp_handle* h, cudaStream_t st, const double* Xc, int nv, int d, const double* Z, int m,
@@ -960,6 +1018,7 @@ int ggp_sgpr_pass1(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doub
   const bool prefetched = h->kc_all && h->pf_valid && h->pf_X == X && h->pf_Z == Z && h->pf_theta == theta && h->pf_n == n_local &&
                           h->pf_batch == batch && h->pf_kind.kind == kind.kind && h->pf_kind.p == kind.p && (!i8 || h->kq_all);
   h->pf_valid = false;
+  h->pf_next_row = 0;
   h->atq_valid = false;
   if (i8) {
     // fixed exponents of the bounded operands: k(x,z) <= sf2 and |A[m,n]| <= sqrt(k_nn) = sqrt(sf2), computed ON THE DEVICE into

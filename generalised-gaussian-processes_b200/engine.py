@@ -147,8 +147,10 @@ class Engine:
         return out.value
 
     # ------------------------------------------------------------------------------------------------------
-    def factor(self, Z, theta, jitter_policy="gpytorch", raise_on_fail=True):
-        """Kzz + jitter I = L L^T with the host-side jitter ladder.  Returns (jitter[batch] tensor, info[batch] cpu)."""
+    def factor(self, Z, theta, jitter_policy="gpytorch", raise_on_fail=True, after_first_enqueue=None):
+        """Kzz + jitter I = L L^T with the host-side jitter ladder.  Returns (jitter[batch] tensor, info[batch] cpu).
+        after_first_enqueue: called once, right after the first attempt has been enqueued and before its status is read back
+        (sgpr_eval enqueues the tile prefetch there, so that the factorisation is already running when the build arrives)."""
         m, d = Z.shape
         batch = theta.shape[0]
         ladder = jitter_ladder(jitter_policy)
@@ -156,8 +158,13 @@ class Engine:
         jit = torch.full((batch,), ladder[0], dtype=torch.float64, device=self.device)
         info = torch.zeros(batch, dtype=torch.int32, device=self.device)
         while True:
+            if after_first_enqueue is not None:
+                check(self.lib.ggp_sgpr_expect_prefetch(self.h, 1), "ggp_sgpr_expect_prefetch")
             check(self.lib.ggp_sgpr_factor(self.h, ctypes.byref(self.cfg), _stream(), _ptr(Z), _ptr(theta), _ptr(jit),
                                            m, d, batch, _ptr(info)), "ggp_sgpr_factor")
+            if after_first_enqueue is not None:
+                after_first_enqueue()
+                after_first_enqueue = None
             self.ladder_levels = level
             if len(ladder) == 1 and not raise_on_fail:
                 # fixed jitter (pymc3 stabilize / gpflow default) and the caller handles info[b] != 0 itself: nothing to retry, so
@@ -293,11 +300,19 @@ class Engine:
                 X, y = _f64c(X, dev), _f64c(y, dev)
                 # the k(X,Z) tiles do not depend on the Cholesky of Kzz: build them into the tile cache on a side stream while the
                 # factorisation (latency-bound m x m kernels) runs on the caller's stream; pass 1 then finds them in place
-                if use_side:
+            prefetch = None
+            if use_side and not host_rows:
+                # enqueued right AFTER the first factorisation attempt (Engine.factor calls it back): the factorisation is a single
+                # cluster launch that takes its SMs first, the build then fills the others
+                evbox = []
+
+                def prefetch():
                     check(self.lib.ggp_sgpr_prefetch_tiles(self.h, cfgp, ctypes.c_void_p(self._side.cuda_stream), _ptr(X), n_local,
                                                            _ptr(Z), _ptr(theta), m, d, batch), "ggp_sgpr_prefetch_tiles")
-                    ev = self._side.record_event()
-            jit, info1 = self.factor(Z, theta, jitter_policy, raise_on_fail)
+                    evbox.append(self._side.record_event())
+            jit, info1 = self.factor(Z, theta, jitter_policy, raise_on_fail, after_first_enqueue=prefetch)
+            if prefetch is not None:
+                ev = evbox[0]
             on_dmma = self.cfg.precision != PRECISIONS["fp64_i8"]
             if self.cfg.precision == PRECISIONS["fp64_i8"] and any(l > 0 for l in self.ladder_levels):
                 # Kzz was numerically singular (exactly duplicated inducing rows: the with-replacement draw of

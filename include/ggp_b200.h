@@ -91,6 +91,12 @@ int ggp_set_kernel_params(ggp_handle_t* h, const double* kparams, double* kgrad_
  *                             -> pass2 -> [allreduce grad_partial]  ; total grad = grad_mm + sum(grad_partial)
  */
 
+/* Scheduling hint: the caller is about to enqueue ggp_sgpr_prefetch_tiles[_part] (on another stream) right AFTER the next
+ * ggp_sgpr_factor.  The Kzz factorisation then runs as one thread-block-cluster launch that keeps its own 8 SMs (on a high-priority
+ * stream of the handle, joined back into `stream`), so that it runs next to the tile build instead of queueing behind its CTAs.
+ * (A prefetch enqueued BEFORE the factorisation is detected without this call.)  Same results either way. */
+int ggp_sgpr_expect_prefetch(ggp_handle_t* h, int on);
+
 /* Kzz(theta_b) + jitter_b I = L L^T ; L^{-1} kept in the handle.  info[b] device int32.
  * (InducingPointKernel._inducing_mat / _inducing_inv_root + psd_safe_cholesky, reached from models/sgpr.py:41) */
 int ggp_sgpr_factor(ggp_handle_t* h, const ggp_cfg* cfg, void* stream,
