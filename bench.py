@@ -642,6 +642,9 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "breakdown_ms_per_step": {k: v / args.steps for k, v in cat_ms.items()},
+            "breakdown_note": "CUDA-event spans per category on the stream the category runs on; `build` (side stream) and `mm` overlap: the "
+                              "explicit inverse that follows the cluster-resident Kzz factorisation queues behind the build's CTAs, so the mm span "
+                              "contains most of the build's duration and the spans do not add up to the step (mm work itself: ~1.4 ms)",
             "breakdown_note": "CUDA-event spans per kernel category; the tile build of pass 1 runs on a side stream next to the Kzz "
                               "factorisation, so the build and mm spans overlap (their sum exceeds their wall time)",
             "bound_value": head_F,
