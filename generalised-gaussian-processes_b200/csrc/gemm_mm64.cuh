@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_mm64(const GemmP p) {
   int tm, tn;
   mm64_tile(p, t, tm, tn);
   const int pz = z % p.nz2, bz = z / p.nz2;
+  if (p.sym == 2 && tn > tm) return;   // lower tiles only (the caller reads the lower triangle): the other CTAs leave at once
   int k_lo = 0, k_hi = p.K;
   if (p.kmode & KM_A_LOWER) k_hi = min(k_hi, (tm + 1) * S_T);
   if (p.kmode & KM_B_LOWER) k_hi = min(k_hi, (tn + 1) * S_T);

@@ -279,7 +279,7 @@ static bool mm64_eligible(const ggp_handle* h, int epi, const GemmP& p, int nbat
   };
   const int64_t t128 = (int64_t)((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * nbatch * p.nz2;
   // (skinny outputs -- the moment products of the SVGP path, N = 2 d + 1 -- always: a 128-wide tile is mostly padding there)
-  return epi == EPI_STORE && (t128 <= h->mm64_max_tiles || (p.N <= S_T && h->mm64_max_tiles > 0)) && !p.rowdot && p.splits == 1 && p.sym == 0 && p.C != p.A && p.C != p.B &&
+  return epi == EPI_STORE && (t128 <= h->mm64_max_tiles || (p.N <= S_T && h->mm64_max_tiles > 0)) && !p.rowdot && p.splits == 1 && (p.sym == 0 || p.sym == 2) && p.C != p.A && p.C != p.B &&
          even16(p.A, p.lda, p.sA, p.sA2) && even16(p.B, p.ldb, p.sB, p.sB2);
 }
 
@@ -1568,14 +1568,22 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
       CKL();
       k_transpose_rect<<<gT, bT, 0, st>>>(wT, nullptr, Mp, sC, nullptr, 0, nv, Mp, tC, nvp, sC);
       CKL();
-      RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(tB, nvp, sC, tC, nvp, sC, dLsraw, Mp, sM, m, m, nv, 1.0, 1.0), batch));
+      {   // only tril(dLsraw) enters the gradient (k_svgp_final): lower tiles
+        GemmP gl = gemm_basic(tB, nvp, sC, tC, nvp, sC, dLsraw, Mp, sM, m, m, nv, 1.0, 1.0);
+        gl.sym = 2;
+        RUN(launch_gemm(h, st, EPI_STORE, gl, batch));
+      }
     }
     // Gbar += GAT^T aT
     k_transpose_rect<<<gT, bT, 0, st>>>(aT, nullptr, Mp, sC, nullptr, 0, nv, Mp, tA, nvp, sC);
     CKL();
     k_transpose_rect<<<gT, bT, 0, st>>>(SL, nullptr, Mp, sC, nullptr, 0, nv, Mp, tB, nvp, sC);
     CKL();
-    RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(tB, nvp, sC, tA, nvp, sC, Gb, Mp, sM, m, m, nv, 1.0, 1.0), batch));
+    {   // only the lower triangle of Gbar is read (k_sym_phi: H = sym(Phi(Gbar))): lower tiles, 10 of 16 at M = 512
+      GemmP gg = gemm_basic(tB, nvp, sC, tA, nvp, sC, Gb, Mp, sM, m, m, nv, 1.0, 1.0);
+      gg.sym = 2;
+      RUN(launch_gemm(h, st, EPI_STORE, gg, batch));
+    }
     // dKc = GAT * Linv  (into wT's buffer) ;  mom += (dKc o Kc)^T [1, x, x^2]
     RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(SL, Mp, sC, h->LinvT, Mp, sM, wT, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_UPPER), batch));
     if (kind != GGP_KERNEL_RBF) {
