@@ -1558,12 +1558,10 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
     // SL = wT * Ls^T = (S a)^T ;  GAT = gmu m^T + 2 gv (SL - aT)
     if (hasS)
       RUN(launch_gemm(h, st, EPI_STORE, gemm_basic(wT, Mp, sC, LsP, Mp, 0, SL, Mp, sC, nv, m, m, 1.0, 0.0, KM_B_LOWER), batch));
-    k_svgp_gat<<<dim3((Mp + 255) / 256, nv, batch), 256, 0, st>>>(SL, aT, Mp, sC, qm, sqm, h->rowout, nsv, m, Mp, hasS ? 1 : 0);
-    CKL();
     k_svgp_dm<<<dim3((m + 31) / 32, batch), 256, 0, st>>>(aT, Mp, sC, h->rowout, nsv, m, nv, dm, Mp);
     CKL();
     const dim3 gT((nvp + 31) / 32, Mp / 32, batch), bT(32, 8);
-    if (hasS) {  // dLsraw += (aT o gv)^T wT
+    if (hasS) {  // dLsraw += (aT o gv)^T wT   (tB / tC are scratch here; the fused kernel below rewrites tB)
       k_transpose_rect<<<gT, bT, 0, st>>>(aT, nullptr, Mp, sC, h->rowout + 2 * nsv, (int64_t)4 * nsv, nv, Mp, tB, nvp, sC);
       CKL();
       k_transpose_rect<<<gT, bT, 0, st>>>(wT, nullptr, Mp, sC, nullptr, 0, nv, Mp, tC, nvp, sC);
@@ -1574,10 +1572,8 @@ int ggp_svgp_elbo(ggp_handle_t* h, const ggp_cfg* cfg, void* stream, const doubl
         RUN(launch_gemm(h, st, EPI_STORE, gl, batch));
       }
     }
-    // Gbar += GAT^T aT
-    k_transpose_rect<<<gT, bT, 0, st>>>(aT, nullptr, Mp, sC, nullptr, 0, nv, Mp, tA, nvp, sC);
-    CKL();
-    k_transpose_rect<<<gT, bT, 0, st>>>(SL, nullptr, Mp, sC, nullptr, 0, nv, Mp, tB, nvp, sC);
+    // GAT = gmu m^T + 2 gv (SL - aT) in place in SL, and the k-contiguous copies tA = aT^T, tB = GAT^T for  Gbar += GAT^T aT
+    k_svgp_gat_t<<<gT, bT, 0, st>>>(SL, aT, Mp, sC, qm, sqm, h->rowout, nsv, m, Mp, nv, hasS ? 1 : 0, tA, tB, nvp);
     CKL();
     {   // only the lower triangle of Gbar is read (k_sym_phi: H = sym(Phi(Gbar))): lower tiles, 10 of 16 at M = 512
       GemmP gg = gemm_basic(tB, nvp, sC, tA, nvp, sC, Gb, Mp, sM, m, m, nv, 1.0, 1.0);

@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc(const double* __restric
   double* zs = xs + KT_N * d;                          // [d][KT_M]   (z / ell, transposed: conflict-free)
   double* il = zs + KT_M * d;                          // [d]
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(16) double2 etab[64];            // 2^(j/64) table of the exponential (exp_neg)
 
   const int b = blockIdx.z;
+  if (threadIdx.x < 64) etab[threadIdx.x] = make_double2(GGP_EXP2_TAB[2 * threadIdx.x], GGP_EXP2_TAB[2 * threadIdx.x + 1]);
   const double* th = theta + (int64_t)b * (d + 2);
   const double sf2 = th[d];
   const int n0 = blockIdx.y * KT_N, m0 = blockIdx.x * KT_M;
@@ -219,7 +221,9 @@ __global__ void __launch_bounds__(KT_THREADS) k_build_kc(const double* __restric
     for (int j = 0; j < 4; ++j) {
       const int m = m0 + tx + 16 * j;
       if (m >= ldk) continue;
-      out[(int64_t)n * ldk + m] = (nv && m < M) ? (deriv ? kgrad(kind, sf2, d2[i][j]) : kval(kind, sf2, d2[i][j])) : 0.0;
+      // values through the table exponential (<= 0.8 ulp, ~19 instructions instead of ~45: this kernel is 6-7 % of a chain-batched
+      // SGPMC evaluation); the derivative tile keeps the library exp
+      out[(int64_t)n * ldk + m] = (nv && m < M) ? (deriv ? kgrad(kind, sf2, d2[i][j]) : kval_tab(kind, sf2, d2[i][j], etab)) : 0.0;
     }
   }
 }

@@ -176,6 +176,42 @@ __global__ void k_svgp_gat(double* __restrict__ SL, const double* __restrict__ a
   SL[o] = v;
 }
 
+// k_svgp_gat fused with the two transposes that follow it: one pass over aT (and SL) writes
+//   SL[n,i]  = GAT[n,i] = gmu_n m_i + 2 gv_n (SL[n,i] - aT[n,i])    (row-major, A operand of dKc = GAT L^-1)
+//   tA[i,n]  = aT[n,i]                                             (k-contiguous operands of Gbar += GAT^T aT)
+//   tB[i,n]  = GAT[n,i]
+// 4 array passes instead of 6 (gat: 2, two k_transpose_rect: 4).  32 x 32 tiles; columns nv <= n < ldo of tA / tB are zero.
+// grid (ceil(ldo/32), Mp/32, batch), block (32, 8)
+__global__ void __launch_bounds__(256) k_svgp_gat_t(double* __restrict__ SL, const double* __restrict__ aT, int64_t ld, int64_t sC,
+                                                    const double* __restrict__ qm, int64_t sqm, const double* __restrict__ rowout,
+                                                    int64_t ldr, int M, int Mp, int nv, int has_S, double* __restrict__ tA,
+                                                    double* __restrict__ tB, int64_t ldo) {
+  __shared__ double ta[32][33], tg[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  qm += b * sqm;
+  const double* ro = rowout + (int64_t)b * 4 * ldr;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int n = n0 + r, i = i0 + threadIdx.x;
+    double a = 0.0, v = 0.0;
+    if (n < nv && i < Mp) {
+      const int64_t o = b * sC + (int64_t)n * ld + i;
+      a = aT[o];
+      if (i < M) v = ro[ldr + n] * qm[i] + 2.0 * ro[2 * ldr + n] * ((has_S ? SL[o] : 0.0) - a);
+      SL[o] = v;
+    }
+    ta[r][threadIdx.x] = a;
+    tg[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, n = n0 + threadIdx.x;
+    if (i < Mp && n < ldo) {
+      tA[b * sC + (int64_t)i * ldo + n] = ta[threadIdx.x][r];
+      tB[b * sC + (int64_t)i * ldo + n] = tg[threadIdx.x][r];
+    }
+  }
+}
+
 // dm[b][i] += sum_n aT[n,i] * gmu_n      grid (ceil(M/32), batch), block 256 = 32 consecutive columns x 8 row lanes
 // Row lane r sums the rows n = r, r + 8, ... of its column (coalesced 256-byte row segments, four independent partial sums in
 // flight), the 8 lanes are combined in a fixed order: deterministic.  (One thread per column walking all nv rows -- the first
