@@ -347,8 +347,14 @@ __device__ __forceinline__ void cc_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
+// After the factorisation the same launch forms the explicit inverse by recursive doubling on 64 x 64 blocks (what
+// chol_and_inverse_launches does with a merge kernel and 8 products): Linv = L^-1, LinvT = L^-T, strict upper triangle of A zeroed.
+// Level s (blocks), pair p with first block b0 = 2 s p:   W = L21 Inv11 (stored transposed in Wk),   X = -Inv22 W -> Linv, X^T -> LinvT;
+// one work item = one output block with its k loop in registers, items drawn heaviest first from an atomic counter, a cluster
+// barrier after each of the two products of a level.
 __global__ void __launch_bounds__(256) k_chol_cluster(double* __restrict__ A, int Mp, double* __restrict__ T, int32_t* info,
-                                                      const double* __restrict__ piv_tol, int* __restrict__ ctr) {
+                                                      const double* __restrict__ piv_tol, int* __restrict__ ctr,
+                                                      double* __restrict__ Linv, double* __restrict__ LinvT, double* __restrict__ Wk) {
   extern __shared__ __align__(16) unsigned char ct_raw[];
   double* s0 = reinterpret_cast<double*>(ct_raw);
   double* s1 = s0 + NB * CT_LD;
@@ -420,6 +426,72 @@ __global__ void __launch_bounds__(256) k_chol_cluster(double* __restrict__ A, in
       update_block(k + 1 + bi, k + 1 + bj, k);
     }
     cc_cluster_sync();
+  }
+  if (!Linv) return;
+  // ---- explicit inverse.  Start: Linv = blockdiag(T_k), LinvT = blockdiag(T_k^T), zero elsewhere; A: strict upper triangle zero
+  for (int64_t e = (int64_t)rank * 256 + tid; e < (int64_t)Mp * Mp; e += (int64_t)nrank * 256) {
+    const int i = (int)(e / Mp), j = (int)(e % Mp);
+    if (j > i) A[e] = 0.0;
+    double v = 0.0, vt = 0.0;
+    if (i / NB == j / NB) {
+      const double* Tb = T + (int64_t)(i / NB) * NB * NB;
+      v = __ldcg(Tb + (i % NB) * NB + (j % NB));
+      vt = __ldcg(Tb + (j % NB) * NB + (i % NB));
+    }
+    Linv[e] = v;
+    LinvT[e] = vt;
+  }
+  cc_cluster_sync();
+  auto block = [&](double* base, int bi, int bj) { return base + (int64_t)bi * NB * ld + (int64_t)bj * NB; };
+  int lvl = 0;
+  for (int sb = 1; sb < nblk; sb *= 2, ++lvl) {
+    const int npairs = nblk / (2 * sb), items = npairs * sb * sb;
+    for (int phase = 0; phase < 2; ++phase) {
+      int* c = ctr + 64 + 2 * lvl + phase;   // ctr[0 .. nblk - 2]: the steps of the factorisation (nblk <= 64)
+      for (;;) {
+        if (tid == 0) s_w = atomicAdd(c, 1);
+        __syncthreads();
+        const int w = s_w;
+        __syncthreads();
+        if (w >= items) break;
+        // heaviest first: phase 0 has sb - j terms (j ascending), phase 1 has i + 1 terms (i descending)
+        const int pr = w % npairs, r = w / npairs, b0 = 2 * sb * pr;
+        const int i = phase == 0 ? r % sb : sb - 1 - r / sb, j = phase == 0 ? r / sb : r % sb;
+        double acc[8][2];
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) acc[cb][0] = acc[cb][1] = 0.0;
+        const int k_lo = phase == 0 ? j : 0, k_hi = phase == 0 ? sb - 1 : i;
+        for (int k = k_lo; k <= k_hi; ++k) {
+          // phase 0:  W(i,j)  += L21(i,k) Inv11(k,j)      sa = L(b0+sb+i, b0+k),          sb[c][kk] = LinvT(b0+j, b0+k)
+          // phase 1:  X(i,j)  += Inv22(i,k) W(k,j)        sa = Linv(b0+sb+i, b0+sb+k),    sb[c][kk] = WkT(b0+j, b0+sb+k)
+          ct_load_block_async(s0, phase == 0 ? block(A, b0 + sb + i, b0 + k) : block(Linv, b0 + sb + i, b0 + sb + k), ld, tid);
+          ct_load_block_async(s1, phase == 0 ? block(LinvT, b0 + j, b0 + k) : block(Wk, b0 + j, b0 + sb + k), ld, tid);
+          cp_async_commit();
+          cp_async_wait<0>();
+          __syncthreads();
+          ct_mm_nt(s0, s1, w8, lane, acc);
+          __syncthreads();
+        }
+        if (phase == 0) {   // W(i,j) transposed into Wk block (b0 + j, b0 + sb + i)
+          double* dst = block(Wk, b0 + j, b0 + sb + i);
+#pragma unroll
+          for (int cb = 0; cb < 8; ++cb) {
+            dst[(int64_t)(8 * cb + 2 * q) * ld + 8 * w8 + g] = acc[cb][0];
+            dst[(int64_t)(8 * cb + 2 * q + 1) * ld + 8 * w8 + g] = acc[cb][1];
+          }
+        } else {            // X = -acc -> Linv block (b0 + sb + i, b0 + j), X^T -> LinvT block (b0 + j, b0 + sb + i)
+          double* dx = block(Linv, b0 + sb + i, b0 + j) + (int64_t)(8 * w8 + g) * ld + 2 * q;
+          double* dt = block(LinvT, b0 + j, b0 + sb + i);
+#pragma unroll
+          for (int cb = 0; cb < 8; ++cb) {
+            *reinterpret_cast<double2*>(dx + 8 * cb) = make_double2(-acc[cb][0], -acc[cb][1]);
+            dt[(int64_t)(8 * cb + 2 * q) * ld + 8 * w8 + g] = -acc[cb][0];
+            dt[(int64_t)(8 * cb + 2 * q + 1) * ld + 8 * w8 + g] = -acc[cb][1];
+          }
+        }
+      }
+      cc_cluster_sync();
+    }
   }
 }
 

@@ -440,7 +440,7 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
                             bool beside_build = false) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   CK(cudaStreamIsCapturing(st, &cs));
-  const bool cluster = beside_build && h->chol_cluster && batch == 1 && h->Mp >= 4 * NB && cs == cudaStreamCaptureStatusNone && h->use_graphs;
+  bool cluster = beside_build && h->chol_cluster && batch == 1 && h->Mp >= 4 * NB && cs == cudaStreamCaptureStatusNone && h->use_graphs;
   if (cs != cudaStreamCaptureStatusNone || !h->use_graphs) {
     CK(cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, st));
     return chol_and_inverse_launches(h, st, A, Linv, LinvT, batch, info);
@@ -453,12 +453,12 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
       CK(cudaStreamCreateWithPriority(&h->hp_stream, cudaStreamNonBlocking, hi));
       CK(cudaEventCreateWithFlags(&h->ev_hp0, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_hp1, cudaEventDisableTiming));
-      CK(cudaMalloc((void**)&h->chol_ctr, 64 * sizeof(int)));
+      CK(cudaMalloc((void**)&h->chol_ctr, 128 * sizeof(int)));
     }
     CK(cudaEventRecord(h->ev_hp0, st));
     CK(cudaStreamWaitEvent(h->hp_stream, h->ev_hp0, 0));
     CK(cudaMemsetAsync(h->info_ws, 0, sizeof(int32_t), h->hp_stream));
-    CK(cudaMemsetAsync(h->chol_ctr, 0, 64 * sizeof(int), h->hp_stream));
+    CK(cudaMemsetAsync(h->chol_ctr, 0, 128 * sizeof(int), h->hp_stream));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(CC_N, 1, 1);
     lc.blockDim = dim3(256, 1, 1);
@@ -469,10 +469,28 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
     at[0].val.clusterDim.x = CC_N; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&lc, k_chol_cluster, A, h->Mp, h->Tblk, h->info_ws, (const double*)h->piv_tol, h->chol_ctr));
-    h->launches++;
+    // the explicit inverse rides in the same launch when the tile build beside it is long enough to cover it (the 8 SMs need ~1.1 ms for
+    // factor + inverse at Mp = 1024, the build 5.8 us per 1000 rows); behind a short build the inverse is quicker as launches on all SMs
+    // (one rank's share of the 8-GPU run, 125 000 rows: 8.90 ms with the inverse in the cluster launch, 8.50 without)
+    const bool inv_in_cluster = !getenv("GGP_CHOL_CLUSTER_NO_INV") && (h->n_local >= (int64_t)1 << 18 || getenv("GGP_CHOL_CLUSTER_INV"));
+    double* nul = nullptr;
+    const cudaError_t le = cudaLaunchKernelEx(&lc, k_chol_cluster, A, h->Mp, h->Tblk, h->info_ws, (const double*)h->piv_tol, h->chol_ctr,
+                                              inv_in_cluster ? Linv : nul, inv_in_cluster ? LinvT : nul, h->Wk);
+    if (le == cudaSuccess) {
+      h->launches++;
+    } else {
+      // a device / partition that cannot co-schedule the cluster (8 SMs of one GPC with 52 KB of shared memory and a full register file
+      // each): not an error of the evaluation -- clear it and use the launch chain from now on
+      (void)cudaGetLastError();
+      h->chol_cluster = false;
+      cluster = false;
+    }
     CK(cudaEventRecord(h->ev_hp1, h->hp_stream));
     CK(cudaStreamWaitEvent(st, h->ev_hp1, 0));
+    if (cluster && inv_in_cluster) {   // factor, inverse and transposed inverse all came out of the one launch
+      CK(cudaMemcpyAsync(info, h->info_ws, sizeof(int32_t) * batch, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
   }
   ggp_handle::CholGraph* g = nullptr;
   for (auto& c : h->chol_graphs)
