@@ -131,6 +131,41 @@ def test_i8_host_rows_match_device_rows():
         assert torch.equal(out["bound"], ref["bound"]) and torch.equal(out["grad"], ref["grad"])
 
 
+def test_cluster_resident_factorisation_plans_agree(monkeypatch):
+    """The Kzz factorisation next to the tile build is one thread-block-cluster launch (k_chol_cluster); with a long build beside it the
+    explicit inverse rides in the same launch.  Both plans against the oracle at 1e-8 and against each other (same arithmetic per block,
+    different summation order inside the inverse: rounding level), also with a failing pivot (LAPACK-style info through the cluster launch)."""
+    import ggp_b200
+    from oracle import sgpr as osgpr
+    dev = torch.device("cuda:0")
+    eng = ggp_b200.Engine.get(dev, precision="fp64_i8")
+    N, M, D = 70000, 300, 4          # padded M = 512: 8 diagonal blocks, 3 inverse levels; N >= prefetch_min_rows: the side-stream build
+    X, y, Z, th = make_problem(N, M, D, seed=11)
+    Xd, yd, Zd, thd = X.to(dev), y.to(dev), Z.to(dev), th.to(dev)
+    Fo, go = osgpr.sgpr_grads_closed_form(X, y, Z, th[:D], th[D], th[D + 1], jitter_policy=1e-4, normalize="none")
+    outs = {}
+    for plan, env in (("inverse in the cluster launch", {"GGP_CHOL_CLUSTER_INV": "1"}), ("inverse as launches", {"GGP_CHOL_CLUSTER_NO_INV": "1"})):
+        for k in ("GGP_CHOL_CLUSTER_INV", "GGP_CHOL_CLUSTER_NO_INV"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = eng.sgpr_eval(Xd, yd, Zd, thd, jitter_policy=1e-4)
+        g = out["grad"][0].cpu()
+        assert relerr(out["bound"], Fo) < TOL, plan
+        for key, mine in (("ell", g[:D]), ("sf2", g[D]), ("s2", g[D + 1]), ("Z", g[D + 2:].view(M, D))):
+            assert relerr(mine, go[key]) < TOL, (plan, key)
+        outs[plan] = out
+    a, b = outs.values()
+    assert relerr(a["bound"], b["bound"]) < 1e-13 and relerr(a["grad"], b["grad"]) < 1e-10
+    # a Kzz that is not positive definite at jitter 0 (duplicated inducing rows): the ladder engages through the cluster launch's info
+    monkeypatch.setenv("GGP_CHOL_CLUSTER_INV", "1")
+    monkeypatch.delenv("GGP_CHOL_CLUSTER_NO_INV", raising=False)
+    Zdup = Zd.clone()
+    Zdup[200] = Zdup[3]
+    out = eng.sgpr_eval(Xd, yd, Zdup, thd, jitter_policy="gpytorch")
+    assert float(out["jitter"][0]) > 0.0 and bool(torch.isfinite(out["bound"]).all())
+
+
 @pytest.mark.parametrize("D", [11, 12])
 def test_i8_moment_block_boundary(D):
     """2 D + 1 = 23 moments still fit the register-resident accumulation (three DMMA blocks); D = 12 takes the per-tile path."""
