@@ -472,7 +472,10 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
     // the explicit inverse rides in the same launch when the tile build beside it is long enough to cover it (the 8 SMs need ~1.1 ms for
     // factor + inverse at Mp = 1024, the build 5.8 us per 1000 rows); behind a short build the inverse is quicker as launches on all SMs
     // (one rank's share of the 8-GPU run, 125 000 rows: 8.90 ms with the inverse in the cluster launch, 8.50 without)
-    const bool inv_in_cluster = !getenv("GGP_CHOL_CLUSTER_NO_INV") && (h->n_local >= (int64_t)1 << 18 || getenv("GGP_CHOL_CLUSTER_INV"));
+    // Threshold: validated with whole bench runs at 1e6 and 5e5 local rows; `bench.py --rows 400000` measured 30.2 ms per step with the
+    // inverse in the launch against 24.0 without, an effect that a plain loop of evaluations at the same size does not show (23.7 both:
+    // scripts/step_times.py) and that is not understood yet -- so the plan is kept to the sizes where the build is at least twice as long
+    const bool inv_in_cluster = !getenv("GGP_CHOL_CLUSTER_NO_INV") && (h->n_local >= 450000 || getenv("GGP_CHOL_CLUSTER_INV"));
     double* nul = nullptr;
     const cudaError_t le = cudaLaunchKernelEx(&lc, k_chol_cluster, A, h->Mp, h->Tblk, h->info_ws, (const double*)h->piv_tol, h->chol_ctr,
                                               inv_in_cluster ? Linv : nul, inv_in_cluster ? LinvT : nul, h->Wk);
