@@ -83,6 +83,7 @@ struct GemmP {
   // k_mm64 only, optional: the result is ALSO stored transposed, Ct[j * ldct + i] = C[i, j] (same batch / pair strides as C):
   // the recursive triangular inverse keeps L^-1 and L^-T in step without a transpose kernel per level
   double* Ct;       int64_t ldct;
+  int fold;         // k_mm64 only: work items beyond the first `fold` (= SM count) are taken in reverse order, 0 = plain order
 };
 
 struct WorkItem {

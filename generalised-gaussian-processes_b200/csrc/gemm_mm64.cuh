@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_mm64(const GemmP p) {
   // rest as second CTAs of the same SMs in the same order, so the items beyond the first wave are taken in REVERSE: the lightest tile
   // shares an SM with the heaviest one (two co-resident CTAs split the FP64 pipe; heavy + heavy took 62 us for a triangular 1024^3 product)
   int w = blockIdx.x;
-  if (w >= p.heavy_first && p.heavy_first > 0) w = p.total - 1 - (w - p.heavy_first);
+  if (p.fold > 0 && w >= p.fold) w = p.total - 1 - (w - p.fold);
   // slices (batch x pair) are interleaved so that "heaviest first" holds across them
   const int nz = p.total / p.tiles_per_z;
   int z = w % nz;

@@ -296,7 +296,7 @@ static int launch_gemm(ggp_handle* h, cudaStream_t st, int epi, const GemmP& pin
     p.ntn = (p.N + S_T - 1) / S_T;
     p.tiles_per_z = p.ntm * p.ntn;
     p.total = p.tiles_per_z * nbatch * p.nz2;
-    p.heavy_first = (p.kmode != 0 && p.total > h->sm_count && !getenv("GGP_MM64_NO_FOLD")) ? h->sm_count : 0;   // k_mm64: fold point of the grid
+    p.fold = (p.kmode != 0 && p.total > h->sm_count && !getenv("GGP_MM64_NO_FOLD")) ? h->sm_count : 0;
     k_mm64<<<p.total, S_THREADS, S_SMEM, st>>>(p);
     CKL();
     return 0;
@@ -459,14 +459,19 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
     CK(cudaStreamWaitEvent(h->hp_stream, h->ev_hp0, 0));
     CK(cudaMemsetAsync(h->info_ws, 0, sizeof(int32_t), h->hp_stream));
     CK(cudaMemsetAsync(h->chol_ctr, 0, 128 * sizeof(int), h->hp_stream));
+    int ccn = CC_N;
+    if (const char* e = getenv("GGP_CHOL_CLUSTER_N")) {   // developer A/B: 16 needs the non-portable cluster size
+      ccn = atoi(e) == 16 ? 16 : (atoi(e) == 4 ? 4 : CC_N);
+      if (ccn == 16) (void)cudaFuncSetAttribute(k_chol_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    }
     cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(CC_N, 1, 1);
+    lc.gridDim = dim3(ccn, 1, 1);
     lc.blockDim = dim3(256, 1, 1);
     lc.dynamicSmemBytes = CT_SMEM;
     lc.stream = h->hp_stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CC_N; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = ccn; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
     // the explicit inverse rides in the same launch when the tile build beside it is long enough to cover it (the 8 SMs need ~1.1 ms for
