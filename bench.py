@@ -467,7 +467,7 @@ def main():
         eng.profile_read()
         eng.profile_enable(True)
         sampler = ClockSampler(local)
-        if rank == 0:
+        if rank == 0 and not os.environ.get("GGP_BENCH_NO_SAMPLER"):   # (developer switch: diagnostics only)
             sampler.start()
         if world > 1:
             dist.barrier()

@@ -477,9 +477,9 @@ static int chol_and_inverse(ggp_handle* h, cudaStream_t st, double* A, double* L
     // the explicit inverse rides in the same launch when the tile build beside it is long enough to cover it (the 8 SMs need ~1.1 ms for
     // factor + inverse at Mp = 1024, the build 5.8 us per 1000 rows); behind a short build the inverse is quicker as launches on all SMs
     // (one rank's share of the 8-GPU run, 125 000 rows: 8.90 ms with the inverse in the cluster launch, 8.50 without)
-    // Threshold: validated with whole bench runs at 1e6 and 5e5 local rows; `bench.py --rows 400000` measured 30.2 ms per step with the
-    // inverse in the launch against 24.0 without, an effect that a plain loop of evaluations at the same size does not show (23.7 both:
-    // scripts/step_times.py) and that is not understood yet -- so the plan is kept to the sizes where the build is at least twice as long
+    // Threshold: validated with whole bench runs at 1e6 and 5e5 local rows.  At 4e5 rows the two plans are within 1 % (24.17 against 24.39 ms
+    // per step; one earlier call on another box had shown 30.2 against 24.0, not reproduced since: scripts/r2_anom.sh, scripts/step_times.py),
+    // below that the inverse as launches wins -- so the plan is kept to the sizes where the build is at least twice as long as the launch
     const bool inv_in_cluster = !getenv("GGP_CHOL_CLUSTER_NO_INV") && (h->n_local >= 450000 || getenv("GGP_CHOL_CLUSTER_INV"));
     double* nul = nullptr;
     const cudaError_t le = cudaLaunchKernelEx(&lc, k_chol_cluster, A, h->Mp, h->Tblk, h->info_ws, (const double*)h->piv_tol, h->chol_ctr,
